@@ -1,0 +1,391 @@
+// board.cuh -- warp-cooperative Go board primitives for sm_100a.
+//
+// Representation ("row-per-lane bitboards"): one game is owned by N consecutive
+// lanes of a warp (N = board size; 19x19 -> 1 game/warp on lanes 0..18, 9x9 ->
+// 3 games/warp on lanes 0..26).  Lane `row` holds row y=row of the position as
+// two N-bit words: `own`/`opp` or `b`/`w`, bit x = intersection (x, y).  With
+// this layout
+//   * left/right neighbours are register shifts, up/down neighbours one
+//     __shfl_up/__shfl_down each, so a 4-neighbour dilation is ~8 instructions;
+//   * group flood fill ("which stones are connected to ...") is dilation to a
+//     fixpoint with a warp vote as the termination test;
+//   * per-game reductions (capture count, Zobrist delta) are REDUX over the
+//     game's lane segment.
+// In HBM a position is N uint64 words (black row | white row << 32) so that a
+// warp loads/stores it with one coalesced 8-byte access per lane.
+//
+// Semantics follow the reference rules engine bit-for-bit on the observable
+// state (hash, legality, captures, ko, superko, score); the reference functions
+// each routine reproduces are cited inline as
+// /root/reference/src_cpp/elfgames/go/base/<file>:<line>.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "elfb200_playout_policy.h"
+
+namespace elfb200 {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+enum : int { S_EMPTY = 0, S_BLACK = 1, S_WHITE = 2 };
+// encodings of "last move" in BoardMeta (points are p = y*N + x)
+enum : int { MV_PASS = -2, MV_INVALID = -1 };
+
+// flags in BoardMeta::flags
+enum : uint8_t { F_KO_ACTIVE = 1, F_SUPERKO = 2 };
+
+// 16-byte per-game metadata (SoA array, one uint4 load per game).
+struct __align__(16) BoardMeta {
+  uint16_t ply;      // reference Board::_ply, starts at 1 (board.cc:106)
+  uint8_t next;      // side to move (board.cc:99)
+  uint8_t flags;     // F_KO_ACTIVE <=> _ko_age == 0 (board.h:144), F_SUPERKO
+  int16_t last1;     // Board::_last_move  (point, MV_PASS, MV_INVALID)
+  int16_t last2;     // Board::_last_move2
+  int16_t ko_pt;     // Board::_simple_ko as point, -1 if never set
+  uint8_t ko_color;  // Board::_simple_ko_color
+  uint8_t pad;
+  uint16_t b_cap;    // Board::_b_cap
+  uint16_t w_cap;    // Board::_w_cap
+};
+static_assert(sizeof(BoardMeta) == 16, "BoardMeta must be 16 bytes");
+
+template <int N>
+struct Geo {
+  static constexpr int GPW = 32 / N;  // games per warp
+  static constexpr int LANES = GPW * N;
+  static constexpr uint32_t ROWMASK = (1u << N) - 1u;
+  static constexpr int E = N + 2;      // expanded stride of the reference (board.h:45)
+  static constexpr int P = N * N;
+  static constexpr int MAX_PLY = 2 * N * N;  // BOARD_MAX_MOVE, go_common.h:15
+  static constexpr int ZOB = E * E;
+};
+
+struct Lane {
+  int lane;          // 0..31
+  int sub;           // game slot inside the warp
+  int row;           // board row y owned by this lane (0 for idle lanes)
+  int base;          // first lane of this game's segment
+  uint32_t rm;       // ROWMASK for active lanes, 0 for idle lanes
+  uint32_t segmask;  // lane mask of this game's segment
+  bool active;
+};
+
+template <int N>
+__device__ __forceinline__ Lane make_lane() {
+  Lane L;
+  L.lane = threadIdx.x & 31;
+  L.active = L.lane < Geo<N>::LANES;
+  L.sub = L.active ? L.lane / N : 0;
+  L.row = L.active ? L.lane - L.sub * N : 0;
+  L.base = L.sub * N;
+  L.rm = L.active ? Geo<N>::ROWMASK : 0u;
+  L.segmask = L.active ? (Geo<N>::ROWMASK << L.base) : 0u;
+  return L;
+}
+
+// ---- neighbour shifts -------------------------------------------------------
+template <int N>
+__device__ __forceinline__ uint32_t up_of(uint32_t v, const Lane& L) {  // value of row y-1
+  uint32_t u = __shfl_up_sync(FULL, v, 1);
+  return L.row == 0 ? 0u : u;
+}
+template <int N>
+__device__ __forceinline__ uint32_t dn_of(uint32_t v, const Lane& L) {  // value of row y+1
+  uint32_t d = __shfl_down_sync(FULL, v, 1);
+  return (L.row == N - 1 || !L.active) ? 0u : d;
+}
+// union of the 4 neighbours of every set point (may carry bit N: AND with rm / a board mask)
+template <int N>
+__device__ __forceinline__ uint32_t nbr4(uint32_t v, const Lane& L) {
+  return (v << 1) | (v >> 1) | up_of<N>(v, L) | dn_of<N>(v, L);
+}
+
+// ---- per-game reductions ----------------------------------------------------
+template <int N>
+__device__ __forceinline__ int game_sum(int v, const Lane& L) {
+  if (Geo<N>::GPW == 1) return __reduce_add_sync(FULL, L.active ? v : 0);
+  int r = 0;
+  if (L.active) r = __reduce_add_sync(L.segmask, v);
+  return r;
+}
+template <int N>
+__device__ __forceinline__ uint64_t game_xor64(uint64_t v, const Lane& L) {
+  uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+  if (Geo<N>::GPW == 1) {
+    if (!L.active) lo = hi = 0;
+    lo = __reduce_xor_sync(FULL, lo);
+    hi = __reduce_xor_sync(FULL, hi);
+  } else if (L.active) {
+    lo = __reduce_xor_sync(L.segmask, lo);
+    hi = __reduce_xor_sync(L.segmask, hi);
+  }
+  return ((uint64_t)hi << 32) | lo;
+}
+template <int N>
+__device__ __forceinline__ bool game_any(bool pred, const Lane& L) {
+  if (Geo<N>::GPW == 1) return __any_sync(FULL, pred && L.active);
+  return (__ballot_sync(FULL, pred) & L.segmask) != 0u;
+}
+
+// ---- flood fill -------------------------------------------------------------
+// Grow `g` through `through` to a fixpoint (4-connectivity).  Two dilations per
+// vote.  All lanes of the warp iterate together; extra iterations are idempotent.
+template <int N>
+__device__ __forceinline__ uint32_t flood(uint32_t g, uint32_t through, const Lane& L) {
+  while (true) {
+    uint32_t n1 = g | (nbr4<N>(g, L) & through);
+    uint32_t n2 = n1 | (nbr4<N>(n1, L) & through);
+    bool ch = n2 != g;
+    g = n2;
+    if (!__any_sync(FULL, ch)) break;
+  }
+  return g;
+}
+
+// K independent fills advanced in lock step (ILP across fills, one vote/iteration).
+template <int N, int K>
+__device__ __forceinline__ void floodK(uint32_t (&g)[K], const uint32_t (&through)[K],
+                                       const Lane& L) {
+  while (true) {
+    bool ch = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      uint32_t n1 = g[k] | (nbr4<N>(g[k], L) & through[k]);
+      ch |= (n1 != g[k]);
+      g[k] = n1;
+    }
+    if (!__any_sync(FULL, ch)) break;
+  }
+}
+
+// ---- Zobrist ----------------------------------------------------------------
+// transform_hash (board.cc:24-36): black -> h, white -> rotate by 32 bits.
+__device__ __forceinline__ uint64_t zob_color(uint64_t h, int color) {
+  return color == S_WHITE ? ((h >> 32) | (h << 32)) : h;
+}
+
+// XOR of the raw table entries of all points set in row word `bits` of row `y`.
+template <int N>
+__device__ __forceinline__ uint64_t zob_row(const uint64_t* __restrict__ zob, int y, uint32_t bits) {
+  uint64_t h = 0;
+  const uint64_t* r = zob + (y + 1) * Geo<N>::E + 1;
+  while (bits) {
+    int x = __ffs(bits) - 1;
+    bits &= bits - 1;
+    h ^= r[x];
+  }
+  return h;
+}
+
+// ---- legality ---------------------------------------------------------------
+// Stones of colour `c` that belong to groups with >=2 liberties (`safe`) and to
+// groups with exactly one liberty (`atari`), restricted to the groups that touch
+// `focus` (other groups may be left unclassified).  `e` = empty points.
+//
+// Cheap sufficient tests for ">= 2 liberties", run as three lock-step fills:
+//   (a) a stone touching two empties;  (b) liberties of both checkerboard
+//   parities (a point's neighbours all have the opposite parity, so touching
+//   stones of different parity can never share a liberty).
+// Whatever stays unresolved is counted group by group.
+template <int N>
+__device__ __forceinline__ void classify_groups(uint32_t c, uint32_t e, uint32_t focus, const Lane& L,
+                                                uint32_t& safe, uint32_t& atari) {
+  const uint32_t e_l = e << 1, e_r = e >> 1, e_u = up_of<N>(e, L), e_d = dn_of<N>(e, L);
+  const uint32_t aL = c & e_l, aR = c & e_r, aU = c & e_u, aD = c & e_d;
+  const uint32_t touch = aL | aR | aU | aD;
+  const uint32_t t2 = (aL & (aR | aU | aD)) | (aR & (aU | aD)) | (aU & aD);
+  // checkerboard: bit x of row y is "even" iff (x + y) even
+  const uint32_t even = (L.row & 1) ? 0xAAAAAAAAu : 0x55555555u;
+  uint32_t g[3] = {t2, touch & even, touch & ~even};
+  const uint32_t thr[3] = {c, c, c};
+  floodK<N, 3>(g, thr, L);
+  safe = g[0] | (g[1] & g[2]);
+  atari = 0;
+  uint32_t cand = c & ~safe & focus;  // seeds of unresolved groups we care about
+  while (__any_sync(FULL, cand != 0u)) {
+    // every game picks the lowest stone of its lowest non-empty row
+    uint32_t bal = __ballot_sync(FULL, cand != 0u) & L.segmask;
+    int src = __ffs(bal) - 1;
+    uint32_t seed = (L.lane == src) ? (cand & (0u - cand)) : 0u;
+    uint32_t grp = flood<N>(seed, c, L);
+    int nl = game_sum<N>(__popc(nbr4<N>(grp, L) & e), L);
+    if (nl == 1)
+      atari |= grp;
+    else
+      safe |= grp;
+    cand &= ~grp;
+  }
+}
+
+// Legal-move rows for the side to move (`own`), TryPlay semantics (board.cc:788-827):
+// empty, not the active simple-ko point for this player (board.cc:234-240), not suicide
+// (board.cc:201-232: an empty neighbour, or a friendly neighbour group with >1 liberty, or
+// an enemy neighbour group with exactly 1 liberty).
+template <int N>
+__device__ __forceinline__ uint32_t legal_rows(uint32_t own, uint32_t opp, const Lane& L,
+                                               bool ko_applies, int ko_pt) {
+  const uint32_t e = ~(own | opp) & L.rm;
+  const uint32_t en = nbr4<N>(e, L);
+  uint32_t legal = e & en;
+  const uint32_t hard = e & ~en;  // empties with no empty neighbour
+  if (__any_sync(FULL, hard != 0u)) {
+    const uint32_t focus = nbr4<N>(hard, L);
+    uint32_t own_safe, own_atari, opp_safe, opp_atari;
+    classify_groups<N>(own, e, focus, L, own_safe, own_atari);
+    classify_groups<N>(opp, e, focus, L, opp_safe, opp_atari);
+    legal |= hard & (nbr4<N>(own_safe, L) | nbr4<N>(opp_atari, L));
+  }
+  if (ko_applies) {
+    int ky = ko_pt / N, kx = ko_pt - ky * N;
+    if (L.row == ky) legal &= ~(1u << kx);
+  }
+  return legal & L.rm;
+}
+
+// Own true eyes: isEye && !isFakeEye (board.cc:1850-1910).
+template <int N>
+__device__ __forceinline__ uint32_t true_eye_rows(uint32_t own, uint32_t opp, const Lane& L) {
+  const uint32_t e = ~(own | opp) & L.rm;
+  const uint32_t notown = ~own & L.rm;                       // on-board, not ours
+  const uint32_t eyeish = e & ~nbr4<N>(notown, L);           // every on-board neighbour is ours
+  const uint32_t o_u = up_of<N>(opp, L), o_d = dn_of<N>(opp, L);
+  const uint32_t d1 = o_u << 1, d2 = o_u >> 1, d3 = o_d << 1, d4 = o_d >> 1;  // 4 diagonals
+  const uint32_t ge1 = d1 | d2 | d3 | d4;
+  const uint32_t ge2 = (d1 & (d2 | d3 | d4)) | (d2 & (d3 | d4)) | (d3 & d4);
+  const uint32_t edge =
+      (L.row == 0 || L.row == N - 1) ? Geo<N>::ROWMASK : (1u | (1u << (N - 1)));
+  const uint32_t fake = (edge & ge1) | (~edge & ge2);
+  return eyeish & ~fake & L.rm;
+}
+
+// simple_tt_scoring (go_state.h:32-93): black area minus white area, where a side's area is
+// its stones plus the empties reachable from them through empties.
+template <int N>
+__device__ __forceinline__ int tt_score(uint32_t b, uint32_t w, const Lane& L) {
+  const uint32_t e = ~(b | w) & L.rm;
+  uint32_t g[2] = {b, w};
+  const uint32_t thr[2] = {e, e};
+  floodK<N, 2>(g, thr, L);
+  return game_sum<N>(__popc(g[0] & ~g[1]) - __popc(g[1] & ~g[0]), L);
+}
+
+// ---- applying a move ----------------------------------------------------------
+// Play (board.cc:1297-1401) for a move already known to be legal.  `b`,`w` are this lane's
+// rows; `meta`,`hash` are game-uniform.  `p` = y*N+x, MV_PASS, or MV_NONE (leave the game
+// untouched).  Fully predicated: the games sharing a warp may take different cases.
+// Returns the number of stones captured.
+enum : int { MV_NONE = -3 };
+
+template <int N>
+__device__ __forceinline__ int play_move(uint32_t& b, uint32_t& w, BoardMeta& meta, uint64_t& hash,
+                                         int p, const uint64_t* __restrict__ zob, const Lane& L) {
+  const int player = meta.next;
+  const int oppc = S_BLACK + S_WHITE - player;
+  const bool is_stone = p >= 0;
+  uint32_t own = player == S_BLACK ? b : w;
+  uint32_t opp = player == S_BLACK ? w : b;
+  const int y = is_stone ? p / N : 0, x = is_stone ? p - y * N : 0;
+  const uint32_t mybit = (is_stone && L.row == y && L.active) ? (1u << x) : 0u;
+  const uint32_t nb = nbr4<N>(mybit, L) & L.rm;  // the (<=4) neighbour points
+  const bool single = !game_any<N>((nb & own) != 0u, L);
+  own |= mybit;
+  uint64_t dh = 0;
+  int ncap = 0;
+  uint32_t dead = 0;
+  if (__any_sync(FULL, (nb & opp) != 0u)) {
+    // enemy stones still connected to a liberty once our stone is down; the rest is captured
+    // (EmptyGroup, board.cc:548-572).  Only groups next to the new stone can have died.
+    const uint32_t e = ~(own | opp) & L.rm;
+    const uint32_t alive = flood<N>(opp & nbr4<N>(e, L), opp, L);
+    dead = opp & ~alive;
+    if (__any_sync(FULL, dead != 0u)) {
+      ncap = game_sum<N>(__popc(dead), L);
+      opp &= ~dead;
+      dh = zob_color(game_xor64<N>(zob_row<N>(zob, L.row, dead), L), oppc);
+    }
+  }
+  if (is_stone) {
+    hash ^= dh ^ zob_color(zob[(y + 1) * Geo<N>::E + (x + 1)], player);  // set_color, board.cc:38-51
+    if (player == S_BLACK) {
+      b = own; w = opp; meta.b_cap += ncap;  // board.cc:1348-1351
+    } else {
+      w = own; b = opp; meta.w_cap += ncap;
+    }
+  }
+  // simple ko (board.cc:1384-1393): the new group is one stone with one liberty and exactly one
+  // stone was captured; the ko point is where that stone stood.
+  const int libs = game_sum<N>(__popc(nb & ~(own | opp)), L);
+  {
+    uint32_t bal = __ballot_sync(FULL, dead != 0u) & L.segmask;
+    int src = __ffs(bal) - 1;
+    int dx = __shfl_sync(FULL, __ffs(dead) - 1, src & 31);
+    if (is_stone) {
+      if (ncap == 1 && single && libs == 1) {
+        meta.ko_pt = (int16_t)((src - L.base) * N + dx);
+        meta.ko_color = (uint8_t)oppc;
+        meta.flags |= F_KO_ACTIVE;
+      } else {
+        meta.flags &= ~F_KO_ACTIVE;  // _ko_age++ : cannot be 0 again until a new ko
+      }
+    }
+  }
+  if (p != MV_NONE) {
+    // update_next_move (board.cc:1225-1238); a pass leaves the ko state untouched (board.cc:1306)
+    meta.next = (uint8_t)oppc;
+    meta.last2 = meta.last1;
+    meta.last1 = (int16_t)p;
+    meta.ply++;
+  }
+  return ncap;
+}
+
+// GoState::terminated (go_state.h:145-147) from the cached superko flag.
+template <int N>
+__device__ __forceinline__ bool is_terminated(const BoardMeta& m) {
+  return (m.last1 == MV_PASS && m.last2 == MV_PASS) || m.ply >= Geo<N>::MAX_PLY ||
+         (m.flags & F_SUPERKO);
+}
+
+// GoState::_check_superko (go_state.cc:96-111): does `hash` equal any recorded pre-move
+// position hash?  (64-bit hash equality stands in for the reference's hash + 2-bit-board
+// comparison; see DESIGN.md.)  `hist` points at this game's record, `n` entries.
+template <int N>
+__device__ __forceinline__ bool superko_scan(const uint64_t* __restrict__ hist, int n, uint64_t hash,
+                                             const Lane& L) {
+  bool found = false;
+  if (L.active)
+    for (int i = L.row; i < n; i += N) found |= (hist[i] == hash);
+  return game_any<N>(found, L);
+}
+
+// k-th (0-based) set point of `cand` in ascending ACTION order a = x*N + y (x outer, y inner);
+// returns the point p = y*N + x.  n = number of candidates of this game (k < n).
+// Transposes rows->columns with N ballots, then a segmented prefix sum over columns.
+template <int N>
+__device__ __forceinline__ int select_kth_action_order(uint32_t cand, int k, const Lane& L) {
+  uint32_t col = 0;  // lane `row` ends up holding COLUMN x=row: bit y = point (x, y)
+#pragma unroll
+  for (int x = 0; x < N; ++x) {
+    uint32_t bal = __ballot_sync(FULL, (cand >> x) & 1u);
+    if (L.row == x) col = (bal >> L.base) & Geo<N>::ROWMASK;
+  }
+  if (!L.active) col = 0;
+  int cnt = __popc(col);
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < N; d <<= 1) {
+    int t = __shfl_up_sync(FULL, incl, d);
+    if (L.row >= d) incl += t;
+  }
+  int excl = incl - cnt;
+  bool mine = L.active && k >= excl && k < incl;
+  uint32_t bal = __ballot_sync(FULL, mine) & L.segmask;
+  int src = __ffs(bal) - 1;
+  int yy = mine ? (int)__fns(col, 0, k - excl + 1) : 0;
+  int p = yy * N + L.row;  // column index is this lane's row number
+  return __shfl_sync(FULL, p, src & 31);
+}
+
+}  // namespace elfb200

@@ -1,0 +1,696 @@
+// elfb200.cu -- kernels + C ABI of libelfb200.so (board path).
+//
+// Kernels (all templated on the board size N in {9, 19}; one game per N-lane warp segment):
+//   k_reset     clear selected games
+//   k_step      GoState::forward for a batch: validate, play, superko, next legal mask
+//   k_export_*  host-facing views (legal/stones/eyes by action index, info words)
+//   k_score     simple_tt_scoring
+//   k_features  BoardFeature::extractAGZ, float32 [G][18][N][N]
+//   k_playout   whole random-policy games with the position held in registers
+//
+// HBM layout (structure of arrays, G games):
+//   cur   uint64 [G][N]      current position, row y = black_row | white_row << 32
+//   ring  uint64 [G][8][N]   last 8 positions (AGZ history), slot (ply-2) & 7 is the newest
+//   legal uint32 [G][N]      legal-move rows for the side to move
+//   hash  uint64 [G]         Zobrist hash
+//   meta  BoardMeta [G]      16 B: ply, side, ko, last moves, captures
+//   sk    uint64 [G][2N^2]   pre-move hashes of all non-pass moves (superko record), sk_n int32[G]
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "board.cuh"
+#include "elfb200.h"
+
+namespace elfb200 {
+
+__device__ const uint64_t g_zobrist[441] = {
+#include "elfb200_zobrist.inc"
+};
+
+constexpr int BLOCK = 128;  // 4 warps per CTA
+constexpr int WARPS = BLOCK / 32;
+
+template <int N>
+__device__ __forceinline__ void load_zobrist(uint64_t* s_zob) {
+  for (int i = threadIdx.x; i < Geo<N>::ZOB; i += blockDim.x) s_zob[i] = g_zobrist[i];
+  __syncthreads();
+}
+
+template <int N>
+__device__ __forceinline__ int warp_game(const Lane& L, int G, bool& valid) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int g = warp * Geo<N>::GPW + L.sub;
+  valid = L.active && g < G;
+  return g;
+}
+
+__device__ __forceinline__ BoardMeta initial_meta() {
+  BoardMeta m;
+  m.ply = 1;
+  m.next = S_BLACK;
+  m.flags = 0;
+  m.last1 = MV_INVALID;
+  m.last2 = MV_INVALID;
+  m.ko_pt = -1;
+  m.ko_color = 0;
+  m.pad = 0;
+  m.b_cap = 0;
+  m.w_cap = 0;
+  return m;
+}
+
+__device__ __forceinline__ BoardMeta load_meta(const BoardMeta* p) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  BoardMeta m;
+  memcpy(&m, &v, 16);
+  return m;
+}
+__device__ __forceinline__ void store_meta(BoardMeta* p, const BoardMeta& m) {
+  uint4 v;
+  memcpy(&v, &m, 16);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+struct DevState {
+  uint64_t* cur;
+  uint64_t* ring;
+  uint32_t* legal;
+  uint64_t* hash;
+  BoardMeta* meta;
+  uint64_t* sk;
+  int32_t* sk_n;
+  int G;
+};
+
+// ---------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(BLOCK) k_reset(DevState st, const uint8_t* __restrict__ mask) {
+  const Lane L = make_lane<N>();
+  bool valid;
+  const int g = warp_game<N>(L, st.G, valid);
+  if (!valid) return;
+  if (mask && !mask[g]) return;
+  st.cur[(size_t)g * N + L.row] = 0;
+  st.legal[(size_t)g * N + L.row] = Geo<N>::ROWMASK;  // every point of the empty board is legal
+  for (int s = 0; s < 8; ++s) st.ring[((size_t)g * 8 + s) * N + L.row] = 0;
+  if (L.row == 0) {
+    st.hash[g] = 0;
+    store_meta(&st.meta[g], initial_meta());
+    st.sk_n[g] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GoState::forward (go_state.cc:74-94) for all games.
+template <int N>
+__global__ void __launch_bounds__(BLOCK)
+    k_step(DevState st, const int32_t* __restrict__ actions, uint8_t* __restrict__ ok) {
+  __shared__ uint64_t s_zob[Geo<N>::ZOB];
+  load_zobrist<N>(s_zob);
+  const Lane L = make_lane<N>();
+  bool valid;
+  const int g = warp_game<N>(L, st.G, valid);
+  const int gs = valid ? g : 0;  // safe index for idle lanes (loads only)
+
+  uint64_t rowv = valid ? st.cur[(size_t)gs * N + L.row] : 0ull;
+  uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
+  BoardMeta meta = load_meta(&st.meta[gs]);
+  uint64_t hash = st.hash[gs];
+  const uint32_t lrow = valid ? st.legal[(size_t)gs * N + L.row] : 0u;
+  int nsk = st.sk_n[gs];
+  const int a = valid ? actions[gs] : -1;
+
+  // validate (forward refuses on terminated state, then TryPlay2; go_state.cc:78-83)
+  const bool term = is_terminated<N>(meta);
+  int pm = MV_NONE;
+  if (valid && !term) {
+    if (a == Geo<N>::P) {
+      pm = MV_PASS;
+    } else if (a >= 0 && a < Geo<N>::P) {
+      pm = (a % N) * N + (a / N);  // a = x*N + y  ->  p = y*N + x
+    }
+  }
+  {
+    const int y = pm >= 0 ? pm / N : -1, x = pm >= 0 ? pm - y * N : 0;
+    const bool bit = (L.row == y) && ((lrow >> x) & 1u);
+    const bool is_legal = game_any<N>(bit, L);
+    if (pm >= 0 && !is_legal) pm = MV_NONE;
+  }
+  const uint64_t pre_hash = hash;
+  play_move<N>(b, w, meta, hash, pm, s_zob, L);
+
+  // superko (go_state.cc:96-121): compare with the recorded pre-move positions, then record.
+  const uint64_t* skg = st.sk + (size_t)gs * Geo<N>::MAX_PLY;
+  const bool sko = superko_scan<N>(skg, pm >= 0 ? nsk : 0, hash, L);
+  if (pm >= 0) {
+    if (sko) meta.flags |= F_SUPERKO;
+    if (L.row == 0) {
+      st.sk[(size_t)g * Geo<N>::MAX_PLY + nsk] = pre_hash;
+      st.sk_n[g] = nsk + 1;
+    }
+  }
+
+  // legal mask of the new position
+  const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
+  const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
+  const uint32_t lnew = legal_rows<N>(own, opp, L, ko_applies, meta.ko_pt);
+
+  if (valid) {
+    if (pm != MV_NONE) {
+      const uint64_t nv = (uint64_t)b | ((uint64_t)w << 32);
+      st.cur[(size_t)g * N + L.row] = nv;
+      st.ring[((size_t)g * 8 + ((meta.ply - 2) & 7)) * N + L.row] = nv;  // go_state.cc:90-92
+      st.legal[(size_t)g * N + L.row] = lnew;
+      if (L.row == 0) {
+        st.hash[g] = hash;
+        store_meta(&st.meta[g], meta);
+      }
+    }
+    if (ok && L.row == 0) ok[g] = pm != MV_NONE ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(BLOCK)
+    k_export(DevState st, uint8_t* __restrict__ legal_out, uint8_t* __restrict__ stones_out,
+             uint8_t* __restrict__ eyes_out, int eye_player, int32_t* __restrict__ info_out,
+             int32_t* __restrict__ score_out) {
+  const Lane L = make_lane<N>();
+  bool valid;
+  const int g = warp_game<N>(L, st.G, valid);
+  const int gs = valid ? g : 0;
+  const uint64_t rowv = valid ? st.cur[(size_t)gs * N + L.row] : 0ull;
+  const uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
+  const BoardMeta meta = load_meta(&st.meta[gs]);
+  constexpr int P = Geo<N>::P;
+  if (legal_out && valid) {
+    const uint32_t l = st.legal[(size_t)g * N + L.row];
+    for (int x = 0; x < N; ++x) legal_out[(size_t)g * (P + 1) + x * N + L.row] = (l >> x) & 1u;
+    if (L.row == 0) legal_out[(size_t)g * (P + 1) + P] = 1;
+  }
+  if (stones_out && valid) {
+    for (int x = 0; x < N; ++x)
+      stones_out[(size_t)g * P + x * N + L.row] = ((b >> x) & 1u) | (((w >> x) & 1u) << 1);
+  }
+  if (eyes_out) {  // warp-collective: no early exit
+    int pl = eye_player ? eye_player : meta.next;
+    const uint32_t own = pl == S_BLACK ? b : w, opp = pl == S_BLACK ? w : b;
+    const uint32_t eye = true_eye_rows<N>(own, opp, L);
+    if (valid)
+      for (int x = 0; x < N; ++x) eyes_out[(size_t)g * P + x * N + L.row] = (eye >> x) & 1u;
+  }
+  if (score_out) {
+    const int sc = tt_score<N>(b, w, L);
+    if (valid && L.row == 0) score_out[g] = sc;
+  }
+  if (info_out && valid && L.row == 0) {
+    auto p2a = [](int p) -> int {
+      if (p == MV_PASS) return Geo<N>::P;
+      if (p < 0) return -1;
+      return (p % N) * N + p / N;
+    };
+    int32_t* o = info_out + (size_t)g * ELFB200_INFO_FIELDS;
+    o[0] = meta.ply;
+    o[1] = meta.next;
+    o[2] = meta.b_cap;
+    o[3] = meta.w_cap;
+    o[4] = p2a(meta.last1);
+    o[5] = p2a(meta.last2);
+    o[6] = (meta.flags & F_KO_ACTIVE) ? p2a(meta.ko_pt) : -1;
+    o[7] = meta.ko_color;
+    o[8] = 0;
+    o[9] = is_terminated<N>(meta) ? 1 : 0;
+    o[10] = (meta.last1 == MV_PASS && meta.last2 == MV_PASS) ? 1 : 0;
+    o[11] = (meta.flags & F_SUPERKO) ? 1 : 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// BoardFeature::extractAGZ (board_feature.cc:247-290).  One CTA per position; the 8 history
+// positions are staged in shared memory, every thread produces float2 outputs so the
+// 25,992-byte plane stack is written with coalesced 8-byte stores.
+__device__ __forceinline__ void d4_inv(int N, int d4, int tx, int ty, int& x, int& y) {
+  // InvTransform, board_feature.h:115-130
+  int a = tx, b = ty;
+  if (d4 & 4) { int t = a; a = b; b = t; }
+  switch (d4 & 3) {
+    case 1: x = N - b - 1; y = a; break;
+    case 2: x = N - a - 1; y = N - b - 1; break;
+    case 3: x = b; y = N - a - 1; break;
+    default: x = a; y = b; break;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ float feature_value(const uint64_t (*rows)[N], int hn, int next, int d4, int o) {
+  constexpr int P = Geo<N>::P;
+  const int plane = o / P, cell = o - plane * P;
+  if (plane >= 16) return (plane == 16) == (next == S_BLACK) ? 1.0f : 0.0f;
+  const int t = plane >> 1;
+  if (t >= hn) return 0.0f;
+  const int tx = cell / N, ty = cell - tx * N;
+  int x, y;
+  d4_inv(N, d4, tx, ty, x, y);
+  const uint64_t r = rows[t][y];
+  // even planes: side to move's stones, odd planes: opponent's (board_feature.cc:268-281)
+  const bool want_black = ((plane & 1) == 0) == (next == S_BLACK);
+  const uint32_t bits = want_black ? (uint32_t)r : (uint32_t)(r >> 32);
+  return (float)((bits >> x) & 1u);
+}
+
+template <int N>
+__global__ void __launch_bounds__(256)
+    k_features(DevState st, const int32_t* __restrict__ d4codes, float* __restrict__ out) {
+  constexpr int P = Geo<N>::P;
+  constexpr int TOTAL = 18 * P;  // even for N = 9, 19
+  __shared__ uint64_t rows[8][N];
+  const int g = blockIdx.x;
+  const BoardMeta meta = load_meta(&st.meta[g]);
+  const int hn = min(8, (int)meta.ply - 1);
+  for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
+    const int t = i / N, y = i - t * N;
+    rows[t][y] = t < hn ? st.ring[((size_t)g * 8 + ((meta.ply - 2 - t) & 7)) * N + y] : 0ull;
+  }
+  __syncthreads();
+  const int d4 = d4codes ? d4codes[g] : 0;
+  float2* o2 = reinterpret_cast<float2*>(out + (size_t)g * TOTAL);
+  for (int i = threadIdx.x; i < TOTAL / 2; i += blockDim.x) {
+    float2 v;
+    v.x = feature_value<N>(rows, hn, meta.next, d4, 2 * i);
+    v.y = feature_value<N>(rows, hn, meta.next, d4, 2 * i + 1);
+    o2[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Whole random-policy games, position in registers (BASELINE configs 1/2/5).
+template <int N>
+__global__ void __launch_bounds__(BLOCK)
+    k_playout(int G, uint64_t seed, uint64_t first_id, int max_plies, uint64_t* __restrict__ sk,
+              uint64_t* __restrict__ out_chk, int32_t* __restrict__ out_plies,
+              int32_t* __restrict__ out_score, uint64_t* __restrict__ out_hash) {
+  __shared__ uint64_t s_zob[Geo<N>::ZOB];
+  load_zobrist<N>(s_zob);
+  const Lane L = make_lane<N>();
+  bool valid;
+  const int g = warp_game<N>(L, G, valid);
+  const uint64_t gid = first_id + (uint64_t)g;
+  uint64_t* skg = sk + (size_t)(valid ? g : 0) * Geo<N>::MAX_PLY;
+
+  uint32_t b = 0, w = 0;
+  BoardMeta meta = initial_meta();
+  uint64_t hash = 0, chk = 0;
+  int nsk = 0, t = 0;
+
+  while (true) {
+    const bool term = !valid || is_terminated<N>(meta) || t >= max_plies;
+    if (__all_sync(FULL, term)) break;
+    const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
+    const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
+    const uint32_t legal = legal_rows<N>(own, opp, L, ko_applies, meta.ko_pt);
+    const uint32_t cand = legal & ~true_eye_rows<N>(own, opp, L);
+    const int n = game_sum<N>(__popc(cand), L);
+    const uint64_t rx = game_xor64<N>(L.active ? pp_row_term((uint32_t)L.row, legal) : 0ull, L);
+    const uint64_t chk2 = pp_fold3(chk, hash, rx, meta.b_cap, meta.w_cap, meta.next);
+    const int k = n > 0 ? (int)pp_pick(seed, gid, meta.ply, (uint32_t)n) : 0;
+    const int p = select_kth_action_order<N>(cand, k, L);
+    const int pm = term ? MV_NONE : (n > 0 ? p : MV_PASS);
+    const uint64_t pre_hash = hash;
+    play_move<N>(b, w, meta, hash, pm, s_zob, L);
+    const bool sko = superko_scan<N>(skg, pm >= 0 ? nsk : 0, hash, L);
+    if (pm >= 0) {
+      if (sko) meta.flags |= F_SUPERKO;
+      if (L.row == 0) skg[nsk] = pre_hash;
+      nsk++;
+    }
+    if (!term) {
+      chk = chk2;
+      t++;
+    }
+    __syncwarp();
+  }
+  chk = pp_fold_final(chk, hash, meta.ply);
+  const int score = tt_score<N>(b, w, L);
+  if (valid && L.row == 0) {
+    if (out_chk) out_chk[g] = chk;
+    if (out_plies) out_plies[g] = t;
+    if (out_score) out_score[g] = score;
+    if (out_hash) out_hash[g] = hash;
+  }
+}
+
+}  // namespace elfb200
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+using namespace elfb200;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ELFB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+struct elfb200_ctx {
+  int N = 0, G = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  DevState st{};
+  // scratch
+  int32_t* d_actions = nullptr;
+  uint8_t* d_ok = nullptr;
+  uint8_t* d_bytes = nullptr;   // G * (P+1) export buffer
+  int32_t* d_words = nullptr;   // G * 12 export buffer
+  int32_t* d_d4 = nullptr;
+  float* d_feat = nullptr;      // lazily allocated G*18*P floats
+  // playout outputs
+  uint64_t* d_po_sk = nullptr;
+  uint64_t* d_po_chk = nullptr;
+  uint64_t* d_po_hash = nullptr;
+  int32_t* d_po_plies = nullptr;
+  int32_t* d_po_score = nullptr;
+  // pinned staging
+  void* h_pin = nullptr;
+  size_t h_pin_bytes = 0;
+  int64_t launches = 0;
+};
+
+static inline int grid_for(const elfb200_ctx* c) {
+  int gpw = 32 / c->N;
+  int warps = (c->G + gpw - 1) / gpw;
+  return (warps + WARPS - 1) / WARPS;
+}
+
+#define DISPATCH_N(ctx, expr19, expr9) \
+  do {                                 \
+    if ((ctx)->N == 19) {              \
+      expr19;                          \
+    } else {                           \
+      expr9;                           \
+    }                                  \
+  } while (0)
+
+extern "C" {
+
+const char* elfb200_last_error(void) { return g_err.c_str(); }
+const char* elfb200_version(void) { return "elfb200 0.1 (sm_100a)"; }
+
+int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out) {
+  if (!out) return fail(ELFB200_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (board_size != 9 && board_size != 19)
+    return fail(ELFB200_ERR_ARG, "board_size must be 9 or 19 (got %d)", board_size);
+  if (num_games <= 0) return fail(ELFB200_ERR_ARG, "num_games must be positive");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(ELFB200_ERR_CUDA, "no CUDA device available (%s); elfb200 has no CPU fallback",
+                cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(ELFB200_ERR_ARG, "bad device %d", device);
+  CK(cudaSetDevice(device));
+  elfb200_ctx* c = new elfb200_ctx();
+  c->N = board_size;
+  c->G = num_games;
+  c->device = device;
+  const size_t N = board_size, G = num_games, P = N * N, MAXPLY = 2 * P;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&c->st.cur, G * N * 8));
+  CK(cudaMalloc(&c->st.ring, G * 8 * N * 8));
+  CK(cudaMalloc(&c->st.legal, G * N * 4));
+  CK(cudaMalloc(&c->st.hash, G * 8));
+  CK(cudaMalloc(&c->st.meta, G * sizeof(BoardMeta)));
+  CK(cudaMalloc(&c->st.sk, G * MAXPLY * 8));
+  CK(cudaMalloc(&c->st.sk_n, G * 4));
+  c->st.G = num_games;
+  CK(cudaMalloc(&c->d_actions, G * 4));
+  CK(cudaMalloc(&c->d_ok, G));
+  CK(cudaMalloc(&c->d_bytes, G * (P + 1)));
+  CK(cudaMalloc(&c->d_words, G * ELFB200_INFO_FIELDS * 4));
+  CK(cudaMalloc(&c->d_d4, G * 4));
+  CK(cudaMalloc(&c->d_po_sk, G * MAXPLY * 8));
+  CK(cudaMalloc(&c->d_po_chk, G * 8));
+  CK(cudaMalloc(&c->d_po_hash, G * 8));
+  CK(cudaMalloc(&c->d_po_plies, G * 4));
+  CK(cudaMalloc(&c->d_po_score, G * 4));
+  c->h_pin_bytes = G * (P + 1) > G * 64 ? G * (P + 1) : G * 64;
+  CK(cudaMallocHost(&c->h_pin, c->h_pin_bytes));
+  *out = c;
+  int rc = elfb200_reset(c, nullptr);
+  if (rc) return rc;
+  return ELFB200_OK;
+}
+
+void elfb200_destroy(elfb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  void* ptrs[] = {c->st.cur,  c->st.ring, c->st.legal, c->st.hash,   c->st.meta,   c->st.sk,
+                  c->st.sk_n, c->d_actions, c->d_ok,   c->d_bytes,   c->d_words,   c->d_d4,
+                  c->d_feat,  c->d_po_sk, c->d_po_chk, c->d_po_hash, c->d_po_plies, c->d_po_score};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int elfb200_num_games(const elfb200_ctx* c) { return c ? c->G : 0; }
+int elfb200_board_size(const elfb200_ctx* c) { return c ? c->N : 0; }
+void* elfb200_stream(const elfb200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int64_t elfb200_launch_count(const elfb200_ctx* c) { return c ? c->launches : 0; }
+
+int elfb200_synchronize(elfb200_ctx* c) {
+  if (!c) return fail(ELFB200_ERR_ARG, "ctx is NULL");
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_reset(elfb200_ctx* c, const uint8_t* mask_host) {
+  if (!c) return fail(ELFB200_ERR_ARG, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  const uint8_t* dmask = nullptr;
+  if (mask_host) {
+    memcpy(c->h_pin, mask_host, c->G);
+    CK(cudaMemcpyAsync(c->d_ok, c->h_pin, c->G, cudaMemcpyHostToDevice, c->stream));
+    dmask = c->d_ok;
+  }
+  DISPATCH_N(c, (k_reset<19><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, dmask)),
+             (k_reset<9><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, dmask)));
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_step_dev(elfb200_ctx* c, const int32_t* actions_dev, uint8_t* ok_dev) {
+  if (!c || !actions_dev) return fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
+  CK(cudaSetDevice(c->device));
+  DISPATCH_N(c, (k_step<19><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, actions_dev, ok_dev)),
+             (k_step<9><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, actions_dev, ok_dev)));
+  c->launches++;
+  CK(cudaGetLastError());
+  return ELFB200_OK;
+}
+
+int elfb200_step(elfb200_ctx* c, const int32_t* actions_host, uint8_t* ok_host) {
+  if (!c || !actions_host) return fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
+  CK(cudaSetDevice(c->device));
+  memcpy(c->h_pin, actions_host, (size_t)c->G * 4);
+  CK(cudaMemcpyAsync(c->d_actions, c->h_pin, (size_t)c->G * 4, cudaMemcpyHostToDevice, c->stream));
+  int rc = elfb200_step_dev(c, c->d_actions, c->d_ok);
+  if (rc) return rc;
+  if (ok_host) {
+    CK(cudaMemcpyAsync(ok_host, c->d_ok, c->G, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_get_hash(elfb200_ctx* c, uint64_t* hash_host) {
+  if (!c || !hash_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(hash_host, c->st.hash, (size_t)c->G * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+static int run_export(elfb200_ctx* c, uint8_t* legal, uint8_t* stones, uint8_t* eyes, int eye_player,
+                      int32_t* info, int32_t* score) {
+  DISPATCH_N(c,
+             (k_export<19><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, legal, stones, eyes,
+                                                                  eye_player, info, score)),
+             (k_export<9><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, legal, stones, eyes,
+                                                                 eye_player, info, score)));
+  c->launches++;
+  CK(cudaGetLastError());
+  return ELFB200_OK;
+}
+
+int elfb200_get_info(elfb200_ctx* c, int32_t* info_host) {
+  if (!c || !info_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  int rc = run_export(c, nullptr, nullptr, nullptr, 0, c->d_words, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(info_host, c->d_words, (size_t)c->G * ELFB200_INFO_FIELDS * 4,
+                     cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_get_stones(elfb200_ctx* c, uint8_t* stones_host) {
+  if (!c || !stones_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  int rc = run_export(c, nullptr, c->d_bytes, nullptr, 0, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(stones_host, c->d_bytes, (size_t)c->G * c->N * c->N, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_get_legal(elfb200_ctx* c, uint8_t* legal_host) {
+  if (!c || !legal_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  int rc = run_export(c, c->d_bytes, nullptr, nullptr, 0, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(legal_host, c->d_bytes, (size_t)c->G * (c->N * c->N + 1),
+                     cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_get_true_eyes(elfb200_ctx* c, int player, uint8_t* eyes_host) {
+  if (!c || !eyes_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (player < 0 || player > 2) return fail(ELFB200_ERR_ARG, "player must be 0, 1 or 2");
+  CK(cudaSetDevice(c->device));
+  int rc = run_export(c, nullptr, nullptr, c->d_bytes, player, nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(eyes_host, c->d_bytes, (size_t)c->G * c->N * c->N, cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_get_tt_score(elfb200_ctx* c, int32_t* score_host) {
+  if (!c || !score_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  int rc = run_export(c, nullptr, nullptr, nullptr, 0, nullptr, c->d_words);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(score_host, c->d_words, (size_t)c->G * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_evaluate(elfb200_ctx* c, float komi, float* value_host) {
+  if (!c || !value_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  // GoState::evaluate (go_state.h:194-203): superko-terminated -> +-1 for the side to move,
+  // else tt score - komi.  Scores and flags come from one export launch.
+  int rc = run_export(c, nullptr, nullptr, nullptr, 0, c->d_words, (int32_t*)c->d_bytes);
+  if (rc) return rc;
+  std::string info((size_t)c->G * ELFB200_INFO_FIELDS * 4, '\0'), sc((size_t)c->G * 4, '\0');
+  CK(cudaMemcpyAsync(&info[0], c->d_words, info.size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&sc[0], c->d_bytes, sc.size(), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int32_t* in = (const int32_t*)info.data();
+  const int32_t* s = (const int32_t*)sc.data();
+  for (int g = 0; g < c->G; ++g) {
+    if (in[g * ELFB200_INFO_FIELDS + 11])
+      value_host[g] = in[g * ELFB200_INFO_FIELDS + 1] == S_BLACK ? 1.0f : -1.0f;
+    else
+      value_host[g] = (float)s[g] - komi;
+  }
+  return ELFB200_OK;
+}
+
+int elfb200_features_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) {
+  if (!c || !out_dev) return fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  DISPATCH_N(c, (k_features<19><<<c->G, 256, 0, c->stream>>>(c->st, d4_dev, out_dev)),
+             (k_features<9><<<c->G, 256, 0, c->stream>>>(c->st, d4_dev, out_dev)));
+  c->launches++;
+  CK(cudaGetLastError());
+  return ELFB200_OK;
+}
+
+int elfb200_features(elfb200_ctx* c, const int32_t* d4_host, float* out_host) {
+  if (!c || !out_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)c->G * 18 * c->N * c->N * 4;
+  if (!c->d_feat) CK(cudaMalloc(&c->d_feat, bytes));
+  const int32_t* d4 = nullptr;
+  if (d4_host) {
+    memcpy(c->h_pin, d4_host, (size_t)c->G * 4);
+    CK(cudaMemcpyAsync(c->d_d4, c->h_pin, (size_t)c->G * 4, cudaMemcpyHostToDevice, c->stream));
+    d4 = c->d_d4;
+  }
+  int rc = elfb200_features_dev(c, d4, c->d_feat);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(out_host, c->d_feat, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id, int max_plies) {
+  if (!c) return fail(ELFB200_ERR_ARG, "ctx is NULL");
+  if (max_plies <= 0) return fail(ELFB200_ERR_ARG, "max_plies must be positive");
+  CK(cudaSetDevice(c->device));
+  DISPATCH_N(c,
+             (k_playout<19><<<grid_for(c), BLOCK, 0, c->stream>>>(
+                 c->G, seed, first_game_id, max_plies, c->d_po_sk, c->d_po_chk, c->d_po_plies,
+                 c->d_po_score, c->d_po_hash)),
+             (k_playout<9><<<grid_for(c), BLOCK, 0, c->stream>>>(
+                 c->G, seed, first_game_id, max_plies, c->d_po_sk, c->d_po_chk, c->d_po_plies,
+                 c->d_po_score, c->d_po_hash)));
+  c->launches++;
+  CK(cudaGetLastError());
+  return ELFB200_OK;
+}
+
+int elfb200_playout_results(elfb200_ctx* c, uint64_t* chk_host, int32_t* plies_host,
+                            int32_t* score_host, uint64_t* final_hash_host, int64_t* total_plies) {
+  if (!c) return fail(ELFB200_ERR_ARG, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  const size_t G = c->G;
+  // plies are always fetched (into pinned staging) to form the total
+  int32_t* hp = (int32_t*)c->h_pin;
+  CK(cudaMemcpyAsync(hp, c->d_po_plies, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (chk_host) CK(cudaMemcpyAsync(chk_host, c->d_po_chk, G * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (score_host)
+    CK(cudaMemcpyAsync(score_host, c->d_po_score, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (final_hash_host)
+    CK(cudaMemcpyAsync(final_hash_host, c->d_po_hash, G * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int64_t tot = 0;
+  for (size_t g = 0; g < G; ++g) tot += hp[g];
+  if (plies_host) memcpy(plies_host, hp, G * 4);
+  if (total_plies) *total_plies = tot;
+  return ELFB200_OK;
+}
+
+int elfb200_playout(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id, int max_plies,
+                    uint64_t* chk_host, int32_t* plies_host, int32_t* score_host,
+                    uint64_t* final_hash_host, int64_t* total_plies) {
+  int rc = elfb200_playout_launch(c, seed, first_game_id, max_plies);
+  if (rc) return rc;
+  return elfb200_playout_results(c, chk_host, plies_host, score_host, final_hash_host, total_plies);
+}
+
+}  // extern "C"

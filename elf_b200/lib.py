@@ -1,0 +1,76 @@
+"""ctypes binding of libelfb200.so (C ABI in include/elfb200.h)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libelfb200.so")
+
+INFO_FIELDS = 12
+
+
+class ElfB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+i32p = ctypes.POINTER(ctypes.c_int32)
+u8p = ctypes.POINTER(ctypes.c_uint8)
+f32p = ctypes.POINTER(ctypes.c_float)
+i64p = ctypes.POINTER(ctypes.c_int64)
+vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); every symbol include/elfb200.h declares
+SIGNATURES = {
+    "elfb200_last_error": (ctypes.c_char_p, []),
+    "elfb200_version": (ctypes.c_char_p, []),
+    "elfb200_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
+    "elfb200_destroy": (None, [vp]),
+    "elfb200_num_games": (ctypes.c_int, [vp]),
+    "elfb200_board_size": (ctypes.c_int, [vp]),
+    "elfb200_stream": (vp, [vp]),
+    "elfb200_synchronize": (ctypes.c_int, [vp]),
+    "elfb200_reset": (ctypes.c_int, [vp, vp]),
+    "elfb200_step": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_step_dev": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_get_hash": (ctypes.c_int, [vp, vp]),
+    "elfb200_get_info": (ctypes.c_int, [vp, vp]),
+    "elfb200_get_stones": (ctypes.c_int, [vp, vp]),
+    "elfb200_get_legal": (ctypes.c_int, [vp, vp]),
+    "elfb200_get_true_eyes": (ctypes.c_int, [vp, ctypes.c_int, vp]),
+    "elfb200_get_tt_score": (ctypes.c_int, [vp, vp]),
+    "elfb200_evaluate": (ctypes.c_int, [vp, ctypes.c_float, vp]),
+    "elfb200_features": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_features_dev": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_playout": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp, vp, vp, vp, vp]),
+    "elfb200_playout_launch": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]),
+    "elfb200_playout_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
+    "elfb200_launch_count": (ctypes.c_int64, [vp]),
+}
+
+
+def load_library(path=None):
+    """Load libelfb200.so and attach signatures.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ElfB200Error(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  elf_b200 has no CPU fallback."
+        )
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(lib, rc):
+    if rc != 0:
+        raise ElfB200Error(f"elfb200 error {rc}: {lib.elfb200_last_error().decode()}")

@@ -431,6 +431,35 @@ void go_features_agz(const GoOracle* s, int d4, float* out) { /* extractAGZ boar
   for (int p = 0; p < P; ++p) ind[p] = 1.0f;
 }
 
+/* group liberties / stones at `action` (-1 if empty): what Board::_groups[id] holds in the
+ * reference (board.h:71-76), recomputed by flood fill here. */
+int go_group_liberties(const GoOracle* s, int action) {
+  int p = a2p(s->N, action), grp[MAXP], libs;
+  if (s->color[p] == EMPTY) return -1;
+  group_of(s, p, grp, &libs);
+  return libs;
+}
+
+int go_group_stones(const GoOracle* s, int action) {
+  int p = a2p(s->N, action), grp[MAXP], libs;
+  if (s->color[p] == EMPTY) return -1;
+  return group_of(s, p, grp, &libs);
+}
+
+/* number of groups + 1, as Board::_num_groups counts (board.h:111-113) */
+int go_num_groups(const GoOracle* s) {
+  int N = s->N, P = N * N, n = 1, grp[MAXP];
+  uint8_t seen[MAXP];
+  memset(seen, 0, sizeof(seen));
+  for (int p = 0; p < P; ++p) {
+    if (s->color[p] == EMPTY || seen[p]) continue;
+    int k = group_of(s, p, grp, NULL);
+    for (int i = 0; i < k; ++i) seen[grp[i]] = 1;
+    n++;
+  }
+  return n;
+}
+
 /* ---- the deterministic playout workload (include/elfb200_playout_policy.h) ---- */
 int go_playout(int N, uint64_t seed, uint64_t game_id, int max_plies, int32_t* moves,
                uint64_t* hashes, int32_t* caps, uint64_t* out_chk, int32_t* out_score) {

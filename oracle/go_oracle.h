@@ -49,6 +49,10 @@ int go_ply(const GoOracle* s);
 int go_next_player(const GoOracle* s);
 int go_last_move(const GoOracle* s);
 
+int go_group_liberties(const GoOracle* s, int action);
+int go_group_stones(const GoOracle* s, int action);
+int go_num_groups(const GoOracle* s);
+
 int go_playout(int board_size, uint64_t seed, uint64_t game_id, int max_plies, int32_t* moves,
                uint64_t* hashes, int32_t* caps, uint64_t* out_chk, int32_t* out_score);
 

@@ -160,6 +160,30 @@ int ref_d4_action2action(int d4, int nn_action) {
   return EXPORT_OFFSET(c);
 }
 
+// liberties / stones of the group at `action` from the reference's own group table
+// (Board::_groups, board.h:71-76); -1 if the point is empty.  Used to port the
+// reference gtests' liberty assertions (base/test/go_test.cc).
+int ref_group_liberties(void* p, int action) {
+  const Board& b = static_cast<RefState*>(p)->board();
+  unsigned char id = b._infos[action_to_coord(action)].id;
+  if (id == 0 || id == MAX_GROUP)
+    return -1;
+  return b._groups[id].liberties;
+}
+
+int ref_group_stones(void* p, int action) {
+  const Board& b = static_cast<RefState*>(p)->board();
+  unsigned char id = b._infos[action_to_coord(action)].id;
+  if (id == 0 || id == MAX_GROUP)
+    return -1;
+  return b._groups[id].stones;
+}
+
+int ref_num_groups(void* p) {
+  return static_cast<RefState*>(p)->board()._num_groups;
+}
+
+
 // One deterministic random-policy playout (SURVEY 8d "config 1"), driven
 // through the reference GoState.  Per ply t (0-based) writes, if non-null:
 //   moves[t]  action played, hashes[t] hash AFTER the move, caps[2t],caps[2t+1]

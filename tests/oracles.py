@@ -1,0 +1,268 @@
+"""ctypes wrappers around the TEST-ONLY checkers in oracle/:
+
+* ``Oracle``  -- the C restatement (oracle/go_oracle.c -> oracle/libgo_oracle.so), runtime board size.
+* ``Ref``     -- the compiled unmodified reference (oracle/_ref/libref_go{19,9}.so), when present.
+
+Both expose the same methods so tests can be parametrised over them.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+vp = ctypes.c_void_p
+
+
+def load_oracle():
+    path = os.path.join(ORACLE_DIR, "libgo_oracle.so")
+    if not os.path.exists(path):
+        subprocess.check_call([os.environ.get("PYTHON", "python"), os.path.join(ROOT, "scripts", "gen_zobrist.py")])
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "oracle"])
+    L = ctypes.CDLL(path)
+    L.go_new.restype = vp
+    L.go_new.argtypes = [ctypes.c_int]
+    L.go_clone.restype = vp
+    L.go_clone.argtypes = [vp]
+    L.go_free.argtypes = [vp]
+    L.go_reset.argtypes = [vp]
+    L.go_forward.argtypes = [vp, ctypes.c_int]
+    L.go_check_move.argtypes = [vp, ctypes.c_int]
+    L.go_hash.restype = ctypes.c_uint64
+    L.go_hash.argtypes = [vp]
+    L.go_info.argtypes = [vp, vp]
+    L.go_stones.argtypes = [vp, vp]
+    L.go_legal_mask.argtypes = [vp, vp]
+    L.go_true_eye_mask.argtypes = [vp, ctypes.c_int, vp]
+    L.go_tt_score.argtypes = [vp]
+    L.go_evaluate.restype = ctypes.c_float
+    L.go_evaluate.argtypes = [vp, ctypes.c_float]
+    L.go_features_agz.argtypes = [vp, ctypes.c_int, vp]
+    L.go_d4_action2action.argtypes = [ctypes.c_int] * 3
+    L.go_terminated.argtypes = [vp]
+    L.go_playout.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int] + [vp] * 5
+    L.go_playout_many.restype = ctypes.c_int64
+    L.go_playout_many.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    return L
+
+
+def ref_path(n):
+    return os.path.join(ORACLE_DIR, "_ref", f"libref_go{n}.so")
+
+
+def have_ref(n):
+    return os.path.exists(ref_path(n))
+
+
+_ref_cache = {}
+
+
+def load_ref(n):
+    if n in _ref_cache:
+        return _ref_cache[n]
+    L = ctypes.CDLL(ref_path(n))
+    L.ref_new.restype = vp
+    L.ref_clone.restype = vp
+    L.ref_clone.argtypes = [vp]
+    L.ref_free.argtypes = [vp]
+    L.ref_reset.argtypes = [vp]
+    L.ref_forward.argtypes = [vp, ctypes.c_int]
+    L.ref_hash.restype = ctypes.c_uint64
+    L.ref_hash.argtypes = [vp]
+    L.ref_info.argtypes = [vp, vp]
+    L.ref_stones.argtypes = [vp, vp]
+    L.ref_legal_mask.argtypes = [vp, vp]
+    L.ref_find_all_valid_moves.argtypes = [vp, vp]
+    L.ref_true_eye_mask.argtypes = [vp, ctypes.c_int, vp]
+    L.ref_tt_score.argtypes = [vp]
+    L.ref_evaluate.restype = ctypes.c_float
+    L.ref_evaluate.argtypes = [vp, ctypes.c_float]
+    L.ref_features_agz.argtypes = [vp, ctypes.c_int, vp]
+    L.ref_d4_action2action.argtypes = [ctypes.c_int] * 2
+    L.ref_playout.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int] + [vp] * 5
+    assert L.ref_board_size() == n
+    _ref_cache[n] = L
+    return L
+
+
+class _Base:
+    """One game state with the GoState-like observer set used by the tests."""
+
+    def snapshot(self):
+        n = self.n
+        return {
+            "hash": self.hash(),
+            "info": self.info(),
+            "stones": self.stones(),
+            "legal": self.legal(),
+        }
+
+
+class Oracle(_Base):
+    def __init__(self, n=19, lib=None):
+        self.L = lib or load_oracle()
+        self.n = n
+        self.p = self.L.go_new(n)
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            self.L.go_free(self.p)
+            self.p = None
+
+    def forward(self, a):
+        return bool(self.L.go_forward(self.p, int(a)))
+
+    def hash(self):
+        return int(self.L.go_hash(self.p))
+
+    def info(self):
+        o = np.zeros(12, np.int32)
+        self.L.go_info(self.p, o.ctypes.data)
+        return o
+
+    def stones(self):
+        o = np.zeros(self.n * self.n, np.uint8)
+        self.L.go_stones(self.p, o.ctypes.data)
+        return o
+
+    def legal(self):
+        o = np.zeros(self.n * self.n, np.uint8)
+        self.L.go_legal_mask(self.p, o.ctypes.data)
+        return o
+
+    def true_eyes(self, player):
+        o = np.zeros(self.n * self.n, np.uint8)
+        self.L.go_true_eye_mask(self.p, player, o.ctypes.data)
+        return o
+
+    def tt_score(self):
+        return int(self.L.go_tt_score(self.p))
+
+    def evaluate(self, komi):
+        return float(self.L.go_evaluate(self.p, komi))
+
+    def features(self, d4=0):
+        o = np.zeros((18, self.n, self.n), np.float32)
+        self.L.go_features_agz(self.p, d4, o.ctypes.data)
+        return o
+
+    def terminated(self):
+        return bool(self.L.go_terminated(self.p))
+
+
+class Ref(_Base):
+    def __init__(self, n=19):
+        self.L = load_ref(n)
+        self.n = n
+        self.p = self.L.ref_new()
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            self.L.ref_free(self.p)
+            self.p = None
+
+    def forward(self, a):
+        return bool(self.L.ref_forward(self.p, int(a)))
+
+    def hash(self):
+        return int(self.L.ref_hash(self.p))
+
+    def info(self):
+        o = np.zeros(12, np.int32)
+        self.L.ref_info(self.p, o.ctypes.data)
+        return o
+
+    def stones(self):
+        o = np.zeros(self.n * self.n, np.uint8)
+        self.L.ref_stones(self.p, o.ctypes.data)
+        return o
+
+    def legal(self):
+        o = np.zeros(self.n * self.n, np.uint8)
+        self.L.ref_legal_mask(self.p, o.ctypes.data)
+        return o
+
+    def true_eyes(self, player):
+        o = np.zeros(self.n * self.n, np.uint8)
+        self.L.ref_true_eye_mask(self.p, player, o.ctypes.data)
+        return o
+
+    def tt_score(self):
+        return int(self.L.ref_tt_score(self.p))
+
+    def evaluate(self, komi):
+        return float(self.L.ref_evaluate(self.p, komi))
+
+    def features(self, d4=0):
+        o = np.zeros((18, self.n, self.n), np.float32)
+        self.L.ref_features_agz(self.p, d4, o.ctypes.data)
+        return o
+
+    def terminated(self):
+        return bool(self.info()[9])
+
+
+def oracle_playout(n, seed, gid, max_plies=None, trace=False, lib=None):
+    L = lib or load_oracle()
+    max_plies = max_plies or 2 * n * n
+    chk = ctypes.c_uint64()
+    sc = ctypes.c_int32()
+    if trace:
+        moves = np.zeros(max_plies, np.int32)
+        hashes = np.zeros(max_plies, np.uint64)
+        caps = np.zeros(2 * max_plies, np.int32)
+        t = L.go_playout(n, seed, gid, max_plies, moves.ctypes.data, hashes.ctypes.data, caps.ctypes.data,
+                         ctypes.byref(chk), ctypes.byref(sc))
+        return t, chk.value, sc.value, moves[:t], hashes[:t], caps[: 2 * t].reshape(-1, 2)
+    t = L.go_playout(n, seed, gid, max_plies, None, None, None, ctypes.byref(chk), ctypes.byref(sc))
+    return t, chk.value, sc.value
+
+
+def oracle_playout_many(n, seed, first, count, max_plies=None, lib=None):
+    L = lib or load_oracle()
+    max_plies = max_plies or 2 * n * n
+    chk = np.zeros(count, np.uint64)
+    plies = np.zeros(count, np.int32)
+    score = np.zeros(count, np.int32)
+    tot = L.go_playout_many(n, seed, first, count, max_plies, chk.ctypes.data, plies.ctypes.data, score.ctypes.data)
+    return {"chk": chk, "plies": plies, "score": score, "total_plies": int(tot)}
+
+
+def ref_playout(n, seed, gid, max_plies=None):
+    L = load_ref(n)
+    max_plies = max_plies or 2 * n * n
+    chk = ctypes.c_uint64()
+    sc = ctypes.c_int32()
+    t = L.ref_playout(seed, gid, max_plies, None, None, None, ctypes.byref(chk), ctypes.byref(sc))
+    return t, chk.value, sc.value
+
+
+# group accessors (reference Board::_groups) -------------------------------------------------
+def _bind_groups():
+    L = load_oracle()
+    for f in ("go_group_liberties", "go_group_stones"):
+        getattr(L, f).argtypes = [vp, ctypes.c_int]
+    L.go_num_groups.argtypes = [vp]
+
+
+def oracle_group(o, action):
+    _bind_groups()
+    return int(o.L.go_group_liberties(o.p, action)), int(o.L.go_group_stones(o.p, action))
+
+
+def oracle_num_groups(o):
+    _bind_groups()
+    return int(o.L.go_num_groups(o.p))
+
+
+def ref_group(r, action):
+    r.L.ref_group_liberties.argtypes = [vp, ctypes.c_int]
+    r.L.ref_group_stones.argtypes = [vp, ctypes.c_int]
+    return int(r.L.ref_group_liberties(r.p, action)), int(r.L.ref_group_stones(r.p, action))
+
+
+def ref_num_groups(r):
+    r.L.ref_num_groups.argtypes = [vp]
+    return int(r.L.ref_num_groups(r.p))

@@ -1,0 +1,124 @@
+"""GPU parity tests for the board path: CUDA (through the C ABI) vs the oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from tests import oracles
+
+pytestmark = pytest.mark.gpu
+
+
+def _gobatch(G, n):
+    import elf_b200
+
+    return elf_b200.GoBatch(G, board_size=n)
+
+
+def _random_candidate(rng, o, avoid_eyes=True):
+    """pick a move like the playout policy but with numpy randomness (covers other streams)"""
+    n = o.n
+    legal = o.legal()
+    nxt = int(o.info()[1])
+    cand = legal.copy()
+    if avoid_eyes:
+        cand &= 1 - o.true_eyes(nxt)
+    idx = np.flatnonzero(cand)
+    if len(idx) == 0:
+        return n * n
+    return int(rng.choice(idx))
+
+
+@pytest.mark.parametrize("n,G,plies", [(19, 64, 600), (9, 96, 200)])
+def test_step_parity_every_ply(n, G, plies, oracle_lib):
+    """GoState::forward for a batch: after EVERY ply compare hash, info words, stones, legal
+    mask, and periodically score / eyes / features with the oracle."""
+    rng = np.random.default_rng(1234 + n)
+    gb = _gobatch(G, n)
+    os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+    for t in range(plies):
+        acts = np.empty(G, np.int32)
+        exp_ok = np.empty(G, bool)
+        for g, o in enumerate(os_):
+            r = rng.random()
+            if o.terminated():
+                a = n * n if r < 0.5 else int(rng.integers(0, n * n))
+            elif r < 0.03:
+                a = n * n  # pass
+            elif r < 0.08:
+                a = int(rng.integers(0, n * n))  # arbitrary, often illegal, point
+            elif r < 0.10:
+                a = -1  # untouched
+            else:
+                a = _random_candidate(rng, o, avoid_eyes=(r < 0.9))
+            acts[g] = a
+            exp_ok[g] = o.forward(a) if a >= 0 else False
+        ok = gb.forward(acts)
+        np.testing.assert_array_equal(ok, exp_ok, err_msg=f"ok flags at ply {t}")
+        h = gb.getHashCode()
+        info = gb.info()
+        st = gb.stones()
+        lg = gb.legal_mask()
+        for g, o in enumerate(os_):
+            assert int(h[g]) == o.hash(), f"hash g={g} t={t}"
+            oi = o.info()
+            oi[8] = 0  # ko_age is not part of the device state
+            np.testing.assert_array_equal(info[g], oi, err_msg=f"info g={g} t={t}")
+            np.testing.assert_array_equal(st[g], o.stones(), err_msg=f"stones g={g} t={t}")
+            np.testing.assert_array_equal(lg[g, :-1], o.legal(), err_msg=f"legal g={g} t={t}")
+            assert lg[g, -1] == 1
+        if t % 37 == 5 or t == plies - 1:
+            sc = gb.tt_score()
+            ev = gb.evaluate(7.5)
+            e0 = gb.true_eyes(0)
+            e1 = gb.true_eyes(1)
+            d4 = rng.integers(0, 8, G).astype(np.int32)
+            ft = gb.features(d4)
+            for g, o in enumerate(os_):
+                assert sc[g] == o.tt_score()
+                assert ev[g] == np.float32(o.evaluate(7.5))
+                np.testing.assert_array_equal(e0[g], o.true_eyes(int(o.info()[1])))
+                np.testing.assert_array_equal(e1[g], o.true_eyes(1))
+                np.testing.assert_array_equal(ft[g], o.features(int(d4[g])), err_msg=f"features g={g} t={t}")
+    gb.close()
+
+
+@pytest.mark.parametrize("n,G", [(19, 256), (9, 300)])
+def test_playout_matches_oracle(n, G, oracle_lib):
+    """whole device-resident playouts: per-game checksum (hash, captures, legal mask of every
+    position), ply count, final score and hash identical to the oracle's."""
+    gb = _gobatch(G, n)
+    res = gb.playout(seed=77, first_game_id=1000)
+    exp = oracles.oracle_playout_many(n, 77, 1000, G, lib=oracle_lib)
+    np.testing.assert_array_equal(res["plies"], exp["plies"])
+    np.testing.assert_array_equal(res["chk"], exp["chk"])
+    np.testing.assert_array_equal(res["score"], exp["score"])
+    assert res["total_plies"] == exp["total_plies"]
+    gb.close()
+
+
+def test_reset_mask_and_edge_cases(oracle_lib):
+    n, G = 19, 5
+    gb = _gobatch(G, n)
+    # empty board: everything legal, hash 0, ply 1, black to move
+    info = gb.info()
+    assert (info[:, 0] == 1).all() and (info[:, 1] == 1).all()
+    assert (gb.getHashCode() == 0).all()
+    assert gb.legal_mask().all()
+    assert (gb.features() [:, :16] == 0).all() and (gb.features()[:, 16] == 1).all()
+    # out-of-range actions are rejected, game untouched
+    ok = gb.forward(np.array([n * n + 1, 10**6, -5, 0, n * n], np.int32))
+    assert ok.tolist() == [False, False, False, True, True]
+    # playing on an occupied point is rejected
+    ok = gb.forward(np.array([0, 0, 0, 0, 0], np.int32))
+    assert ok.tolist() == [True, True, True, False, True]
+    # two passes terminate; further moves are refused (go_state.cc:78)
+    gb.forward(np.array([-1, -1, -1, -1, n * n], np.int32))
+    gb.forward(np.array([-1, -1, -1, -1, n * n], np.int32))
+    info = gb.info()
+    assert info[4, 9] == 1 and info[4, 10] == 1
+    ok = gb.forward(np.full(G, 5, np.int32))
+    assert ok.tolist() == [True, True, True, True, False]
+    # masked reset
+    gb.reset(np.array([0, 0, 0, 0, 1], np.uint8))
+    info = gb.info()
+    assert info[4, 0] == 1 and info[4, 9] == 0 and info[0, 0] > 1
+    gb.close()
