@@ -102,6 +102,17 @@ __device__ __forceinline__ uint32_t nbr4(uint32_t v, const Lane& L) {
   return (v << 1) | (v >> 1) | up_of<N>(v, L) | dn_of<N>(v, L);
 }
 
+// Dilation for flood fills: result is always ANDed with a board mask and ORed with `v`, so for
+// one-game-per-warp boards the segment-boundary selects can be dropped: lane 0's "up" is its
+// own word (already in v), the last row's "down" comes from an idle lane that holds 0, and idle
+// lanes are masked by `through` (0 there).
+template <int N>
+__device__ __forceinline__ uint32_t grow4(uint32_t v, const Lane& L) {
+  if (Geo<N>::GPW == 1)
+    return (v << 1) | (v >> 1) | __shfl_up_sync(FULL, v, 1) | __shfl_down_sync(FULL, v, 1);
+  return nbr4<N>(v, L);
+}
+
 // ---- per-game reductions ----------------------------------------------------
 template <int N>
 __device__ __forceinline__ int game_sum(int v, const Lane& L) {
@@ -135,8 +146,8 @@ __device__ __forceinline__ bool game_any(bool pred, const Lane& L) {
 template <int N>
 __device__ __forceinline__ uint32_t flood(uint32_t g, uint32_t through, const Lane& L) {
   while (true) {
-    uint32_t n1 = g | (nbr4<N>(g, L) & through);
-    uint32_t n2 = n1 | (nbr4<N>(n1, L) & through);
+    uint32_t n1 = g | (grow4<N>(g, L) & through);
+    uint32_t n2 = n1 | (grow4<N>(n1, L) & through);
     bool ch = n2 != g;
     g = n2;
     if (!__any_sync(FULL, ch)) break;
@@ -152,7 +163,7 @@ __device__ __forceinline__ void floodK(uint32_t (&g)[K], const uint32_t (&throug
     bool ch = false;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      uint32_t n1 = g[k] | (nbr4<N>(g[k], L) & through[k]);
+      uint32_t n1 = g[k] | (grow4<N>(g[k], L) & through[k]);
       ch |= (n1 != g[k]);
       g[k] = n1;
     }
@@ -184,7 +195,7 @@ __device__ __forceinline__ uint64_t zob_row(const uint64_t* __restrict__ zob, in
 // groups with exactly one liberty (`atari`), restricted to the groups that touch
 // `focus` (other groups may be left unclassified).  `e` = empty points.
 //
-// Cheap sufficient tests for ">= 2 liberties", run as three lock-step fills:
+// Cheap sufficient tests for ">= 2 liberties", run as two lock-step fills:
 //   (a) a stone touching two empties;  (b) liberties of both checkerboard
 //   parities (a point's neighbours all have the opposite parity, so touching
 //   stones of different parity can never share a liberty).
@@ -198,10 +209,12 @@ __device__ __forceinline__ void classify_groups(uint32_t c, uint32_t e, uint32_t
   const uint32_t t2 = (aL & (aR | aU | aD)) | (aR & (aU | aD)) | (aU & aD);
   // checkerboard: bit x of row y is "even" iff (x + y) even
   const uint32_t even = (L.row & 1) ? 0xAAAAAAAAu : 0x55555555u;
-  uint32_t g[3] = {t2, touch & even, touch & ~even};
-  const uint32_t thr[3] = {c, c, c};
-  floodK<N, 3>(g, thr, L);
-  safe = g[0] | (g[1] & g[2]);
+  // group is safe iff it holds a t2 stone, or touching stones of both parities:
+  //   X = fill(even-touching | t2), Y = fill(odd-touching | t2)  ->  safe = X & Y
+  uint32_t g[2] = {(touch & even) | t2, (touch & ~even) | t2};
+  const uint32_t thr[2] = {c, c};
+  floodK<N, 2>(g, thr, L);
+  safe = g[0] & g[1];
   atari = 0;
   uint32_t cand = c & ~safe & focus;  // seeds of unresolved groups we care about
   while (__any_sync(FULL, cand != 0u)) {
@@ -361,31 +374,25 @@ __device__ __forceinline__ bool superko_scan(const uint64_t* __restrict__ hist, 
 }
 
 // k-th (0-based) set point of `cand` in ascending ACTION order a = x*N + y (x outer, y inner);
-// returns the point p = y*N + x.  n = number of candidates of this game (k < n).
-// Transposes rows->columns with N ballots, then a segmented prefix sum over columns.
+// returns the point p = y*N + x.  Requires k < number of candidates of this game.
+// Binary search over the column x with per-game REDUX counts, then one ballot for the column.
 template <int N>
 __device__ __forceinline__ int select_kth_action_order(uint32_t cand, int k, const Lane& L) {
-  uint32_t col = 0;  // lane `row` ends up holding COLUMN x=row: bit y = point (x, y)
+  int lo = 0, hi = N - 1;  // smallest x with count(columns <= x) > k
 #pragma unroll
-  for (int x = 0; x < N; ++x) {
-    uint32_t bal = __ballot_sync(FULL, (cand >> x) & 1u);
-    if (L.row == x) col = (bal >> L.base) & Geo<N>::ROWMASK;
+  for (int it = 0; it < 5; ++it) {  // ceil(log2(19)) = 5 halvings (also enough for 9)
+    const int mid = (lo + hi) >> 1;
+    const int c = game_sum<N>(__popc(cand & ((2u << mid) - 1u)), L);
+    if (c > k)
+      hi = mid;
+    else
+      lo = mid + 1;
   }
-  if (!L.active) col = 0;
-  int cnt = __popc(col);
-  int incl = cnt;
-#pragma unroll
-  for (int d = 1; d < N; d <<= 1) {
-    int t = __shfl_up_sync(FULL, incl, d);
-    if (L.row >= d) incl += t;
-  }
-  int excl = incl - cnt;
-  bool mine = L.active && k >= excl && k < incl;
-  uint32_t bal = __ballot_sync(FULL, mine) & L.segmask;
-  int src = __ffs(bal) - 1;
-  int yy = mine ? (int)__fns(col, 0, k - excl + 1) : 0;
-  int p = yy * N + L.row;  // column index is this lane's row number
-  return __shfl_sync(FULL, p, src & 31);
+  const int x = lo < N ? lo : N - 1;
+  const int before = game_sum<N>(__popc(cand & ((1u << x) - 1u)), L);
+  const uint32_t colmask = (__ballot_sync(FULL, (cand >> x) & 1u) >> L.base) & Geo<N>::ROWMASK;
+  const int y = (int)__fns(colmask, 0, k - before + 1);
+  return y * N + x;
 }
 
 }  // namespace elfb200

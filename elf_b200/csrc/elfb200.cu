@@ -293,11 +293,19 @@ __global__ void __launch_bounds__(BLOCK)
               uint64_t* __restrict__ out_chk, int32_t* __restrict__ out_plies,
               int32_t* __restrict__ out_score, uint64_t* __restrict__ out_hash) {
   __shared__ uint64_t s_zob[Geo<N>::ZOB];
+  // 4096-bit Bloom filter per game over the recorded pre-move hashes: the exact superko scan
+  // (go_state.cc:96-111) only runs when both probe bits are set (false-positive rate ~3 % at
+  // 400 recorded positions), which removes ~1.8 KB of history reads per ply.
+  __shared__ uint32_t s_bloom[WARPS][Geo<N>::GPW][128];
   load_zobrist<N>(s_zob);
   const Lane L = make_lane<N>();
   bool valid;
   const int g = warp_game<N>(L, G, valid);
   const uint64_t gid = first_id + (uint64_t)g;
+  uint32_t* bloom = s_bloom[threadIdx.x >> 5][L.sub];
+  for (int i = L.row; i < 128; i += N)
+    if (L.active) bloom[i] = 0u;
+  __syncwarp();
   uint64_t* skg = sk + (size_t)(valid ? g : 0) * Geo<N>::MAX_PLY;
 
   uint32_t b = 0, w = 0;
@@ -320,10 +328,19 @@ __global__ void __launch_bounds__(BLOCK)
     const int pm = term ? MV_NONE : (n > 0 ? p : MV_PASS);
     const uint64_t pre_hash = hash;
     play_move<N>(b, w, meta, hash, pm, s_zob, L);
-    const bool sko = superko_scan<N>(skg, pm >= 0 ? nsk : 0, hash, L);
+    const uint32_t q1 = (uint32_t)hash & 4095u, q2 = (uint32_t)(hash >> 12) & 4095u;
+    const bool maybe = pm >= 0 && ((bloom[q1 >> 5] >> (q1 & 31)) & (bloom[q2 >> 5] >> (q2 & 31)) & 1u);
+    bool sko = false;
+    if (__any_sync(FULL, maybe)) sko = superko_scan<N>(skg, maybe ? nsk : 0, hash, L);
+    __syncwarp();
     if (pm >= 0) {
       if (sko) meta.flags |= F_SUPERKO;
-      if (L.row == 0) skg[nsk] = pre_hash;
+      if (L.row == 0) {
+        skg[nsk] = pre_hash;
+        const uint32_t i1 = (uint32_t)pre_hash & 4095u, i2 = (uint32_t)(pre_hash >> 12) & 4095u;
+        bloom[i1 >> 5] |= 1u << (i1 & 31);
+        bloom[i2 >> 5] |= 1u << (i2 & 31);
+      }
       nsk++;
     }
     if (!term) {

@@ -122,3 +122,94 @@ def test_reset_mask_and_edge_cases(oracle_lib):
     info = gb.info()
     assert info[4, 0] == 1 and info[4, 9] == 0 and info[0, 0] > 1
     gb.close()
+
+
+# ---- committed golden fixtures (generated from the compiled reference) ---------------------
+import json
+import os
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    with open(os.path.join(GOLD, name)) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("n", [19, 9])
+def test_golden_playouts(n):
+    gold = _load(f"playouts_{n}.json")
+    G = len(gold["games"])
+    gb = _gobatch(G, n)
+    res = gb.playout(seed=gold["seed"], first_game_id=0)
+    for e in gold["games"]:
+        g = e["game_id"]
+        assert (int(res["plies"][g]), f"{int(res['chk'][g]):016x}", int(res["score"][g])) == (e["plies"], e["chk"], e["score"])
+    gb.close()
+
+
+@pytest.mark.parametrize("n", [19, 9])
+def test_golden_traces_and_positions(n):
+    """replay the reference's own move lists through the step API: hash and captures after every
+    ply, and the full observable state at the fixture positions."""
+    games = [e for e in _load(f"playouts_{n}.json")["games"] if "moves" in e]
+    positions = _load(f"positions_{n}.json")["positions"]
+    gb = _gobatch(len(games), n)
+    T = max(e["plies"] for e in games)
+    for t in range(T):
+        acts = np.array([e["moves"][t] if t < e["plies"] else -1 for e in games], np.int32)
+        ok = gb.forward(acts)
+        h = gb.getHashCode()
+        info = gb.info()
+        for g, e in enumerate(games):
+            if t < e["plies"]:
+                assert ok[g]
+                assert f"{int(h[g]):016x}" == e["hashes"][t]
+                assert info[g, 2:4].tolist() == e["caps"][t]
+        here = [p for p in positions if p["after_ply"] == t + 1]
+        if here:
+            st, lg, sc, ev = gb.stones(), gb.legal_mask(), gb.tt_score(), gb.evaluate(7.5)
+            eb, ew = gb.true_eyes(1), gb.true_eyes(2)
+            feats = {d4: gb.features(np.full(len(games), d4, np.int32)) for d4 in (0, 3, 5, 6)}
+            for p in here:
+                g = p["game_id"]
+                if p["after_ply"] > games[g]["plies"]:
+                    continue
+                gi = info[g].tolist()
+                pi = list(p["info"])
+                pi[8] = 0
+                assert gi == pi
+                assert st[g].tolist() == p["stones"]
+                assert lg[g, :-1].tolist() == p["legal"]
+                assert np.flatnonzero(eb[g]).tolist() == p["eyes_black"]
+                assert np.flatnonzero(ew[g]).tolist() == p["eyes_white"]
+                assert sc[g] == p["tt_score"] and ev[g] == np.float32(p["evaluate_7_5"])
+                for d4, ones in p["features_ones"].items():
+                    assert np.flatnonzero(feats[int(d4)][g].reshape(-1)).tolist() == ones
+    gb.close()
+
+
+def test_full_size_playout_properties(oracle_lib):
+    """BASELINE config 2 at full size (4096 games): size-independent properties + a sampled
+    exact check against the oracle."""
+    n, G = 19, 4096
+    gb = _gobatch(G, n)
+    a = gb.playout(seed=11, first_game_id=0)
+    b = gb.playout(seed=11, first_game_id=0)
+    for k in ("chk", "plies", "score", "hash"):
+        np.testing.assert_array_equal(a[k], b[k])  # deterministic / idempotent
+    assert (a["plies"] > 100).all() and (a["plies"] <= 2 * n * n).all()
+    assert a["total_plies"] == int(a["plies"].sum())
+    assert (np.abs(a["score"]) <= n * n).all()
+    # different game ids give different games
+    c = gb.playout(seed=11, first_game_id=G)
+    assert (a["chk"] != c["chk"]).mean() > 0.999
+    # shifting the id window reproduces the overlap exactly
+    d = gb.playout(seed=11, first_game_id=100)
+    np.testing.assert_array_equal(d["chk"][: G - 100], a["chk"][100:])
+    # sampled exact parity
+    idx = np.linspace(0, G - 1, 48).astype(int)
+    for g in idx:
+        t, chk, sc = oracles.oracle_playout(n, 11, int(g), lib=oracle_lib)
+        assert (t, chk, sc) == (int(a["plies"][g]), int(a["chk"][g]), int(a["score"][g]))
+    gb.close()
