@@ -20,69 +20,9 @@
 #include <cstring>
 #include <string>
 
-#include "board.cuh"
-#include "elfb200.h"
+#include "common.cuh"
 
 namespace elfb200 {
-
-__device__ const uint64_t g_zobrist[441] = {
-#include "elfb200_zobrist.inc"
-};
-
-constexpr int BLOCK = 128;  // 4 warps per CTA
-constexpr int WARPS = BLOCK / 32;
-
-template <int N>
-__device__ __forceinline__ void load_zobrist(uint64_t* s_zob) {
-  for (int i = threadIdx.x; i < Geo<N>::ZOB; i += blockDim.x) s_zob[i] = g_zobrist[i];
-  __syncthreads();
-}
-
-template <int N>
-__device__ __forceinline__ int warp_game(const Lane& L, int G, bool& valid) {
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int g = warp * Geo<N>::GPW + L.sub;
-  valid = L.active && g < G;
-  return g;
-}
-
-__device__ __forceinline__ BoardMeta initial_meta() {
-  BoardMeta m;
-  m.ply = 1;
-  m.next = S_BLACK;
-  m.flags = 0;
-  m.last1 = MV_INVALID;
-  m.last2 = MV_INVALID;
-  m.ko_pt = -1;
-  m.ko_color = 0;
-  m.pad = 0;
-  m.b_cap = 0;
-  m.w_cap = 0;
-  return m;
-}
-
-__device__ __forceinline__ BoardMeta load_meta(const BoardMeta* p) {
-  uint4 v = *reinterpret_cast<const uint4*>(p);
-  BoardMeta m;
-  memcpy(&m, &v, 16);
-  return m;
-}
-__device__ __forceinline__ void store_meta(BoardMeta* p, const BoardMeta& m) {
-  uint4 v;
-  memcpy(&v, &m, 16);
-  *reinterpret_cast<uint4*>(p) = v;
-}
-
-struct DevState {
-  uint64_t* cur;
-  uint64_t* ring;
-  uint32_t* legal;
-  uint64_t* hash;
-  BoardMeta* meta;
-  uint64_t* sk;
-  int32_t* sk_n;
-  int G;
-};
 
 // ---------------------------------------------------------------------------------------
 template <int N>
@@ -368,7 +308,7 @@ using namespace elfb200;
 
 static thread_local std::string g_err;
 
-static int fail(int code, const char* fmt, ...) {
+int elfb200_fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
   va_start(ap, fmt);
@@ -378,51 +318,11 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-#define CK(call)                                                                          \
-  do {                                                                                    \
-    cudaError_t e_ = (call);                                                              \
-    if (e_ != cudaSuccess)                                                                \
-      return fail(ELFB200_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                  __FILE__, __LINE__);                                                    \
-  } while (0)
-
-struct elfb200_ctx {
-  int N = 0, G = 0, device = 0;
-  cudaStream_t stream = nullptr;
-  DevState st{};
-  // scratch
-  int32_t* d_actions = nullptr;
-  uint8_t* d_ok = nullptr;
-  uint8_t* d_bytes = nullptr;   // G * (P+1) export buffer
-  int32_t* d_words = nullptr;   // G * 12 export buffer
-  int32_t* d_d4 = nullptr;
-  float* d_feat = nullptr;      // lazily allocated G*18*P floats
-  // playout outputs
-  uint64_t* d_po_sk = nullptr;
-  uint64_t* d_po_chk = nullptr;
-  uint64_t* d_po_hash = nullptr;
-  int32_t* d_po_plies = nullptr;
-  int32_t* d_po_score = nullptr;
-  // pinned staging
-  void* h_pin = nullptr;
-  size_t h_pin_bytes = 0;
-  int64_t launches = 0;
-};
-
 static inline int grid_for(const elfb200_ctx* c) {
   int gpw = 32 / c->N;
   int warps = (c->G + gpw - 1) / gpw;
   return (warps + WARPS - 1) / WARPS;
 }
-
-#define DISPATCH_N(ctx, expr19, expr9) \
-  do {                                 \
-    if ((ctx)->N == 19) {              \
-      expr19;                          \
-    } else {                           \
-      expr9;                           \
-    }                                  \
-  } while (0)
 
 extern "C" {
 
@@ -430,17 +330,17 @@ const char* elfb200_last_error(void) { return g_err.c_str(); }
 const char* elfb200_version(void) { return "elfb200 0.1 (sm_100a)"; }
 
 int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out) {
-  if (!out) return fail(ELFB200_ERR_ARG, "out is NULL");
+  if (!out) return elfb200_fail(ELFB200_ERR_ARG, "out is NULL");
   *out = nullptr;
   if (board_size != 9 && board_size != 19)
-    return fail(ELFB200_ERR_ARG, "board_size must be 9 or 19 (got %d)", board_size);
-  if (num_games <= 0) return fail(ELFB200_ERR_ARG, "num_games must be positive");
+    return elfb200_fail(ELFB200_ERR_ARG, "board_size must be 9 or 19 (got %d)", board_size);
+  if (num_games <= 0) return elfb200_fail(ELFB200_ERR_ARG, "num_games must be positive");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
-    return fail(ELFB200_ERR_CUDA, "no CUDA device available (%s); elfb200 has no CPU fallback",
+    return elfb200_fail(ELFB200_ERR_CUDA, "no CUDA device available (%s); elfb200 has no CPU fallback",
                 cudaGetErrorString(e));
-  if (device < 0 || device >= ndev) return fail(ELFB200_ERR_ARG, "bad device %d", device);
+  if (device < 0 || device >= ndev) return elfb200_fail(ELFB200_ERR_ARG, "bad device %d", device);
   CK(cudaSetDevice(device));
   elfb200_ctx* c = new elfb200_ctx();
   c->N = board_size;
@@ -494,13 +394,13 @@ void* elfb200_stream(const elfb200_ctx* c) { return c ? (void*)c->stream : nullp
 int64_t elfb200_launch_count(const elfb200_ctx* c) { return c ? c->launches : 0; }
 
 int elfb200_synchronize(elfb200_ctx* c) {
-  if (!c) return fail(ELFB200_ERR_ARG, "ctx is NULL");
+  if (!c) return elfb200_fail(ELFB200_ERR_ARG, "ctx is NULL");
   CK(cudaStreamSynchronize(c->stream));
   return ELFB200_OK;
 }
 
 int elfb200_reset(elfb200_ctx* c, const uint8_t* mask_host) {
-  if (!c) return fail(ELFB200_ERR_ARG, "ctx is NULL");
+  if (!c) return elfb200_fail(ELFB200_ERR_ARG, "ctx is NULL");
   CK(cudaSetDevice(c->device));
   const uint8_t* dmask = nullptr;
   if (mask_host) {
@@ -517,7 +417,7 @@ int elfb200_reset(elfb200_ctx* c, const uint8_t* mask_host) {
 }
 
 int elfb200_step_dev(elfb200_ctx* c, const int32_t* actions_dev, uint8_t* ok_dev) {
-  if (!c || !actions_dev) return fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
+  if (!c || !actions_dev) return elfb200_fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
   CK(cudaSetDevice(c->device));
   DISPATCH_N(c, (k_step<19><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, actions_dev, ok_dev)),
              (k_step<9><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, actions_dev, ok_dev)));
@@ -527,7 +427,7 @@ int elfb200_step_dev(elfb200_ctx* c, const int32_t* actions_dev, uint8_t* ok_dev
 }
 
 int elfb200_step(elfb200_ctx* c, const int32_t* actions_host, uint8_t* ok_host) {
-  if (!c || !actions_host) return fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
+  if (!c || !actions_host) return elfb200_fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
   CK(cudaSetDevice(c->device));
   memcpy(c->h_pin, actions_host, (size_t)c->G * 4);
   CK(cudaMemcpyAsync(c->d_actions, c->h_pin, (size_t)c->G * 4, cudaMemcpyHostToDevice, c->stream));
@@ -541,7 +441,7 @@ int elfb200_step(elfb200_ctx* c, const int32_t* actions_host, uint8_t* ok_host) 
 }
 
 int elfb200_get_hash(elfb200_ctx* c, uint64_t* hash_host) {
-  if (!c || !hash_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (!c || !hash_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   CK(cudaMemcpyAsync(hash_host, c->st.hash, (size_t)c->G * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -561,7 +461,7 @@ static int run_export(elfb200_ctx* c, uint8_t* legal, uint8_t* stones, uint8_t* 
 }
 
 int elfb200_get_info(elfb200_ctx* c, int32_t* info_host) {
-  if (!c || !info_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (!c || !info_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   int rc = run_export(c, nullptr, nullptr, nullptr, 0, c->d_words, nullptr);
   if (rc) return rc;
@@ -572,7 +472,7 @@ int elfb200_get_info(elfb200_ctx* c, int32_t* info_host) {
 }
 
 int elfb200_get_stones(elfb200_ctx* c, uint8_t* stones_host) {
-  if (!c || !stones_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (!c || !stones_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   int rc = run_export(c, nullptr, c->d_bytes, nullptr, 0, nullptr, nullptr);
   if (rc) return rc;
@@ -583,7 +483,7 @@ int elfb200_get_stones(elfb200_ctx* c, uint8_t* stones_host) {
 }
 
 int elfb200_get_legal(elfb200_ctx* c, uint8_t* legal_host) {
-  if (!c || !legal_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (!c || !legal_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   int rc = run_export(c, c->d_bytes, nullptr, nullptr, 0, nullptr, nullptr);
   if (rc) return rc;
@@ -594,8 +494,8 @@ int elfb200_get_legal(elfb200_ctx* c, uint8_t* legal_host) {
 }
 
 int elfb200_get_true_eyes(elfb200_ctx* c, int player, uint8_t* eyes_host) {
-  if (!c || !eyes_host) return fail(ELFB200_ERR_ARG, "NULL argument");
-  if (player < 0 || player > 2) return fail(ELFB200_ERR_ARG, "player must be 0, 1 or 2");
+  if (!c || !eyes_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  if (player < 0 || player > 2) return elfb200_fail(ELFB200_ERR_ARG, "player must be 0, 1 or 2");
   CK(cudaSetDevice(c->device));
   int rc = run_export(c, nullptr, nullptr, c->d_bytes, player, nullptr, nullptr);
   if (rc) return rc;
@@ -606,7 +506,7 @@ int elfb200_get_true_eyes(elfb200_ctx* c, int player, uint8_t* eyes_host) {
 }
 
 int elfb200_get_tt_score(elfb200_ctx* c, int32_t* score_host) {
-  if (!c || !score_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (!c || !score_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   int rc = run_export(c, nullptr, nullptr, nullptr, 0, nullptr, c->d_words);
   if (rc) return rc;
@@ -616,7 +516,7 @@ int elfb200_get_tt_score(elfb200_ctx* c, int32_t* score_host) {
 }
 
 int elfb200_evaluate(elfb200_ctx* c, float komi, float* value_host) {
-  if (!c || !value_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (!c || !value_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   // GoState::evaluate (go_state.h:194-203): superko-terminated -> +-1 for the side to move,
   // else tt score - komi.  Scores and flags come from one export launch.
@@ -638,7 +538,7 @@ int elfb200_evaluate(elfb200_ctx* c, float komi, float* value_host) {
 }
 
 int elfb200_features_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) {
-  if (!c || !out_dev) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (!c || !out_dev) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   DISPATCH_N(c, (k_features<19><<<c->G, 256, 0, c->stream>>>(c->st, d4_dev, out_dev)),
              (k_features<9><<<c->G, 256, 0, c->stream>>>(c->st, d4_dev, out_dev)));
@@ -648,7 +548,7 @@ int elfb200_features_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) 
 }
 
 int elfb200_features(elfb200_ctx* c, const int32_t* d4_host, float* out_host) {
-  if (!c || !out_host) return fail(ELFB200_ERR_ARG, "NULL argument");
+  if (!c || !out_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
   const size_t bytes = (size_t)c->G * 18 * c->N * c->N * 4;
   if (!c->d_feat) CK(cudaMalloc(&c->d_feat, bytes));
@@ -666,8 +566,8 @@ int elfb200_features(elfb200_ctx* c, const int32_t* d4_host, float* out_host) {
 }
 
 int elfb200_playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id, int max_plies) {
-  if (!c) return fail(ELFB200_ERR_ARG, "ctx is NULL");
-  if (max_plies <= 0) return fail(ELFB200_ERR_ARG, "max_plies must be positive");
+  if (!c) return elfb200_fail(ELFB200_ERR_ARG, "ctx is NULL");
+  if (max_plies <= 0) return elfb200_fail(ELFB200_ERR_ARG, "max_plies must be positive");
   CK(cudaSetDevice(c->device));
   DISPATCH_N(c,
              (k_playout<19><<<grid_for(c), BLOCK, 0, c->stream>>>(
@@ -683,7 +583,7 @@ int elfb200_playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id
 
 int elfb200_playout_results(elfb200_ctx* c, uint64_t* chk_host, int32_t* plies_host,
                             int32_t* score_host, uint64_t* final_hash_host, int64_t* total_plies) {
-  if (!c) return fail(ELFB200_ERR_ARG, "ctx is NULL");
+  if (!c) return elfb200_fail(ELFB200_ERR_ARG, "ctx is NULL");
   CK(cudaSetDevice(c->device));
   const size_t G = c->G;
   // plies are always fetched (into pinned staging) to form the total

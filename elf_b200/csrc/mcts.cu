@@ -1,0 +1,1018 @@
+// mcts.cu -- batched Monte-Carlo tree search on the GPU (search path of libelfb200.so).
+//
+// Replaces, for a batch of G games at once, the reference's per-game multi-threaded search
+//   elf::ai::tree_search::TreeSearchT / NodeT / EdgeInfo  (src_cpp/elf/ai/tree_search/*.h)
+//   MCTSActor::{pre_evaluate, remove_pass_if_dangerous, pi2response} (src_cpp/elfgames/go/mcts/mcts.h)
+// with a flat node pool in HBM and one warp per game.  A "wave" is what the reference calls
+// batch_rollouts (tree_search.h:201-262): B sequential descents per game (they depend on each
+// other through virtual loss), one batched network evaluation of the newly reached leaves of ALL
+// games, expansion, and one backup per unique leaf.
+//
+// Node pool (structure of arrays; game g owns slots [g*C, (g+1)*C), 16-bit local ids):
+//   pos    uint64 [G*C][N]      position rows (black | white << 32), set when the node is created
+//   hash   uint64 [G*C]         Zobrist hash
+//   meta   BoardMeta [G*C]      ply, side, ko, last moves, terminal flags
+//   hdr    NodeHdr [G*C]        visits, V, running unsigned mean Q, parent link, status
+//   estat  float4 [G*C][E]      per edge {prior P, visits N (int bits), reward sum W, virtual loss}
+//   elink  uint32 [G*C][E]      per edge action (low 16) | child id (high 16, 0xFFFF = none)
+// E = N*N+1.  Edges of a node are stored in descending-prior order (the order the reference
+// inserts them, go/mcts/mcts.h:292-329), only the legal ones.
+//
+// Kernels: k_begin (root set-up), k_select (PUCT descent + child state creation + terminal
+// evaluation + leaf claim), k_leaf_features (18-plane stack per claimed leaf, history gathered
+// along the parent chain), k_expand (mask/sort/renormalise the net's policy into edges),
+// k_backup, k_results, k_advance (tree reuse: keep the chosen child's subtree, free the rest).
+#include <cfloat>
+
+#include "common.cuh"
+#include "elfb200_mcts.h"
+
+namespace elfb200 {
+
+constexpr uint16_t NONE16 = 0xFFFFu;
+enum : uint8_t { NS_FREE = 0, NS_UNVISITED = 1, NS_REQUESTED = 2, NS_VISITED = 3 };
+enum : uint8_t { NF_FLIP = 1, NF_KEEP = 2 };
+
+struct __align__(16) NodeHdr {  // 32 bytes
+  int32_t num_visits;    // NodeT::numVisits_
+  float V;               // NodeT::V_
+  float mean_q;          // NodeT::unsignedMeanQ_
+  float parent_q;        // NodeT::unsignedParentQ_
+  uint16_t n_edges;
+  uint16_t parent;       // NONE16 for the root
+  uint16_t parent_edge;  // index of the edge in the parent that leads here
+  uint8_t status;        // NodeT::status_ (NOT_VISITED / EVAL_REQUESTED / VISITED)
+  uint8_t flags;         // NF_FLIP = NodeT::flipQSign_
+  int32_t depth_hint;    // unused by the algorithm (debug)
+  int32_t pad;
+};
+static_assert(sizeof(NodeHdr) == 32, "NodeHdr must be 32 bytes");
+
+struct TreeDev {
+  uint64_t* pos;
+  uint64_t* hash;
+  BoardMeta* meta;
+  NodeHdr* hdr;
+  float4* estat;
+  uint32_t* elink;
+  uint16_t* free_list;  // [G][C] stack of free local ids
+  int32_t* free_n;      // [G]
+  uint16_t* root;       // [G]
+  uint16_t* leaves;     // [G][B]
+  uint8_t* active;      // [G]
+  int32_t* eval_count;  // [1]
+  int32_t* eval_game;   // [G*B]
+  uint16_t* eval_node;  // [G*B]
+  uint8_t* eval_d4;     // [G*B]
+  uint16_t* bfs_q;      // [G][C]
+  int32_t* errors;      // [4]: root-hash mismatches, pool overflows, ...
+  int C, B, E;
+};
+
+struct SearchOpts {
+  int num_rollouts, virtual_loss, persistent, use_prior, uqz, ruqz, ply_pass_enabled,
+      remove_pass_if_dangerous, rotation_flip, seed;
+  float c_puct, komi;
+};
+
+template <int N>
+__device__ __forceinline__ Lane make_lane_single() {  // one game per warp, also for 9x9
+  Lane L;
+  L.lane = threadIdx.x & 31;
+  L.active = L.lane < N;
+  L.sub = 0;
+  L.row = L.active ? L.lane : 0;
+  L.base = 0;
+  L.rm = L.active ? Geo<N>::ROWMASK : 0u;
+  L.segmask = Geo<N>::ROWMASK;
+  return L;
+}
+
+// NOTE: the board primitives take the reductions' lane set from Lane::segmask / Lane::active when
+// Geo<N>::GPW != 1, so a single-segment Lane gives a one-game-per-warp mode for 9x9 as well.
+
+__device__ __forceinline__ NodeHdr load_hdr(const NodeHdr* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = q[0], b = q[1];
+  NodeHdr h;
+  memcpy(&h, &a, 16);
+  memcpy(reinterpret_cast<char*>(&h) + 16, &b, 16);
+  return h;
+}
+__device__ __forceinline__ void store_hdr(NodeHdr* p, const NodeHdr& h) {
+  uint4 a, b;
+  memcpy(&a, &h, 16);
+  memcpy(&b, reinterpret_cast<const char*>(&h) + 16, 16);
+  uint4* q = reinterpret_cast<uint4*>(p);
+  q[0] = a;
+  q[1] = b;
+}
+
+__device__ __forceinline__ int pop_free(const TreeDev& tr, int g) {  // lane 0 only
+  int n = tr.free_n[g];
+  if (n <= 0) return -1;
+  tr.free_n[g] = n - 1;
+  return tr.free_list[(size_t)g * tr.C + n - 1];
+}
+
+// ---------------------------------------------------------------------------------------
+// Root set-up: SearchTreeT::allocateRoot + TreeSearchT::setRootNodeState (tree_search_node.h:555,
+// tree_search.h:478-493).  One warp per game.
+template <int N>
+__global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int rollouts_needed) {
+  const Lane L = make_lane_single<N>();
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= st.G || !tr.active[g]) return;
+  const size_t nb = (size_t)g * tr.C;
+  int root = tr.root[g];
+  // not enough room for this move's new nodes: drop the persistent tree (documented deviation;
+  // the reference's heap is unbounded)
+  if (tr.free_n[g] < rollouts_needed + 1) {
+    if (L.lane == 0) atomicAdd(&tr.errors[1], 1);
+    for (int i = L.lane; i < tr.C; i += 32) {
+      tr.free_list[nb + i] = (uint16_t)(tr.C - 1 - i);
+      tr.hdr[nb + i].status = NS_FREE;
+    }
+    __syncwarp();
+    if (L.lane == 0) tr.free_n[g] = tr.C;
+    root = NONE16;
+    __syncwarp();
+  }
+  if (root == NONE16) {
+    int id = 0;
+    if (L.lane == 0) id = pop_free(tr, g);
+    id = __shfl_sync(FULL, id, 0);
+    if (L.active) tr.pos[(nb + id) * N + L.row] = st.cur[(size_t)g * N + L.row];
+    if (L.lane == 0) {
+      tr.hash[nb + id] = st.hash[g];
+      tr.meta[nb + id] = st.meta[g];
+      NodeHdr h;
+      h.num_visits = 0;
+      h.V = 0.f;
+      h.mean_q = 0.f;
+      h.parent_q = 0.f;  // allocateRoot: addNode(0.0)
+      h.n_edges = 0;
+      h.parent = NONE16;
+      h.parent_edge = 0;
+      h.status = NS_UNVISITED;
+      h.flags = 0;
+      h.depth_hint = 0;
+      h.pad = 0;
+      store_hdr(&tr.hdr[nb + id], h);
+      tr.root[g] = (uint16_t)id;
+    }
+  } else if (L.lane == 0) {
+    // "TreeSearch::Root state is not the same as the input state" (tree_search.h:488-492)
+    if (tr.hash[nb + root] != st.hash[g]) atomicAdd(&tr.errors[0], 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// One wave of descents: TreeSearchSingleThreadT::single_rollout x B (tree_search.h:265-322) with
+// NodeT::findMove/UCT (tree_search_node.h:205-231,361-397), EdgeInfo::getScore
+// (tree_search_base.h:132-157), addVirtualLoss (:233-251), followEdge (:280-302), allocateState
+// (tree_search.h:175-190) and the leaf claim of batch_rollouts (tree_search.h:222-233).
+template <int N>
+__global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, SearchOpts o, int wave) {
+  __shared__ uint64_t s_zob[Geo<N>::ZOB];
+  load_zobrist<N>(s_zob);
+  const Lane L = make_lane_single<N>();
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= st.G || !tr.active[g]) return;
+  const size_t nb = (size_t)g * tr.C;
+  const int E = tr.E;
+  const int root = tr.root[g];
+  uint64_t* skg = st.sk + (size_t)g * Geo<N>::MAX_PLY;
+  const int nsk0 = st.sk_n[g];
+  const float vl = (float)o.virtual_loss;
+
+  for (int j = 0; j < tr.B; ++j) {
+    int node = root, depth = 0, cnt = nsk0;
+    while (true) {
+      const NodeHdr h = load_hdr(&tr.hdr[nb + node]);
+      if (h.status != NS_VISITED || h.n_edges == 0) break;
+      // ---- UCT over the node's edges -------------------------------------------------------
+      const bool flip = h.flags & NF_FLIP;
+      const float fpu = (o.uqz || (o.ruqz && depth == 0)) ? 0.f : h.mean_q;
+      const double sq = sqrt((double)(h.num_visits + 1));  // std::sqrt(int) -> double
+      const float4* es = tr.estat + (nb + node) * E;
+      float best = -FLT_MAX, tuq = 0.f;
+      int besti = 0x7FFFFFFF, tv = 0;
+      for (int i = L.lane; i < h.n_edges; i += 32) {
+        const float4 e = es[i];
+        const int n = __float_as_int(e.y);
+        float r = flip ? -e.z : e.z;
+        r -= e.w;
+        const int nwl = (int)((float)n + e.w);
+        const float q = nwl > 0 ? r / (float)nwl : (flip ? -fpu : fpu);
+        const float uq = n > 0 ? e.z / (float)n : fpu;
+        const float u = (float)((double)(e.x / (float)(1 + n)) * sq);
+        const float score = o.use_prior ? __fmaf_rn(u, o.c_puct, q) : q;
+        if (score > best) {  // strict >, ascending i: first maximum wins
+          best = score;
+          besti = i;
+        }
+        if (nwl != 0) {
+          tuq += uq;
+          tv++;
+        }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const float ob = __shfl_xor_sync(FULL, best, d);
+        const int oi = __shfl_xor_sync(FULL, besti, d);
+        if (ob > best || (ob == best && oi < besti)) {
+          best = ob;
+          besti = oi;
+        }
+        tuq += __shfl_xor_sync(FULL, tuq, d);
+        tv += __shfl_xor_sync(FULL, tv, d);
+      }
+      const int ei = besti;
+      const float new_mean = (h.parent_q + tuq) / (float)(tv + 1);
+      const uint32_t link = tr.elink[(nb + node) * E + ei];
+      const int action = link & 0xFFFFu;
+      int child = link >> 16;
+      if (L.lane == 0) {
+        tr.hdr[nb + node].mean_q = new_mean;
+        if (o.virtual_loss > 0) tr.estat[(nb + node) * E + ei].w += vl;
+        if (action != Geo<N>::P) skg[cnt] = tr.hash[nb + node];  // pre-move position of a stone move
+      }
+      if (action != Geo<N>::P) cnt++;
+      // ---- followEdge + allocateState ----------------------------------------------------------
+      if (child == NONE16) {
+        int id = 0;
+        if (L.lane == 0) id = pop_free(tr, g);
+        id = __shfl_sync(FULL, id, 0);
+        if (id < 0) {  // cannot happen when k_begin reserved enough room
+          if (L.lane == 0) atomicAdd(&tr.errors[1], 1);
+          break;
+        }
+        child = id;
+        const uint64_t rowv = L.active ? tr.pos[(nb + node) * N + L.row] : 0ull;
+        uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
+        BoardMeta meta = load_meta(&tr.meta[nb + node]);
+        uint64_t hash = tr.hash[nb + node];
+        const int pm = action == Geo<N>::P ? MV_PASS : (action % N) * N + action / N;
+        __syncwarp();
+        play_move<N>(b, w, meta, hash, pm, s_zob, L);
+        if (pm >= 0 && superko_scan<N>(skg, cnt, hash, L)) meta.flags |= F_SUPERKO;
+        if (L.active) tr.pos[(nb + child) * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);
+        if (L.lane == 0) {
+          tr.hash[nb + child] = hash;
+          store_meta(&tr.meta[nb + child], meta);
+          NodeHdr c;
+          c.num_visits = 0;
+          c.V = 0.f;
+          c.mean_q = new_mean;    // NodeT ctor: unsignedMeanQ_ = unsignedParentQ_
+          c.parent_q = new_mean;  // followEdge: tree.addNode(unsignedMeanQ_)
+          c.n_edges = 0;
+          c.parent = (uint16_t)node;
+          c.parent_edge = (uint16_t)ei;
+          c.status = NS_UNVISITED;
+          c.flags = 0;
+          c.depth_hint = depth + 1;
+          c.pad = 0;
+          store_hdr(&tr.hdr[nb + child], c);
+          tr.elink[(nb + node) * E + ei] = (uint32_t)action | ((uint32_t)child << 16);
+        }
+      }
+      __syncwarp();
+      node = child;
+      depth++;
+    }
+    // ---- leaf claim: requestEvaluation (tree_search_node.h:157-167) + pre_evaluate (mcts.h:185)
+    const NodeHdr lh = load_hdr(&tr.hdr[nb + node]);
+    if (lh.status == NS_UNVISITED) {
+      const BoardMeta meta = load_meta(&tr.meta[nb + node]);
+      if (is_terminated<N>(meta)) {
+        // terminal: V = sign(evaluate(komi)) (go_state.h:194-203), no edges
+        const uint64_t rowv = L.active ? tr.pos[(nb + node) * N + L.row] : 0ull;
+        const int sc = tt_score<N>((uint32_t)rowv, (uint32_t)(rowv >> 32), L);
+        float fv;
+        if (meta.flags & F_SUPERKO)
+          fv = meta.next == S_BLACK ? 1.0f : -1.0f;
+        else
+          fv = (float)sc - o.komi;
+        if (L.lane == 0) {
+          NodeHdr h2 = lh;
+          h2.V = fv > 0 ? 1.0f : -1.0f;
+          h2.flags = meta.next == S_WHITE ? NF_FLIP : 0;
+          h2.status = NS_VISITED;
+          h2.n_edges = 0;
+          store_hdr(&tr.hdr[nb + node], h2);
+        }
+      } else if (L.lane == 0) {
+        tr.hdr[nb + node].status = NS_REQUESTED;
+        const int slot = atomicAdd(tr.eval_count, 1);
+        tr.eval_game[slot] = g;
+        tr.eval_node[slot] = (uint16_t)node;
+        uint8_t d4 = 0;
+        if (o.rotation_flip)
+          d4 = (uint8_t)(pp_splitmix64(((uint64_t)o.seed << 40) ^ ((uint64_t)g << 20) ^
+                                       ((uint64_t)wave << 8) ^ (uint64_t)node ^ tr.hash[nb + node]) & 7u);
+        tr.eval_d4[slot] = d4;
+      }
+    }
+    if (L.lane == 0) tr.leaves[(size_t)g * tr.B + j] = (uint16_t)node;
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// BoardFeature::extractAGZ for every claimed leaf: the 8-position history is the leaf, its
+// ancestors up to the root, then the game's own ring (go_state.cc:90-92).  One CTA per leaf.
+__device__ __forceinline__ void d4_inv_m(int N, int d4, int tx, int ty, int& x, int& y) {
+  int a = tx, b = ty;
+  if (d4 & 4) { int t = a; a = b; b = t; }
+  switch (d4 & 3) {
+    case 1: x = N - b - 1; y = a; break;
+    case 2: x = N - a - 1; y = N - b - 1; break;
+    case 3: x = b; y = N - a - 1; break;
+    default: x = a; y = b; break;
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256) k_leaf_features(DevState st, TreeDev tr, float* __restrict__ out) {
+  constexpr int P = Geo<N>::P;
+  constexpr int TOTAL = 18 * P;
+  __shared__ uint64_t rows[8][N];
+  __shared__ int s_src[8];  // >=0: node local id, <0: -(ring slot)-1, INT_MIN: none
+  const int slot = blockIdx.x;
+  if (slot >= *tr.eval_count) return;
+  const int g = tr.eval_game[slot];
+  const int leaf = tr.eval_node[slot];
+  const size_t nb = (size_t)g * tr.C;
+  const BoardMeta meta = load_meta(&tr.meta[nb + leaf]);
+  const int hn = min(8, (int)meta.ply - 1);
+  if (threadIdx.x == 0) {
+    int node = leaf, t = 0;
+    while (t < hn && node != NONE16) {
+      s_src[t++] = node;
+      node = tr.hdr[nb + node].parent;
+    }
+    // beyond the root: the game's ring; the root itself is ring slot (ply_root-2)&7
+    const int pr = st.meta[g].ply;
+    int k = 1;
+    while (t < hn) {
+      s_src[t++] = -(((pr - 2 - k) & 7)) - 1;
+      ++k;
+    }
+    for (; t < 8; ++t) s_src[t] = INT_MIN;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
+    const int t = i / N, y = i - t * N;
+    const int src = s_src[t];
+    uint64_t v = 0;
+    if (src >= 0)
+      v = tr.pos[(nb + src) * N + y];
+    else if (src != INT_MIN)
+      v = st.ring[((size_t)g * 8 + (-src - 1)) * N + y];
+    rows[t][y] = v;
+  }
+  __syncthreads();
+  const int d4 = tr.eval_d4[slot];
+  const int next = meta.next;
+  float2* o2 = reinterpret_cast<float2*>(out + (size_t)slot * TOTAL);
+  for (int i = threadIdx.x; i < TOTAL / 2; i += blockDim.x) {
+    float v[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int o = 2 * i + k;
+      const int plane = o / P, cell = o - plane * P;
+      float val;
+      if (plane >= 16) {
+        val = (plane == 16) == (next == S_BLACK) ? 1.0f : 0.0f;
+      } else {
+        const int t = plane >> 1;
+        if (t >= hn) {
+          val = 0.f;
+        } else {
+          const int tx = cell / N, ty = cell - tx * N;
+          int x, y;
+          d4_inv_m(N, d4, tx, ty, x, y);
+          const uint64_t r = rows[t][y];
+          const bool want_black = ((plane & 1) == 0) == (next == S_BLACK);
+          const uint32_t bits = want_black ? (uint32_t)r : (uint32_t)(r >> 32);
+          val = (float)((bits >> x) & 1u);
+        }
+      }
+      v[k] = val;
+    }
+    o2[i] = make_float2(v[0], v[1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Expansion: MCTSActor::post_nn_result / remove_pass_if_dangerous / pi2response / normalize
+// (go/mcts/mcts.h:209-332) + NodeT::setEvaluation (tree_search_node.h:176-203).  One warp per
+// claimed leaf; the candidate list is bitonic-sorted in shared memory by descending probability.
+template <int N>
+__global__ void __launch_bounds__(BLOCK)
+    k_expand(DevState st, TreeDev tr, SearchOpts o, const float* __restrict__ pi, const float* __restrict__ val) {
+  constexpr int P = Geo<N>::P;
+  constexpr int SORTN = P + 1 <= 128 ? 128 : 512;
+  __shared__ uint64_t s_key[WARPS][SORTN];
+  __shared__ float s_tot[WARPS];
+  __shared__ uint32_t s_legal[WARPS][N];
+  const Lane L = make_lane_single<N>();
+  const int wib = threadIdx.x >> 5;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= *tr.eval_count) return;
+  const int g = tr.eval_game[slot];
+  const int node = tr.eval_node[slot];
+  const int d4 = tr.eval_d4[slot];
+  const size_t nb = (size_t)g * tr.C;
+  const uint64_t rowv = L.active ? tr.pos[(nb + node) * N + L.row] : 0ull;
+  const uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
+  const BoardMeta meta = load_meta(&tr.meta[nb + node]);
+  const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
+  const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
+  const uint32_t legal = legal_rows<N>(own, opp, L, ko_applies, meta.ko_pt);
+  // pass handling (mcts.h:225-242)
+  bool pass_enabled = (int)meta.ply >= o.ply_pass_enabled;
+  if (o.remove_pass_if_dangerous && pass_enabled && meta.last1 != MV_PASS) {
+    const int sc = tt_score<N>(b, w, L);
+    const bool black_win = ((float)sc - o.komi) > 0;
+    if ((black_win && meta.next == S_WHITE) || (!black_win && meta.next == S_BLACK)) pass_enabled = false;
+  }
+  // candidates: NN action a -> board action through the inverse D4 (board_feature.h:139-144)
+  if (L.active) s_legal[wib][L.row] = legal;
+  __syncwarp();
+  uint64_t* key = s_key[wib];
+  const float* pr = pi + (size_t)slot * (P + 1);
+  for (int a = L.lane; a < SORTN; a += 32) {
+    uint64_t k = ~0ull;
+    if (a <= P) {
+      int act;
+      bool ok;
+      if (a == P) {
+        act = P;
+        ok = pass_enabled;
+      } else {
+        int x, y;
+        d4_inv_m(N, d4, a / N, a - (a / N) * N, x, y);
+        act = x * N + y;
+        ok = (s_legal[wib][y] >> x) & 1u;
+      }
+      // probabilities are non-negative floats: their bit patterns order like the values
+      if (ok) k = ((uint64_t)(0xFFFFFFFFu - __float_as_uint(pr[a])) << 32) | (uint32_t)act;
+    }
+    key[a] = k;
+  }
+  __syncwarp();
+  // bitonic sort ascending on the composite key == descending probability, then action
+  for (int k2 = 2; k2 <= SORTN; k2 <<= 1) {
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int t = L.lane; t < SORTN / 2; t += 32) {
+        const int i = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));
+        const int p2 = i | j2;
+        const bool up = (i & k2) == 0;
+        const uint64_t a0 = key[i], a1 = key[p2];
+        if ((a0 > a1) == up) {
+          key[i] = a1;
+          key[p2] = a0;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // count valid, sequential float sum in sorted order (normalize, mcts.h:244-254)
+  int nvalid = 0;
+  for (int a = L.lane; a < SORTN; a += 32) nvalid += key[a] != ~0ull;
+  nvalid = __reduce_add_sync(FULL, nvalid);
+  if (L.lane == 0) {
+    float tot = 1e-10f;
+    for (int i = 0; i < nvalid; ++i) tot += __uint_as_float(0xFFFFFFFFu - (uint32_t)(key[i] >> 32));
+    s_tot[wib] = tot;
+  }
+  __syncwarp();
+  const float tot = s_tot[wib];
+  const int E = tr.E;
+  float4* es = tr.estat + (nb + node) * E;
+  uint32_t* el = tr.elink + (nb + node) * E;
+  int n_edges = nvalid;
+  if (nvalid == 0 && !pass_enabled) {  // mcts.h:324-327: pass with probability 1
+    n_edges = 1;
+    if (L.lane == 0) {
+      es[0] = make_float4(1.0f / (1e-10f + 1.0f), __int_as_float(0), 0.f, 0.f);
+      el[0] = (uint32_t)P | ((uint32_t)NONE16 << 16);
+    }
+  } else {
+    for (int i = L.lane; i < nvalid; i += 32) {
+      const uint64_t k = key[i];
+      const float p = __uint_as_float(0xFFFFFFFFu - (uint32_t)(k >> 32));
+      es[i] = make_float4(p / tot, __int_as_float(0), 0.f, 0.f);
+      el[i] = (uint32_t)(k & 0xFFFFu) | ((uint32_t)NONE16 << 16);
+    }
+  }
+  __syncwarp();
+  if (L.lane == 0) {
+    NodeHdr h = load_hdr(&tr.hdr[nb + node]);
+    h.V = val[slot];
+    h.flags = meta.next == S_WHITE ? NF_FLIP : 0;  // q_flip, mcts.h:186
+    h.n_edges = (uint16_t)n_edges;
+    h.status = NS_VISITED;
+    store_hdr(&tr.hdr[nb + node], h);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Backup: batch_rollouts' second half (tree_search.h:245-259) + NodeT::updateEdgeStats
+// (tree_search_node.h:253-278).  One unique leaf = one visit; duplicates only return their
+// virtual loss.  One thread per game (the walk is a dependent pointer chase).
+__global__ void k_backup(int G, TreeDev tr, int virtual_loss) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G || !tr.active[g]) return;
+  const size_t nb = (size_t)g * tr.C;
+  const int B = tr.B, E = tr.E;
+  const uint16_t* lv = tr.leaves + (size_t)g * B;
+  for (int j = 0; j < B; ++j) {
+    const int leaf = lv[j];
+    bool first = true;
+    int count = 0;
+    for (int k = 0; k < B; ++k) {
+      if (lv[k] == leaf) {
+        if (k < j) first = false;
+        count++;
+      }
+    }
+    if (!first) continue;
+    const float reward = tr.hdr[nb + leaf].V;
+    const float dvl = (float)virtual_loss * (float)count;
+    int node = leaf;
+    while (true) {
+      const NodeHdr h = load_hdr(&tr.hdr[nb + node]);
+      if (h.parent == NONE16) break;
+      const int p = h.parent;
+      tr.hdr[nb + p].num_visits += 1;
+      float4 e = tr.estat[(nb + p) * E + h.parent_edge];
+      e.z += reward;
+      e.y = __int_as_float(__float_as_int(e.y) + 1);
+      e.w -= dvl;
+      tr.estat[(nb + p) * E + h.parent_edge] = e;
+      node = p;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Results at the root: TreeSearchT::chooseAction / MCTSResultT::addActions (most_visited,
+// tree_search.h:495-528, tree_search_base.h:237-294) and MCTSGoAI::getValue (go/mcts/mcts.h:358).
+template <int N>
+__global__ void __launch_bounds__(BLOCK)
+    k_results(int G, TreeDev tr, int32_t* __restrict__ best_action, int32_t* __restrict__ visits,
+              float* __restrict__ root_value, float* __restrict__ best_q, int32_t* __restrict__ total_visits) {
+  constexpr int P1 = Geo<N>::P + 1;
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= G) return;
+  if (visits)
+    for (int a = lane; a < P1; a += 32) visits[(size_t)g * P1 + a] = -1;
+  __syncwarp();
+  const int root = tr.root[g];
+  if (!tr.active[g] || root == NONE16) {
+    if (lane == 0) {
+      if (best_action) best_action[g] = -1;
+      if (root_value) root_value[g] = 0.f;
+      if (best_q) best_q[g] = 0.f;
+      if (total_visits) total_visits[g] = 0;
+    }
+    return;
+  }
+  const size_t nb = (size_t)g * tr.C;
+  const NodeHdr h = load_hdr(&tr.hdr[nb + root]);
+  const float4* es = tr.estat + (nb + root) * tr.E;
+  const uint32_t* el = tr.elink + (nb + root) * tr.E;
+  int bestn = -1, besti = 0x7FFFFFFF, tot = 0;
+  for (int i = lane; i < h.n_edges; i += 32) {
+    const int n = __float_as_int(es[i].y);
+    if (visits) visits[(size_t)g * P1 + (el[i] & 0xFFFFu)] = n;
+    tot += n;
+    if (n > bestn) {
+      bestn = n;
+      besti = i;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const int on = __shfl_xor_sync(FULL, bestn, d), oi = __shfl_xor_sync(FULL, besti, d);
+    if (on > bestn || (on == bestn && oi < besti)) {
+      bestn = on;
+      besti = oi;
+    }
+    tot += __shfl_xor_sync(FULL, tot, d);
+  }
+  if (lane == 0) {
+    const bool any = h.n_edges > 0 && besti != 0x7FFFFFFF;
+    if (best_action) best_action[g] = any ? (int)(el[besti] & 0xFFFFu) : -1;
+    if (root_value) root_value[g] = h.V;
+    if (total_visits) total_visits[g] = tot;
+    if (best_q) {
+      float q = h.V;
+      if (any && tot > 0) {
+        const float4 e = es[besti];
+        q = e.z / (float)__float_as_int(e.y);  // EdgeInfo::getQSA
+      }
+      best_q[g] = q;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// SearchTreeT::treeAdvance (tree_search_node.h:420-436): keep the subtree under the played move,
+// free everything else.  One warp per game; BFS over the kept subtree marks it, one sweep frees
+// the rest and rebuilds the free stack.
+__global__ void __launch_bounds__(BLOCK)
+    k_advance(int G, TreeDev tr, const int32_t* __restrict__ actions, int persistent) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= G) return;
+  const int a = actions[g];
+  if (a < 0) return;  // game untouched
+  const size_t nb = (size_t)g * tr.C;
+  const int E = tr.E, C = tr.C;
+  const int root = tr.root[g];
+  int keep = NONE16;
+  if (root != NONE16 && persistent) {
+    const NodeHdr h = load_hdr(&tr.hdr[nb + root]);
+    const uint32_t* el = tr.elink + (nb + root) * E;
+    int found = NONE16;
+    for (int i = lane; i < h.n_edges; i += 32) {
+      const uint32_t l = el[i];
+      if ((int)(l & 0xFFFFu) == a) found = l >> 16;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) found = min(found, __shfl_xor_sync(FULL, found, d));
+    keep = found;
+  }
+  uint16_t* q = tr.bfs_q + nb;
+  if (keep != NONE16) {
+    int head = 0, tail = 1;
+    if (lane == 0) {
+      q[0] = (uint16_t)keep;
+      tr.hdr[nb + keep].flags |= NF_KEEP;
+      tr.hdr[nb + keep].parent = NONE16;
+    }
+    __syncwarp();
+    while (head < tail) {
+      const int node = q[head++];
+      const int ne = tr.hdr[nb + node].n_edges;
+      const uint32_t* el = tr.elink + (nb + node) * E;
+      for (int i0 = 0; i0 < ne; i0 += 32) {
+        const int i = i0 + lane;
+        int child = NONE16;
+        if (i < ne) child = el[i] >> 16;
+        const bool has = child != NONE16;
+        const uint32_t bal = __ballot_sync(FULL, has);
+        if (has) {
+          q[tail + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)child;
+          tr.hdr[nb + child].flags |= NF_KEEP;
+        }
+        tail += __popc(bal);
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  // sweep: everything not kept becomes free
+  int nfree = 0;
+  for (int i0 = 0; i0 < C; i0 += 32) {
+    const int i = i0 + lane;
+    bool fr = false;
+    if (i < C) {
+      NodeHdr* hp = &tr.hdr[nb + i];
+      const uint8_t fl = hp->flags;
+      if (fl & NF_KEEP) {
+        hp->flags = fl & ~NF_KEEP;
+      } else {
+        hp->status = NS_FREE;
+        fr = true;
+      }
+    }
+    const uint32_t bal = __ballot_sync(FULL, fr);
+    if (fr) tr.free_list[nb + nfree + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+    nfree += __popc(bal);
+  }
+  if (lane == 0) {
+    tr.free_n[g] = nfree;
+    tr.root[g] = (uint16_t)keep;
+  }
+}
+
+__global__ void k_tree_reset(int G, TreeDev tr, const uint8_t* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= G) return;
+  if (mask && !mask[g]) return;
+  const size_t nb = (size_t)g * tr.C;
+  for (int i = lane; i < tr.C; i += 32) {
+    tr.free_list[nb + i] = (uint16_t)(tr.C - 1 - i);
+    tr.hdr[nb + i].status = NS_FREE;
+    tr.hdr[nb + i].flags = 0;
+  }
+  if (lane == 0) {
+    tr.free_n[g] = tr.C;
+    tr.root[g] = NONE16;
+  }
+}
+
+__global__ void k_leaf_info(TreeDev tr, uint64_t* __restrict__ hash, int32_t* __restrict__ game,
+                            int32_t* __restrict__ ply) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= *tr.eval_count) return;
+  const size_t id = (size_t)tr.eval_game[s] * tr.C + tr.eval_node[s];
+  if (hash) hash[s] = tr.hash[id];
+  if (game) game[s] = tr.eval_game[s];
+  if (ply) ply[s] = tr.meta[id].ply;
+}
+
+}  // namespace elfb200
+
+// =========================================================================================
+// C ABI (include/elfb200_mcts.h)
+// =========================================================================================
+using namespace elfb200;
+
+struct elfb200_mcts {
+  elfb200_ctx* ctx = nullptr;
+  elfb200_mcts_options opt{};
+  TreeDev tr{};
+  SearchOpts so{};
+  int waves_per_move = 0;
+  int wave = 0;
+  int64_t n_eval_total = 0;
+  uint8_t* d_mask = nullptr;
+  int32_t* d_actions = nullptr;
+  int32_t* d_best = nullptr;
+  int32_t* d_visits = nullptr;
+  float* d_rootv = nullptr;
+  float* d_bestq = nullptr;
+  int32_t* d_total = nullptr;
+  uint64_t* d_leaf_hash = nullptr;
+  int32_t* d_leaf_game = nullptr;
+  int32_t* d_leaf_ply = nullptr;
+  int last_eval_count = 0;
+};
+
+static inline int warp_grid(int G) { return (G + WARPS - 1) / WARPS; }
+
+extern "C" {
+
+int elfb200_mcts_default_options(elfb200_mcts_options* o) {
+  if (!o) return elfb200_fail(ELFB200_ERR_ARG, "options is NULL");
+  memset(o, 0, sizeof(*o));
+  // TSOptions / SearchAlgoOptions defaults (tree_search_options.h:22-111) and MCTSActorParams
+  // (go/mcts/mcts.h:17-27), with the self-play script's settings for the search itself
+  o->num_rollouts = 800;
+  o->num_rollouts_per_batch = 8;
+  o->virtual_loss = 1;
+  o->persistent_tree = 1;
+  o->use_prior = 1;
+  o->unexplored_q_zero = 0;
+  o->root_unexplored_q_zero = 0;
+  o->ply_pass_enabled = 0;
+  o->remove_pass_if_dangerous = 1;
+  o->rotation_flip = 1;
+  o->seed = 0;
+  o->nodes_per_game = 0;  // 0 = 2 * rollouts + 256
+  o->c_puct = 1.5f;
+  o->komi = 7.5f;
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200_mcts** out) {
+  if (!c || !opt || !out) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  *out = nullptr;
+  if (opt->num_rollouts <= 0 || opt->num_rollouts_per_batch <= 0 || opt->num_rollouts_per_batch > 64)
+    return elfb200_fail(ELFB200_ERR_ARG, "num_rollouts must be > 0 and num_rollouts_per_batch in [1, 64]");
+  if (opt->virtual_loss < 0) return elfb200_fail(ELFB200_ERR_ARG, "virtual_loss must be >= 0");
+  CK(cudaSetDevice(c->device));
+  elfb200_mcts* m = new elfb200_mcts();
+  m->ctx = c;
+  m->opt = *opt;
+  const int B = opt->num_rollouts_per_batch;
+  m->waves_per_move = (opt->num_rollouts + B - 1) / B;  // for (idx = 0; idx < R; idx += B)
+  int C = opt->nodes_per_game > 0 ? opt->nodes_per_game : 2 * m->waves_per_move * B + 256;
+  if (C < m->waves_per_move * B + 2) C = m->waves_per_move * B + 2;
+  if (C > 65534) return elfb200_fail(ELFB200_ERR_ARG, "nodes_per_game must be < 65535 (16-bit node ids)");
+  const size_t G = c->G, N = c->N, E = N * N + 1, GC = G * (size_t)C;
+  TreeDev& t = m->tr;
+  t.C = C;
+  t.B = B;
+  t.E = (int)E;
+  CK(cudaMalloc(&t.pos, GC * N * 8));
+  CK(cudaMalloc(&t.hash, GC * 8));
+  CK(cudaMalloc(&t.meta, GC * sizeof(BoardMeta)));
+  CK(cudaMalloc(&t.hdr, GC * sizeof(NodeHdr)));
+  CK(cudaMalloc(&t.estat, GC * E * sizeof(float4)));
+  CK(cudaMalloc(&t.elink, GC * E * 4));
+  CK(cudaMalloc(&t.free_list, GC * 2));
+  CK(cudaMalloc(&t.free_n, G * 4));
+  CK(cudaMalloc(&t.root, G * 2));
+  CK(cudaMalloc(&t.leaves, G * B * 2));
+  CK(cudaMalloc(&t.active, G));
+  CK(cudaMalloc(&t.eval_count, 4));
+  CK(cudaMalloc(&t.eval_game, G * B * 4));
+  CK(cudaMalloc(&t.eval_node, G * B * 2));
+  CK(cudaMalloc(&t.eval_d4, G * B));
+  CK(cudaMalloc(&t.bfs_q, GC * 2));
+  CK(cudaMalloc(&t.errors, 16));
+  CK(cudaMemsetAsync(t.errors, 0, 16, c->stream));
+  CK(cudaMemsetAsync(t.hdr, 0, GC * sizeof(NodeHdr), c->stream));
+  CK(cudaMemsetAsync(t.active, 1, G, c->stream));
+  CK(cudaMemsetAsync(t.eval_count, 0, 4, c->stream));
+  CK(cudaMalloc(&m->d_mask, G));
+  CK(cudaMalloc(&m->d_actions, G * 4));
+  CK(cudaMalloc(&m->d_best, G * 4));
+  CK(cudaMalloc(&m->d_visits, G * E * 4));
+  CK(cudaMalloc(&m->d_rootv, G * 4));
+  CK(cudaMalloc(&m->d_bestq, G * 4));
+  CK(cudaMalloc(&m->d_total, G * 4));
+  CK(cudaMalloc(&m->d_leaf_hash, G * B * 8));
+  CK(cudaMalloc(&m->d_leaf_game, G * B * 4));
+  CK(cudaMalloc(&m->d_leaf_ply, G * B * 4));
+  SearchOpts& s = m->so;
+  s.num_rollouts = opt->num_rollouts;
+  s.virtual_loss = opt->virtual_loss;
+  s.persistent = opt->persistent_tree;
+  s.use_prior = opt->use_prior;
+  s.uqz = opt->unexplored_q_zero;
+  s.ruqz = opt->root_unexplored_q_zero;
+  s.ply_pass_enabled = opt->ply_pass_enabled;
+  s.remove_pass_if_dangerous = opt->remove_pass_if_dangerous;
+  s.rotation_flip = opt->rotation_flip;
+  s.seed = opt->seed;
+  s.c_puct = opt->c_puct;
+  s.komi = opt->komi;
+  k_tree_reset<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, t, nullptr);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  *out = m;
+  return ELFB200_OK;
+}
+
+void elfb200_mcts_destroy(elfb200_mcts* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  TreeDev& t = m->tr;
+  void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.free_list,
+                  t.free_n,    t.root,      t.leaves,    t.active,     t.eval_count,  t.eval_game,  t.eval_node,
+                  t.eval_d4,   t.bfs_q,     t.errors,    m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
+                  m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete m;
+}
+
+int elfb200_mcts_waves_per_move(const elfb200_mcts* m) { return m ? m->waves_per_move : 0; }
+int elfb200_mcts_max_leaves(const elfb200_mcts* m) { return m ? m->ctx->G * m->tr.B : 0; }
+int elfb200_mcts_nodes_per_game(const elfb200_mcts* m) { return m ? m->tr.C : 0; }
+
+int elfb200_mcts_reset(elfb200_mcts* m, const uint8_t* mask_host) {
+  if (!m) return elfb200_fail(ELFB200_ERR_ARG, "mcts is NULL");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const uint8_t* dm = nullptr;
+  if (mask_host) {
+    memcpy(c->h_pin, mask_host, c->G);
+    CK(cudaMemcpyAsync(m->d_mask, c->h_pin, c->G, cudaMemcpyHostToDevice, c->stream));
+    dm = m->d_mask;
+  }
+  k_tree_reset<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, dm);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_begin_move(elfb200_mcts* m, const uint8_t* active_host) {
+  if (!m) return elfb200_fail(ELFB200_ERR_ARG, "mcts is NULL");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  if (active_host) {
+    memcpy(c->h_pin, active_host, c->G);
+    CK(cudaMemcpyAsync(m->tr.active, c->h_pin, c->G, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    CK(cudaMemsetAsync(m->tr.active, 1, c->G, c->stream));
+  }
+  const int need = m->waves_per_move * m->tr.B;
+  DISPATCH_N(c, (k_begin<19><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, need)),
+             (k_begin<9><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, need)));
+  c->launches++;
+  CK(cudaGetLastError());
+  m->wave = 0;
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves) {
+  if (!m || !feat_dev || !n_leaves) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(m->tr.eval_count, 0, 4, c->stream));
+  DISPATCH_N(c, (k_select<19><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, m->wave)),
+             (k_select<9><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, m->wave)));
+  c->launches++;
+  CK(cudaGetLastError());
+  int32_t* hp = (int32_t*)c->h_pin;
+  CK(cudaMemcpyAsync(hp, m->tr.eval_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int n = hp[0];
+  m->last_eval_count = n;
+  m->n_eval_total += n;
+  *n_leaves = n;
+  if (n > 0) {
+    DISPATCH_N(c, (k_leaf_features<19><<<n, 256, 0, c->stream>>>(c->st, m->tr, feat_dev)),
+               (k_leaf_features<9><<<n, 256, 0, c->stream>>>(c->st, m->tr, feat_dev)));
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  m->wave++;
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_leaf_info(elfb200_mcts* m, uint64_t* hash_host, int32_t* game_host, int32_t* ply_host) {
+  if (!m) return elfb200_fail(ELFB200_ERR_ARG, "mcts is NULL");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const int n = m->last_eval_count;
+  if (n <= 0) return ELFB200_OK;
+  k_leaf_info<<<(n + 127) / 128, 128, 0, c->stream>>>(m->tr, m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply);
+  c->launches++;
+  CK(cudaGetLastError());
+  if (hash_host) CK(cudaMemcpyAsync(hash_host, m->d_leaf_hash, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (game_host) CK(cudaMemcpyAsync(game_host, m->d_leaf_game, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (ply_host) CK(cudaMemcpyAsync(ply_host, m->d_leaf_ply, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float* value_dev) {
+  if (!m) return elfb200_fail(ELFB200_ERR_ARG, "mcts is NULL");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const int n = m->last_eval_count;
+  if (n > 0) {
+    if (!pi_dev || !value_dev) return elfb200_fail(ELFB200_ERR_ARG, "pi/value is NULL with %d leaves pending", n);
+    DISPATCH_N(c, (k_expand<19><<<warp_grid(n), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)),
+               (k_expand<9><<<warp_grid(n), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)));
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  k_backup<<<(c->G + 63) / 64, 64, 0, c->stream>>>(c->G, m->tr, m->so.virtual_loss);
+  c->launches++;
+  CK(cudaGetLastError());
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_results(elfb200_mcts* m, int32_t* best_action_host, int32_t* visits_host,
+                         float* root_value_host, float* best_q_host, int32_t* total_visits_host) {
+  if (!m) return elfb200_fail(ELFB200_ERR_ARG, "mcts is NULL");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t G = c->G, P1 = (size_t)c->N * c->N + 1;
+  DISPATCH_N(c,
+             (k_results<19><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->d_best, m->d_visits,
+                                                                       m->d_rootv, m->d_bestq, m->d_total)),
+             (k_results<9><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->d_best, m->d_visits,
+                                                                      m->d_rootv, m->d_bestq, m->d_total)));
+  c->launches++;
+  CK(cudaGetLastError());
+  if (best_action_host) CK(cudaMemcpyAsync(best_action_host, m->d_best, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (visits_host) CK(cudaMemcpyAsync(visits_host, m->d_visits, G * P1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (root_value_host) CK(cudaMemcpyAsync(root_value_host, m->d_rootv, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (best_q_host) CK(cudaMemcpyAsync(best_q_host, m->d_bestq, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (total_visits_host) CK(cudaMemcpyAsync(total_visits_host, m->d_total, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host) {
+  if (!m || !actions_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  memcpy(c->h_pin, actions_host, (size_t)c->G * 4);
+  CK(cudaMemcpyAsync(m->d_actions, c->h_pin, (size_t)c->G * 4, cudaMemcpyHostToDevice, c->stream));
+  k_advance<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->d_actions, m->so.persistent);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_errors(elfb200_mcts* m, int32_t* counters_host4) {
+  if (!m || !counters_host4) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(counters_host4, m->tr.errors, 16, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int64_t elfb200_mcts_eval_count(const elfb200_mcts* m) { return m ? m->n_eval_total : 0; }
+
+}  // extern "C"

@@ -47,7 +47,35 @@ SIGNATURES = {
     "elfb200_playout_launch": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]),
     "elfb200_playout_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "elfb200_launch_count": (ctypes.c_int64, [vp]),
+    # include/elfb200_mcts.h
+    "elfb200_mcts_default_options": (ctypes.c_int, [vp]),
+    "elfb200_mcts_create": (ctypes.c_int, [vp, vp, ctypes.POINTER(vp)]),
+    "elfb200_mcts_destroy": (None, [vp]),
+    "elfb200_mcts_waves_per_move": (ctypes.c_int, [vp]),
+    "elfb200_mcts_max_leaves": (ctypes.c_int, [vp]),
+    "elfb200_mcts_nodes_per_game": (ctypes.c_int, [vp]),
+    "elfb200_mcts_reset": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_begin_move": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_select": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_mcts_leaf_info": (ctypes.c_int, [vp, vp, vp, vp]),
+    "elfb200_mcts_expand_backup": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_mcts_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
+    "elfb200_mcts_advance": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_errors": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_eval_count": (ctypes.c_int64, [vp]),
 }
+
+
+class MctsOptions(ctypes.Structure):
+    """elfb200_mcts_options (include/elfb200_mcts.h); names follow TSOptions / MCTSActorParams."""
+    _fields_ = [
+        ("num_rollouts", ctypes.c_int32), ("num_rollouts_per_batch", ctypes.c_int32),
+        ("virtual_loss", ctypes.c_int32), ("persistent_tree", ctypes.c_int32), ("use_prior", ctypes.c_int32),
+        ("unexplored_q_zero", ctypes.c_int32), ("root_unexplored_q_zero", ctypes.c_int32),
+        ("ply_pass_enabled", ctypes.c_int32), ("remove_pass_if_dangerous", ctypes.c_int32),
+        ("rotation_flip", ctypes.c_int32), ("seed", ctypes.c_int32), ("nodes_per_game", ctypes.c_int32),
+        ("c_puct", ctypes.c_float), ("komi", ctypes.c_float), ("reserved", ctypes.c_float * 2),
+    ]
 
 
 def load_library(path=None):

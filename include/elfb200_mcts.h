@@ -1,0 +1,93 @@
+/* elfb200_mcts.h -- C ABI of the batched GPU tree search in libelfb200.so.
+ *
+ * Replaces, for all G games of an elfb200_ctx at once, the reference's per-game search objects
+ *   elf::ai::tree_search::MCTSAI_T / TreeSearchT / SearchTreeT / NodeT / EdgeInfo
+ *     (src_cpp/elf/ai/tree_search/{mcts.h,tree_search.h,tree_search_node.h,tree_search_base.h})
+ *   MCTSActor / MCTSGoAI (src_cpp/elfgames/go/mcts/mcts.h)
+ * The network stays outside: the caller (the rlpytorch model-interface callback in the
+ * reference, src_py/rlpytorch/trainer/trainer.py:73-115) is handed the leaf feature batch
+ * "s" float32 [n][18][N][N] in device memory and hands back "pi" float32 [n][N*N+1] and "V"
+ * float32 [n] (GoFeature tensor contract, src_cpp/elfgames/go/common/game_feature.h:159-206).
+ *
+ * One move of all games (== MCTSAI_T::act, elf/ai/tree_search/mcts.h:59-81):
+ *     elfb200_mcts_begin_move(m, active)
+ *     repeat elfb200_mcts_waves_per_move(m) times:          // TreeSearchSingleThreadT::run
+ *         elfb200_mcts_select(m, feat_dev, &n)              //   batch_rollouts: descents + leaf claim
+ *         pi, V = net(feat_dev[:n])                         //   actor.evaluate -> the NN
+ *         elfb200_mcts_expand_backup(m, pi_dev, v_dev)      //   setEvaluation + updateEdgeStats
+ *     elfb200_mcts_results(m, ...)                          // chooseAction (most_visited)
+ *     elfb200_step(ctx, actions, ...)                       // GoState::forward
+ *     elfb200_mcts_advance(m, actions)                      // SearchTreeT::treeAdvance
+ *
+ * Search semantics are those of ONE reference search thread (num_threads = 1) with
+ * num_rollouts_per_batch descents per wave; batching comes from the G games instead of from
+ * threads.  All functions return 0 or a negative ELFB200_ERR_* code (see elfb200.h).
+ */
+#ifndef ELFB200_MCTS_H_
+#define ELFB200_MCTS_H_
+
+#include <stdint.h>
+
+#include "elfb200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct elfb200_mcts elfb200_mcts;
+
+/* TSOptions + SearchAlgoOptions (tree_search_options.h:22-111) and MCTSActorParams
+ * (go/mcts/mcts.h:17-27).  Field names follow the reference. */
+typedef struct {
+  int32_t num_rollouts;            /* TSOptions::num_rollouts_per_thread */
+  int32_t num_rollouts_per_batch;  /* TSOptions::num_rollouts_per_batch */
+  int32_t virtual_loss;            /* TSOptions::virtual_loss */
+  int32_t persistent_tree;         /* TSOptions::persistent_tree */
+  int32_t use_prior;               /* SearchAlgoOptions::use_prior */
+  int32_t unexplored_q_zero;       /* SearchAlgoOptions::unexplored_q_zero */
+  int32_t root_unexplored_q_zero;  /* SearchAlgoOptions::root_unexplored_q_zero */
+  int32_t ply_pass_enabled;        /* MCTSActorParams::ply_pass_enabled */
+  int32_t remove_pass_if_dangerous;/* MCTSActorParams::remove_pass_if_dangerous */
+  int32_t rotation_flip;           /* MCTSActorParams::rotation_flip: random D4 per evaluation */
+  int32_t seed;
+  int32_t nodes_per_game;          /* node-pool slots per game; 0 = 2*rollouts + 256 */
+  float c_puct;                    /* SearchAlgoOptions::c_puct */
+  float komi;                      /* MCTSActorParams::komi */
+  float reserved[2];
+} elfb200_mcts_options;
+
+int elfb200_mcts_default_options(elfb200_mcts_options* opt);
+int elfb200_mcts_create(elfb200_ctx* ctx, const elfb200_mcts_options* opt, elfb200_mcts** out);
+void elfb200_mcts_destroy(elfb200_mcts* m);
+
+int elfb200_mcts_waves_per_move(const elfb200_mcts* m);  /* ceil(num_rollouts / per_batch) */
+int elfb200_mcts_max_leaves(const elfb200_mcts* m);      /* G * num_rollouts_per_batch */
+int elfb200_mcts_nodes_per_game(const elfb200_mcts* m);
+
+/* MCTSAI_T::endGame / resetTree (mcts.h:90-93,134-137) for games with mask[g] != 0 (all if NULL). */
+int elfb200_mcts_reset(elfb200_mcts* m, const uint8_t* mask_host);
+/* Search prologue: root allocation + root-state check (tree_search.h:478-493).  active[g] == 0
+ * excludes a game from this move (NULL = all active). */
+int elfb200_mcts_begin_move(elfb200_mcts* m, const uint8_t* active_host);
+/* One wave of descents.  Writes the feature planes of the *n_leaves leaves that need the network
+ * to feat_dev (device, capacity elfb200_mcts_max_leaves * 18*N*N floats). */
+int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves);
+/* Hash / game index / ply of the pending leaves (host, each may be NULL); test & debug aid. */
+int elfb200_mcts_leaf_info(elfb200_mcts* m, uint64_t* hash_host, int32_t* game_host, int32_t* ply_host);
+/* Network reply for the pending leaves (device pointers, same order as feat_dev), then backup. */
+int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float* value_dev);
+/* Root statistics (host, each may be NULL): best_action int32[G] (most visited, -1 if none),
+ * visits int32[G][N*N+1] (-1 where the root has no such edge), root_value float[G] (NodeT::V_),
+ * best_q float[G] (MCTSGoAI::getValue), total_visits int32[G]. */
+int elfb200_mcts_results(elfb200_mcts* m, int32_t* best_action_host, int32_t* visits_host,
+                         float* root_value_host, float* best_q_host, int32_t* total_visits_host);
+/* SearchTreeT::treeAdvance for the move just played in each game (actions[g] < 0: untouched). */
+int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host);
+/* int32[4]: root-hash mismatches, node-pool drops/overflows, reserved, reserved. */
+int elfb200_mcts_errors(elfb200_mcts* m, int32_t* counters_host4);
+int64_t elfb200_mcts_eval_count(const elfb200_mcts* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELFB200_MCTS_H_ */

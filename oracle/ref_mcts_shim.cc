@@ -39,6 +39,26 @@
 
 #include "fakenet.h"
 
+
+// ---- link-time stubs ---------------------------------------------------------------------------
+// go/mcts/mcts.h drags in the ELF batching client (elf/base/context.h -> elf/comm -> TBB
+// concurrent_hash_map); its virtual methods are instantiated but never called here because the
+// shim bypasses the client.  libtbb is not built for the oracle, so the handful of out-of-line TBB
+// entry points those instantiations reference are defined as traps: reaching one is a bug.
+#include <cstdlib>
+namespace tbb {
+bool spin_rw_mutex_v3::internal_upgrade() { std::abort(); }
+void spin_rw_mutex_v3::internal_acquire_reader() { std::abort(); }
+bool spin_rw_mutex_v3::internal_try_acquire_reader() { std::abort(); }
+bool spin_rw_mutex_v3::internal_try_acquire_writer() { std::abort(); }
+namespace internal {
+void* NFS_Allocate(size_t, size_t, void*) { std::abort(); }
+void throw_exception_v4(exception_id) { std::abort(); }
+void* allocate_via_handler_v3(size_t) { std::abort(); }
+void deallocate_via_handler_v3(void*) { std::abort(); }
+} // namespace internal
+} // namespace tbb
+
 namespace {
 
 using elf::ai::tree_search::TSOptions;

@@ -266,3 +266,87 @@ def ref_group(r, action):
 def ref_num_groups(r):
     r.L.ref_num_groups.argtypes = [vp]
     return int(r.L.ref_num_groups(r.p))
+
+
+# ---- deterministic fake network (oracle/fakenet.h) in numpy -------------------------------
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+
+
+def _splitmix64(x):
+    with np.errstate(over="ignore"):
+        x = x + _GOLD
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def fakenet(hashes, num_actions):
+    """bit-exact numpy twin of oracle/fakenet.h: returns (pi float32 [n, A], v float32 [n])"""
+    h = np.asarray(hashes, dtype=np.uint64).reshape(-1, 1)
+    a = (np.arange(num_actions, dtype=np.uint64) + np.uint64(1)).reshape(1, -1)
+    with np.errstate(over="ignore"):
+        r = _splitmix64(h ^ (a * _GOLD))
+    u = ((r >> np.uint64(40)) + np.uint64(1)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    t = u * u
+    t = t * t
+    t = t * t
+    r2 = _splitmix64(h[:, 0] ^ np.uint64(0x5EED5EED))
+    v = (r2 >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 8388608.0) - np.float32(1.0)
+    return t.astype(np.float32), v.astype(np.float32)
+
+
+class RefMcts:
+    """the reference search (MCTSAI_T + MCTSActor logic) through oracle/_ref, fake net or callback"""
+
+    def __init__(self, n, num_rollouts=200, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1,
+                 use_prior=1, unexplored_q_zero=0, root_unexplored_q_zero=0, ply_pass_enabled=0,
+                 remove_pass_if_dangerous=1, seed=7, c_puct=1.5, komi=7.5, callback=None):
+        self.L = load_ref(n)
+        self.n = n
+        L = self.L
+        L.ref_mcts_new.restype = vp
+        L.ref_mcts_new.argtypes = [vp, vp, vp]
+        L.ref_mcts_act.argtypes = [vp, vp] + [vp] * 6
+        L.ref_mcts_free.argtypes = [vp]
+        L.ref_mcts_num_evals.restype = ctypes.c_long
+        L.ref_mcts_num_evals.argtypes = [vp]
+        iopts = np.array([num_rollouts, num_rollouts_per_batch, virtual_loss, persistent_tree, use_prior,
+                          unexplored_q_zero, root_unexplored_q_zero, ply_pass_enabled, remove_pass_if_dangerous,
+                          seed, 1], np.int32)
+        fopts = np.array([c_puct, komi, 0, 0], np.float32)
+        self._cb = None
+        if callback is not None:
+            CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64),
+                                  ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float))
+            P1 = n * n + 1
+
+            def tramp(cnt, feats, hashes, pi, v):
+                f = np.ctypeslib.as_array(feats, shape=(cnt, 18, n, n))
+                h = np.ctypeslib.as_array(hashes, shape=(cnt,))
+                p, val = callback(f, h)
+                np.ctypeslib.as_array(pi, shape=(cnt, P1))[:] = p
+                np.ctypeslib.as_array(v, shape=(cnt,))[:] = val
+
+            self._cb = CB(tramp)
+        self.m = L.ref_mcts_new(iopts.ctypes.data, fopts.ctypes.data, ctypes.cast(self._cb, vp) if self._cb else None)
+
+    def act(self, ref_state):
+        P1 = self.n * self.n + 1
+        vis = np.zeros(P1, np.int32)
+        w = np.zeros(P1, np.float32)
+        pr = np.zeros(P1, np.float32)
+        rv = ctypes.c_float()
+        bq = ctypes.c_float()
+        tv = ctypes.c_int32()
+        a = self.L.ref_mcts_act(self.m, ref_state.p, vis.ctypes.data, w.ctypes.data, pr.ctypes.data,
+                                ctypes.byref(rv), ctypes.byref(bq), ctypes.byref(tv))
+        return {"best_action": int(a), "visits": vis, "wsum": w, "prior": pr, "root_value": rv.value,
+                "best_q": bq.value, "total_visits": tv.value}
+
+    def num_evals(self):
+        return int(self.L.ref_mcts_num_evals(self.m))
+
+    def __del__(self):
+        if getattr(self, "m", None):
+            self.L.ref_mcts_free(self.m)
+            self.m = None
