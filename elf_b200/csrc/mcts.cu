@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(BLOCK)
   // pass handling (mcts.h:225-242)
   bool pass_enabled = (int)meta.ply >= o.ply_pass_enabled;
   if (o.remove_pass_if_dangerous && pass_enabled && meta.last1 != MV_PASS) {
-    const int sc = tt_score<N>(b, w, L);
+    // (per-game reductions are only defined on the game's own lanes: take lane 0's copy)
+    const int sc = __shfl_sync(FULL, tt_score<N>(b, w, L), 0);
     const bool black_win = ((float)sc - o.komi) > 0;
     if ((black_win && meta.next == S_WHITE) || (!black_win && meta.next == S_BLACK)) pass_enabled = false;
   }

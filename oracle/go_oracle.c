@@ -51,6 +51,9 @@ struct GoOracle {
   /* superko table: pre-move positions of every non-pass move (go_state.cc:113-121) */
   PosRecord* sk;
   int sk_n, sk_cap;
+  /* GoState::_moves (go_state.h:217): every accepted action, for moves_since (go_state.h:158-168) */
+  int16_t moves[2 * MAXP];
+  int n_moves;
 };
 
 /* ---- helpers ---------------------------------------------------------- */
@@ -161,6 +164,8 @@ static int mv2action(int N, int m) {
   return p2a(N, m);
 }
 int go_last_move(const GoOracle* s) { return mv2action(s->N, s->last[0]); }
+int go_num_moves(const GoOracle* s) { return s->n_moves; }
+int go_move_at(const GoOracle* s, int i) { return (i >= 0 && i < s->n_moves) ? s->moves[i] : -1; }
 
 /* ---- rules ------------------------------------------------------------ */
 /* GoState::_check_superko go_state.cc:96-111 */
@@ -281,6 +286,7 @@ int go_forward(GoOracle* s, int action) {
     s->sk_n++;
     play_point(s, p);
   }
+  s->moves[s->n_moves++] = (int16_t)action; /* _moves.push_back(c), go_state.cc:89 */
   /* _history.emplace_back(_board), trimmed to 8: go_state.cc:90-92 */
   memcpy(s->hist[s->hist_pos], s->color, (size_t)(N * N));
   s->hist_pos = (s->hist_pos + 1) % HIST;

@@ -48,6 +48,8 @@ int go_terminated(const GoOracle* s);
 int go_ply(const GoOracle* s);
 int go_next_player(const GoOracle* s);
 int go_last_move(const GoOracle* s);
+int go_num_moves(const GoOracle* s);
+int go_move_at(const GoOracle* s, int i);
 
 int go_group_liberties(const GoOracle* s, int action);
 int go_group_stones(const GoOracle* s, int action);

@@ -71,3 +71,24 @@ if __name__ == "__main__":
     for n in (19, 9):
         gen(n)
         print("golden fixtures written for", n)
+
+
+def gen_mcts():
+    """tests/golden/mcts_<scenario>.json: root visit counts of the compiled reference search."""
+    from tests.test_mcts_oracle_vs_ref import SCENARIOS, run_search
+
+    for name, sc in sorted(SCENARIOS.items()):
+        n = sc["n"]
+        res, evals = run_search(sc, lambda: oracles.Ref(n), lambda: oracles.RefMcts(n, **sc["opts"]))
+        steps = []
+        for r in res:
+            v = r["visits"]
+            steps.append({"best_action": r["best_action"], "total_visits": r["total_visits"],
+                          "visits": {str(int(a)): int(v[a]) for a in np.flatnonzero(v >= 0)}})
+        with open(os.path.join(ROOT, "tests", "golden", f"mcts_{name}.json"), "w") as f:
+            json.dump({"scenario": name, "num_evals": evals, "steps": steps}, f)
+        print("golden mcts fixture", name)
+
+
+if __name__ == "__main__" and (len(sys.argv) == 1 or "mcts" in sys.argv):
+    gen_mcts()

@@ -350,3 +350,47 @@ class RefMcts:
         if getattr(self, "m", None):
             self.L.ref_mcts_free(self.m)
             self.m = None
+
+
+class OracleMcts:
+    """the C restatement of the search (oracle/mcts_oracle.c); same interface as RefMcts but acts
+    on Oracle states"""
+
+    def __init__(self, n, num_rollouts=200, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1,
+                 use_prior=1, unexplored_q_zero=0, root_unexplored_q_zero=0, ply_pass_enabled=0,
+                 remove_pass_if_dangerous=1, seed=7, c_puct=1.5, komi=7.5, lib=None):
+        self.L = lib or load_oracle()
+        self.n = n
+        L = self.L
+        L.mo_new.restype = vp
+        L.mo_new.argtypes = [ctypes.c_int, vp, vp, vp]
+        L.mo_act.argtypes = [vp, vp] + [vp] * 6
+        L.mo_free.argtypes = [vp]
+        L.mo_num_evals.restype = ctypes.c_long
+        L.mo_num_evals.argtypes = [vp]
+        iopts = np.array([num_rollouts, num_rollouts_per_batch, virtual_loss, persistent_tree, use_prior,
+                          unexplored_q_zero, root_unexplored_q_zero, ply_pass_enabled, remove_pass_if_dangerous,
+                          seed, 1], np.int32)
+        fopts = np.array([c_puct, komi, 0, 0], np.float32)
+        self.m = L.mo_new(n, iopts.ctypes.data, fopts.ctypes.data, None)
+
+    def act(self, oracle_state):
+        P1 = self.n * self.n + 1
+        vis = np.zeros(P1, np.int32)
+        w = np.zeros(P1, np.float32)
+        pr = np.zeros(P1, np.float32)
+        rv = ctypes.c_float()
+        bq = ctypes.c_float()
+        tv = ctypes.c_int32()
+        a = self.L.mo_act(self.m, oracle_state.p, vis.ctypes.data, w.ctypes.data, pr.ctypes.data,
+                          ctypes.byref(rv), ctypes.byref(bq), ctypes.byref(tv))
+        return {"best_action": int(a), "visits": vis, "wsum": w, "prior": pr, "root_value": rv.value,
+                "best_q": bq.value, "total_visits": tv.value}
+
+    def num_evals(self):
+        return int(self.L.mo_num_evals(self.m))
+
+    def __del__(self):
+        if getattr(self, "m", None):
+            self.L.mo_free(self.m)
+            self.m = None

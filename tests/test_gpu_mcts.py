@@ -1,81 +1,134 @@
-"""GPU parity of the batched tree search against the UNMODIFIED reference search
-(elf::ai::tree_search::MCTSAI_T + the reference Go actor logic, through oracle/_ref) with one
-search thread, fixed rollouts per batch, rotation_flip off and the deterministic fake net
-(oracle/fakenet.h): root visit counts must agree within +-1 per edge (BASELINE.json north_star)."""
+"""GPU parity of the batched tree search (CUDA, through the C ABI) against the oracle: the C
+restatement (oracle/mcts_oracle.c, itself pinned exactly to the compiled reference search) and,
+when oracle/_ref is present, the UNMODIFIED reference search itself.  One search thread, fixed
+rollouts per batch, rotation_flip off, deterministic fake net (oracle/fakenet.h).
+Bar (BASELINE.json north_star): root visit counts within +-1 per edge."""
+import json
+import os
+
 import numpy as np
 import pytest
 
 from tests import oracles
+from tests.test_mcts_oracle_vs_ref import SCENARIOS, GOLD
 
 pytestmark = pytest.mark.gpu
 
 
-def _fake_actor(mcts, n):
+def fake_actor(mcts, n):
     import torch
 
     def actor(batch):
         h, _, _ = mcts.leaf_info()
         pi, v = oracles.fakenet(h, n * n + 1)
+        assert batch["s"].shape[0] == len(h)
         return {"pi": torch.from_numpy(pi).to(mcts.device), "V": torch.from_numpy(v).to(mcts.device)}
 
     return actor
 
 
-def _run_parity(n, G, moves, opts, open_plies, tol=1):
+def run_gpu_vs_cpu(sc, use_ref, tol=1):
     import elf_b200
 
-    if not oracles.have_ref(n):
-        pytest.skip("oracle/_ref not built")
+    n, G = sc["n"], sc["G"]
     rng = np.random.default_rng(5 + n)
     gb = elf_b200.GoBatch(G, board_size=n)
-    refs = [oracles.Ref(n) for _ in range(G)]
-    # distinct openings
-    for t in range(open_plies):
+    make = (lambda: oracles.Ref(n)) if use_ref else (lambda: oracles.Oracle(n))
+    states = [make() for _ in range(G)]
+    for _ in range(sc["open_plies"]):
         acts = np.empty(G, np.int32)
-        for g, r in enumerate(refs):
-            idx = np.flatnonzero(r.legal())
+        for g, s in enumerate(states):
+            idx = np.flatnonzero(s.legal())
             acts[g] = int(rng.choice(idx))
-            assert r.forward(acts[g])
+            assert s.forward(acts[g])
         assert gb.forward(acts).all()
-    mc = elf_b200.MctsBatch(gb, rotation_flip=0, **opts)
-    rms = [oracles.RefMcts(n, **opts) for _ in range(G)]
-    actor = _fake_actor(mc, n)
-    worst = 0
-    for mv in range(moves):
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, **sc["opts"])
+    cpu = [(oracles.RefMcts if use_ref else oracles.OracleMcts)(n, **sc["opts"]) for _ in range(G)]
+    actor = fake_actor(mc, n)
+    worst, exact = 0, 0
+    for mv in range(sc["moves"]):
         res = mc.act(actor)
         acts = np.empty(G, np.int32)
         for g in range(G):
-            rr = rms[g].act(refs[g])
+            rr = cpu[g].act(states[g])
             gv, rv = res["visits"][g], rr["visits"]
             assert ((gv >= 0) == (rv >= 0)).all(), f"edge sets differ: move {mv} game {g}"
-            d = np.abs(gv - rv)[rv >= 0]
-            worst = max(worst, int(d.max()))
-            assert d.max() <= tol, f"visits differ by {d.max()} at move {mv} game {g}: gpu {gv[rv>=0][d.argmax()]} ref {rv[rv>=0][d.argmax()]}"
+            d = int(np.abs(gv - rv)[rv >= 0].max())
+            worst = max(worst, d)
+            exact += d == 0
+            assert d <= tol, f"visits differ by {d} at move {mv} game {g}"
             assert res["total_visits"][g] == rr["total_visits"]
-            assert abs(res["root_value"][g] - rr["root_value"]) < 1e-6
+            assert res["root_value"][g] == np.float32(rr["root_value"])
+            if d == 0:
+                assert res["best_action"][g] == rr["best_action"] or gv[res["best_action"][g]] == rv[rr["best_action"]]
+                assert abs(res["best_q"][g] - rr["best_q"]) < 1e-5
             acts[g] = rr["best_action"]
-            assert refs[g].forward(acts[g])
+            assert states[g].forward(acts[g])
         assert gb.forward(acts).all()
         mc.advance(acts)
     assert (mc.errors() == 0).all(), mc.errors()
-    # same number of network evaluations as the reference (no extra / missing expansions)
-    assert mc.eval_count() == sum(r.num_evals() for r in rms)
+    assert mc.eval_count() == sum(c.num_evals() for c in cpu)
     mc.close()
     gb.close()
-    return worst
+    return worst, exact
 
 
-def test_mcts_parity_19_persistent():
-    _run_parity(19, G=6, moves=6, open_plies=6,
-                opts=dict(num_rollouts=200, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1, c_puct=1.5))
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_gpu_search_vs_restatement(name):
+    worst, exact = run_gpu_vs_cpu(SCENARIOS[name], use_ref=False)
+    print(f"{name}: worst visit deviation {worst}, exact root tables {exact}")
 
 
-def test_mcts_parity_19_fresh_tree_batch1():
-    _run_parity(19, G=4, moves=3, open_plies=30,
-                opts=dict(num_rollouts=128, num_rollouts_per_batch=1, virtual_loss=0, persistent_tree=0, c_puct=0.85))
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_gpu_search_vs_reference(name):
+    if not oracles.have_ref(SCENARIOS[name]["n"]):
+        pytest.skip("oracle/_ref not built")
+    run_gpu_vs_cpu(SCENARIOS[name], use_ref=True)
 
 
-def test_mcts_parity_9_endgame():
-    # 9x9 late in the game: terminal leaves, passes, pass suppression, superko inside the tree
-    _run_parity(9, G=8, moves=12, open_plies=60,
-                opts=dict(num_rollouts=160, num_rollouts_per_batch=4, virtual_loss=2, persistent_tree=1, c_puct=1.5))
+def test_gpu_search_many_games_batched():
+    """64 games searched together must give each game exactly what it gets alone (games are
+    independent; the leaf batch interleaves them)."""
+    import elf_b200
+
+    n, G = 9, 64
+    opts = dict(num_rollouts=64, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1, c_puct=1.5)
+    gb = elf_b200.GoBatch(G, board_size=n)
+    os_ = [oracles.Oracle(n) for _ in range(G)]
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        acts = np.empty(G, np.int32)
+        for g, s in enumerate(os_):
+            idx = np.flatnonzero(s.legal())
+            acts[g] = int(rng.choice(idx))
+            s.forward(acts[g])
+        gb.forward(acts)
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, **opts)
+    cpu = [oracles.OracleMcts(n, **opts) for _ in range(G)]
+    for mv in range(3):
+        res = mc.act(fake_actor(mc, n))
+        acts = np.empty(G, np.int32)
+        for g in range(G):
+            rr = cpu[g].act(os_[g])
+            assert np.abs(res["visits"][g] - rr["visits"]).max() <= 1
+            acts[g] = rr["best_action"]
+            os_[g].forward(acts[g])
+        gb.forward(acts)
+        mc.advance(acts)
+    assert (mc.errors() == 0).all()
+
+
+def test_gpu_search_inactive_and_reset():
+    import elf_b200
+
+    n, G = 9, 4
+    gb = elf_b200.GoBatch(G, board_size=n)
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, num_rollouts=32, num_rollouts_per_batch=4)
+    res = mc.act(fake_actor(mc, n), active=np.array([1, 0, 1, 0], np.uint8))
+    assert res["best_action"][1] == -1 and res["best_action"][3] == -1
+    assert res["total_visits"][0] == 28 and res["total_visits"][2] == 28  # first wave expands the root
+    mc.reset(np.array([1, 0, 0, 0], np.uint8))
+    res2 = mc.act(fake_actor(mc, n))
+    assert res2["total_visits"][0] == 28            # tree dropped: root expanded again
+    assert res2["total_visits"][2] == 28 + 32       # tree kept (same root: no move was played)
+    assert res2["total_visits"][1] == 28

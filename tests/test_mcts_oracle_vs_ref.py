@@ -1,0 +1,81 @@
+"""Pin the C restatement of the tree search (oracle/mcts_oracle.c) against the compiled UNMODIFIED
+reference search (MCTSAI_T / TreeSearchT / MCTSActor logic through oracle/_ref): identical root
+edge sets, visit counts, reward sums, priors, values and number of network evaluations, move after
+move with a persistent tree.  Also against the committed golden vectors (no reference needed)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracles
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+SCENARIOS = {
+    "19_persistent_b8": dict(n=19, G=3, moves=5, open_plies=6,
+                             opts=dict(num_rollouts=200, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1, c_puct=1.5)),
+    "19_fresh_b1": dict(n=19, G=2, moves=3, open_plies=30,
+                        opts=dict(num_rollouts=96, num_rollouts_per_batch=1, virtual_loss=0, persistent_tree=0, c_puct=0.85)),
+    "9_endgame": dict(n=9, G=6, moves=12, open_plies=60,
+                      opts=dict(num_rollouts=160, num_rollouts_per_batch=4, virtual_loss=2, persistent_tree=1, c_puct=1.5)),
+    "9_uqz_pass": dict(n=9, G=4, moves=10, open_plies=50,
+                       opts=dict(num_rollouts=120, num_rollouts_per_batch=6, virtual_loss=1, persistent_tree=1, c_puct=2.0,
+                                 unexplored_q_zero=1, ply_pass_enabled=40, remove_pass_if_dangerous=0)),
+}
+
+
+def opening(n, G, open_plies, make):
+    rng = np.random.default_rng(5 + n)
+    states = [make() for _ in range(G)]
+    for _ in range(open_plies):
+        for s in states:
+            idx = np.flatnonzero(s.legal())
+            assert s.forward(int(rng.choice(idx)))
+    return states
+
+
+def run_search(sc, make_state, make_mcts):
+    states = opening(sc["n"], sc["G"], sc["open_plies"], make_state)
+    ms = [make_mcts() for _ in range(sc["G"])]
+    out = []
+    for _ in range(sc["moves"]):
+        for s, m in zip(states, ms):
+            r = m.act(s)
+            out.append(r)
+            s.forward(r["best_action"])
+    return out, sum(m.num_evals() for m in ms)
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_restatement_equals_reference(name, oracle_lib):
+    sc = SCENARIOS[name]
+    n = sc["n"]
+    if not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    a, ea = run_search(sc, lambda: oracles.Ref(n), lambda: oracles.RefMcts(n, **sc["opts"]))
+    b, eb = run_search(sc, lambda: oracles.Oracle(n, oracle_lib), lambda: oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]))
+    assert ea == eb
+    for i, (ra, rb) in enumerate(zip(a, b)):
+        assert ra["best_action"] == rb["best_action"], i
+        np.testing.assert_array_equal(ra["visits"], rb["visits"], err_msg=f"step {i}")
+        np.testing.assert_array_equal(ra["prior"], rb["prior"], err_msg=f"step {i}")
+        np.testing.assert_allclose(ra["wsum"], rb["wsum"], rtol=0, atol=1e-4)
+        assert ra["total_visits"] == rb["total_visits"]
+        assert ra["root_value"] == rb["root_value"]
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_restatement_equals_golden(name, oracle_lib):
+    path = os.path.join(GOLD, f"mcts_{name}.json")
+    gold = json.load(open(path))
+    sc = SCENARIOS[name]
+    n = sc["n"]
+    b, eb = run_search(sc, lambda: oracles.Oracle(n, oracle_lib), lambda: oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]))
+    assert eb == gold["num_evals"]
+    assert len(b) == len(gold["steps"])
+    for r, gsv in zip(b, gold["steps"]):
+        assert r["best_action"] == gsv["best_action"]
+        assert r["total_visits"] == gsv["total_visits"]
+        vis = {int(a): int(v) for a, v in zip(np.flatnonzero(r["visits"] >= 0), r["visits"][r["visits"] >= 0])}
+        assert vis == {int(k): v for k, v in gsv["visits"].items()}
