@@ -324,6 +324,165 @@ def run_ours(args):
     return 0
 
 
+# --------------------------------------------------------------------------------------------
+# secondary workload: BASELINE configs[2] -- MCTS self-play (the network is PyTorch/cuDNN plumbing;
+# our kernels are select / leaf features / expand / backup).  `--workload mcts`.
+# --------------------------------------------------------------------------------------------
+def cpu_mcts_rollouts(seconds, rollouts, per_batch):
+    """reference TreeSearchT (oracle/_ref) with the deterministic fake net on every host thread:
+    rollouts/s without any network cost."""
+    from tests import oracles
+
+    cores = effective_cores()
+    if not oracles.have_ref(BOARD):
+        return None
+    done = [0] * cores
+    t0 = time.perf_counter()
+    deadline = t0 + seconds
+
+    def work(tid):
+        st = oracles.Ref(BOARD)
+        m = oracles.RefMcts(BOARD, num_rollouts=rollouts, num_rollouts_per_batch=per_batch, virtual_loss=1,
+                            persistent_tree=1, c_puct=1.5, seed=tid)
+        while time.perf_counter() < deadline:
+            r = m.act(st)
+            st.forward(r["best_action"])
+            done[tid] += 1
+            if st.terminated():
+                break
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    return {"moves": sum(done), "seconds": dt, "cores": cores}
+
+
+def run_mcts(args):
+    import torch
+
+    import elf_b200
+    from elf_b200.model import Actor, PolicyValueNet, broadcast_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    G, R, B = args.games, args.rollouts, args.per_batch
+    dev = torch.device("cuda", local)
+    torch.manual_seed(1234)
+    if args.fake_net:
+        P1 = BOARD * BOARD + 1
+        table = torch.rand(4096, P1, device=dev).softmax(1)
+        vals = torch.rand(4096, device=dev) * 2 - 1
+
+        def actor(batch):
+            n = batch["s"].shape[0]
+            idx = torch.arange(n, device=dev) % 4096
+            return {"pi": table[idx], "V": vals[idx]}
+        net_desc = "fake (table lookup, engine-only timing)"
+    else:
+        model = PolicyValueNet(BOARD, num_block=args.blocks, dim=args.dim).to(dev)
+        t_b0 = time.perf_counter()
+        broadcast_weights(model)  # frozen weights from rank 0: the only collective of the path
+        torch.cuda.synchronize()
+        t_bcast = time.perf_counter() - t_b0
+        actor = Actor(model, batchsize=args.nn_batch)
+        net_desc = f"random-init resnet {args.blocks}x{args.dim}, bf16 autocast, channels_last, NN batch {args.nn_batch}"
+    sp = elf_b200.selfplay.SelfPlay(actor, num_games=G, board_size=BOARD, device=local, policy_distri_cutoff=0,
+                                    resign_thres=0.0, never_resign_ratio=1.0, num_rollouts=R,
+                                    num_rollouts_per_batch=B, virtual_loss=1, persistent_tree=1, c_puct=1.5,
+                                    rotation_flip=1, seed=rank)
+    ext = torch.cuda.ExternalStream(sp.gb.stream, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(ext):
+        for _ in range(args.warmup):
+            sp.step()
+        sp.mcts.timings(reset=True)
+        st0 = sp.mcts.stats().astype(np.int64)
+        ev0 = sp.mcts.eval_count()
+        l0 = sp.gb.launch_count()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        t0 = time.perf_counter()
+        moves = 0
+        for _ in range(args.steps):
+            moves += sp.step()
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        dev_ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        ms, waves = sp.mcts.timings()
+        st = sp.mcts.stats().astype(np.int64) - st0
+        evals = sp.mcts.eval_count() - ev0
+        launches = sp.gb.launch_count() - l0
+    if dist is not None:
+        t = torch.tensor([dev_ms, wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall = t.tolist()
+        c = torch.tensor([moves, launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        moves, launches = c.tolist()
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        E = BOARD * BOARD + 1
+        sel_bytes = int(st[0]) * (32 + 4) + int(st[1]) * 16  # SURVEY 8d: header + E_n*16 + vl write
+        feat_bytes = evals * 26792
+        sel_gbs = sel_bytes / (ms[0] / 1e3) / 1e9 if ms[0] > 0 else 0.0
+        feat_gbs = feat_bytes / (ms[1] / 1e3) / 1e9 if ms[1] > 0 else 0.0
+        line = {
+            "metric": "self-play moves/sec (MCTS, 19x19)", "value": moves / (dev_ms / 1e3), "unit": "moves/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 search / bf16 net",
+            "data": "synthetic",
+            "config": {"workload": f"configs[2]-shaped: {G} games/GPU x {R} rollouts/move, {B} rollouts/wave, puct 1.5, vloss 1, persistent tree",
+                       "net": net_desc, "games_per_gpu": G, "rollouts": R, "l2": "node pool >> L2 (7.4 KB/node)",
+                       "parallelism": f"games sharded x{world}, NCCL weight broadcast only"},
+            "e2e": {"value": moves / wall, "unit": "moves/s", "h2d_bytes_per_step": 4 * G + G,
+                    "d2h_bytes_per_step": int(G * (E * 4 + 16 + 48 * 2)),
+                    "note": "through SelfPlay.step(): actions H2D, root tables + info D2H each move; leaf features never leave the GPU"},
+            "gpu_launches": int(launches),
+            "kernels_ms_per_wave": {"select": ms[0] / max(waves, 1), "leaf_features": ms[1] / max(waves, 1),
+                                    "expand": ms[2] / max(waves, 1), "backup": ms[3] / max(waves, 1)},
+            "waves": int(waves), "nn_evals": int(evals), "rollouts_per_s": (int(waves) * B * G * world) / (dev_ms / 1e3),
+            "roofline": {"bound": "hbm", "achieved": sel_gbs, "peak": peak, "unit": "GB/s", "frac": sel_gbs / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_select<19>",
+                         "algorithmic_bytes": sel_bytes, "nodes_visited": int(st[0]), "edges_scanned": int(st[1]),
+                         "leaf_features_GBps": feat_gbs},
+            "clocks": clocks,
+        }
+        if not args.fake_net:
+            line["weight_broadcast_s"] = t_bcast
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_mcts_rollouts(min(args.cpu_seconds, 15.0), R, B)
+            if cb:
+                line["cpu_baseline"] = {"value": cb["moves"] / cb["seconds"], "unit": "moves/s", "cores": cb["cores"],
+                                        "kind": "reference",
+                                        "sample": f"reference TreeSearchT, {R} rollouts/move, 1 search thread per game, fake net (no NN cost), {cb['moves']} moves in {cb['seconds']:.1f} s on {cb['cores']} threads"}
+        print(json.dumps(line), flush=True)
+    sp.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -332,7 +491,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="playout", choices=["playout", "mcts"])
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--rollouts", type=int, default=64)
+    ap.add_argument("--per-batch", type=int, default=8)
+    ap.add_argument("--blocks", type=int, default=20)
+    ap.add_argument("--dim", type=int, default=256)
+    ap.add_argument("--nn-batch", type=int, default=2048)
+    ap.add_argument("--fake-net", action="store_true")
     args = ap.parse_args()
+    if args.workload == "mcts" and args.impl == "ours":
+        return run_mcts(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

@@ -12,5 +12,6 @@ and every call fails without a CUDA device.  There is no CPU fallback.
 from .lib import ElfB200Error, load_library  # noqa: F401
 from .board import GoBatch  # noqa: F401
 from .mcts import MctsBatch  # noqa: F401
+from . import selfplay  # noqa: F401
 
 __all__ = ["GoBatch", "MctsBatch", "ElfB200Error", "load_library"]

@@ -66,6 +66,7 @@ struct TreeDev {
   uint8_t* eval_d4;     // [G*B]
   uint16_t* bfs_q;      // [G][C]
   int32_t* errors;      // [4]: root-hash mismatches, pool overflows, ...
+  unsigned long long* stats;  // [4]: descent steps, edges scanned, nodes created, terminal leaves
   int C, B, E;
 };
 
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
   uint64_t* skg = st.sk + (size_t)g * Geo<N>::MAX_PLY;
   const int nsk0 = st.sk_n[g];
   const float vl = (float)o.virtual_loss;
+  unsigned st_steps = 0, st_edges = 0, st_new = 0, st_term = 0;
 
   for (int j = 0; j < tr.B; ++j) {
     int node = root, depth = 0, cnt = nsk0;
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
       const NodeHdr h = load_hdr(&tr.hdr[nb + node]);
       if (h.status != NS_VISITED || h.n_edges == 0) break;
       // ---- UCT over the node's edges -------------------------------------------------------
+      st_steps++;
+      st_edges += h.n_edges;
       const bool flip = h.flags & NF_FLIP;
       const float fpu = (o.uqz || (o.ruqz && depth == 0)) ? 0.f : h.mean_q;
       const double sq = sqrt((double)(h.num_visits + 1));  // std::sqrt(int) -> double
@@ -249,6 +253,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           break;
         }
         child = id;
+        st_new++;
         const uint64_t rowv = L.active ? tr.pos[(nb + node) * N + L.row] : 0ull;
         uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
         BoardMeta meta = load_meta(&tr.meta[nb + node]);
@@ -294,6 +299,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           fv = meta.next == S_BLACK ? 1.0f : -1.0f;
         else
           fv = (float)sc - o.komi;
+        st_term++;
         if (L.lane == 0) {
           NodeHdr h2 = lh;
           h2.V = fv > 0 ? 1.0f : -1.0f;
@@ -316,6 +322,12 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
     }
     if (L.lane == 0) tr.leaves[(size_t)g * tr.B + j] = (uint16_t)node;
     __syncwarp();
+  }
+  if (L.lane == 0) {
+    atomicAdd(&tr.stats[0], (unsigned long long)st_steps);
+    atomicAdd(&tr.stats[1], (unsigned long long)st_edges);
+    atomicAdd(&tr.stats[2], (unsigned long long)st_new);
+    atomicAdd(&tr.stats[3], (unsigned long long)st_term);
   }
 }
 
@@ -721,13 +733,14 @@ __global__ void k_tree_reset(int G, TreeDev tr, const uint8_t* __restrict__ mask
 }
 
 __global__ void k_leaf_info(TreeDev tr, uint64_t* __restrict__ hash, int32_t* __restrict__ game,
-                            int32_t* __restrict__ ply) {
+                            int32_t* __restrict__ ply, int32_t* __restrict__ d4) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= *tr.eval_count) return;
   const size_t id = (size_t)tr.eval_game[s] * tr.C + tr.eval_node[s];
   if (hash) hash[s] = tr.hash[id];
   if (game) game[s] = tr.eval_game[s];
   if (ply) ply[s] = tr.meta[id].ply;
+  if (d4) d4[s] = tr.eval_d4[s];
 }
 
 }  // namespace elfb200
@@ -755,8 +768,27 @@ struct elfb200_mcts {
   uint64_t* d_leaf_hash = nullptr;
   int32_t* d_leaf_game = nullptr;
   int32_t* d_leaf_ply = nullptr;
+  int32_t* d_leaf_d4 = nullptr;
   int last_eval_count = 0;
+  // per-kernel device timing (CUDA events on the context stream), accumulated on the host
+  cudaEvent_t ev[7] = {};  // sel0 sel1 feat0 feat1 exp0 exp1 bak1
+  bool pending_feat = false, pending_eb = false;
+  double acc_ms[4] = {0, 0, 0, 0};  // select, features, expand, backup
+  int64_t acc_waves = 0;
 };
+
+static void flush_timings(elfb200_mcts* m) {  // caller has synchronised the stream
+  float ms = 0.f;
+  if (m->pending_feat) {
+    if (cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->acc_ms[1] += ms;
+    m->pending_feat = false;
+  }
+  if (m->pending_eb) {
+    if (cudaEventElapsedTime(&ms, m->ev[4], m->ev[5]) == cudaSuccess) m->acc_ms[2] += ms;
+    if (cudaEventElapsedTime(&ms, m->ev[5], m->ev[6]) == cudaSuccess) m->acc_ms[3] += ms;
+    m->pending_eb = false;
+  }
+}
 
 static inline int warp_grid(int G) { return (G + WARPS - 1) / WARPS; }
 
@@ -822,6 +854,8 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   CK(cudaMalloc(&t.bfs_q, GC * 2));
   CK(cudaMalloc(&t.errors, 16));
   CK(cudaMemsetAsync(t.errors, 0, 16, c->stream));
+  CK(cudaMalloc(&t.stats, 32));
+  CK(cudaMemsetAsync(t.stats, 0, 32, c->stream));
   CK(cudaMemsetAsync(t.hdr, 0, GC * sizeof(NodeHdr), c->stream));
   CK(cudaMemsetAsync(t.active, 1, G, c->stream));
   CK(cudaMemsetAsync(t.eval_count, 0, 4, c->stream));
@@ -835,6 +869,7 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   CK(cudaMalloc(&m->d_leaf_hash, G * B * 8));
   CK(cudaMalloc(&m->d_leaf_game, G * B * 4));
   CK(cudaMalloc(&m->d_leaf_ply, G * B * 4));
+  CK(cudaMalloc(&m->d_leaf_d4, G * B * 4));
   SearchOpts& s = m->so;
   s.num_rollouts = opt->num_rollouts;
   s.virtual_loss = opt->virtual_loss;
@@ -848,6 +883,7 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   s.seed = opt->seed;
   s.c_puct = opt->c_puct;
   s.komi = opt->komi;
+  for (auto& e : m->ev) CK(cudaEventCreate(&e));
   k_tree_reset<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, t, nullptr);
   c->launches++;
   CK(cudaGetLastError());
@@ -863,10 +899,12 @@ void elfb200_mcts_destroy(elfb200_mcts* m) {
   TreeDev& t = m->tr;
   void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.free_list,
                   t.free_n,    t.root,      t.leaves,    t.active,     t.eval_count,  t.eval_game,  t.eval_node,
-                  t.eval_d4,   t.bfs_q,     t.errors,    m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
-                  m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply};
+                  t.eval_d4,   t.bfs_q,     t.errors,    t.stats,     m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
+                  m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (auto& e : m->ev)
+    if (e) cudaEventDestroy(e);
   delete m;
 }
 
@@ -915,39 +953,53 @@ int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves) {
   elfb200_ctx* c = m->ctx;
   CK(cudaSetDevice(c->device));
   CK(cudaMemsetAsync(m->tr.eval_count, 0, 4, c->stream));
+  CK(cudaEventRecord(m->ev[0], c->stream));
   DISPATCH_N(c, (k_select<19><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, m->wave)),
              (k_select<9><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, m->wave)));
   c->launches++;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(m->ev[1], c->stream));
   int32_t* hp = (int32_t*)c->h_pin;
   CK(cudaMemcpyAsync(hp, m->tr.eval_count, 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  {
+    flush_timings(m);  // previous wave's features / expand / backup are complete by now
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->acc_ms[0] += ms;
+    m->acc_waves++;
+  }
   const int n = hp[0];
   m->last_eval_count = n;
   m->n_eval_total += n;
   *n_leaves = n;
   if (n > 0) {
+    CK(cudaEventRecord(m->ev[2], c->stream));
     DISPATCH_N(c, (k_leaf_features<19><<<n, 256, 0, c->stream>>>(c->st, m->tr, feat_dev)),
                (k_leaf_features<9><<<n, 256, 0, c->stream>>>(c->st, m->tr, feat_dev)));
     c->launches++;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(m->ev[3], c->stream));
+    m->pending_feat = true;
   }
   m->wave++;
   return ELFB200_OK;
 }
 
-int elfb200_mcts_leaf_info(elfb200_mcts* m, uint64_t* hash_host, int32_t* game_host, int32_t* ply_host) {
+int elfb200_mcts_leaf_info(elfb200_mcts* m, uint64_t* hash_host, int32_t* game_host, int32_t* ply_host,
+                           int32_t* d4_host) {
   if (!m) return elfb200_fail(ELFB200_ERR_ARG, "mcts is NULL");
   elfb200_ctx* c = m->ctx;
   CK(cudaSetDevice(c->device));
   const int n = m->last_eval_count;
   if (n <= 0) return ELFB200_OK;
-  k_leaf_info<<<(n + 127) / 128, 128, 0, c->stream>>>(m->tr, m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply);
+  k_leaf_info<<<(n + 127) / 128, 128, 0, c->stream>>>(m->tr, m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply,
+                                                         m->d_leaf_d4);
   c->launches++;
   CK(cudaGetLastError());
   if (hash_host) CK(cudaMemcpyAsync(hash_host, m->d_leaf_hash, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
   if (game_host) CK(cudaMemcpyAsync(game_host, m->d_leaf_game, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   if (ply_host) CK(cudaMemcpyAsync(ply_host, m->d_leaf_ply, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (d4_host) CK(cudaMemcpyAsync(d4_host, m->d_leaf_d4, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ELFB200_OK;
 }
@@ -957,6 +1009,7 @@ int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float
   elfb200_ctx* c = m->ctx;
   CK(cudaSetDevice(c->device));
   const int n = m->last_eval_count;
+  CK(cudaEventRecord(m->ev[4], c->stream));
   if (n > 0) {
     if (!pi_dev || !value_dev) return elfb200_fail(ELFB200_ERR_ARG, "pi/value is NULL with %d leaves pending", n);
     DISPATCH_N(c, (k_expand<19><<<warp_grid(n), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)),
@@ -964,9 +1017,12 @@ int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float
     c->launches++;
     CK(cudaGetLastError());
   }
+  CK(cudaEventRecord(m->ev[5], c->stream));
   k_backup<<<(c->G + 63) / 64, 64, 0, c->stream>>>(c->G, m->tr, m->so.virtual_loss);
   c->launches++;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(m->ev[6], c->stream));
+  m->pending_eb = true;
   return ELFB200_OK;
 }
 
@@ -1015,5 +1071,29 @@ int elfb200_mcts_errors(elfb200_mcts* m, int32_t* counters_host4) {
 }
 
 int64_t elfb200_mcts_eval_count(const elfb200_mcts* m) { return m ? m->n_eval_total : 0; }
+
+int elfb200_mcts_timings(elfb200_mcts* m, double* ms_host4, int64_t* waves, int reset) {
+  if (!m || !ms_host4) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  flush_timings(m);
+  for (int i = 0; i < 4; ++i) ms_host4[i] = m->acc_ms[i];
+  if (waves) *waves = m->acc_waves;
+  if (reset) {
+    for (int i = 0; i < 4; ++i) m->acc_ms[i] = 0;
+    m->acc_waves = 0;
+  }
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_stats(elfb200_mcts* m, uint64_t* counters_host4) {
+  if (!m || !counters_host4) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(counters_host4, m->tr.stats, 32, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
 
 }  // extern "C"

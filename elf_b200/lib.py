@@ -57,12 +57,14 @@ SIGNATURES = {
     "elfb200_mcts_reset": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_begin_move": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_select": (ctypes.c_int, [vp, vp, vp]),
-    "elfb200_mcts_leaf_info": (ctypes.c_int, [vp, vp, vp, vp]),
+    "elfb200_mcts_leaf_info": (ctypes.c_int, [vp, vp, vp, vp, vp]),
     "elfb200_mcts_expand_backup": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_mcts_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "elfb200_mcts_advance": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_errors": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_eval_count": (ctypes.c_int64, [vp]),
+    "elfb200_mcts_stats": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_timings": (ctypes.c_int, [vp, vp, vp, ctypes.c_int]),
 }
 
 

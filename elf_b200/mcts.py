@@ -69,7 +69,9 @@ class MctsBatch:
         h = np.empty(n, np.uint64)
         g = np.empty(n, np.int32)
         p = np.empty(n, np.int32)
-        _l.check(self._lib, self._lib.elfb200_mcts_leaf_info(self._m, h.ctypes.data, g.ctypes.data, p.ctypes.data))
+        self.leaf_d4 = np.empty(n, np.int32)
+        _l.check(self._lib, self._lib.elfb200_mcts_leaf_info(self._m, h.ctypes.data, g.ctypes.data, p.ctypes.data,
+                                                             self.leaf_d4.ctypes.data))
         return h, g, p
 
     def expand_backup(self, pi, v):
@@ -104,6 +106,19 @@ class MctsBatch:
 
     def eval_count(self):
         return self._lib.elfb200_mcts_eval_count(self._m)
+
+    def timings(self, reset=False):
+        """(ms[4] = select, features, expand, backup kernel time; number of waves)"""
+        ms = np.zeros(4, np.float64)
+        w = ctypes.c_int64()
+        _l.check(self._lib, self._lib.elfb200_mcts_timings(self._m, ms.ctypes.data, ctypes.byref(w), int(reset)))
+        return ms, w.value
+
+    def stats(self):
+        """uint64[4]: descent steps, edges scanned, nodes created, terminal leaves (running totals)"""
+        s = np.zeros(4, np.uint64)
+        _l.check(self._lib, self._lib.elfb200_mcts_stats(self._m, s.ctypes.data))
+        return s
 
     # -- MCTSAI_T::act for all games -----------------------------------------------------------
     def act(self, actor, active=None):

@@ -1,0 +1,87 @@
+"""SelfPlay: the per-move driver of the reference's self-play game loop, for G games at once.
+
+Mirrors ``GoGameSelfPlay::act`` (``src_cpp/elfgames/go/common/game_selfplay.cc:272-430``):
+one MCTS per move, ``mcts_make_diverse_move`` (sample from the visit distribution while
+``ply <= policy_distri_cutoff``, ``:80-95``), ``MCTSGoAI::getValue`` as predicted value,
+``ResignCheck`` (``common/game_utils.h:15-54``: resign when the side to move's value is below
+``-1 + resign_thres`` and ``ply >= 50``; a ``never_resign_ratio`` fraction of games never resigns),
+``GoState::forward``, game end on two passes / ply cap / superko / ``move_cutoff`` with the final
+value from ``GoState::evaluate(komi)`` (``go_state_ext.h:79-105``), then restart.
+
+Randomness (move sampling, never-resign draw) comes from a numpy Generator, not from the
+reference's per-game ``std::mt19937`` streams: distributions are the same, streams are not.
+"""
+import numpy as np
+
+from .board import GoBatch
+from .mcts import MctsBatch
+
+
+class SelfPlay:
+    def __init__(self, actor, num_games=4096, board_size=19, device=0, policy_distri_cutoff=20,
+                 resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0, **mcts_opts):
+        self.gb = GoBatch(num_games, board_size=board_size, device=device)
+        mcts_opts.setdefault("komi", komi)
+        self.mcts = MctsBatch(self.gb, **mcts_opts)
+        self.actor = actor
+        self.G = num_games
+        self.N = board_size
+        self.komi = komi
+        self.policy_distri_cutoff = policy_distri_cutoff
+        self.resign_thres = resign_thres
+        self.never_resign_ratio = never_resign_ratio
+        self.move_cutoff = move_cutoff
+        self.rng = np.random.default_rng(seed)
+        self.never_resign = self.rng.random(num_games) < never_resign_ratio
+        self.moves_played = 0
+        self.games_finished = 0
+        self.results = []  # (final_value, plies, reason) of finished games
+
+    def close(self):
+        self.mcts.close()
+        self.gb.close()
+
+    def _choose(self, res, info):
+        """mcts_make_diverse_move: sample ~ visits while ply <= cutoff, else most visited."""
+        acts = res["best_action"].copy()
+        ply = info[:, 0]
+        for g in np.flatnonzero(ply <= self.policy_distri_cutoff):
+            v = np.maximum(res["visits"][g], 0).astype(np.float64)
+            tot = v.sum()
+            if tot > 0:
+                acts[g] = int(self.rng.choice(len(v), p=v / tot))
+        return acts
+
+    def step(self):
+        """one move of every game; returns the number of moves played"""
+        P = self.N * self.N
+        info = self.gb.info()
+        res = self.mcts.act(self.actor)
+        acts = self._choose(res, info)
+        # resign check (game_selfplay.cc:387-391, go_state_ext.h:207-214)
+        val = np.where(info[:, 1] == 1, res["best_q"], -res["best_q"])
+        resign = (~self.never_resign) & (val < -1.0 + self.resign_thres) & (info[:, 0] >= 50)
+        acts[resign] = -1
+        ok = self.gb.forward(acts)
+        assert ok[~resign].all(), "MCTS proposed an illegal move"
+        self.mcts.advance(acts)
+        self.moves_played += int((~resign).sum())
+        info2 = self.gb.info()
+        done = resign | (info2[:, 9] == 1)
+        if self.move_cutoff > 0:
+            done |= info2[:, 0] >= self.move_cutoff
+        if done.any():
+            final = self.gb.evaluate(self.komi)
+            for g in np.flatnonzero(done):
+                if resign[g]:
+                    fv, why = (1.0 if info[g, 1] == 2 else -1.0), "resign"
+                else:
+                    fv = float(final[g])
+                    why = "two_pass" if info2[g, 10] else ("superko" if info2[g, 11] else "max_step")
+                self.results.append((fv, int(info2[g, 0]), why))
+            m = done.astype(np.uint8)
+            self.gb.reset(m)
+            self.mcts.reset(m)
+            self.never_resign[done] = self.rng.random(int(done.sum())) < self.never_resign_ratio
+            self.games_finished += int(done.sum())
+        return int((~resign).sum())

@@ -72,8 +72,9 @@ int elfb200_mcts_begin_move(elfb200_mcts* m, const uint8_t* active_host);
 /* One wave of descents.  Writes the feature planes of the *n_leaves leaves that need the network
  * to feat_dev (device, capacity elfb200_mcts_max_leaves * 18*N*N floats). */
 int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves);
-/* Hash / game index / ply of the pending leaves (host, each may be NULL); test & debug aid. */
-int elfb200_mcts_leaf_info(elfb200_mcts* m, uint64_t* hash_host, int32_t* game_host, int32_t* ply_host);
+/* Hash / game index / ply / D4 code of the pending leaves (host, each may be NULL); test & debug aid. */
+int elfb200_mcts_leaf_info(elfb200_mcts* m, uint64_t* hash_host, int32_t* game_host, int32_t* ply_host,
+                           int32_t* d4_host);
 /* Network reply for the pending leaves (device pointers, same order as feat_dev), then backup. */
 int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float* value_dev);
 /* Root statistics (host, each may be NULL): best_action int32[G] (most visited, -1 if none),
@@ -86,6 +87,12 @@ int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host);
 /* int32[4]: root-hash mismatches, node-pool drops/overflows, reserved, reserved. */
 int elfb200_mcts_errors(elfb200_mcts* m, int32_t* counters_host4);
 int64_t elfb200_mcts_eval_count(const elfb200_mcts* m);
+/* uint64[4] running totals: descent steps (nodes visited by PUCT), edges scanned, nodes created,
+ * terminal leaves evaluated.  Used by bench.py for the select kernel's algorithmic bytes. */
+int elfb200_mcts_stats(elfb200_mcts* m, uint64_t* counters_host4);
+/* double[4]: accumulated device time (ms, CUDA events on the context stream) of the select,
+ * leaf-feature, expand and backup kernels, and the number of waves they cover; reset != 0 clears. */
+int elfb200_mcts_timings(elfb200_mcts* m, double* ms_host4, int64_t* waves, int reset);
 
 #ifdef __cplusplus
 }

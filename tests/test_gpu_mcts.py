@@ -132,3 +132,97 @@ def test_gpu_search_inactive_and_reset():
     assert res2["total_visits"][0] == 28            # tree dropped: root expanded again
     assert res2["total_visits"][2] == 28 + 32       # tree kept (same root: no move was played)
     assert res2["total_visits"][1] == 28
+
+
+def test_rotation_flip_is_a_pure_relabelling():
+    """rotation_flip draws a D4 code per evaluation: the features are written under that symmetry
+    and the policy is mapped back through the inverse (board_feature.h:97-144).  A net that answers
+    in BOARD coordinates, pushed through the forward symmetry by the test, must therefore give
+    exactly the search it gives without rotation."""
+    import torch
+    import elf_b200
+
+    n, G = 9, 6
+    P = n * n
+    opts = dict(num_rollouts=96, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5)
+
+    def fwd(d4, x, y):  # BoardFeature::Transform
+        rot, flip = d4 & 3, d4 >> 2
+        if rot == 1:
+            a, b = y, n - x - 1
+        elif rot == 2:
+            a, b = n - x - 1, n - y - 1
+        elif rot == 3:
+            a, b = n - y - 1, x
+        else:
+            a, b = x, y
+        return (b, a) if flip else (a, b)
+
+    perm = np.zeros((8, P + 1), np.int64)  # perm[d4][nn_action] = board_action
+    for d4 in range(8):
+        for x in range(n):
+            for y in range(n):
+                tx, ty = fwd(d4, x, y)
+                perm[d4][tx * n + ty] = x * n + y
+        perm[d4][P] = P
+
+    def run(rotation):
+        gb = elf_b200.GoBatch(G, board_size=n)
+        rng = np.random.default_rng(3)
+        os_ = [oracles.Oracle(n) for _ in range(G)]
+        for _ in range(16):
+            acts = np.empty(G, np.int32)
+            for g, s in enumerate(os_):
+                idx = np.flatnonzero(s.legal())
+                acts[g] = int(rng.choice(idx))
+                s.forward(acts[g])
+            gb.forward(acts)
+        mc = elf_b200.MctsBatch(gb, rotation_flip=rotation, seed=5, **opts)
+        feats_seen = []
+
+        def actor(batch):
+            h, _, _ = mc.leaf_info()
+            pi_board, v = oracles.fakenet(h, P + 1)
+            d4 = mc.leaf_d4
+            if rotation:
+                assert len(set(d4.tolist())) > 1
+            pi_nn = np.take_along_axis(pi_board, perm[d4], axis=1)  # pi_nn[a] = pi_board[board(a)]
+            feats_seen.append(batch["s"].sum().item())
+            return {"pi": torch.from_numpy(pi_nn).to(mc.device), "V": torch.from_numpy(v).to(mc.device)}
+
+        out = []
+        for _ in range(3):
+            res = mc.act(actor)
+            out.append(res["visits"].copy())
+            a = res["best_action"]
+            gb.forward(a)
+            mc.advance(a)
+        return out, feats_seen
+
+    a, fa = run(0)
+    b, fb = run(1)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    assert fa == fb  # plane sums are invariant under the symmetry
+
+
+def test_selfplay_driver_smoke():
+    """GoGameSelfPlay::act mirror: a few moves of real self-play with a small random-init net:
+    legal moves only, games restart on termination, counters consistent."""
+    import torch
+    import elf_b200
+    from elf_b200.model import Actor, PolicyValueNet
+
+    torch.manual_seed(0)
+    n, G = 9, 32
+    net = PolicyValueNet(n, num_block=2, dim=32).cuda()
+    sp = elf_b200.selfplay.SelfPlay(Actor(net, batchsize=64), num_games=G, board_size=n, policy_distri_cutoff=4,
+                                    num_rollouts=32, num_rollouts_per_batch=4, move_cutoff=30, seed=1)
+    total = 0
+    for _ in range(36):
+        total += sp.step()
+    assert total == sp.moves_played and total > 30 * G
+    assert sp.games_finished >= G  # move_cutoff 30 forces restarts
+    assert all(abs(fv) <= n * n + 7.5 for fv, _, _ in sp.results)
+    assert (sp.mcts.errors() == 0).all()
+    sp.close()
