@@ -218,8 +218,10 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(gb.stream, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
 
+    from elf_b200.dist_utils import reduce_timing_and_counts, shard_first_game_id
+
     def first_id(step):  # distinct games per (step, rank)
-        return (step * world + rank) * G
+        return shard_first_game_id(step, world, rank, G)
 
     def barrier():
         if dist is not None:
@@ -281,14 +283,9 @@ def run_ours(args):
         except Exception as e:  # oracle missing is not fatal for the bench
             parity = f"unchecked: {e}"
 
-    # ---- reduce over ranks --------------------------------------------------------------------
-    if dist is not None:
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = t.tolist()
-        c = torch.tensor([plies_total, e2e_plies, launches], dtype=torch.int64, device=f"cuda:{local}")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        plies_total, e2e_plies, launches = c.tolist()
+    # ---- reduce over ranks (MAX of times, SUM of counters) ----------------------------------------
+    (dev_ms, e2e_s), (plies_total, e2e_plies, launches) = reduce_timing_and_counts(
+        dist, f"cuda:{local}", [dev_ms, e2e_s], [plies_total, e2e_plies, launches])
 
     if rank == 0:
         peak, peak_src = measured_peaks()

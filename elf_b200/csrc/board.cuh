@@ -162,10 +162,11 @@ __device__ __forceinline__ void floodK(uint32_t (&g)[K], const uint32_t (&throug
   while (true) {
     bool ch = false;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      uint32_t n1 = g[k] | (grow4<N>(g[k], L) & through[k]);
-      ch |= (n1 != g[k]);
-      g[k] = n1;
+    for (int k = 0; k < K; ++k) {  // two dilations per vote
+      const uint32_t n1 = g[k] | (grow4<N>(g[k], L) & through[k]);
+      const uint32_t n2 = n1 | (grow4<N>(n1, L) & through[k]);
+      ch |= (n2 != g[k]);
+      g[k] = n2;
     }
     if (!__any_sync(FULL, ch)) break;
   }

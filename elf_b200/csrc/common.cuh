@@ -71,6 +71,50 @@ struct DevState {
   int G;
 };
 
+
+// ---- AGZ feature planes -------------------------------------------------------------------------
+// BoardFeature::extractAGZ (board_feature.cc:247-290) for one position whose <=8 history positions
+// (newest first) are staged in shared memory as rows[t][y] = black_row | white_row << 32.
+// One thread per OUTPUT cell: the thread resolves its cell through the inverse D4 once
+// (InvTransform, board_feature.h:115-130), then emits the 16 stone planes and the 2 side-to-move
+// planes; for a fixed plane consecutive threads write consecutive floats (coalesced 128 B/warp).
+__device__ __forceinline__ void d4_inverse(int N, int d4, int tx, int ty, int& x, int& y) {
+  int a = tx, b = ty;
+  if (d4 & 4) { int t = a; a = b; b = t; }
+  switch (d4 & 3) {
+    case 1: x = N - b - 1; y = a; break;
+    case 2: x = N - a - 1; y = N - b - 1; break;
+    case 3: x = b; y = N - a - 1; break;
+    default: x = a; y = b; break;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void write_agz_planes(const uint64_t (*rows)[N], int hn, int next, int d4,
+                                                 float* __restrict__ out) {
+  constexpr int P = Geo<N>::P;
+  for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
+    const int tx = cell / N, ty = cell - tx * N;
+    int x, y;
+    d4_inverse(N, d4, tx, ty, x, y);
+    const bool black_first = next == S_BLACK;  // even planes = side to move (board_feature.cc:268-281)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      float mine = 0.f, theirs = 0.f;
+      if (t < hn) {
+        const uint64_t r = rows[t][y];
+        const float bl = (float)(((uint32_t)r >> x) & 1u), wh = (float)(((uint32_t)(r >> 32) >> x) & 1u);
+        mine = black_first ? bl : wh;
+        theirs = black_first ? wh : bl;
+      }
+      out[(2 * t) * P + cell] = mine;
+      out[(2 * t + 1) * P + cell] = theirs;
+    }
+    out[16 * P + cell] = black_first ? 1.0f : 0.0f;
+    out[17 * P + cell] = black_first ? 0.0f : 1.0f;
+  }
+}
+
 }  // namespace elfb200
 
 // ---- host side ---------------------------------------------------------------------------------

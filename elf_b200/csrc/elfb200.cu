@@ -170,42 +170,12 @@ __global__ void __launch_bounds__(BLOCK)
 
 // ---------------------------------------------------------------------------------------
 // BoardFeature::extractAGZ (board_feature.cc:247-290).  One CTA per position; the 8 history
-// positions are staged in shared memory, every thread produces float2 outputs so the
-// 25,992-byte plane stack is written with coalesced 8-byte stores.
-__device__ __forceinline__ void d4_inv(int N, int d4, int tx, int ty, int& x, int& y) {
-  // InvTransform, board_feature.h:115-130
-  int a = tx, b = ty;
-  if (d4 & 4) { int t = a; a = b; b = t; }
-  switch (d4 & 3) {
-    case 1: x = N - b - 1; y = a; break;
-    case 2: x = N - a - 1; y = N - b - 1; break;
-    case 3: x = b; y = N - a - 1; break;
-    default: x = a; y = b; break;
-  }
-}
-
+// positions are staged in shared memory and every thread owns one output cell of all 18 planes
+// (write_agz_planes, common.cuh).
 template <int N>
-__device__ __forceinline__ float feature_value(const uint64_t (*rows)[N], int hn, int next, int d4, int o) {
-  constexpr int P = Geo<N>::P;
-  const int plane = o / P, cell = o - plane * P;
-  if (plane >= 16) return (plane == 16) == (next == S_BLACK) ? 1.0f : 0.0f;
-  const int t = plane >> 1;
-  if (t >= hn) return 0.0f;
-  const int tx = cell / N, ty = cell - tx * N;
-  int x, y;
-  d4_inv(N, d4, tx, ty, x, y);
-  const uint64_t r = rows[t][y];
-  // even planes: side to move's stones, odd planes: opponent's (board_feature.cc:268-281)
-  const bool want_black = ((plane & 1) == 0) == (next == S_BLACK);
-  const uint32_t bits = want_black ? (uint32_t)r : (uint32_t)(r >> 32);
-  return (float)((bits >> x) & 1u);
-}
-
-template <int N>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(384)
     k_features(DevState st, const int32_t* __restrict__ d4codes, float* __restrict__ out) {
   constexpr int P = Geo<N>::P;
-  constexpr int TOTAL = 18 * P;  // even for N = 9, 19
   __shared__ uint64_t rows[8][N];
   const int g = blockIdx.x;
   const BoardMeta meta = load_meta(&st.meta[g]);
@@ -215,14 +185,7 @@ __global__ void __launch_bounds__(256)
     rows[t][y] = t < hn ? st.ring[((size_t)g * 8 + ((meta.ply - 2 - t) & 7)) * N + y] : 0ull;
   }
   __syncthreads();
-  const int d4 = d4codes ? d4codes[g] : 0;
-  float2* o2 = reinterpret_cast<float2*>(out + (size_t)g * TOTAL);
-  for (int i = threadIdx.x; i < TOTAL / 2; i += blockDim.x) {
-    float2 v;
-    v.x = feature_value<N>(rows, hn, meta.next, d4, 2 * i);
-    v.y = feature_value<N>(rows, hn, meta.next, d4, 2 * i + 1);
-    o2[i] = v;
-  }
+  write_agz_planes<N>(rows, hn, meta.next, d4codes ? d4codes[g] : 0, out + (size_t)g * 18 * P);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -540,8 +503,8 @@ int elfb200_evaluate(elfb200_ctx* c, float komi, float* value_host) {
 int elfb200_features_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) {
   if (!c || !out_dev) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   CK(cudaSetDevice(c->device));
-  DISPATCH_N(c, (k_features<19><<<c->G, 256, 0, c->stream>>>(c->st, d4_dev, out_dev)),
-             (k_features<9><<<c->G, 256, 0, c->stream>>>(c->st, d4_dev, out_dev)));
+  DISPATCH_N(c, (k_features<19><<<c->G, 384, 0, c->stream>>>(c->st, d4_dev, out_dev)),
+             (k_features<9><<<c->G, 96, 0, c->stream>>>(c->st, d4_dev, out_dev)));
   c->launches++;
   CK(cudaGetLastError());
   return ELFB200_OK;

@@ -334,19 +334,8 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
 // ---------------------------------------------------------------------------------------
 // BoardFeature::extractAGZ for every claimed leaf: the 8-position history is the leaf, its
 // ancestors up to the root, then the game's own ring (go_state.cc:90-92).  One CTA per leaf.
-__device__ __forceinline__ void d4_inv_m(int N, int d4, int tx, int ty, int& x, int& y) {
-  int a = tx, b = ty;
-  if (d4 & 4) { int t = a; a = b; b = t; }
-  switch (d4 & 3) {
-    case 1: x = N - b - 1; y = a; break;
-    case 2: x = N - a - 1; y = N - b - 1; break;
-    case 3: x = b; y = N - a - 1; break;
-    default: x = a; y = b; break;
-  }
-}
-
 template <int N>
-__global__ void __launch_bounds__(256) k_leaf_features(DevState st, TreeDev tr, float* __restrict__ out) {
+__global__ void __launch_bounds__(384) k_leaf_features(DevState st, TreeDev tr, float* __restrict__ out) {
   constexpr int P = Geo<N>::P;
   constexpr int TOTAL = 18 * P;
   __shared__ uint64_t rows[8][N];
@@ -385,36 +374,7 @@ __global__ void __launch_bounds__(256) k_leaf_features(DevState st, TreeDev tr, 
     rows[t][y] = v;
   }
   __syncthreads();
-  const int d4 = tr.eval_d4[slot];
-  const int next = meta.next;
-  float2* o2 = reinterpret_cast<float2*>(out + (size_t)slot * TOTAL);
-  for (int i = threadIdx.x; i < TOTAL / 2; i += blockDim.x) {
-    float v[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int o = 2 * i + k;
-      const int plane = o / P, cell = o - plane * P;
-      float val;
-      if (plane >= 16) {
-        val = (plane == 16) == (next == S_BLACK) ? 1.0f : 0.0f;
-      } else {
-        const int t = plane >> 1;
-        if (t >= hn) {
-          val = 0.f;
-        } else {
-          const int tx = cell / N, ty = cell - tx * N;
-          int x, y;
-          d4_inv_m(N, d4, tx, ty, x, y);
-          const uint64_t r = rows[t][y];
-          const bool want_black = ((plane & 1) == 0) == (next == S_BLACK);
-          const uint32_t bits = want_black ? (uint32_t)r : (uint32_t)(r >> 32);
-          val = (float)((bits >> x) & 1u);
-        }
-      }
-      v[k] = val;
-    }
-    o2[i] = make_float2(v[0], v[1]);
-  }
+  write_agz_planes<N>(rows, hn, meta.next, tr.eval_d4[slot], out + (size_t)slot * TOTAL);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -466,7 +426,7 @@ __global__ void __launch_bounds__(BLOCK)
         ok = pass_enabled;
       } else {
         int x, y;
-        d4_inv_m(N, d4, a / N, a - (a / N) * N, x, y);
+        d4_inverse(N, d4, a / N, a - (a / N) * N, x, y);
         act = x * N + y;
         ok = (s_legal[wib][y] >> x) & 1u;
       }
@@ -974,8 +934,8 @@ int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves) {
   *n_leaves = n;
   if (n > 0) {
     CK(cudaEventRecord(m->ev[2], c->stream));
-    DISPATCH_N(c, (k_leaf_features<19><<<n, 256, 0, c->stream>>>(c->st, m->tr, feat_dev)),
-               (k_leaf_features<9><<<n, 256, 0, c->stream>>>(c->st, m->tr, feat_dev)));
+    DISPATCH_N(c, (k_leaf_features<19><<<n, 384, 0, c->stream>>>(c->st, m->tr, feat_dev)),
+               (k_leaf_features<9><<<n, 96, 0, c->stream>>>(c->st, m->tr, feat_dev)));
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m->ev[3], c->stream));

@@ -126,9 +126,15 @@ class MctsBatch:
         callback and return the root statistics.  The callback sees ``batch["s"]`` on the GPU."""
         torch = self._torch
         self.begin_move(active)
+        pad = int(getattr(actor, "batchsize", 0) or 0)
         for _ in range(self.waves_per_move):
             s = self.select()
             if s.shape[0] > 0:
+                if pad > 1:
+                    # static NN shapes: round the batch up to a multiple of the actor's batch size
+                    # (rows past n are stale features; their replies are never read)
+                    n_pad = min(-(-s.shape[0] // pad) * pad, self.max_leaves)
+                    s = self.feat[:n_pad]
                 self.gb.synchronize()  # features written on the context stream
                 with torch.no_grad():
                     reply = actor({"s": s})
