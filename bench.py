@@ -391,7 +391,7 @@ def run_mcts(args):
         torch.cuda.synchronize()
         t_bcast = time.perf_counter() - t_b0
         actor = Actor(model, batchsize=args.nn_batch)
-        net_desc = f"random-init resnet {args.blocks}x{args.dim}, bf16 autocast, channels_last, NN batch {args.nn_batch}"
+        net_desc = f"random-init resnet {args.blocks}x{args.dim}, fp16 weights, channels_last, NN batch {args.nn_batch}"
     sp = elf_b200.selfplay.SelfPlay(actor, num_games=G, board_size=BOARD, device=local, policy_distri_cutoff=0,
                                     resign_thres=0.0, never_resign_ratio=1.0, num_rollouts=R,
                                     num_rollouts_per_batch=B, virtual_loss=1, persistent_tree=1, c_puct=1.5,
@@ -446,7 +446,7 @@ def run_mcts(args):
         line = {
             "metric": "self-play moves/sec (MCTS, 19x19)", "value": moves / (dev_ms / 1e3), "unit": "moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 search / bf16 net",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 search / fp16 net",
             "data": "synthetic",
             "config": {"workload": f"configs[2]-shaped: {G} games/GPU x {R} rollouts/move, {B} rollouts/wave, puct 1.5, vloss 1, persistent tree",
                        "net": net_desc, "games_per_gpu": G, "rollouts": R, "l2": "node pool >> L2 (7.4 KB/node)",
@@ -494,7 +494,7 @@ def main():
     ap.add_argument("--per-batch", type=int, default=8)
     ap.add_argument("--blocks", type=int, default=20)
     ap.add_argument("--dim", type=int, default=256)
-    ap.add_argument("--nn-batch", type=int, default=2048)
+    ap.add_argument("--nn-batch", type=int, default=256)
     ap.add_argument("--fake-net", action="store_true")
     args = ap.parse_args()
     if args.workload == "mcts" and args.impl == "ours":

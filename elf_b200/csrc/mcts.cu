@@ -15,6 +15,7 @@
 //   hdr    NodeHdr [G*C]        visits, V, running unsigned mean Q, parent link, status
 //   estat  float4 [G*C][E]      per edge {prior P, visits N (int bits), reward sum W, virtual loss}
 //   elink  uint32 [G*C][E]      per edge action (low 16) | child id (high 16, 0xFFFF = none)
+//   anc    8 x uint16 [G*C]     the node's 8 nearest ancestors (valid up to the current root)
 // E = N*N+1.  Edges of a node are stored in descending-prior order (the order the reference
 // inserts them, go/mcts/mcts.h:292-329), only the legal ones.
 //
@@ -55,6 +56,7 @@ struct TreeDev {
   NodeHdr* hdr;
   float4* estat;
   uint32_t* elink;
+  uint4* anc;           // [G*C] 8 x u16: ids of the 8 nearest ancestors (parent first), for the history gather
   uint16_t* free_list;  // [G][C] stack of free local ids
   int32_t* free_n;      // [G]
   uint16_t* root;       // [G]
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int ro
       h.depth_hint = 0;
       h.pad = 0;
       store_hdr(&tr.hdr[nb + id], h);
+      tr.anc[nb + id] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
       tr.root[g] = (uint16_t)id;
     }
   } else if (L.lane == 0) {
@@ -280,6 +283,14 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           c.pad = 0;
           store_hdr(&tr.hdr[nb + child], c);
           tr.elink[(nb + node) * E + ei] = (uint32_t)action | ((uint32_t)child << 16);
+          // ancestors of the child = {node, node's ancestors[0..6]}
+          const uint4 pa = tr.anc[nb + node];
+          uint4 ca;
+          ca.x = (uint32_t)node | (pa.x << 16);
+          ca.y = (pa.x >> 16) | (pa.y << 16);
+          ca.z = (pa.y >> 16) | (pa.z << 16);
+          ca.w = (pa.z >> 16) | (pa.w << 16);
+          tr.anc[nb + child] = ca;
         }
       }
       __syncwarp();
@@ -347,20 +358,25 @@ __global__ void __launch_bounds__(384) k_leaf_features(DevState st, TreeDev tr, 
   const size_t nb = (size_t)g * tr.C;
   const BoardMeta meta = load_meta(&tr.meta[nb + leaf]);
   const int hn = min(8, (int)meta.ply - 1);
-  if (threadIdx.x == 0) {
-    int node = leaf, t = 0;
-    while (t < hn && node != NONE16) {
-      s_src[t++] = node;
-      node = tr.hdr[nb + node].parent;
+  if (threadIdx.x < 8) {
+    // history slot t: the leaf (t = 0), its t-th ancestor while still inside the current tree,
+    // then the game's own ring (the root is ring slot (ply_root-2)&7, go_state.cc:90-92)
+    const int t = threadIdx.x;
+    const int pr = st.meta[g].ply;            // ply of the root == ply of the game
+    const int depth = (int)meta.ply - pr;     // leaf depth below the root
+    int src = INT_MIN;
+    if (t < hn) {
+      if (t == 0) {
+        src = leaf;
+      } else if (t <= depth) {
+        const uint4 a4 = tr.anc[nb + leaf];
+        const uint32_t w = (t - 1) < 2 ? a4.x : (t - 1) < 4 ? a4.y : (t - 1) < 6 ? a4.z : a4.w;
+        src = (int)((w >> (((t - 1) & 1) * 16)) & 0xFFFFu);
+      } else {
+        src = -(((pr - 2 - (t - depth)) & 7)) - 1;
+      }
     }
-    // beyond the root: the game's ring; the root itself is ring slot (ply_root-2)&7
-    const int pr = st.meta[g].ply;
-    int k = 1;
-    while (t < hn) {
-      s_src[t++] = -(((pr - 2 - k) & 7)) - 1;
-      ++k;
-    }
-    for (; t < 8; ++t) s_src[t] = INT_MIN;
+    s_src[t] = src;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
@@ -802,6 +818,7 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   CK(cudaMalloc(&t.hdr, GC * sizeof(NodeHdr)));
   CK(cudaMalloc(&t.estat, GC * E * sizeof(float4)));
   CK(cudaMalloc(&t.elink, GC * E * 4));
+  CK(cudaMalloc(&t.anc, GC * sizeof(uint4)));
   CK(cudaMalloc(&t.free_list, GC * 2));
   CK(cudaMalloc(&t.free_n, G * 4));
   CK(cudaMalloc(&t.root, G * 2));
@@ -857,7 +874,7 @@ void elfb200_mcts_destroy(elfb200_mcts* m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   TreeDev& t = m->tr;
-  void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.free_list,
+  void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.anc, t.free_list,
                   t.free_n,    t.root,      t.leaves,    t.active,     t.eval_count,  t.eval_game,  t.eval_node,
                   t.eval_d4,   t.bfs_q,     t.errors,    t.stats,     m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
                   m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4};

@@ -57,13 +57,19 @@ class PolicyValueNet(nn.Module):
 class Actor:
     """The model-interface callback (``Evaluator.actor``, rlpytorch/trainer/trainer.py:73-115) for
     inference: ``actor(batch) -> {"pi", "V"}`` on the GPU.  Evaluates in chunks of ``batchsize``
-    positions (the reference's NN batch; BASELINE config 3 uses 256) with autocast to ``dtype``."""
+    positions (the reference's NN batch; BASELINE config 3 uses 256).  ``dtype`` float16/bfloat16
+    converts the weights once (channels_last, tensor-core convolutions through cuDNN); float32
+    keeps them as they are.  (Measured on B200, 20x256 net: fp16 weights + channels_last reach
+    ~32 k positions/s already at batch 256; bf16 autocast on the 18-channel stem was pathologically
+    slow to start, see scripts/nn_probe.py.)"""
 
-    def __init__(self, model, batchsize=256, dtype=torch.bfloat16, channels_last=True):
+    def __init__(self, model, batchsize=256, dtype=torch.float16, channels_last=True):
         self.model = model.eval()
         self.batchsize = batchsize
         self.dtype = dtype
         self.channels_last = channels_last
+        if dtype != torch.float32:
+            self.model = self.model.to(dtype)
         if channels_last:
             self.model = self.model.to(memory_format=torch.channels_last)
         self.num_batches = 0
@@ -75,11 +81,10 @@ class Actor:
         n = s.shape[0]
         pis, vs = [], []
         for i in range(0, n, self.batchsize):
-            x = s[i:i + self.batchsize]
+            x = s[i:i + self.batchsize].to(self.dtype)
             if self.channels_last:
                 x = x.contiguous(memory_format=torch.channels_last)
-            with torch.autocast("cuda", dtype=self.dtype, enabled=self.dtype != torch.float32):
-                out = self.model(x)
+            out = self.model(x)
             pis.append(out["pi"].float())
             vs.append(out["V"].float().reshape(-1))
             self.num_batches += 1
