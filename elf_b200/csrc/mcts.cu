@@ -13,8 +13,10 @@
 //   hash   uint64 [G*C]         Zobrist hash
 //   meta   BoardMeta [G*C]      ply, side, ko, last moves, terminal flags
 //   hdr    NodeHdr [G*C]        visits, V, running unsigned mean Q, parent link, status
-//   estat  float4 [G*C][E]      per edge {prior P, visits N (int bits), reward sum W, virtual loss}
-//   elink  uint32 [G*C][E]      per edge action (low 16) | child id (high 16, 0xFFFF = none)
+//   estat  float4 [G*C][E]      per edge {prior P, visits N (int bits), reward sum W,
+//                               packed word: virtual-loss applications (low 16) | child id (high 16)}
+//   elink  uint32 [G*C][E]      per edge action (low 16) | child id (high 16, 0xFFFF = none); only read
+//                               when a child is created and by results/advance (off the hot loop)
 //   anc    8 x uint16 [G*C]     the node's 8 nearest ancestors (valid up to the current root)
 // E = N*N+1.  Edges of a node are stored in descending-prior order (the order the reference
 // inserts them, go/mcts/mcts.h:292-329), only the legal ones.
@@ -44,7 +46,8 @@ struct __align__(16) NodeHdr {  // 32 bytes
   uint16_t parent_edge;  // index of the edge in the parent that leads here
   uint8_t status;        // NodeT::status_ (NOT_VISITED / EVAL_REQUESTED / VISITED)
   uint8_t flags;         // NF_FLIP = NodeT::flipQSign_
-  int32_t depth_hint;    // unused by the algorithm (debug)
+  uint16_t n_touched;    // edges [0, n_touched) have been selected at least once (see k_select)
+  uint16_t pass_edge;    // index of the pass edge, NONE16 if the node has none
   int32_t pad;
 };
 static_assert(sizeof(NodeHdr) == 32, "NodeHdr must be 32 bytes");
@@ -68,7 +71,7 @@ struct TreeDev {
   uint8_t* eval_d4;     // [G*B]
   uint16_t* bfs_q;      // [G][C]
   int32_t* errors;      // [4]: root-hash mismatches, pool overflows, ...
-  unsigned long long* stats;  // [4]: descent steps, edges scanned, nodes created, terminal leaves
+  unsigned long long* stats;  // [4]: descent steps, edge records read, nodes created, stored edges of visited nodes
   int C, B, E;
 };
 
@@ -159,7 +162,8 @@ __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int ro
       h.parent_edge = 0;
       h.status = NS_UNVISITED;
       h.flags = 0;
-      h.depth_hint = 0;
+      h.n_touched = 0;
+      h.pass_edge = NONE16;
       h.pad = 0;
       store_hdr(&tr.hdr[nb + id], h);
       tr.anc[nb + id] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
@@ -176,9 +180,28 @@ __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int ro
 // NodeT::findMove/UCT (tree_search_node.h:205-231,361-397), EdgeInfo::getScore
 // (tree_search_base.h:132-157), addVirtualLoss (:233-251), followEdge (:280-302), allocateState
 // (tree_search.h:175-190) and the leaf claim of batch_rollouts (tree_search.h:222-233).
+//
+// PUCT scan: edges are stored by descending prior and an edge that was never selected has
+// N = 0, vl = 0, hence score = c_puct * P * sqrt(n) + FPU, monotone in P.  The best never-selected
+// edge is therefore the FIRST one in storage order, the selected edges always form a prefix
+// [0, n_touched), and the arg-max over all edges equals the arg-max over [0, n_touched] -- the
+// same result as the reference's full scan with O(touched) instead of O(legal moves) reads.
+// (Exact prior ties between never-selected edges resolve to the lower index; the reference
+// resolves them by unordered_map order.)  The running-mean update only involves selected edges.
+//
+// The per-level dependent memory chain is one round trip: the node header and the first 32 edge
+// records are requested together; the child id rides in the edge record; the pre-move hashes the
+// superko test needs are gathered once, when a child is actually created.
+constexpr int MAX_DEPTH = 128;
+
+__device__ __forceinline__ float vl_value(uint32_t wbits, int virtual_loss) {
+  return (float)((int)(wbits & 0xFFFFu) * virtual_loss);  // exact: small integers
+}
+
 template <int N>
 __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, SearchOpts o, int wave) {
   __shared__ uint64_t s_zob[Geo<N>::ZOB];
+  __shared__ uint32_t s_path[WARPS][MAX_DEPTH];  // node id | is_pass << 16, root first
   load_zobrist<N>(s_zob);
   const Lane L = make_lane_single<N>();
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -188,29 +211,37 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
   const int root = tr.root[g];
   uint64_t* skg = st.sk + (size_t)g * Geo<N>::MAX_PLY;
   const int nsk0 = st.sk_n[g];
-  const float vl = (float)o.virtual_loss;
+  uint32_t* path = s_path[threadIdx.x >> 5];
   unsigned st_steps = 0, st_edges = 0, st_new = 0, st_term = 0;
 
   for (int j = 0; j < tr.B; ++j) {
-    int node = root, depth = 0, cnt = nsk0;
+    int node = root, depth = 0;
     while (true) {
+      const float4* es = tr.estat + (nb + node) * E;
       const NodeHdr h = load_hdr(&tr.hdr[nb + node]);
+      float4 e = es[L.lane];  // speculative first chunk (E >= 82 > 32: always in bounds)
       if (h.status != NS_VISITED || h.n_edges == 0) break;
-      // ---- UCT over the node's edges -------------------------------------------------------
+      if (depth >= MAX_DEPTH) {
+        if (L.lane == 0) atomicAdd(&tr.errors[2], 1);
+        break;
+      }
+      // ---- UCT over the selected prefix plus the first never-selected edge ------------------------
+      const int lim = min((int)h.n_edges, (int)h.n_touched + 1);
       st_steps++;
-      st_edges += h.n_edges;
+      st_edges += lim;
+      st_term += h.n_edges;  // stored edges: what a full scan (SURVEY 8d formula) would read
       const bool flip = h.flags & NF_FLIP;
       const float fpu = (o.uqz || (o.ruqz && depth == 0)) ? 0.f : h.mean_q;
       const double sq = sqrt((double)(h.num_visits + 1));  // std::sqrt(int) -> double
-      const float4* es = tr.estat + (nb + node) * E;
       float best = -FLT_MAX, tuq = 0.f;
       int besti = 0x7FFFFFFF, tv = 0;
-      for (int i = L.lane; i < h.n_edges; i += 32) {
-        const float4 e = es[i];
+      for (int i = L.lane; i < lim; i += 32) {
+        if (i >= 32) e = es[i];
         const int n = __float_as_int(e.y);
+        const float evl = vl_value(__float_as_uint(e.w), o.virtual_loss);
         float r = flip ? -e.z : e.z;
-        r -= e.w;
-        const int nwl = (int)((float)n + e.w);
+        r -= evl;
+        const int nwl = (int)((float)n + evl);
         const float q = nwl > 0 ? r / (float)nwl : (flip ? -fpu : fpu);
         const float uq = n > 0 ? e.z / (float)n : fpu;
         const float u = (float)((double)(e.x / (float)(1 + n)) * sq);
@@ -237,26 +268,46 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
       }
       const int ei = besti;
       const float new_mean = (h.parent_q + tuq) / (float)(tv + 1);
-      const uint32_t link = tr.elink[(nb + node) * E + ei];
-      const int action = link & 0xFFFFu;
-      int child = link >> 16;
+      const bool is_pass = ei == (int)h.pass_edge;
+      // ---- addVirtualLoss + followEdge: one read-modify-write of the packed word -----------------
+      uint32_t wb = 0;
       if (L.lane == 0) {
-        tr.hdr[nb + node].mean_q = new_mean;
-        if (o.virtual_loss > 0) tr.estat[(nb + node) * E + ei].w += vl;
-        if (action != Geo<N>::P) skg[cnt] = tr.hash[nb + node];  // pre-move position of a stone move
+        float* wp = &tr.estat[(nb + node) * E + ei].w;
+        wb = __float_as_uint(*wp);
+        if (o.virtual_loss > 0) *wp = __uint_as_float(wb + 1u);
+        NodeHdr* hp = &tr.hdr[nb + node];
+        hp->mean_q = new_mean;
+        if (ei == (int)h.n_touched) hp->n_touched = (uint16_t)(h.n_touched + 1);
+        path[depth] = (uint32_t)node | (is_pass ? 0x10000u : 0u);
       }
-      if (action != Geo<N>::P) cnt++;
-      // ---- followEdge + allocateState ----------------------------------------------------------
+      wb = __shfl_sync(FULL, wb, 0);
+      int child = wb >> 16;
+      // ---- allocateState for a new child ------------------------------------------------------------
       if (child == NONE16) {
-        int id = 0;
-        if (L.lane == 0) id = pop_free(tr, g);
+        int id = 0, action = 0;
+        if (L.lane == 0) {
+          id = pop_free(tr, g);
+          action = tr.elink[(nb + node) * E + ei] & 0xFFFFu;
+        }
         id = __shfl_sync(FULL, id, 0);
+        action = __shfl_sync(FULL, action, 0);
         if (id < 0) {  // cannot happen when k_begin reserved enough room
           if (L.lane == 0) atomicAdd(&tr.errors[1], 1);
           break;
         }
         child = id;
         st_new++;
+        __syncwarp();
+        // superko record along the path: the position before every stone move (go_state.cc:113-121)
+        int cnt = nsk0;
+        for (int d0 = 0; d0 <= depth; d0 += 32) {
+          const int d = d0 + L.lane;
+          const uint32_t pe = d <= depth ? path[d] : 0x10000u;
+          const bool stone = !(pe & 0x10000u);
+          const uint32_t bal = __ballot_sync(FULL, stone);
+          if (stone) skg[cnt + __popc(bal & ((1u << L.lane) - 1u))] = tr.hash[nb + (pe & 0xFFFFu)];
+          cnt += __popc(bal);
+        }
         const uint64_t rowv = L.active ? tr.pos[(nb + node) * N + L.row] : 0ull;
         uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
         BoardMeta meta = load_meta(&tr.meta[nb + node]);
@@ -279,10 +330,13 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           c.parent_edge = (uint16_t)ei;
           c.status = NS_UNVISITED;
           c.flags = 0;
-          c.depth_hint = depth + 1;
+          c.n_touched = 0;
+          c.pass_edge = NONE16;
           c.pad = 0;
           store_hdr(&tr.hdr[nb + child], c);
           tr.elink[(nb + node) * E + ei] = (uint32_t)action | ((uint32_t)child << 16);
+          float* wp = &tr.estat[(nb + node) * E + ei].w;
+          *wp = __uint_as_float((__float_as_uint(*wp) & 0xFFFFu) | ((uint32_t)child << 16));
           // ancestors of the child = {node, node's ancestors[0..6]}
           const uint4 pa = tr.anc[nb + node];
           uint4 ca;
@@ -310,7 +364,6 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           fv = meta.next == S_BLACK ? 1.0f : -1.0f;
         else
           fv = (float)sc - o.komi;
-        st_term++;
         if (L.lane == 0) {
           NodeHdr h2 = lh;
           h2.V = fv > 0 ? 1.0f : -1.0f;
@@ -486,23 +539,34 @@ __global__ void __launch_bounds__(BLOCK)
   if (nvalid == 0 && !pass_enabled) {  // mcts.h:324-327: pass with probability 1
     n_edges = 1;
     if (L.lane == 0) {
-      es[0] = make_float4(1.0f / (1e-10f + 1.0f), __int_as_float(0), 0.f, 0.f);
+      es[0] = make_float4(1.0f / (1e-10f + 1.0f), __int_as_float(0), 0.f, __uint_as_float(0xFFFF0000u));
       el[0] = (uint32_t)P | ((uint32_t)NONE16 << 16);
     }
   } else {
     for (int i = L.lane; i < nvalid; i += 32) {
       const uint64_t k = key[i];
       const float p = __uint_as_float(0xFFFFFFFFu - (uint32_t)(k >> 32));
-      es[i] = make_float4(p / tot, __int_as_float(0), 0.f, 0.f);
+      es[i] = make_float4(p / tot, __int_as_float(0), 0.f, __uint_as_float(0xFFFF0000u));
       el[i] = (uint32_t)(k & 0xFFFFu) | ((uint32_t)NONE16 << 16);
     }
   }
+  // index of the pass edge (if any) for the descent's pass test
+  int pass_idx = 0x7FFFFFFF;
+  if (nvalid == 0 && !pass_enabled) {
+    pass_idx = 0;
+  } else {
+    for (int i = L.lane; i < nvalid; i += 32)
+      if ((int)(key[i] & 0xFFFFu) == P) pass_idx = i;
+  }
+  pass_idx = __reduce_min_sync(FULL, pass_idx);
   __syncwarp();
   if (L.lane == 0) {
     NodeHdr h = load_hdr(&tr.hdr[nb + node]);
     h.V = val[slot];
     h.flags = meta.next == S_WHITE ? NF_FLIP : 0;  // q_flip, mcts.h:186
     h.n_edges = (uint16_t)n_edges;
+    h.n_touched = 0;
+    h.pass_edge = pass_idx == 0x7FFFFFFF ? NONE16 : (uint16_t)pass_idx;
     h.status = NS_VISITED;
     store_hdr(&tr.hdr[nb + node], h);
   }
@@ -530,7 +594,7 @@ __global__ void k_backup(int G, TreeDev tr, int virtual_loss) {
     }
     if (!first) continue;
     const float reward = tr.hdr[nb + leaf].V;
-    const float dvl = (float)virtual_loss * (float)count;
+    const uint32_t dunits = virtual_loss > 0 ? (uint32_t)count : 0u;  // one application per descent
     int node = leaf;
     while (true) {
       const NodeHdr h = load_hdr(&tr.hdr[nb + node]);
@@ -540,7 +604,7 @@ __global__ void k_backup(int G, TreeDev tr, int virtual_loss) {
       float4 e = tr.estat[(nb + p) * E + h.parent_edge];
       e.z += reward;
       e.y = __int_as_float(__float_as_int(e.y) + 1);
-      e.w -= dvl;
+      e.w = __uint_as_float(__float_as_uint(e.w) - dunits);  // low 16 bits: virtual-loss applications
       tr.estat[(nb + p) * E + h.parent_edge] = e;
       node = p;
     }

@@ -115,7 +115,7 @@ class MctsBatch:
         return ms, w.value
 
     def stats(self):
-        """uint64[4]: descent steps, edges scanned, nodes created, terminal leaves (running totals)"""
+        """uint64[4]: descent steps, edge records read, nodes created, stored edges of visited nodes"""
         s = np.zeros(4, np.uint64)
         _l.check(self._lib, self._lib.elfb200_mcts_stats(self._m, s.ctypes.data))
         return s

@@ -87,8 +87,9 @@ int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host);
 /* int32[4]: root-hash mismatches, node-pool drops/overflows, reserved, reserved. */
 int elfb200_mcts_errors(elfb200_mcts* m, int32_t* counters_host4);
 int64_t elfb200_mcts_eval_count(const elfb200_mcts* m);
-/* uint64[4] running totals: descent steps (nodes visited by PUCT), edges scanned, nodes created,
- * terminal leaves evaluated.  Used by bench.py for the select kernel's algorithmic bytes. */
+/* uint64[4] running totals: descent steps (nodes visited by PUCT), edge records actually read
+ * (selected prefix + 1), nodes created, stored edges of the visited nodes (what the reference's
+ * full scan touches).  Used by bench.py for the select kernel's algorithmic bytes. */
 int elfb200_mcts_stats(elfb200_mcts* m, uint64_t* counters_host4);
 /* double[4]: accumulated device time (ms, CUDA events on the context stream) of the select,
  * leaf-feature, expand and backup kernels, and the number of waves they cover; reset != 0 clears. */

@@ -216,7 +216,7 @@ def test_selfplay_driver_smoke():
     torch.manual_seed(0)
     n, G = 9, 32
     net = PolicyValueNet(n, num_block=2, dim=32).cuda()
-    sp = elf_b200.selfplay.SelfPlay(Actor(net, batchsize=64), num_games=G, board_size=n, policy_distri_cutoff=4,
+    sp = elf_b200.selfplay.SelfPlay(Actor(net, batchsize=64, dtype=torch.float32, channels_last=False), num_games=G, board_size=n, policy_distri_cutoff=4,
                                     num_rollouts=32, num_rollouts_per_batch=4, move_cutoff=30, seed=1)
     total = 0
     for _ in range(36):
