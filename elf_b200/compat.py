@@ -1,0 +1,360 @@
+"""compat -- the reference's Python-visible batching surface, served by the GPU engine.
+
+The reference's scripts talk to C++ through three pybind objects:
+
+* ``GameContext(ContextOptions, GameOptions)`` with ``.ctx()`` and ``.getParams()``
+  (``src_cpp/elfgames/go/train/Pybind.cc:22-62``, ``inference/Pybind.cc:22-43``);
+* ``elf::Context`` with ``createSharedMemOptions / allocateSharedMem / start / wait / step / stop /
+  version`` (``src_cpp/elf/Pybind.cc:46-62``);
+* ``SharedMem`` / ``AnyP`` through which ``GCWrapper`` (``src_py/elf/utils_elf.py:32-57,378-405``)
+  learns each field's name / element type / shape and registers the memory it allocated
+  (``AnyP.set(ptr, byte_strides)``, ``src_cpp/elf/base/extractor.h:302-305``).
+
+This module re-creates exactly that surface in Python on top of the batched GPU search, so the
+unmodified ``GCWrapper.run()`` loop -- ``smem = ctx.wait(); cb(batch) -> reply; ctx.step()`` -- and
+the unmodified rlpytorch ``Evaluator.actor`` callback drive it:
+
+* ``wait()`` advances the engine to the next chunk (<= the label's batchsize) of MCTS leaves that
+  need the network, writes their feature planes into the tensor registered for ``"s"`` and returns
+  the label's ``SharedMem`` with ``effective_batchsize()`` set;
+* ``step()`` reads ``"pi"`` / ``"V"`` back from the registered reply tensors; when the last chunk
+  of a wave has been answered the engine expands, backs up and carries on (next wave, or move
+  selection + ``GoState::forward`` + tree advance for every game).
+
+Registered memory may be pinned host memory (the reference's ``Allocator``; features are copied
+device->host, replies host->device) or CUDA memory (fast mode: device-to-device copies only).
+
+There are no game threads: the search of all games runs on the GPU between two ``wait()`` calls.
+"""
+import ctypes
+
+import numpy as np
+
+_TYPES = {  # GoFeature::registerExtractor element types (common/game_feature.h:159-206)
+    "float": (np.float32, "float"),
+    "int64_t": (np.int64, "int64_t"),
+    "int32_t": (np.int32, "int32_t"),
+}
+
+
+class Size:
+    def __init__(self, dims):
+        self._d = [int(x) for x in dims]
+
+    def vec(self):
+        return list(self._d)
+
+
+class FieldInfo:
+    def __init__(self, name, type_name, dims):
+        self._n, self._t, self._s = name, type_name, Size(dims)
+
+    def name(self):
+        return self._n
+
+    def type_name(self):
+        return self._t
+
+    def sz(self):
+        return self._s
+
+
+class AnyP:
+    """One field of one SharedMem: shape/type description + the caller's memory (AnyP, extractor.h:280-360)."""
+
+    def __init__(self, name, type_name, dims):
+        self._field = FieldInfo(name, type_name, dims)
+        self.ptr = 0
+        self.strides = None
+        self._view = None
+
+    def field(self):
+        return self._field
+
+    def set(self, ptr, strides):
+        self.ptr = int(ptr)
+        self.strides = [int(s) for s in strides]
+        self._view = None
+
+    setAddress = set
+
+    def view(self):
+        """torch tensor aliasing the registered memory (host or device)"""
+        import torch
+
+        if self._view is not None:
+            return self._view
+        if not self.ptr:
+            raise RuntimeError(f"field {self._field.name()} has no memory registered (AnyP.set was not called)")
+        dims = self._field.sz().vec()
+        npdt = _TYPES[self._field.type_name()][0]
+        item = np.dtype(npdt).itemsize
+        attr = None
+        try:
+            try:
+                from cuda.bindings import runtime as cudart  # cuda-python >= 12.8
+            except Exception:
+                from cuda import cudart
+
+            err, a = cudart.cudaPointerGetAttributes(self.ptr)
+            if int(err) == 0:
+                attr = int(a.type)
+        except Exception:
+            attr = None
+        is_dev = attr == 2  # cudaMemoryTypeDevice
+        if is_dev:
+            class _CAI:  # __cuda_array_interface__ holder
+                pass
+
+            o = _CAI()
+            o.__cuda_array_interface__ = {
+                "shape": tuple(dims), "typestr": np.dtype(npdt).str, "data": (self.ptr, False), "version": 3,
+                "strides": tuple(self.strides),
+            }
+            self._view = torch.as_tensor(o, device="cuda")
+        else:
+            nbytes = sum((d - 1) * s for d, s in zip(dims, self.strides)) + item
+            buf = (ctypes.c_char * nbytes).from_address(self.ptr)
+            arr = np.ndarray(shape=tuple(dims), dtype=npdt, buffer=buf, strides=tuple(self.strides))
+            self._view = torch.from_numpy(arr)
+        return self._view
+
+
+class SharedMemOptions:
+    def __init__(self, idx, label, batchsize):
+        self._idx, self._label, self._bs, self._timeout = idx, label, int(batchsize), 0
+
+    def idx(self):
+        return self._idx
+
+    def label(self):
+        return self._label
+
+    def batchsize(self):
+        return self._bs
+
+    def setTimeout(self, usec):
+        self._timeout = int(usec)
+
+    def info(self):
+        return f"SMem[{self._label}], idx: {self._idx}, batchsize: {self._bs}"
+
+
+class SharedMem:
+    def __init__(self, opts, fields):
+        self._opts = opts
+        self._fields = fields
+        self._eff = 0
+
+    def __getitem__(self, key):
+        return self._fields[key]
+
+    def getSharedMemOptions(self):
+        return self._opts
+
+    def effective_batchsize(self):
+        return self._eff
+
+    def info(self):
+        return self._opts.info()
+
+
+class ReplyStatus:
+    SUCCESS, FAILED, UNKNOWN = 0, 1, 2
+
+
+class Context:
+    """elf::Context (src_cpp/elf/base/context.h:110-394) as seen from Python."""
+
+    def __init__(self, engine, batchsize):
+        self._engine = engine
+        self._batchsize = int(batchsize)  # co.batchsize: every field's leading extent
+        self._smems = []
+        self._by_label = {}
+        self._rr = {}
+        self._cur = None
+        self._started = False
+        self._stopped = False
+
+    def version(self):
+        return "elf_b200-compat"
+
+    def createSharedMemOptions(self, name, batchsize):
+        return SharedMemOptions(-1, name, batchsize)
+
+    def _field_dims(self, key):
+        n, a = self._engine.board_size, self._engine.num_action
+        bs = self._batchsize
+        table = {
+            "s": ("float", [bs, 18, n, n]), "pi": ("float", [bs, a]), "V": ("float", [bs]),
+            "a": ("int64_t", [bs]), "rv": ("int64_t", [bs]),
+            "black_ver": ("int64_t", [bs]), "white_ver": ("int64_t", [bs]), "selfplay_ver": ("int64_t", [bs]),
+        }
+        if key not in table:
+            raise KeyError(f"field '{key}' is not provided by the elf_b200 engine")
+        return table[key]
+
+    def allocateSharedMem(self, opts, keys):
+        o = SharedMemOptions(len(self._smems), opts.label(), opts.batchsize())
+        o.setTimeout(opts._timeout)
+        fields = {}
+        for k in keys:
+            t, dims = self._field_dims(k)
+            fields[k] = AnyP(k, t, dims)
+        sm = SharedMem(o, fields)
+        self._smems.append(sm)
+        self._by_label.setdefault(o.label(), []).append(sm)
+        return sm
+
+    def start(self):
+        self._started = True
+        self._engine.start()
+
+    def stop(self):
+        self._stopped = True
+        self._engine.stop()
+
+    def wait(self, timeout_usec=0):
+        if not self._started or self._stopped:
+            raise RuntimeError("Context.wait() outside start()/stop()")
+        label = "actor_black"
+        sms = self._by_label.get(label)
+        if not sms:
+            raise RuntimeError("no SharedMem allocated for label 'actor_black'")
+        i = self._rr.get(label, 0)
+        self._rr[label] = (i + 1) % len(sms)  # num_recv SharedMems are used round-robin
+        sm = sms[i]
+        n, feats = self._engine.next_batch(sm.getSharedMemOptions().batchsize())
+        dst = sm["s"].view()
+        dst[:n].copy_(feats, non_blocking=False)
+        sm._eff = int(n)
+        self._cur = sm
+        return sm
+
+    def step(self, status=ReplyStatus.SUCCESS):
+        sm = self._cur
+        if sm is None:
+            raise RuntimeError("Context.step() without a pending wait()")
+        n = sm._eff
+        pi = sm["pi"].view()[:n]
+        v = sm["V"].view()[:n]
+        self._engine.reply(pi, v)
+        self._cur = None
+
+
+class _Client:
+    def __init__(self, engine):
+        self._e = engine
+
+    def setRequest(self, black_ver, white_ver, resign_thres, num_threads=1):  # distri_client.h:318-331
+        self._e.resign_thres = float(resign_thres)
+
+    def getGameStats(self):
+        return self
+
+    def getWinRateStats(self):
+        return self._e.win_stats()
+
+
+class GameContext:
+    """go.GameContext (train/game_context.h:37-85, inference/game_context.h:31) over an engine."""
+
+    def __init__(self, engine, batchsize):
+        self._engine = engine
+        self._ctx = Context(engine, batchsize)
+
+    def ctx(self):
+        return self._ctx
+
+    def getParams(self):  # GoFeature::getParams, common/game_feature.h:208-221
+        n = self._engine.board_size
+        return {
+            "num_action": n * n + 1, "board_size": n, "num_future_actions": 1, "num_planes": 18,
+            "our_stone_plane": 0, "opponent_stone_plane": 1,
+            "ACTION_SKIP": -100, "ACTION_PASS": -99, "ACTION_RESIGN": -98, "ACTION_CLEAR": -97,
+        }
+
+    def getClient(self):
+        return _Client(self._engine)
+
+
+class SelfPlayEngine:
+    """The engine behind compat.Context: SelfPlay's move loop cut at the network round trip."""
+
+    def __init__(self, selfplay):
+        self.sp = selfplay
+        self.board_size = selfplay.N
+        self.num_action = selfplay.N * selfplay.N + 1
+        self.resign_thres = selfplay.resign_thres
+        self._wave = None  # (features tensor [n,...], n, offset, pi buffer, v buffer)
+        self._wave_idx = 0
+        self._in_move = False
+        self._info = None
+
+    def start(self):
+        pass
+
+    def stop(self):
+        pass
+
+    def win_stats(self):
+        r = self.sp.results
+        return {"black_wins": sum(1 for fv, _, _ in r if fv > 0), "white_wins": sum(1 for fv, _, _ in r if fv <= 0),
+                "total_games": len(r)}
+
+    def _advance_until_leaves(self):
+        import torch
+
+        sp = self.sp
+        while True:
+            if not self._in_move:
+                self._info = sp.gb.info()
+                sp.mcts.begin_move()
+                self._wave_idx = 0
+                self._in_move = True
+            if self._wave_idx >= sp.mcts.waves_per_move:
+                self._finish_move()
+                continue
+            s = sp.mcts.select()
+            self._wave_idx += 1
+            n = s.shape[0]
+            if n == 0:
+                sp.mcts.expand_backup(None, None)
+                continue
+            sp.gb.synchronize()
+            dev = s.device
+            self._wave = {"s": s, "n": n, "off": 0, "got": 0,
+                          "pi": torch.empty((n, self.num_action), dtype=torch.float32, device=dev),
+                          "v": torch.empty((n,), dtype=torch.float32, device=dev)}
+            return
+
+    def _finish_move(self):
+        sp = self.sp
+        res = sp.mcts.results()
+        sp.resign_thres = self.resign_thres
+        sp.finish_move(res, self._info)
+        self._in_move = False
+
+    def next_batch(self, max_n):
+        if self._wave is None or self._wave["off"] >= self._wave["n"]:
+            if self._wave is not None and self._wave["got"] < self._wave["n"]:
+                raise RuntimeError("wait() called again before step() answered the previous batch")
+            self._advance_until_leaves()
+        w = self._wave
+        k = min(int(max_n), w["n"] - w["off"])
+        feats = w["s"][w["off"]:w["off"] + k]
+        w["last"] = (w["off"], k)
+        w["off"] += k
+        return k, feats
+
+    def reply(self, pi, v):
+        import torch
+
+        w = self._wave
+        off, k = w["last"]
+        w["pi"][off:off + k].copy_(pi.to(torch.float32), non_blocking=False)
+        w["v"][off:off + k].copy_(v.to(torch.float32).reshape(-1), non_blocking=False)
+        w["got"] += k
+        if w["got"] >= w["n"]:
+            torch.cuda.current_stream(w["pi"].device).synchronize()
+            self.sp.mcts.expand_backup(w["pi"], w["v"])

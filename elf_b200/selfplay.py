@@ -54,9 +54,13 @@ class SelfPlay:
 
     def step(self):
         """one move of every game; returns the number of moves played"""
-        P = self.N * self.N
         info = self.gb.info()
         res = self.mcts.act(self.actor)
+        return self.finish_move(res, info)
+
+    def finish_move(self, res, info):
+        """everything GoGameSelfPlay::act does after the search returned (game_selfplay.cc:372-429);
+        ``info`` are the games' info words from before the search, ``res`` the root statistics"""
         acts = self._choose(res, info)
         # resign check (game_selfplay.cc:387-391, go_state_ext.h:207-214)
         val = np.where(info[:, 1] == 1, res["best_q"], -res["best_q"])

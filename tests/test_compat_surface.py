@@ -1,0 +1,111 @@
+"""The pybind-compatible surface (elf_b200.compat) against the UNMODIFIED reference GCWrapper
+(/root/reference/src_py/elf/utils_elf.py, loaded straight from the reference tree when present):
+the reference's own allocation code (Allocator.spec2batches -> AnyP.field()/set()) and its
+wait -> callback -> step pump must run on our Context/SharedMem/AnyP objects without change.
+A stub engine stands in for the GPU search here (CPU-only box); the GPU test of the same surface
+with the real engine is tests/test_gpu_compat.py."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+REF_UTILS = "/root/reference/src_py/elf/utils_elf.py"
+
+
+class StubEngine:
+    """emits two waves of 5 and 3 'leaves' per move with recognisable features, records replies"""
+
+    board_size = 9
+    num_action = 82
+
+    def __init__(self):
+        self.waves = [5, 3]
+        self.w = 0
+        self.off = 0
+        self.cur = None
+        self.replies = []
+        self.started = False
+
+    def start(self):
+        self.started = True
+
+    def stop(self):
+        self.started = False
+
+    def next_batch(self, max_n):
+        if self.cur is None or self.off >= self.cur.shape[0]:
+            n = self.waves[self.w % 2]
+            self.cur = torch.arange(n, dtype=torch.float32).reshape(n, 1, 1, 1).expand(n, 18, 9, 9) + 100 * self.w
+            self.w += 1
+            self.off = 0
+        k = min(max_n, self.cur.shape[0] - self.off)
+        out = self.cur[self.off:self.off + k]
+        self.off += k
+        return k, out
+
+    def reply(self, pi, v):
+        self.replies.append((pi.clone(), v.clone()))
+
+
+def _load_reference_gcwrapper():
+    if not os.path.exists(REF_UTILS):
+        pytest.skip("reference tree not present")
+    spec = importlib.util.spec_from_file_location("ref_utils_elf", REF_UTILS)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_reference_gcwrapper_runs_on_compat_surface(capsys):
+    from elf_b200 import compat
+
+    ref = _load_reference_gcwrapper()
+    eng = StubEngine()
+    GC = compat.GameContext(eng, batchsize=4)
+    # the reference's own desc for selfplay's actor_black (src_py/elfgames/go/game.py:375-381)
+    desc = {"actor_black": dict(input=["s"], reply=["pi", "V", "a", "rv"], batchsize=4, timeout_usec=10)}
+    gcw = ref.GCWrapper(GC, 4, desc, num_recv=2, gpu=None, use_numpy=False, params=GC.getParams())
+    seen = []
+
+    def actor(batch):
+        s = batch["s"]
+        assert s.shape[1:] == (18, 9, 9)
+        assert batch.batchsize == s.shape[0] and batch.max_batchsize == 4
+        seen.append(s[:, 0, 0, 0].clone())
+        n = s.shape[0]
+        pi = torch.full((n, 82), 1.0 / 82) + s[:, 0, 0, 0].reshape(-1, 1)
+        return dict(pi=pi, V=s[:, 0, 0, 0] * 0.5, a=torch.zeros(n, dtype=torch.int64), rv=torch.zeros(n, dtype=torch.int64))
+
+    gcw.reg_callback("actor_black", actor)
+    gcw.start()
+    for _ in range(4):  # wave of 5 -> chunks 4 + 1, wave of 3 -> 3, next wave of 5 -> 4
+        gcw.run()
+    gcw.stop()
+    assert [t.tolist() for t in seen] == [[0, 1, 2, 3], [4], [100, 101, 102], [200, 201, 202, 203]]
+    assert len(eng.replies) == 4
+    np.testing.assert_allclose(eng.replies[1][1].numpy(), [2.0])
+    np.testing.assert_allclose(eng.replies[2][0][:, 0].numpy(), np.array([100, 101, 102]) + 1 / 82, rtol=1e-6)
+    p = GC.getParams()
+    assert p["num_action"] == 82 and p["num_planes"] == 18 and p["ACTION_PASS"] == -99
+
+
+def test_compat_objects_have_the_pybind_names():
+    from elf_b200 import compat
+
+    eng = StubEngine()
+    ctx = compat.GameContext(eng, 8).ctx()
+    o = ctx.createSharedMemOptions("actor_black", 8)
+    o.setTimeout(10)
+    sm = ctx.allocateSharedMem(o, ["s", "pi", "V", "a", "rv"])
+    assert sm.getSharedMemOptions().label() == "actor_black" and sm.getSharedMemOptions().batchsize() == 8
+    assert sm.getSharedMemOptions().idx() == 0
+    f = sm["s"].field()
+    assert (f.name(), f.type_name(), f.sz().vec()) == ("s", "float", [8, 18, 9, 9])
+    assert sm["a"].field().type_name() == "int64_t" and sm["pi"].field().sz().vec() == [8, 82]
+    with pytest.raises(KeyError):
+        ctx.allocateSharedMem(o, ["offline_a_not_supported"])
+    with pytest.raises(RuntimeError):
+        ctx.wait()  # before start()
+    assert isinstance(ctx.version(), str)
