@@ -228,9 +228,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    PLIES = args.plies_per_slot
+
     # ---- warm-up -----------------------------------------------------------------------------
     for w in range(args.warmup):
-        gb.playout_launch(SEED, first_id(10_000 + w))
+        gb.playout_stream_launch(SEED, first_id(10_000 + w), PLIES)
     gb.synchronize()
 
     sampler = ClockSampler(local)
@@ -247,7 +249,7 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             flush.fill_(s & 0xFF)  # evict L2 (outside the event pair)
             ev[s][0].record(stream)
-        gb.playout_launch(SEED, first_id(s))
+        gb.playout_stream_launch(SEED, first_id(s), PLIES)
         with torch.cuda.stream(stream):
             ev[s][1].record(stream)
         gb.synchronize()
@@ -262,10 +264,23 @@ def run_ours(args):
     t0 = time.perf_counter()
     e2e_plies = 0
     for s in range(args.steps):
-        r = gb.playout(SEED, first_id(s))  # launch + D2H(chk, plies, score, hash) + sync
+        r = gb.playout_stream(SEED, first_id(s), PLIES)  # launch + D2H(chk, plies, games, hash) + sync
         e2e_plies += r["total_plies"]
     barrier()
     e2e_s = time.perf_counter() - t0
+
+    # ---- secondary: one batch of G games played to terminal (includes the ragged tail) -----------
+    tt_ms, tt_plies = 0.0, 0
+    for s in range(min(args.steps, 10)):
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            a.record(stream)
+        gb.playout_launch(SEED, first_id(s))
+        with torch.cuda.stream(stream):
+            b2.record(stream)
+        gb.synchronize()
+        tt_ms += a.elapsed_time(b2)
+        tt_plies += gb.playout_results()["total_plies"]
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- spot parity of timed work (rank 0): a few games of step 0 against the oracle ------------
@@ -274,11 +289,11 @@ def run_ours(args):
         try:
             from tests import oracles
 
-            r0 = gb.playout(SEED, first_id(0))
+            r0 = gb.playout_stream(SEED, first_id(0), PLIES)
             ok = True
             for g in (0, 1337, G - 1):
-                t, chk, sc = oracles.oracle_playout(BOARD, SEED, first_id(0) + g)
-                ok &= (t, chk, sc) == (int(r0["plies"][g]), int(r0["chk"][g]), int(r0["score"][g]))
+                t, acc, games = oracles.oracle_playout_stream(BOARD, SEED, first_id(0), g, G, PLIES)
+                ok &= (t, acc, games) == (int(r0["plies"][g]), int(r0["chk"][g]), int(r0["games"][g]))
             parity = bool(ok)
         except Exception as e:  # oracle missing is not fatal for the bench
             parity = f"unchecked: {e}"
@@ -296,17 +311,21 @@ def run_ours(args):
             "metric": "self-play moves/sec (random-policy playouts, 19x19)", "value": value, "unit": "moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 4096 concurrent 19x19 games per GPU, random-policy playouts to terminal",
+            "config": {"workload": f"configs[1]: 4096 concurrent 19x19 games per GPU, random-policy playouts, steady state: every game slot plays {PLIES} plies per step and restarts finished games",
                        "games_per_gpu": G, "board": BOARD, "seed": SEED, "plies_per_step": plies_total / args.steps,
+                       "plies_per_slot": PLIES,
                        "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"games sharded x{world}, no collective"},
             "e2e": {"value": e2e_plies / e2e_s, "unit": "moves/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 24 * G, "note": "inputs are 3 scalars (seed, first id, max plies) passed as kernel params"},
+                    "d2h_bytes_per_step": 24 * G, "note": "inputs are 3 scalars (seed, first id, plies per slot) passed as kernel params"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "k_playout<19>",
                          "algorithmic_bytes_per_ply": ALGO_BYTES_PER_PLY,
                          "note": "state lives in registers; kernel is issue/latency bound, see DESIGN.md"},
             "clocks": clocks, "wall_s_timed_region": t_wall, "parity_spot_check": parity,
+            "batch_to_terminal": {"value": tt_plies / (tt_ms / 1e3) * 1.0, "unit": "moves/s (this rank)",
+                                  "ms_per_batch": tt_ms / max(1, min(args.steps, 10)),
+                                  "note": "one batch of 4096 games from the empty board to terminated(): includes the ragged tail"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_playouts(seconds=args.cpu_seconds)
@@ -491,6 +510,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plies-per-slot", type=int, default=512)
     ap.add_argument("--workload", default="playout", choices=["playout", "mcts"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--rollouts", type=int, default=64)

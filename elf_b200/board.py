@@ -154,5 +154,22 @@ class GoBatch:
             self._ctx, chk.ctypes.data, plies.ctypes.data, score.ctypes.data, fh.ctypes.data, ctypes.byref(tot)))
         return {"chk": chk, "plies": plies, "score": score, "hash": fh, "total_plies": tot.value}
 
+    def playout_stream(self, seed, first_game_id=0, plies_per_slot=512):
+        """steady-state playouts: every slot plays exactly ``plies_per_slot`` plies, restarting
+        games as they end; returns per-slot checksum fold / plies / games started / last hash"""
+        G = self.num_games
+        chk = np.empty(G, np.uint64)
+        plies = np.empty(G, np.int32)
+        games = np.empty(G, np.int32)
+        fh = np.empty(G, np.uint64)
+        tot = ctypes.c_int64()
+        _l.check(self._lib, self._lib.elfb200_playout_stream(
+            self._ctx, seed, first_game_id, plies_per_slot, chk.ctypes.data, plies.ctypes.data,
+            games.ctypes.data, fh.ctypes.data, ctypes.byref(tot)))
+        return {"chk": chk, "plies": plies, "games": games, "hash": fh, "total_plies": tot.value}
+
+    def playout_stream_launch(self, seed, first_game_id=0, plies_per_slot=512):
+        _l.check(self._lib, self._lib.elfb200_playout_stream_launch(self._ctx, seed, first_game_id, plies_per_slot))
+
     def launch_count(self):
         return self._lib.elfb200_launch_count(self._ctx)

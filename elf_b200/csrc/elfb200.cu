@@ -190,10 +190,17 @@ __global__ void __launch_bounds__(384)
 
 // ---------------------------------------------------------------------------------------
 // Whole random-policy games, position in registers (BASELINE configs 1/2/5).
+//
+// stream_plies == 0: every slot plays ONE game (id first_id + g) to terminated() / max_plies.
+// stream_plies  > 0: "4096 concurrent games" in steady state -- every slot plays exactly
+//   stream_plies plies, starting a new game (id += G) whenever its game ends, so that G games are
+//   in flight at all times like the reference's game threads (GoGameBase::mainLoop,
+//   common/game_base.h:41).  Per slot: out_chk = fold of the games' checksums in order,
+//   out_plies = plies played, out_score = number of games started, out_hash = last position hash.
 template <int N>
 __global__ void __launch_bounds__(BLOCK)
-    k_playout(int G, uint64_t seed, uint64_t first_id, int max_plies, uint64_t* __restrict__ sk,
-              uint64_t* __restrict__ out_chk, int32_t* __restrict__ out_plies,
+    k_playout(int G, uint64_t seed, uint64_t first_id, int max_plies, int stream_plies,
+              uint64_t* __restrict__ sk, uint64_t* __restrict__ out_chk, int32_t* __restrict__ out_plies,
               int32_t* __restrict__ out_score, uint64_t* __restrict__ out_hash) {
   __shared__ uint64_t s_zob[Geo<N>::ZOB];
   // 4096-bit Bloom filter per game over the recorded pre-move hashes: the exact superko scan
@@ -204,20 +211,42 @@ __global__ void __launch_bounds__(BLOCK)
   const Lane L = make_lane<N>();
   bool valid;
   const int g = warp_game<N>(L, G, valid);
-  const uint64_t gid = first_id + (uint64_t)g;
+  uint64_t gid = first_id + (uint64_t)g;
+  uint64_t* skg = sk + (size_t)(valid ? g : 0) * Geo<N>::MAX_PLY;
   uint32_t* bloom = s_bloom[threadIdx.x >> 5][L.sub];
   for (int i = L.row; i < 128; i += N)
     if (L.active) bloom[i] = 0u;
   __syncwarp();
-  uint64_t* skg = sk + (size_t)(valid ? g : 0) * Geo<N>::MAX_PLY;
 
   uint32_t b = 0, w = 0;
   BoardMeta meta = initial_meta();
-  uint64_t hash = 0, chk = 0;
-  int nsk = 0, t = 0;
+  uint64_t hash = 0, chk = 0, acc = 0;
+  int nsk = 0, t = 0, ts = 0, ngames = 0;
+  const bool stream = stream_plies > 0;
 
   while (true) {
-    const bool term = !valid || is_terminated<N>(meta) || t >= max_plies;
+    const bool over = is_terminated<N>(meta) || t >= max_plies;
+    bool term;
+    if (stream) {
+      const bool budget_out = ts >= stream_plies;
+      const bool restart = valid && over && !budget_out;
+      if (__any_sync(FULL, restart)) {
+        if (restart) {  // finish this game, start the slot's next one
+          acc = pp_splitmix64(acc ^ pp_fold_final(chk, hash, meta.ply));
+          ngames++;
+          gid += (uint64_t)G;
+          b = w = 0;
+          meta = initial_meta();
+          hash = chk = 0;
+          nsk = t = 0;
+          for (int i = L.row; i < 128; i += N) bloom[i] = 0u;
+        }
+        __syncwarp();
+      }
+      term = !valid || budget_out;
+    } else {
+      term = !valid || over;
+    }
     if (__all_sync(FULL, term)) break;
     const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
     const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
@@ -249,15 +278,22 @@ __global__ void __launch_bounds__(BLOCK)
     if (!term) {
       chk = chk2;
       t++;
+      ts++;
     }
     __syncwarp();
   }
   chk = pp_fold_final(chk, hash, meta.ply);
   const int score = tt_score<N>(b, w, L);
   if (valid && L.row == 0) {
-    if (out_chk) out_chk[g] = chk;
-    if (out_plies) out_plies[g] = t;
-    if (out_score) out_score[g] = score;
+    if (stream) {
+      if (out_chk) out_chk[g] = pp_splitmix64(acc ^ chk);
+      if (out_plies) out_plies[g] = ts;
+      if (out_score) out_score[g] = ngames + 1;
+    } else {
+      if (out_chk) out_chk[g] = chk;
+      if (out_plies) out_plies[g] = t;
+      if (out_score) out_score[g] = score;
+    }
     if (out_hash) out_hash[g] = hash;
   }
 }
@@ -528,20 +564,38 @@ int elfb200_features(elfb200_ctx* c, const int32_t* d4_host, float* out_host) {
   return ELFB200_OK;
 }
 
-int elfb200_playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id, int max_plies) {
+static int playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id, int max_plies, int stream_plies) {
   if (!c) return elfb200_fail(ELFB200_ERR_ARG, "ctx is NULL");
   if (max_plies <= 0) return elfb200_fail(ELFB200_ERR_ARG, "max_plies must be positive");
+  if (stream_plies < 0) return elfb200_fail(ELFB200_ERR_ARG, "plies_per_slot must be positive");
   CK(cudaSetDevice(c->device));
   DISPATCH_N(c,
              (k_playout<19><<<grid_for(c), BLOCK, 0, c->stream>>>(
-                 c->G, seed, first_game_id, max_plies, c->d_po_sk, c->d_po_chk, c->d_po_plies,
+                 c->G, seed, first_game_id, max_plies, stream_plies, c->d_po_sk, c->d_po_chk, c->d_po_plies,
                  c->d_po_score, c->d_po_hash)),
              (k_playout<9><<<grid_for(c), BLOCK, 0, c->stream>>>(
-                 c->G, seed, first_game_id, max_plies, c->d_po_sk, c->d_po_chk, c->d_po_plies,
+                 c->G, seed, first_game_id, max_plies, stream_plies, c->d_po_sk, c->d_po_chk, c->d_po_plies,
                  c->d_po_score, c->d_po_hash)));
   c->launches++;
   CK(cudaGetLastError());
   return ELFB200_OK;
+}
+
+int elfb200_playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id, int max_plies) {
+  return playout_launch(c, seed, first_game_id, max_plies, 0);
+}
+
+int elfb200_playout_stream_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id, int plies_per_slot) {
+  if (plies_per_slot <= 0) return elfb200_fail(ELFB200_ERR_ARG, "plies_per_slot must be positive");
+  return playout_launch(c, seed, first_game_id, c ? 2 * c->N * c->N : 1, plies_per_slot);
+}
+
+int elfb200_playout_stream(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id, int plies_per_slot,
+                           uint64_t* chk_host, int32_t* plies_host, int32_t* games_host,
+                           uint64_t* last_hash_host, int64_t* total_plies) {
+  int rc = elfb200_playout_stream_launch(c, seed, first_game_id, plies_per_slot);
+  if (rc) return rc;
+  return elfb200_playout_results(c, chk_host, plies_host, games_host, last_hash_host, total_plies);
 }
 
 int elfb200_playout_results(elfb200_ctx* c, uint64_t* chk_host, int32_t* plies_host,

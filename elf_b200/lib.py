@@ -47,6 +47,8 @@ SIGNATURES = {
     "elfb200_playout_launch": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]),
     "elfb200_playout_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "elfb200_launch_count": (ctypes.c_int64, [vp]),
+    "elfb200_playout_stream": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp, vp, vp, vp, vp]),
+    "elfb200_playout_stream_launch": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]),
     # include/elfb200_mcts.h
     "elfb200_mcts_default_options": (ctypes.c_int, [vp]),
     "elfb200_mcts_create": (ctypes.c_int, [vp, vp, ctypes.POINTER(vp)]),

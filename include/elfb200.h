@@ -98,6 +98,17 @@ int elfb200_playout_launch(elfb200_ctx* ctx, uint64_t seed, uint64_t first_game_
 int elfb200_playout_results(elfb200_ctx* ctx, uint64_t* chk_host, int32_t* plies_host,
                             int32_t* score_host, uint64_t* final_hash_host, int64_t* total_plies);
 
+/* Steady-state variant ("G concurrent games"): every one of the G slots plays exactly
+ * plies_per_slot plies, starting its next game (id += G) whenever a game reaches
+ * GoState::terminated(), as the reference's game threads do (common/game_base.h:41).  Outputs per
+ * slot: chk = fold of the slot's game checksums in order, plies (= plies_per_slot), games = number
+ * of games started, last_hash.  elfb200_playout_results() returns the same arrays after
+ * elfb200_playout_stream_launch(). */
+int elfb200_playout_stream(elfb200_ctx* ctx, uint64_t seed, uint64_t first_game_id, int plies_per_slot,
+                           uint64_t* chk_host, int32_t* plies_host, int32_t* games_host,
+                           uint64_t* last_hash_host, int64_t* total_plies);
+int elfb200_playout_stream_launch(elfb200_ctx* ctx, uint64_t seed, uint64_t first_game_id, int plies_per_slot);
+
 /* Number of kernels this library has launched since creation (bench gpu_launches). */
 int64_t elfb200_launch_count(const elfb200_ctx* ctx);
 

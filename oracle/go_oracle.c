@@ -532,3 +532,24 @@ int64_t go_playout_many(int N, uint64_t seed, uint64_t first_id, int n_games, in
   }
   return total;
 }
+
+/* steady-state playouts of one slot (elfb200_playout_stream): games first_id+slot, +G, +2G, ...
+ * until exactly `budget` plies have been played; fold of the games' checksums in order. */
+int go_playout_stream(int N, uint64_t seed, uint64_t first_id, int slot, int G, int budget,
+                      uint64_t* out_acc, int32_t* out_games) {
+  uint64_t acc = 0, gid = first_id + (uint64_t)slot;
+  int remaining = budget, games = 0;
+  while (remaining > 0) {
+    uint64_t chk;
+    int32_t sc;
+    int t = go_playout(N, seed, gid, remaining < 2 * N * N ? remaining : 2 * N * N, NULL, NULL, NULL, &chk, &sc);
+    acc = pp_splitmix64(acc ^ chk);
+    remaining -= t;
+    gid += (uint64_t)G;
+    games++;
+    if (t == 0) break;
+  }
+  if (out_acc) *out_acc = acc;
+  if (out_games) *out_games = games;
+  return budget - remaining;
+}

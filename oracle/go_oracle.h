@@ -62,6 +62,9 @@ int go_playout(int board_size, uint64_t seed, uint64_t game_id, int max_plies, i
 int64_t go_playout_many(int board_size, uint64_t seed, uint64_t first_id, int n_games,
                         int max_plies, uint64_t* chks, int32_t* plies, int32_t* scores);
 
+int go_playout_stream(int board_size, uint64_t seed, uint64_t first_id, int slot, int num_slots, int budget,
+                      uint64_t* out_acc, int32_t* out_games);
+
 #ifdef __cplusplus
 }
 #endif

@@ -394,3 +394,13 @@ class OracleMcts:
         if getattr(self, "m", None):
             self.L.mo_free(self.m)
             self.m = None
+
+
+def oracle_playout_stream(n, seed, first, slot, num_slots, budget, lib=None):
+    L = lib or load_oracle()
+    L.go_playout_stream.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, vp, vp]
+    acc = ctypes.c_uint64()
+    games = ctypes.c_int32()
+    t = L.go_playout_stream(n, seed, first, slot, num_slots, budget, ctypes.byref(acc), ctypes.byref(games))
+    return t, acc.value, games.value

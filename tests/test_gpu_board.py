@@ -213,3 +213,19 @@ def test_full_size_playout_properties(oracle_lib):
         t, chk, sc = oracles.oracle_playout(n, 11, int(g), lib=oracle_lib)
         assert (t, chk, sc) == (int(a["plies"][g]), int(a["chk"][g]), int(a["score"][g]))
     gb.close()
+
+
+@pytest.mark.parametrize("n,G,budget", [(19, 512, 700), (9, 510, 400), (19, 64, 37)])
+def test_stream_playout_matches_oracle(n, G, budget, oracle_lib):
+    """steady-state mode: every slot plays exactly `budget` plies across consecutive games; the
+    per-slot fold of game checksums, the ply count and the number of games equal the oracle's."""
+    gb = _gobatch(G, n)
+    res = gb.playout_stream(seed=5, first_game_id=70, plies_per_slot=budget)
+    assert (res["plies"] == budget).all() and res["total_plies"] == budget * G
+    for slot in np.linspace(0, G - 1, 40).astype(int):
+        t, acc, games = oracles.oracle_playout_stream(n, 5, 70, int(slot), G, budget, lib=oracle_lib)
+        assert t == budget
+        assert (int(res["chk"][slot]), int(res["games"][slot])) == (acc, games), f"slot {slot}"
+    if budget > 2 * n * n // 2:
+        assert (res["games"] >= 2).any()
+    gb.close()
