@@ -192,39 +192,80 @@ __device__ __forceinline__ uint64_t zob_row(const uint64_t* __restrict__ zob, in
 }
 
 // ---- legality ---------------------------------------------------------------
-// Stones of colour `c` that belong to groups with >=2 liberties (`safe`) and to
-// groups with exactly one liberty (`atari`), restricted to the groups that touch
-// `focus` (other groups may be left unclassified).  `e` = empty points.
-//
-// Cheap sufficient tests for ">= 2 liberties", run as two lock-step fills:
-//   (a) a stone touching two empties;  (b) liberties of both checkerboard
-//   parities (a point's neighbours all have the opposite parity, so touching
-//   stones of different parity can never share a liberty).
-// Whatever stays unresolved is counted group by group.
+// Same-colour link masks: bit x of l? is set iff the stone at (x, y) has a stone of the SAME colour
+// as its left / right / upper / lower neighbour.  With them one dilation step grows groups of both
+// colours at once without leaking across colours:
+//   g' = g | (g << 1 & lL) | (g >> 1 & lR) | (up(g) & lU) | (down(g) & lD)
+// and because the masks are zero at board / game-segment borders the raw shuffles need no selects.
+struct Links {
+  uint32_t l, r, u, d;
+};
+
 template <int N>
-__device__ __forceinline__ void classify_groups(uint32_t c, uint32_t e, uint32_t focus, const Lane& L,
-                                                uint32_t& safe, uint32_t& atari) {
+__device__ __forceinline__ Links make_links(uint32_t own, uint32_t opp, const Lane& L) {
+  Links k;
+  k.l = (own & (own << 1)) | (opp & (opp << 1));
+  k.r = (own & (own >> 1)) | (opp & (opp >> 1));
+  k.u = (own & up_of<N>(own, L)) | (opp & up_of<N>(opp, L));
+  k.d = (own & dn_of<N>(own, L)) | (opp & dn_of<N>(opp, L));
+  return k;
+}
+
+__device__ __forceinline__ uint32_t grow_link(uint32_t g, const Links& k) {
+  return g | ((g << 1) & k.l) | ((g >> 1) & k.r) | (__shfl_up_sync(FULL, g, 1) & k.u) |
+         (__shfl_down_sync(FULL, g, 1) & k.d);
+}
+
+// Classify the groups of BOTH colours that touch `focus`: `safe` = stones of groups with >= 2
+// liberties, `atari` = stones of groups with exactly one (other groups may stay unclassified).
+// `c` = all stones, `e` = empty points.
+//
+// Cheap sufficient tests for ">= 2 liberties", run as two lock-step fills over both colours:
+//   (a) a stone touching two empties;  (b) liberties of both checkerboard parities (a point's
+//   neighbours all have the opposite parity, so liberty-touching stones of different parity can
+//   never share a liberty):  X = fill(even-touching | t2), Y = fill(odd-touching | t2),
+//   safe = X & Y.  Whatever stays unresolved is counted group by group.
+template <int N>
+__device__ __forceinline__ void classify_groups(uint32_t own, uint32_t opp, uint32_t e, uint32_t focus,
+                                                const Lane& L, uint32_t& safe, uint32_t& atari) {
+  const uint32_t c = own | opp;
   const uint32_t e_l = e << 1, e_r = e >> 1, e_u = up_of<N>(e, L), e_d = dn_of<N>(e, L);
   const uint32_t aL = c & e_l, aR = c & e_r, aU = c & e_u, aD = c & e_d;
   const uint32_t touch = aL | aR | aU | aD;
   const uint32_t t2 = (aL & (aR | aU | aD)) | (aR & (aU | aD)) | (aU & aD);
+  atari = 0;
+  // every focus stone touches two empties itself: nothing to propagate
+  if (!__any_sync(FULL, (c & focus & ~t2) != 0u)) {
+    safe = t2;
+    return;
+  }
+  const Links k = make_links<N>(own, opp, L);
   // checkerboard: bit x of row y is "even" iff (x + y) even
   const uint32_t even = (L.row & 1) ? 0xAAAAAAAAu : 0x55555555u;
-  // group is safe iff it holds a t2 stone, or touching stones of both parities:
-  //   X = fill(even-touching | t2), Y = fill(odd-touching | t2)  ->  safe = X & Y
-  uint32_t g[2] = {(touch & even) | t2, (touch & ~even) | t2};
-  const uint32_t thr[2] = {c, c};
-  floodK<N, 2>(g, thr, L);
-  safe = g[0] & g[1];
-  atari = 0;
+  uint32_t gx = (touch & even) | t2, gy = (touch & ~even) | t2;
+  while (true) {  // two lock-step fills, two dilations per vote
+    const uint32_t x1 = grow_link(gx, k), y1 = grow_link(gy, k);
+    const uint32_t x2 = grow_link(x1, k), y2 = grow_link(y1, k);
+    const bool ch = (x2 != gx) | (y2 != gy);
+    gx = x2;
+    gy = y2;
+    if (!__any_sync(FULL, ch)) break;
+  }
+  safe = gx & gy;
   uint32_t cand = c & ~safe & focus;  // seeds of unresolved groups we care about
   while (__any_sync(FULL, cand != 0u)) {
     // every game picks the lowest stone of its lowest non-empty row
-    uint32_t bal = __ballot_sync(FULL, cand != 0u) & L.segmask;
-    int src = __ffs(bal) - 1;
-    uint32_t seed = (L.lane == src) ? (cand & (0u - cand)) : 0u;
-    uint32_t grp = flood<N>(seed, c, L);
-    int nl = game_sum<N>(__popc(nbr4<N>(grp, L) & e), L);
+    const uint32_t bal = __ballot_sync(FULL, cand != 0u) & L.segmask;
+    const int src = __ffs(bal) - 1;
+    uint32_t grp = (L.lane == src) ? (cand & (0u - cand)) : 0u;
+    while (true) {
+      const uint32_t g1 = grow_link(grp, k);
+      const uint32_t g2 = grow_link(g1, k);
+      const bool ch = g2 != grp;
+      grp = g2;
+      if (!__any_sync(FULL, ch)) break;
+    }
+    const int nl = game_sum<N>(__popc(nbr4<N>(grp, L) & e), L);
     if (nl == 1)
       atari |= grp;
     else
@@ -246,10 +287,9 @@ __device__ __forceinline__ uint32_t legal_rows(uint32_t own, uint32_t opp, const
   const uint32_t hard = e & ~en;  // empties with no empty neighbour
   if (__any_sync(FULL, hard != 0u)) {
     const uint32_t focus = nbr4<N>(hard, L);
-    uint32_t own_safe, own_atari, opp_safe, opp_atari;
-    classify_groups<N>(own, e, focus, L, own_safe, own_atari);
-    classify_groups<N>(opp, e, focus, L, opp_safe, opp_atari);
-    legal |= hard & (nbr4<N>(own_safe, L) | nbr4<N>(opp_atari, L));
+    uint32_t safe, atari;
+    classify_groups<N>(own, opp, e, focus, L, safe, atari);
+    legal |= hard & (nbr4<N>(safe & own, L) | nbr4<N>(atari & opp, L));
   }
   if (ko_applies) {
     int ky = ko_pt / N, kx = ko_pt - ky * N;
@@ -347,6 +387,123 @@ __device__ __forceinline__ int play_move(uint32_t& b, uint32_t& w, BoardMeta& me
   }
   if (p != MV_NONE) {
     // update_next_move (board.cc:1225-1238); a pass leaves the ko state untouched (board.cc:1306)
+    meta.next = (uint8_t)oppc;
+    meta.last2 = meta.last1;
+    meta.last1 = (int16_t)p;
+    meta.ply++;
+  }
+  return ncap;
+}
+
+// ---- incremental group status (playout kernel) ------------------------------------------------
+// The playout kernel keeps, across plies, two masks over ALL stones: `safe` (stone belongs to a
+// group with >= 2 liberties) and `atari` (exactly 1).  A group's liberty count only changes when a
+// stone lands on one of its liberties, when it merges, or when stones next to it are captured, so
+// after a move only the groups touching the new stone or the captured stones are recounted
+// (typically 2-4 small fills) instead of classifying every group near a dead-end point (~7 fills
+// per ply in random play, 95 % of them groups in atari).  The masks also give:
+//   * captures: the enemy neighbour groups of the new stone that are in `atari` (their single
+//     liberty is necessarily the point just played) -- no global "still alive" fill;
+//   * legality of dead-end points straight from the masks.
+// Same observable behaviour as legal_rows()/play_move(); the playout checksum (hash, captures,
+// legal mask of every position) pins it against the oracle.
+template <int N>
+__device__ __forceinline__ uint32_t legal_rows_cached(uint32_t own, uint32_t opp, uint32_t safe,
+                                                      uint32_t atari, const Lane& L, bool ko_applies,
+                                                      int ko_pt) {
+  const uint32_t e = ~(own | opp) & L.rm;
+  const uint32_t en = nbr4<N>(e, L);
+  uint32_t legal = e & en;
+  const uint32_t hard = e & ~en;
+  if (__any_sync(FULL, hard != 0u))
+    legal |= hard & (nbr4<N>(safe & own, L) | nbr4<N>(atari & opp, L));
+  if (ko_applies) {
+    int ky = ko_pt / N, kx = ko_pt - ky * N;
+    if (L.row == ky) legal &= ~(1u << kx);
+  }
+  return legal & L.rm;
+}
+
+template <int N>
+__device__ __forceinline__ int play_move_cached(uint32_t& b, uint32_t& w, BoardMeta& meta, uint64_t& hash,
+                                                int p, const uint64_t* __restrict__ zob, const Lane& L,
+                                                uint32_t& safe, uint32_t& atari) {
+  const int player = meta.next;
+  const int oppc = S_BLACK + S_WHITE - player;
+  const bool is_stone = p >= 0;
+  uint32_t own = player == S_BLACK ? b : w;
+  uint32_t opp = player == S_BLACK ? w : b;
+  const int y = is_stone ? p / N : 0, x = is_stone ? p - y * N : 0;
+  const uint32_t mybit = (is_stone && L.row == y && L.active) ? (1u << x) : 0u;
+  const uint32_t nb = nbr4<N>(mybit, L) & L.rm;
+  const bool single = !game_any<N>((nb & own) != 0u, L);
+  own |= mybit;
+  uint64_t dh = 0;
+  int ncap = 0;
+  uint32_t dead = 0;
+  // captures (board.cc:1346-1369): enemy neighbour groups whose only liberty was this point
+  const uint32_t dseed = nb & opp & atari;
+  if (__any_sync(FULL, dseed != 0u)) {
+    dead = flood<N>(dseed, opp, L);
+    ncap = game_sum<N>(__popc(dead), L);
+    opp &= ~dead;
+    safe &= ~dead;
+    atari &= ~dead;
+    dh = zob_color(game_xor64<N>(zob_row<N>(zob, L.row, dead), L), oppc);
+  }
+  if (is_stone) {
+    hash ^= dh ^ zob_color(zob[(y + 1) * Geo<N>::E + (x + 1)], player);
+    if (player == S_BLACK) {
+      b = own; w = opp; meta.b_cap += ncap;
+    } else {
+      w = own; b = opp; meta.w_cap += ncap;
+    }
+  }
+  const uint32_t stones = own | opp;
+  const uint32_t e2 = ~stones & L.rm;
+  const int libs = game_sum<N>(__popc(nb & e2), L);
+  {
+    uint32_t bal = __ballot_sync(FULL, dead != 0u) & L.segmask;
+    int src = __ffs(bal) - 1;
+    int dx = __shfl_sync(FULL, __ffs(dead) - 1, src & 31);
+    if (is_stone) {
+      if (ncap == 1 && single && libs == 1) {  // simple ko, board.cc:1384-1393
+        meta.ko_pt = (int16_t)((src - L.base) * N + dx);
+        meta.ko_color = (uint8_t)oppc;
+        meta.flags |= F_KO_ACTIVE;
+      } else {
+        meta.flags &= ~F_KO_ACTIVE;
+      }
+    }
+  }
+  // recount the groups whose liberties may have changed
+  uint32_t seeds = (mybit | nb | nbr4<N>(dead, L)) & stones;
+  if (__any_sync(FULL, seeds != 0u)) {
+    const Links k = make_links<N>(own, opp, L);
+    while (true) {
+      const uint32_t bal = __ballot_sync(FULL, seeds != 0u) & L.segmask;
+      const int src = __ffs(bal) - 1;
+      uint32_t grp = (L.lane == src) ? (seeds & (0u - seeds)) : 0u;
+      while (true) {
+        const uint32_t g1 = grow_link(grp, k);
+        const uint32_t g2 = grow_link(g1, k);
+        const bool ch = g2 != grp;
+        grp = g2;
+        if (!__any_sync(FULL, ch)) break;
+      }
+      const int nl = game_sum<N>(__popc(nbr4<N>(grp, L) & e2), L);
+      if (nl == 1) {
+        atari |= grp;
+        safe &= ~grp;
+      } else {
+        safe |= grp;
+        atari &= ~grp;
+      }
+      seeds &= ~grp;
+      if (!__any_sync(FULL, seeds != 0u)) break;
+    }
+  }
+  if (p != MV_NONE) {
     meta.next = (uint8_t)oppc;
     meta.last2 = meta.last1;
     meta.last1 = (int16_t)p;

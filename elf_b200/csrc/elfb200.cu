@@ -197,8 +197,12 @@ __global__ void __launch_bounds__(384)
 //   in flight at all times like the reference's game threads (GoGameBase::mainLoop,
 //   common/game_base.h:41).  Per slot: out_chk = fold of the games' checksums in order,
 //   out_plies = plies played, out_score = number of games started, out_hash = last position hash.
+// One warp per CTA: 4096 games are 4096 warps over 148 SMs = 27.7 per SM; with 4-warp CTAs
+// the SMs holding 7 CTAs (28 warps) set the kernel time while those with 6 idle 14 % of it.
+constexpr int PLAYOUT_WARPS = 1;
+
 template <int N>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(PLAYOUT_WARPS * 32)
     k_playout(int G, uint64_t seed, uint64_t first_id, int max_plies, int stream_plies,
               uint64_t* __restrict__ sk, uint64_t* __restrict__ out_chk, int32_t* __restrict__ out_plies,
               int32_t* __restrict__ out_score, uint64_t* __restrict__ out_hash) {
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(BLOCK)
   // 4096-bit Bloom filter per game over the recorded pre-move hashes: the exact superko scan
   // (go_state.cc:96-111) only runs when both probe bits are set (false-positive rate ~3 % at
   // 400 recorded positions), which removes ~1.8 KB of history reads per ply.
-  __shared__ uint32_t s_bloom[WARPS][Geo<N>::GPW][128];
+  __shared__ uint32_t s_bloom[PLAYOUT_WARPS][Geo<N>::GPW][128];
   load_zobrist<N>(s_zob);
   const Lane L = make_lane<N>();
   bool valid;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(BLOCK)
     if (L.active) bloom[i] = 0u;
   __syncwarp();
 
-  uint32_t b = 0, w = 0;
+  uint32_t b = 0, w = 0, safe = 0, atari = 0;  // safe/atari: incremental group status (board.cuh)
   BoardMeta meta = initial_meta();
   uint64_t hash = 0, chk = 0, acc = 0;
   int nsk = 0, t = 0, ts = 0, ngames = 0;
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(BLOCK)
           acc = pp_splitmix64(acc ^ pp_fold_final(chk, hash, meta.ply));
           ngames++;
           gid += (uint64_t)G;
-          b = w = 0;
+          b = w = safe = atari = 0;
           meta = initial_meta();
           hash = chk = 0;
           nsk = t = 0;
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(BLOCK)
     if (__all_sync(FULL, term)) break;
     const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
     const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
-    const uint32_t legal = legal_rows<N>(own, opp, L, ko_applies, meta.ko_pt);
+    const uint32_t legal = legal_rows_cached<N>(own, opp, safe, atari, L, ko_applies, meta.ko_pt);
     const uint32_t cand = legal & ~true_eye_rows<N>(own, opp, L);
     const int n = game_sum<N>(__popc(cand), L);
     const uint64_t rx = game_xor64<N>(L.active ? pp_row_term((uint32_t)L.row, legal) : 0ull, L);
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(BLOCK)
     const int p = select_kth_action_order<N>(cand, k, L);
     const int pm = term ? MV_NONE : (n > 0 ? p : MV_PASS);
     const uint64_t pre_hash = hash;
-    play_move<N>(b, w, meta, hash, pm, s_zob, L);
+    play_move_cached<N>(b, w, meta, hash, pm, s_zob, L, safe, atari);
     const uint32_t q1 = (uint32_t)hash & 4095u, q2 = (uint32_t)(hash >> 12) & 4095u;
     const bool maybe = pm >= 0 && ((bloom[q1 >> 5] >> (q1 & 31)) & (bloom[q2 >> 5] >> (q2 & 31)) & 1u);
     bool sko = false;
@@ -569,11 +573,13 @@ static int playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id,
   if (max_plies <= 0) return elfb200_fail(ELFB200_ERR_ARG, "max_plies must be positive");
   if (stream_plies < 0) return elfb200_fail(ELFB200_ERR_ARG, "plies_per_slot must be positive");
   CK(cudaSetDevice(c->device));
+  const int gpw = 32 / c->N;
+  const int pgrid = ((c->G + gpw - 1) / gpw + PLAYOUT_WARPS - 1) / PLAYOUT_WARPS;
   DISPATCH_N(c,
-             (k_playout<19><<<grid_for(c), BLOCK, 0, c->stream>>>(
+             (k_playout<19><<<pgrid, PLAYOUT_WARPS * 32, 0, c->stream>>>(
                  c->G, seed, first_game_id, max_plies, stream_plies, c->d_po_sk, c->d_po_chk, c->d_po_plies,
                  c->d_po_score, c->d_po_hash)),
-             (k_playout<9><<<grid_for(c), BLOCK, 0, c->stream>>>(
+             (k_playout<9><<<pgrid, PLAYOUT_WARPS * 32, 0, c->stream>>>(
                  c->G, seed, first_game_id, max_plies, stream_plies, c->d_po_sk, c->d_po_chk, c->d_po_plies,
                  c->d_po_score, c->d_po_hash)));
   c->launches++;

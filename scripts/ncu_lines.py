@@ -28,8 +28,9 @@ def main():
     base = inst[0][0]
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    dis = ""
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        dis += subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     sec = re.split(r"//-+ \.text\.", dis)
     body = next(s for s in sec if s.startswith("_Z") and kern in s.split(" ", 1)[0])
     line_of = {}
