@@ -40,18 +40,23 @@ PP_HD uint32_t pp_pick(uint64_t seed, uint64_t game_id, uint32_t ply, uint32_t n
   return (uint32_t)(((r >> 32) * (uint64_t)n) >> 32);
 }
 
-/* contribution of one legal-mask row (order independent across rows) */
+/* contribution of one legal-mask row (order independent across rows): one multiply and one
+ * xor-shift of (row index, row bits) -- cheap on the GPU's integer pipe, and not GF(2)-linear, so
+ * the XOR over rows still separates different masks */
 PP_HD uint64_t pp_row_term(uint32_t y, uint32_t row_bits) {
-  return pp_splitmix64(((uint64_t)(y + 1) << 32) | (uint64_t)row_bits);
+  uint64_t v = ((((uint64_t)(y + 1)) << 32) | (uint64_t)row_bits) * 0xBF58476D1CE4E5B9ULL;
+  return v ^ (v >> 29);
 }
 
+PP_HD uint64_t pp_rotl64(uint64_t v, int r) { return (v << r) | (v >> (64 - r)); }
+
+/* fold one position into the running checksum: a single splitmix64 round over the XOR of
+ * bijectively transformed fields (hash, legal-mask digest, capture counters + side to move) */
 PP_HD uint64_t pp_fold3(uint64_t chk, uint64_t hash, uint64_t rows_xor, uint32_t b_cap,
                         uint32_t w_cap, uint32_t next_player) {
-  chk = pp_splitmix64(chk ^ hash);
-  chk = pp_splitmix64(chk ^ rows_xor);
-  chk = pp_splitmix64(chk ^ ((uint64_t)(b_cap & 0xFFFF) | ((uint64_t)(w_cap & 0xFFFF) << 16) |
-                             ((uint64_t)next_player << 32)));
-  return chk;
+  const uint64_t caps = (uint64_t)(b_cap & 0xFFFF) | ((uint64_t)(w_cap & 0xFFFF) << 16) |
+                        ((uint64_t)next_player << 32);
+  return pp_splitmix64(chk ^ hash ^ pp_rotl64(rows_xor, 23) ^ (caps * 0x9E3779B97F4A7C15ULL));
 }
 
 PP_HD uint64_t pp_fold_position(uint64_t chk, uint64_t hash, uint32_t b_cap, uint32_t w_cap,
