@@ -34,7 +34,7 @@ namespace elfb200 {
 
 constexpr uint16_t NONE16 = 0xFFFFu;
 enum : uint8_t { NS_FREE = 0, NS_UNVISITED = 1, NS_REQUESTED = 2, NS_VISITED = 3 };
-enum : uint8_t { NF_FLIP = 1, NF_KEEP = 2 };
+enum : uint8_t { NF_FLIP = 1, NF_KEEP = 2, NF_FULLSCAN = 4 };  // FULLSCAN: priors no longer sorted (root noise)
 
 struct __align__(16) NodeHdr {  // 32 bytes
   int32_t num_visits;    // NodeT::numVisits_
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
         break;
       }
       // ---- UCT over the selected prefix plus the first never-selected edge ------------------------
-      const int lim = min((int)h.n_edges, (int)h.n_touched + 1);
+      const int lim = (h.flags & NF_FULLSCAN) ? (int)h.n_edges : min((int)h.n_edges, (int)h.n_touched + 1);
       st_steps++;
       st_edges += lim;
       st_term += h.n_edges;  // stored edges: what a full scan (SURVEY 8d formula) would read
@@ -755,6 +755,82 @@ __global__ void __launch_bounds__(BLOCK)
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Root exploration noise: NodeT::enhanceExploration (tree_search_node.h:132-155), applied by
+// TreeSearchT::run (tree_search.h:413-417) to a root that already has edges:
+//   P_i <- (1 - eps) P_i + eps * eta_i / (1e-10 + sum eta),  eta_i ~ Gamma(alpha, 1).
+// The reference draws from std::gamma_distribution on the actor's mt19937; here eta comes from a
+// counter-based generator (Marsaglia-Tsang on splitmix64 uniforms), so the distribution is the
+// same and the stream is not.  Afterwards the root's priors are no longer sorted: the node is
+// flagged for a full PUCT scan.
+__device__ __forceinline__ float rng_u01(uint64_t key, uint32_t& ctr) {
+  const uint64_t r = pp_splitmix64(key + 0x9E3779B97F4A7C15ULL * (uint64_t)(ctr++));
+  return ((float)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+}
+
+__device__ __forceinline__ float rng_gamma(float a, uint64_t key, uint32_t& ctr) {
+  float boost = 1.f;
+  if (a < 1.f) {
+    boost = powf(rng_u01(key, ctr), 1.f / a);
+    a += 1.f;
+  }
+  const float d = a - 1.f / 3.f, c = rsqrtf(9.f * d);
+  for (int it = 0; it < 64; ++it) {
+    const float u1 = rng_u01(key, ctr), u2 = rng_u01(key, ctr);
+    const float x = sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+    float v = 1.f + c * x;
+    if (v <= 0.f) continue;
+    v = v * v * v;
+    const float u = rng_u01(key, ctr);
+    if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) return d * v * boost;
+  }
+  return d * boost;
+}
+
+__global__ void __launch_bounds__(BLOCK)
+    k_root_noise(int G, TreeDev tr, float eps, float alpha, uint64_t seed, uint32_t move_counter) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= G || !tr.active[g]) return;
+  const int root = tr.root[g];
+  if (root == NONE16) return;
+  const size_t nb = (size_t)g * tr.C;
+  const NodeHdr h = load_hdr(&tr.hdr[nb + root]);
+  if (h.status != NS_VISITED || h.n_edges == 0) return;
+  float4* es = tr.estat + (nb + root) * tr.E;
+  float z = 0.f;
+  for (int i = lane; i < h.n_edges; i += 32) {
+    uint32_t ctr = 0;
+    const uint64_t key = pp_splitmix64(seed ^ ((uint64_t)g << 32) ^ ((uint64_t)move_counter << 12) ^ (uint64_t)i);
+    const float eta = rng_gamma(alpha, key, ctr);
+    z += eta;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) z += __shfl_xor_sync(FULL, z, d);
+  z += 1e-10f;
+  for (int i = lane; i < h.n_edges; i += 32) {
+    uint32_t ctr = 0;
+    const uint64_t key = pp_splitmix64(seed ^ ((uint64_t)g << 32) ^ ((uint64_t)move_counter << 12) ^ (uint64_t)i);
+    const float eta = rng_gamma(alpha, key, ctr);
+    es[i].x = (1.f - eps) * es[i].x + eps * eta / z;
+  }
+  if (lane == 0) tr.hdr[nb + root].flags |= NF_FULLSCAN;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_root_priors(int G, TreeDev tr, float* __restrict__ out, int P1) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= G) return;
+  for (int a = lane; a < P1; a += 32) out[(size_t)g * P1 + a] = -1.f;
+  __syncwarp();
+  const int root = tr.root[g];
+  if (root == NONE16) return;
+  const size_t nb = (size_t)g * tr.C;
+  const int ne = tr.hdr[nb + root].n_edges;
+  for (int i = lane; i < ne; i += 32)
+    out[(size_t)g * P1 + (tr.elink[(nb + root) * tr.E + i] & 0xFFFFu)] = tr.estat[(nb + root) * tr.E + i].x;
+}
+
 __global__ void k_tree_reset(int G, TreeDev tr, const uint8_t* __restrict__ mask) {
   const int lane = threadIdx.x & 31;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -810,6 +886,8 @@ struct elfb200_mcts {
   int32_t* d_leaf_ply = nullptr;
   int32_t* d_leaf_d4 = nullptr;
   int last_eval_count = 0;
+  uint32_t move_counter = 0;
+  float* d_priors = nullptr;
   // per-kernel device timing (CUDA events on the context stream), accumulated on the host
   cudaEvent_t ev[7] = {};  // sel0 sel1 feat0 feat1 exp0 exp1 bak1
   bool pending_feat = false, pending_eb = false;
@@ -862,6 +940,8 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   if (opt->num_rollouts <= 0 || opt->num_rollouts_per_batch <= 0 || opt->num_rollouts_per_batch > 64)
     return elfb200_fail(ELFB200_ERR_ARG, "num_rollouts must be > 0 and num_rollouts_per_batch in [1, 64]");
   if (opt->virtual_loss < 0) return elfb200_fail(ELFB200_ERR_ARG, "virtual_loss must be >= 0");
+  if (opt->root_epsilon < 0.f || opt->root_epsilon > 1.f || (opt->root_epsilon > 0.f && opt->root_alpha <= 0.f))
+    return elfb200_fail(ELFB200_ERR_ARG, "root_epsilon must be in [0,1] and root_alpha > 0 when noise is on");
   CK(cudaSetDevice(c->device));
   elfb200_mcts* m = new elfb200_mcts();
   m->ctx = c;
@@ -941,7 +1021,7 @@ void elfb200_mcts_destroy(elfb200_mcts* m) {
   void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.anc, t.free_list,
                   t.free_n,    t.root,      t.leaves,    t.active,     t.eval_count,  t.eval_game,  t.eval_node,
                   t.eval_d4,   t.bfs_q,     t.errors,    t.stats,     m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
-                  m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4};
+                  m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4, m->d_priors};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& e : m->ev)
@@ -985,6 +1065,13 @@ int elfb200_mcts_begin_move(elfb200_mcts* m, const uint8_t* active_host) {
              (k_begin<9><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, need)));
   c->launches++;
   CK(cudaGetLastError());
+  if (m->opt.root_epsilon > 0.f) {
+    k_root_noise<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->opt.root_epsilon, m->opt.root_alpha,
+                                                            (uint64_t)(uint32_t)m->opt.seed, m->move_counter);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  m->move_counter++;
   m->wave = 0;
   return ELFB200_OK;
 }
@@ -1098,6 +1185,20 @@ int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host) {
   k_advance<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->d_actions, m->so.persistent);
   c->launches++;
   CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_root_priors(elfb200_mcts* m, float* priors_host) {
+  if (!m || !priors_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t G = c->G, P1 = (size_t)c->N * c->N + 1;
+  if (!m->d_priors) CK(cudaMalloc(&m->d_priors, G * P1 * 4));
+  k_root_priors<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->d_priors, (int)P1);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(priors_host, m->d_priors, G * P1 * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ELFB200_OK;
 }

@@ -64,6 +64,7 @@ SIGNATURES = {
     "elfb200_mcts_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "elfb200_mcts_advance": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_errors": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_root_priors": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_eval_count": (ctypes.c_int64, [vp]),
     "elfb200_mcts_stats": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_timings": (ctypes.c_int, [vp, vp, vp, ctypes.c_int]),
@@ -78,7 +79,7 @@ class MctsOptions(ctypes.Structure):
         ("unexplored_q_zero", ctypes.c_int32), ("root_unexplored_q_zero", ctypes.c_int32),
         ("ply_pass_enabled", ctypes.c_int32), ("remove_pass_if_dangerous", ctypes.c_int32),
         ("rotation_flip", ctypes.c_int32), ("seed", ctypes.c_int32), ("nodes_per_game", ctypes.c_int32),
-        ("c_puct", ctypes.c_float), ("komi", ctypes.c_float), ("reserved", ctypes.c_float * 2),
+        ("c_puct", ctypes.c_float), ("komi", ctypes.c_float), ("root_epsilon", ctypes.c_float), ("root_alpha", ctypes.c_float),
     ]
 
 

@@ -99,6 +99,12 @@ class MctsBatch:
         a = np.ascontiguousarray(actions, dtype=np.int32)
         _l.check(self._lib, self._lib.elfb200_mcts_advance(self._m, a.ctypes.data))
 
+    def root_priors(self):
+        """float32 [G, N*N+1]: prior of every root edge by action, -1 where there is no edge"""
+        o = np.empty((self.gb.num_games, self.gb.num_actions), np.float32)
+        _l.check(self._lib, self._lib.elfb200_mcts_root_priors(self._m, o.ctypes.data))
+        return o
+
     def errors(self):
         e = np.zeros(4, np.int32)
         _l.check(self._lib, self._lib.elfb200_mcts_errors(self._m, e.ctypes.data))

@@ -53,7 +53,8 @@ typedef struct {
   int32_t nodes_per_game;          /* node-pool slots per game; 0 = 2*rollouts + 256 */
   float c_puct;                    /* SearchAlgoOptions::c_puct */
   float komi;                      /* MCTSActorParams::komi */
-  float reserved[2];
+  float root_epsilon;              /* TSOptions::root_epsilon: Dirichlet noise weight at the root (0 = off) */
+  float root_alpha;                /* TSOptions::root_alpha */
 } elfb200_mcts_options;
 
 int elfb200_mcts_default_options(elfb200_mcts_options* opt);
@@ -84,7 +85,10 @@ int elfb200_mcts_results(elfb200_mcts* m, int32_t* best_action_host, int32_t* vi
                          float* root_value_host, float* best_q_host, int32_t* total_visits_host);
 /* SearchTreeT::treeAdvance for the move just played in each game (actions[g] < 0: untouched). */
 int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host);
-/* int32[4]: root-hash mismatches, node-pool drops/overflows, reserved, reserved. */
+/* float[G][N*N+1]: current prior of every root edge by action (-1 where the root has no such
+ * edge), after any exploration noise (NodeT::enhanceExploration, tree_search_node.h:132-155). */
+int elfb200_mcts_root_priors(elfb200_mcts* m, float* priors_host);
+/* int32[4]: root-hash mismatches, node-pool drops/overflows, depth overflows, reserved. */
 int elfb200_mcts_errors(elfb200_mcts* m, int32_t* counters_host4);
 int64_t elfb200_mcts_eval_count(const elfb200_mcts* m);
 /* uint64[4] running totals: descent steps (nodes visited by PUCT), edge records actually read

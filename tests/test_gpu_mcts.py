@@ -226,3 +226,110 @@ def test_selfplay_driver_smoke():
     assert all(abs(fv) <= n * n + 7.5 for fv, _, _ in sp.results)
     assert (sp.mcts.errors() == 0).all()
     sp.close()
+
+
+@pytest.mark.parametrize("n,open_plies", [(9, 30), (19, 12)])
+def test_leaf_features_match_reference_extractor(n, open_plies):
+    """The planes handed to the network for every MCTS leaf (history gathered along the tree's
+    parent chain + the game's ring) must equal what the reference's BoardFeature::extractAGZ
+    produces for the same leaf state.  The reference search runs with a recording callback; every
+    GPU leaf must reproduce one of the reference's recorded (hash -> planes) entries exactly."""
+    import torch
+    import elf_b200
+
+    if not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built")
+    G = 3
+    P1 = n * n + 1
+    opts = dict(num_rollouts=64, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5)
+    rng = np.random.default_rng(21)
+    gb = elf_b200.GoBatch(G, board_size=n)
+    refs = [oracles.Ref(n) for _ in range(G)]
+    for _ in range(open_plies):
+        acts = np.empty(G, np.int32)
+        for g, r in enumerate(refs):
+            idx = np.flatnonzero(r.legal())
+            acts[g] = int(rng.choice(idx))
+            r.forward(acts[g])
+        gb.forward(acts)
+    recorded = {}
+
+    def ref_cb(feats, hashes):
+        for f, h in zip(feats, hashes):
+            recorded.setdefault(int(h), []).append(f.copy())
+        return oracles.fakenet(hashes, P1)
+
+    rms = [oracles.RefMcts(n, callback=ref_cb, **opts) for _ in range(G)]
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, **opts)
+    checked = [0]
+
+    def actor(batch):
+        h, _, _ = mc.leaf_info()
+        s = batch["s"].cpu().numpy()
+        for i, hh in enumerate(h):
+            cands = recorded.get(int(hh))
+            assert cands, "GPU evaluated a state the reference never evaluated"
+            assert any((s[i] == c).all() for c in cands), f"feature planes differ for leaf hash {int(hh):x}"
+            checked[0] += 1
+        pi, v = oracles.fakenet(h, P1)
+        return {"pi": torch.from_numpy(pi).to(mc.device), "V": torch.from_numpy(v).to(mc.device)}
+
+    for mv in range(4):
+        ref_res = [rms[g].act(refs[g]) for g in range(G)]  # reference first: fills `recorded`
+        res = mc.act(actor)
+        acts = np.array([r["best_action"] for r in ref_res], np.int32)
+        for g in range(G):
+            assert np.abs(res["visits"][g] - ref_res[g]["visits"]).max() == 0
+            refs[g].forward(acts[g])
+        gb.forward(acts)
+        mc.advance(acts)
+    assert checked[0] > 300
+
+
+@pytest.mark.parametrize("alpha", [0.03, 2.0])
+def test_root_dirichlet_noise(alpha):
+    """NodeT::enhanceExploration: P <- (1-eps) P + eps * Dir(alpha) on a root that already has
+    edges; nothing on a fresh (unexpanded) root.  Streams differ from the reference's mt19937, so
+    the check is distributional: the mixed-in vector is non-negative, sums to 1, has the Dirichlet
+    mean 1/n and variance (n-1)/(n^2 (n alpha + 1)); and the search still accounts for every rollout."""
+    import elf_b200
+
+    n, G, eps = 9, 96, 0.25
+    gb = elf_b200.GoBatch(G, board_size=n)
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, num_rollouts=32, num_rollouts_per_batch=4, root_epsilon=eps,
+                            root_alpha=alpha, seed=11)
+    actor = fake_actor(mc, n)
+    res = mc.act(actor)  # move 1: the root is unexpanded when the search starts -> no noise
+    a = res["best_action"]
+    assert res["total_visits"].tolist() == [28] * G
+    gb.forward(a)
+    mc.advance(a)
+    before = mc.root_priors()          # the kept child: expanded, priors straight from pi2response
+    mc.begin_move()                    # noise goes in here
+    after = mc.root_priors()
+    has = before >= 0
+    assert (has == (after >= 0)).all() and has.sum(1).min() >= 60
+    d = np.where(has, (after - (1 - eps) * before) / eps, 0.0).astype(np.float64)
+    assert (d > -1e-6).all()
+    np.testing.assert_allclose(d.sum(1), 1.0, atol=1e-4)
+    k = has.sum(1)
+    mean = (d.sum(1) / k)
+    np.testing.assert_allclose(mean, 1.0 / k, rtol=1e-3)
+    var_emp = np.mean([(d[g][has[g]] - 1.0 / k[g]).var() for g in range(G)])
+    kk = k.mean()
+    var_th = (kk - 1) / (kk * kk * (kk * alpha + 1))
+    assert 0.6 * var_th < var_emp < 1.5 * var_th, (var_emp, var_th)
+    # two games never get the same noise
+    assert len({tuple(np.round(d[g][has[g]][:8], 6)) for g in range(G)}) == G
+    # finish the move through the flagged (full-scan) root
+    for _ in range(mc.waves_per_move):
+        s = mc.select()
+        if s.shape[0]:
+            gb.synchronize()
+            r = actor({"s": s})
+            mc.expand_backup(r["pi"], r["V"])
+        else:
+            mc.expand_backup(None, None)
+    res2 = mc.results()
+    assert (res2["total_visits"] >= 32).all()
+    assert (mc.errors() == 0).all()
