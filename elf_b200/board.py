@@ -20,9 +20,15 @@ class GoBatch:
         self.board_size = board_size
         self.num_actions = board_size * board_size + 1
         self.device = device
+        self._children = []  # weakrefs to objects holding handles into this context (MctsBatch)
 
     def close(self):
         if getattr(self, "_ctx", None):
+            for w in getattr(self, "_children", []):
+                c = w()
+                if c is not None:
+                    c.close()  # search handles reference the context: destroy them first
+            self._children = []
             self._lib.elfb200_destroy(self._ctx)
             self._ctx = None
 

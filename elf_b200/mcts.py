@@ -28,6 +28,9 @@ class MctsBatch:
         self.options = o
         self._m = _l.vp()
         _l.check(self._lib, self._lib.elfb200_mcts_create(go_batch._ctx, ctypes.byref(o), ctypes.byref(self._m)))
+        import weakref
+
+        go_batch._children.append(weakref.ref(self))
         n = go_batch.board_size
         self.waves_per_move = self._lib.elfb200_mcts_waves_per_move(self._m)
         self.max_leaves = self._lib.elfb200_mcts_max_leaves(self._m)
