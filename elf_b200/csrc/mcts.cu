@@ -575,39 +575,77 @@ __global__ void __launch_bounds__(BLOCK)
 // ---------------------------------------------------------------------------------------
 // Backup: batch_rollouts' second half (tree_search.h:245-259) + NodeT::updateEdgeStats
 // (tree_search_node.h:253-278).  One unique leaf = one visit; duplicates only return their
-// virtual loss.  One thread per game (the walk is a dependent pointer chase).
-__global__ void k_backup(int G, TreeDev tr, int virtual_loss) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+// virtual loss.  One warp per game, one lane per rollout of the wave: the lanes climb their paths
+// in lock step by ply (deepest first); lanes standing on the same node form a group
+// (__match_any_sync) whose lowest lane applies the group's rewards to the edge above IN LANE
+// ORDER -- the same float additions, in the same order, as backing the unique leaves up one after
+// the other in first-occurrence order.
+__global__ void __launch_bounds__(BLOCK) k_backup(int G, TreeDev tr, int virtual_loss) {
+  __shared__ float s_rew[WARPS][32];
+  __shared__ int s_cnt[WARPS][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= G || !tr.active[g]) return;
   const size_t nb = (size_t)g * tr.C;
   const int B = tr.B, E = tr.E;
   const uint16_t* lv = tr.leaves + (size_t)g * B;
-  for (int j = 0; j < B; ++j) {
-    const int leaf = lv[j];
-    bool first = true;
+  const int root = tr.root[g];
+  const int rootply = tr.meta[nb + root].ply;
+  for (int c0 = 0; c0 < B; c0 += 32) {
+    const int j = c0 + lane;
+    const bool has = j < B;
+    const int leaf = has ? (int)lv[j] : -1;
     int count = 0;
-    for (int k = 0; k < B; ++k) {
-      if (lv[k] == leaf) {
-        if (k < j) first = false;
-        count++;
+    bool first = has;
+    if (has)
+      for (int k = 0; k < B; ++k) {
+        if ((int)lv[k] == leaf) {
+          if (k < j) first = false;
+          count++;
+        }
       }
+    bool act = has && first;
+    s_rew[wib][lane] = act ? tr.hdr[nb + leaf].V : 0.f;
+    s_cnt[wib][lane] = count;
+    __syncwarp();
+    int node = act ? leaf : -1;
+    int ply = act ? (int)tr.meta[nb + leaf].ply : -1;
+    int maxply = ply;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) maxply = max(maxply, __shfl_xor_sync(FULL, maxply, d));
+    for (int P = maxply; P > rootply; --P) {
+      const bool on = act && ply == P;
+      int par = NONE16, pedge = 0;
+      if (on) {
+        const NodeHdr h = load_hdr(&tr.hdr[nb + node]);
+        par = h.parent;
+        pedge = h.parent_edge;
+      }
+      const unsigned grp = __match_any_sync(FULL, on ? node : -1 - lane);
+      if (on && (__ffs(grp) - 1) == lane && par != NONE16) {
+        float4 e = tr.estat[(nb + par) * E + pedge];
+        float wsum = e.z;
+        int m = 0, cnt = 0;
+        for (unsigned mm = grp; mm; mm &= mm - 1) {
+          const int l = __ffs(mm) - 1;
+          wsum += s_rew[wib][l];
+          cnt += s_cnt[wib][l];
+          m++;
+        }
+        e.z = wsum;
+        e.y = __int_as_float(__float_as_int(e.y) + m);
+        e.w = __uint_as_float(__float_as_uint(e.w) - (virtual_loss > 0 ? (uint32_t)cnt : 0u));
+        tr.estat[(nb + par) * E + pedge] = e;
+        atomicAdd(&tr.hdr[nb + par].num_visits, m);  // siblings' leaders may share the parent
+      }
+      if (on) {
+        node = par;
+        ply = P - 1;
+        if (par == NONE16) act = false;
+      }
+      __syncwarp();
     }
-    if (!first) continue;
-    const float reward = tr.hdr[nb + leaf].V;
-    const uint32_t dunits = virtual_loss > 0 ? (uint32_t)count : 0u;  // one application per descent
-    int node = leaf;
-    while (true) {
-      const NodeHdr h = load_hdr(&tr.hdr[nb + node]);
-      if (h.parent == NONE16) break;
-      const int p = h.parent;
-      tr.hdr[nb + p].num_visits += 1;
-      float4 e = tr.estat[(nb + p) * E + h.parent_edge];
-      e.z += reward;
-      e.y = __int_as_float(__float_as_int(e.y) + 1);
-      e.w = __uint_as_float(__float_as_uint(e.w) - dunits);  // low 16 bits: virtual-loss applications
-      tr.estat[(nb + p) * E + h.parent_edge] = e;
-      node = p;
-    }
+    __syncwarp();
   }
 }
 
@@ -1146,7 +1184,7 @@ int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float
     CK(cudaGetLastError());
   }
   CK(cudaEventRecord(m->ev[5], c->stream));
-  k_backup<<<(c->G + 63) / 64, 64, 0, c->stream>>>(c->G, m->tr, m->so.virtual_loss);
+  k_backup<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->so.virtual_loss);
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(m->ev[6], c->stream));

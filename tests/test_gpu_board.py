@@ -229,3 +229,23 @@ def test_stream_playout_matches_oracle(n, G, budget, oracle_lib):
     if budget > 2 * n * n // 2:
         assert (res["games"] >= 2).any()
     gb.close()
+
+
+def test_config5_small_board_stress(oracle_lib):
+    """BASELINE config 5: 9x9, 16384 concurrent games (three games per warp): deterministic,
+    ply counts in range, sampled exact parity with the oracle, stream mode consistent."""
+    n, G = 9, 16384
+    gb = _gobatch(G, n)
+    a = gb.playout(seed=9, first_game_id=0)
+    b = gb.playout(seed=9, first_game_id=0)
+    np.testing.assert_array_equal(a["chk"], b["chk"])
+    assert (a["plies"] > 20).all() and (a["plies"] <= 2 * n * n).all()
+    for g in np.linspace(0, G - 1, 64).astype(int):
+        t, chk, sc = oracles.oracle_playout(n, 9, int(g), lib=oracle_lib)
+        assert (t, chk, sc) == (int(a["plies"][g]), int(a["chk"][g]), int(a["score"][g]))
+    s = gb.playout_stream(seed=9, first_game_id=0, plies_per_slot=300)
+    assert (s["plies"] == 300).all() and (s["games"] >= 2).all()
+    for slot in (0, 5, 16383):
+        t, acc, games = oracles.oracle_playout_stream(n, 9, 0, slot, G, 300, lib=oracle_lib)
+        assert (acc, games) == (int(s["chk"][slot]), int(s["games"][slot]))
+    gb.close()
