@@ -1,0 +1,97 @@
+"""Self-play game records in the reference's wire format.
+
+Mirrors ``GoStateExt::addMCTSPolicy`` / ``dumpRecord`` (``src_cpp/elfgames/go/common/
+go_state_ext.h:128-195``) and the JSON layout of ``Record`` / ``MsgResult`` / ``MsgRequest``
+(``common/record.h:20-260``): the move list as the SGF-like string of ``coords2sgfstr``
+(``sgf/sgf.h:46-95``), one u8-quantised MCTS policy per recorded move indexed by the reference's
+expanded coordinate (``(y+1)*(N+2) + (x+1)``, pass = 0), the predicted values, the final reward.
+Host-side bookkeeping only: nothing here touches the GPU.
+"""
+import json
+import time
+
+import numpy as np
+
+
+def action_to_coord(a, n):
+    """action x*N+y (pass N*N) -> reference Coord (expanded (N+2)^2 board, M_PASS = 0)"""
+    if a == n * n:
+        return 0
+    x, y = a // n, a % n
+    return (y + 1) * (n + 2) + (x + 1)
+
+
+def coord2str(a, n):  # sgf.h:46-55: 'a'+x, 'a'+y; pass -> ""
+    if a == n * n:
+        return ""
+    return chr(97 + a // n) + chr(97 + a % n)
+
+
+def moves_to_sgf(actions, n):  # coords2sgfstr, sgf.h:87-95 (colour alternates with the index)
+    return "(" + "".join(";" + ("B" if i % 2 == 0 else "W") + "[" + coord2str(a, n) + "]"
+                         for i, a in enumerate(actions)) + ")"
+
+
+def quantise_policy(visits_row, n):
+    """addMCTSPolicy: normalised visit policy (MCTSPolicy::normalize, t = 1) scaled so that the most
+    visited move maps to 255, truncated to u8, stored at the move's expanded coordinate."""
+    out = [0] * ((n + 2) * (n + 2))
+    idx = np.flatnonzero(visits_row >= 0)
+    v = visits_row[idx].astype(np.float32)
+    s = np.float32(v.sum(dtype=np.float32))
+    if s <= 0:
+        return out
+    p = v / s
+    mx = np.float32(p.max())
+    q = (p / mx * np.float32(255)).astype(np.float32)
+    for a, c in zip(idx, q):
+        out[action_to_coord(int(a), n)] = int(c)
+    return out
+
+
+class GameRecorder:
+    """per-slot accumulation of one game's record fields"""
+
+    def __init__(self, n, thread_id, policy_distri_cutoff, policy_distri_training_for_all=False):
+        self.n = n
+        self.thread_id = thread_id
+        self.cutoff = policy_distri_cutoff
+        self.for_all = policy_distri_training_for_all
+        self.seq = 0
+        self.restart()
+
+    def restart(self):
+        self.moves = []
+        self.policies = []
+        self.values = []
+
+    def on_move(self, ply_before, action, visits_row, predicted_value):
+        if self.for_all or ply_before <= self.cutoff:  # mcts_make_diverse_move, game_selfplay.cc:88-93
+            self.policies.append(quantise_policy(visits_row, self.n))
+        self.values.append(float(predicted_value))  # addPredictedValue
+        if action >= 0:
+            self.moves.append(int(action))
+
+    def finish(self, final_value, never_resign, model_ver=-1, resign_thres=0.0, never_resign_prob=0.0):
+        rec = {
+            "request": {
+                "vers": {"black_ver": model_ver, "white_ver": -1, "mcts_opt": {}},
+                "client_ctrl": {"client_type": 1, "num_game_thread_used": -1, "black_resign_thres": resign_thres,
+                                "white_resign_thres": resign_thres, "never_resign_prob": never_resign_prob,
+                                "player_swap": False, "async": False},
+            },
+            "result": {
+                "num_move": len(self.moves), "reward": float(final_value),
+                "black_never_resign": bool(never_resign), "white_never_resign": bool(never_resign),
+                "using_models": [model_ver], "content": moves_to_sgf(self.moves, self.n),
+                "policies": self.policies, "values": self.values,
+            },
+            "timestamp": int(time.time()), "thread_id": self.thread_id, "seq": self.seq, "pri": 0.0, "offline": False,
+        }
+        self.seq += 1
+        self.restart()
+        return rec
+
+
+def dumps(records):
+    return json.dumps(records)

@@ -19,7 +19,8 @@ from .mcts import MctsBatch
 
 class SelfPlay:
     def __init__(self, actor, num_games=4096, board_size=19, device=0, policy_distri_cutoff=20,
-                 resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0, **mcts_opts):
+                 resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0,
+                 record_games=False, **mcts_opts):
         self.gb = GoBatch(num_games, board_size=board_size, device=device)
         mcts_opts.setdefault("komi", komi)
         self.mcts = MctsBatch(self.gb, **mcts_opts)
@@ -36,6 +37,12 @@ class SelfPlay:
         self.moves_played = 0
         self.games_finished = 0
         self.results = []  # (final_value, plies, reason) of finished games
+        self.records = []  # reference-format game records (elf_b200.record) when record_games is on
+        self.recorders = None
+        if record_games:
+            from .record import GameRecorder
+
+            self.recorders = [GameRecorder(board_size, g, policy_distri_cutoff) for g in range(num_games)]
 
     def close(self):
         self.mcts.close()
@@ -66,6 +73,9 @@ class SelfPlay:
         val = np.where(info[:, 1] == 1, res["best_q"], -res["best_q"])
         resign = (~self.never_resign) & (val < -1.0 + self.resign_thres) & (info[:, 0] >= 50)
         acts[resign] = -1
+        if self.recorders is not None:
+            for g in range(self.G):
+                self.recorders[g].on_move(int(info[g, 0]), int(acts[g]), res["visits"][g], float(res["best_q"][g]))
         ok = self.gb.forward(acts)
         assert ok[~resign].all(), "MCTS proposed an illegal move"
         self.mcts.advance(acts)
@@ -83,6 +93,10 @@ class SelfPlay:
                     fv = float(final[g])
                     why = "two_pass" if info2[g, 10] else ("superko" if info2[g, 11] else "max_step")
                 self.results.append((fv, int(info2[g, 0]), why))
+                if self.recorders is not None:
+                    self.records.append(self.recorders[g].finish(fv, bool(self.never_resign[g]),
+                                                                 resign_thres=self.resign_thres,
+                                                                 never_resign_prob=self.never_resign_ratio))
             m = done.astype(np.uint8)
             self.gb.reset(m)
             self.mcts.reset(m)

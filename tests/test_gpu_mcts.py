@@ -217,7 +217,8 @@ def test_selfplay_driver_smoke():
     n, G = 9, 32
     net = PolicyValueNet(n, num_block=2, dim=32).cuda()
     sp = elf_b200.selfplay.SelfPlay(Actor(net, batchsize=64, dtype=torch.float32, channels_last=False), num_games=G, board_size=n, policy_distri_cutoff=4,
-                                    num_rollouts=32, num_rollouts_per_batch=4, move_cutoff=30, seed=1)
+                                    num_rollouts=32, num_rollouts_per_batch=4, move_cutoff=30, seed=1,
+                                    record_games=True)
     total = 0
     for _ in range(36):
         total += sp.step()
@@ -225,6 +226,11 @@ def test_selfplay_driver_smoke():
     assert sp.games_finished >= G  # move_cutoff 30 forces restarts
     assert all(abs(fv) <= n * n + 7.5 for fv, _, _ in sp.results)
     assert (sp.mcts.errors() == 0).all()
+    # reference-format records: one per finished game, policies for the first `cutoff` plies only
+    assert len(sp.records) == sp.games_finished
+    r0 = sp.records[0]["result"]
+    assert r0["content"].startswith("(;B[") and len(r0["policies"]) == 4 and len(r0["policies"][0]) == 121
+    assert len(r0["values"]) >= r0["num_move"] >= 28
     sp.close()
 
 
