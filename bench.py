@@ -36,6 +36,15 @@ SEED = 20260922
 ALGO_BYTES_PER_PLY = 264 + 184  # step + legal mask, 19x19
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture, or None"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -319,9 +328,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": 24 * G, "note": "inputs are 3 scalars (seed, first id, plies per slot) passed as kernel params"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_playout<19>",
+                         "traffic": measured_traffic("k_playout<19>"), "peak_source": peak_src, "kernel": "k_playout<19>",
                          "algorithmic_bytes_per_ply": ALGO_BYTES_PER_PLY,
-                         "note": "state lives in registers; kernel is issue/latency bound, see DESIGN.md"},
+                         "note": "position and group masks live in registers, the superko record in L2: DRAM is idle and the kernel is bound by the integer ALU pipe (profiles/r1_playout_F.md)"},
             "clocks": clocks, "wall_s_timed_region": t_wall, "parity_spot_check": parity,
             "batch_to_terminal": {"value": tt_plies / (tt_ms / 1e3) * 1.0, "unit": "moves/s (this rank)",
                                   "ms_per_batch": tt_ms / max(1, min(args.steps, 10)),
