@@ -433,14 +433,17 @@ __device__ __forceinline__ int play_move_cached(uint32_t& b, uint32_t& w, BoardM
   const bool is_stone = p >= 0;
   uint32_t own = player == S_BLACK ? b : w;
   uint32_t opp = player == S_BLACK ? w : b;
-  const int y = is_stone ? p / N : 0, x = is_stone ? p - y * N : 0;
-  const uint32_t mybit = (is_stone && L.row == y && L.active) ? (1u << x) : 0u;
-  const uint32_t nb = nbr4<N>(mybit, L) & L.rm;
+  const int y = is_stone ? p / N : -9, x = is_stone ? p - y * N : 0;
+  // the new stone and its (<= 4) neighbour points, straight from (x, y): no shuffles
+  const int dy = L.row - y;
+  const uint32_t xb = 1u << x;
+  const uint32_t mybit = (dy == 0 && L.active) ? xb : 0u;
+  const uint32_t nb = (dy == 0 ? ((xb << 1) | (xb >> 1)) : ((dy == 1 || dy == -1) ? xb : 0u)) & L.rm;
   const bool single = !game_any<N>((nb & own) != 0u, L);
   own |= mybit;
   uint64_t dh = 0;
   int ncap = 0;
-  uint32_t dead = 0;
+  uint32_t dead = 0, dead_nb = 0;
   // captures (board.cc:1346-1369): enemy neighbour groups whose only liberty was this point
   const uint32_t dseed = nb & opp & atari;
   if (__any_sync(FULL, dseed != 0u)) {
@@ -450,6 +453,7 @@ __device__ __forceinline__ int play_move_cached(uint32_t& b, uint32_t& w, BoardM
     safe &= ~dead;
     atari &= ~dead;
     dh = zob_color(game_xor64<N>(zob_row<N>(zob, L.row, dead), L), oppc);
+    dead_nb = nbr4<N>(dead, L);
   }
   if (is_stone) {
     hash ^= dh ^ zob_color(zob[(y + 1) * Geo<N>::E + (x + 1)], player);
@@ -462,34 +466,42 @@ __device__ __forceinline__ int play_move_cached(uint32_t& b, uint32_t& w, BoardM
   const uint32_t stones = own | opp;
   const uint32_t e2 = ~stones & L.rm;
   const int libs = game_sum<N>(__popc(nb & e2), L);
-  {
+  if (__any_sync(FULL, dead != 0u)) {
     uint32_t bal = __ballot_sync(FULL, dead != 0u) & L.segmask;
     int src = __ffs(bal) - 1;
     int dx = __shfl_sync(FULL, __ffs(dead) - 1, src & 31);
-    if (is_stone) {
-      if (ncap == 1 && single && libs == 1) {  // simple ko, board.cc:1384-1393
-        meta.ko_pt = (int16_t)((src - L.base) * N + dx);
-        meta.ko_color = (uint8_t)oppc;
-        meta.flags |= F_KO_ACTIVE;
-      } else {
-        meta.flags &= ~F_KO_ACTIVE;
-      }
+    if (is_stone && ncap == 1 && single && libs == 1) {  // simple ko, board.cc:1384-1393
+      meta.ko_pt = (int16_t)((src - L.base) * N + dx);
+      meta.ko_color = (uint8_t)oppc;
+      meta.flags |= F_KO_ACTIVE;
+    } else if (is_stone) {
+      meta.flags &= ~F_KO_ACTIVE;
     }
+  } else if (is_stone) {
+    meta.flags &= ~F_KO_ACTIVE;  // no capture, no new ko: _ko_age++ (board.cc:1391)
   }
   // recount the groups whose liberties may have changed
-  uint32_t seeds = (mybit | nb | nbr4<N>(dead, L)) & stones;
+  uint32_t seeds = (mybit | nb | dead_nb) & stones;
+  if (single) {
+    // the new stone is a group of its own: its liberties are the empty neighbour points
+    if (libs == 1) atari |= mybit; else safe |= mybit;
+    seeds &= ~mybit;
+  }
   if (__any_sync(FULL, seeds != 0u)) {
     const Links k = make_links<N>(own, opp, L);
+    const uint32_t linked = k.l | k.r | k.u | k.d;  // stones with a same-colour neighbour
     while (true) {
       const uint32_t bal = __ballot_sync(FULL, seeds != 0u) & L.segmask;
       const int src = __ffs(bal) - 1;
       uint32_t grp = (L.lane == src) ? (seeds & (0u - seeds)) : 0u;
-      while (true) {
-        const uint32_t g1 = grow_link(grp, k);
-        const uint32_t g2 = grow_link(g1, k);
-        const bool ch = g2 != grp;
-        grp = g2;
-        if (!__any_sync(FULL, ch)) break;
+      if (__any_sync(FULL, (grp & linked) != 0u)) {  // single stones need no fill
+        while (true) {
+          const uint32_t g1 = grow_link(grp, k);
+          const uint32_t g2 = grow_link(g1, k);
+          const bool ch = g2 != grp;
+          grp = g2;
+          if (!__any_sync(FULL, ch)) break;
+        }
       }
       const int nl = game_sum<N>(__popc(nbr4<N>(grp, L) & e2), L);
       if (nl == 1) {
