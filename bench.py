@@ -149,7 +149,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -341,7 +341,7 @@ def run_ours(args):
             line["cpu_baseline"] = {
                 "value": cb["moves"] / cb["seconds"], "unit": "moves/s", "cores": cb["cores"], "kind": cb["kind"],
                 "sample": f"{cb['games']} playouts of the same workload in {cb['seconds']:.1f} s on {cb['cores']} threads"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     gb.close()
     if dist is not None:
         dist.barrier()
@@ -503,7 +503,7 @@ def run_mcts(args):
                 line["cpu_baseline"] = {"value": cb["moves"] / cb["seconds"], "unit": "moves/s", "cores": cb["cores"],
                                         "kind": "reference",
                                         "sample": f"reference TreeSearchT, {R} rollouts/move, 1 search thread per game, fake net (no NN cost), {cb['moves']} moves in {cb['seconds']:.1f} s on {cb['cores']} threads"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     sp.close()
     if dist is not None:
         dist.barrier()
@@ -511,7 +511,22 @@ def run_mcts(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else any library prints (e.g. the
+    'NCCL version' banner) was re-routed to stderr in main()"""
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)  # fd 1 -> stderr for native libraries and stray prints
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
