@@ -339,3 +339,63 @@ def test_root_dirichlet_noise(alpha):
     res2 = mc.results()
     assert (res2["total_visits"] >= 32).all()
     assert (mc.errors() == 0).all()
+
+
+def test_gpu_search_with_a_real_network_matches_reference():
+    """Full loop with a real (small, random-init, fp32) policy/value network: the reference search
+    evaluates the net on the planes ITS extractor produced, the GPU search on the planes OUR leaf
+    feature kernel produced; the same CPU network instance, one position per call (so results do not
+    depend on batch composition).  Identical planes -> identical pi/V -> identical root visits."""
+    import torch
+    import elf_b200
+    from elf_b200.model import PolicyValueNet
+
+    n = 9
+    if not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built")
+    torch.manual_seed(7)
+    torch.set_num_threads(1)
+    net = PolicyValueNet(n, num_block=2, dim=16).eval()
+    G, P1 = 3, n * n + 1
+    opts = dict(num_rollouts=96, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5)
+
+    def eval_cpu(planes):  # planes: numpy [k,18,n,n]
+        pis, vs = [], []
+        with torch.no_grad():
+            for i in range(planes.shape[0]):
+                out = net(torch.from_numpy(np.ascontiguousarray(planes[i:i + 1])))
+                pis.append(out["pi"][0].numpy().copy())
+                vs.append(float(out["V"].reshape(-1)[0]))
+        return np.stack(pis).astype(np.float32), np.array(vs, np.float32)
+
+    rng = np.random.default_rng(31)
+    gb = elf_b200.GoBatch(G, board_size=n)
+    refs = [oracles.Ref(n) for _ in range(G)]
+    for _ in range(24):
+        acts = np.empty(G, np.int32)
+        for g, r in enumerate(refs):
+            idx = np.flatnonzero(r.legal())
+            acts[g] = int(rng.choice(idx))
+            r.forward(acts[g])
+        gb.forward(acts)
+    rms = [oracles.RefMcts(n, callback=lambda f, h: eval_cpu(f), **opts) for _ in range(G)]
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, **opts)
+
+    def actor(batch):
+        pi, v = eval_cpu(batch["s"].cpu().numpy())
+        return {"pi": torch.from_numpy(pi).to(mc.device), "V": torch.from_numpy(v).to(mc.device)}
+
+    worst = 0
+    for mv in range(4):
+        res = mc.act(actor)
+        acts = np.empty(G, np.int32)
+        for g in range(G):
+            rr = rms[g].act(refs[g])
+            assert ((res["visits"][g] >= 0) == (rr["visits"] >= 0)).all()
+            worst = max(worst, int(np.abs(res["visits"][g] - rr["visits"]).max()))
+            acts[g] = rr["best_action"]
+            refs[g].forward(acts[g])
+        gb.forward(acts)
+        mc.advance(acts)
+    assert worst <= 1, worst
+    print("real-network parity: worst visit deviation", worst)

@@ -17,6 +17,8 @@ SCENARIOS = {
                              opts=dict(num_rollouts=200, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1, c_puct=1.5)),
     "19_fresh_b1": dict(n=19, G=2, moves=3, open_plies=30,
                         opts=dict(num_rollouts=96, num_rollouts_per_batch=1, virtual_loss=0, persistent_tree=0, c_puct=0.85)),
+    "19_midgame_800": dict(n=19, G=2, moves=2, open_plies=60,
+                           opts=dict(num_rollouts=800, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1, c_puct=1.5)),
     "9_endgame": dict(n=9, G=6, moves=12, open_plies=60,
                       opts=dict(num_rollouts=160, num_rollouts_per_batch=4, virtual_loss=2, persistent_tree=1, c_puct=1.5)),
     "9_uqz_pass": dict(n=9, G=4, moves=10, open_plies=50,
