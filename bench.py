@@ -33,7 +33,7 @@ import numpy as np  # noqa: E402
 BOARD = 19
 GAMES_PER_GPU = 4096
 SEED = 20260922
-ALGO_BYTES_PER_PLY = 264 + 184  # step + legal mask, 19x19
+ALGO_BYTES_PER_PLY = 264 + 184  # step + legal mask, 19x19 (9x9: 2*(32+32)+8 + 32+32+24 = 224)
 
 
 def measured_traffic(kernel):
@@ -222,7 +222,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    G = GAMES_PER_GPU
+    G = args.games
     gb = elf_b200.GoBatch(G, board_size=BOARD, device=local)
     stream = torch.cuda.ExternalStream(gb.stream, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
@@ -292,6 +292,27 @@ def run_ours(args):
         tt_plies += gb.playout_results()["total_plies"]
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- secondary: the step API (GoState::forward for the whole batch per call, HOST buffers) --------
+    step_api = None
+    if rank == 0:
+        try:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"playouts_{BOARD}.json")))
+            mv = next(e["moves"] for e in gold["games"] if "moves" in e)
+            gb.reset()
+            acts = np.empty(G, np.int32)
+            gb.forward(np.full(G, mv[0], np.int32))
+            gb.reset()
+            t_s = time.perf_counter()
+            for a in mv:
+                acts.fill(a)
+                ok = gb.forward(acts)  # H2D actions, k_step, D2H accept flags, sync
+            dt_s = time.perf_counter() - t_s
+            step_api = {"value": G * len(mv) / dt_s, "unit": "moves/s", "us_per_call": 1e6 * dt_s / len(mv),
+                        "all_accepted": bool(ok.all()), "h2d_bytes_per_call": 4 * G, "d2h_bytes_per_call": G,
+                        "note": "elfb200_step(): every game replays one reference move list, one call per ply"}
+        except Exception as e:
+            step_api = f"unmeasured: {e}"
+
     # ---- spot parity of timed work (rank 0): a few games of step 0 against the oracle ------------
     parity = None
     if rank == 0:
@@ -315,12 +336,13 @@ def run_ours(args):
         peak, peak_src = measured_peaks()
         value = plies_total / (dev_ms / 1e3)
         per_rank_plies = plies_total / world
-        achieved = ALGO_BYTES_PER_PLY * per_rank_plies / args.steps / (dev_ms / args.steps / 1e3) / 1e9
+        algo = ALGO_BYTES_PER_PLY if BOARD == 19 else 224
+        achieved = algo * per_rank_plies / args.steps / (dev_ms / args.steps / 1e3) / 1e9
         line = {
             "metric": "self-play moves/sec (random-policy playouts, 19x19)", "value": value, "unit": "moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"configs[1]: 4096 concurrent 19x19 games per GPU, random-policy playouts, steady state: every game slot plays {PLIES} plies per step and restarts finished games",
+            "config": {"workload": (f"configs[1]: 4096 concurrent 19x19 games per GPU" if (BOARD, G) == (19, 4096) else f"configs[4]-style: {G} concurrent {BOARD}x{BOARD} games per GPU") + f", random-policy playouts, steady state: every game slot plays {PLIES} plies per step and restarts finished games",
                        "games_per_gpu": G, "board": BOARD, "seed": SEED, "plies_per_step": plies_total / args.steps,
                        "plies_per_slot": PLIES,
                        "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"games sharded x{world}, no collective"},
@@ -328,10 +350,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": 24 * G, "note": "inputs are 3 scalars (seed, first id, plies per slot) passed as kernel params"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("k_playout<19>"), "peak_source": peak_src, "kernel": "k_playout<19>",
-                         "algorithmic_bytes_per_ply": ALGO_BYTES_PER_PLY,
+                         "traffic": measured_traffic("k_playout<19>") if BOARD == 19 else None, "peak_source": peak_src,
+                         "kernel": f"k_playout<{BOARD}>", "algorithmic_bytes_per_ply": algo,
                          "note": "position and group masks live in registers, the superko record in L2: DRAM is idle and the kernel is bound by the integer ALU pipe (profiles/r1_playout_F.md)"},
-            "clocks": clocks, "wall_s_timed_region": t_wall, "parity_spot_check": parity,
+            "clocks": clocks, "wall_s_timed_region": t_wall, "parity_spot_check": parity, "step_api": step_api,
             "batch_to_terminal": {"value": tt_plies / (tt_ms / 1e3) * 1.0, "unit": "moves/s (this rank)",
                                   "ms_per_batch": tt_ms / max(1, min(args.steps, 10)),
                                   "note": "one batch of 4096 games from the empty board to terminated(): includes the ragged tail"},
@@ -523,7 +545,7 @@ def emit(line):
 
 
 def main():
-    global _REAL_STDOUT
+    global _REAL_STDOUT, BOARD
     sys.stdout.flush()
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)  # fd 1 -> stderr for native libraries and stray prints
@@ -537,6 +559,7 @@ def main():
     ap.add_argument("--plies-per-slot", type=int, default=512)
     ap.add_argument("--workload", default="playout", choices=["playout", "mcts"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--board", type=int, default=19, choices=[9, 19])
     ap.add_argument("--rollouts", type=int, default=64)
     ap.add_argument("--per-batch", type=int, default=8)
     ap.add_argument("--blocks", type=int, default=20)
@@ -544,6 +567,7 @@ def main():
     ap.add_argument("--nn-batch", type=int, default=256)
     ap.add_argument("--fake-net", action="store_true")
     args = ap.parse_args()
+    BOARD = args.board
     if args.workload == "mcts" and args.impl == "ours":
         return run_mcts(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
