@@ -139,12 +139,12 @@ def run_reference(args):
     val = tot_moves / tot_s
     sample = f"{gpt} playouts/thread/step x {info['cores']} threads (of the 4096-game batch), {args.steps} steps"
     line = {
-        "impl": "reference", "metric": "self-play moves/sec (random-policy playouts, 19x19)", "value": val,
+        "impl": "reference", "metric": f"self-play moves/sec (random-policy playouts, {BOARD}x{BOARD})", "value": val,
         "unit": "moves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "configs[1]: 4096 concurrent 19x19 games, random-policy playouts to terminal",
-                   "games_per_gpu": GAMES_PER_GPU, "board": BOARD, "seed": SEED},
+        "config": {"workload": f"configs[1]: {args.games} concurrent {BOARD}x{BOARD} games, random-policy playouts (each host thread plays games back to back)",
+                   "games_per_gpu": args.games, "board": BOARD, "seed": SEED},
         "cpu_baseline": {"value": val, "unit": "moves/s", "cores": info["cores"], "kind": info["kind"], "sample": sample},
         "e2e": {"value": val, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -339,7 +339,7 @@ def run_ours(args):
         algo = ALGO_BYTES_PER_PLY if BOARD == 19 else 224
         achieved = algo * per_rank_plies / args.steps / (dev_ms / args.steps / 1e3) / 1e9
         line = {
-            "metric": "self-play moves/sec (random-policy playouts, 19x19)", "value": value, "unit": "moves/s",
+            "metric": f"self-play moves/sec (random-policy playouts, {BOARD}x{BOARD})", "value": value, "unit": "moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": (f"configs[1]: 4096 concurrent 19x19 games per GPU" if (BOARD, G) == (19, 4096) else f"configs[4]-style: {G} concurrent {BOARD}x{BOARD} games per GPU") + f", random-policy playouts, steady state: every game slot plays {PLIES} plies per step and restarts finished games",
