@@ -214,16 +214,36 @@ class Context:
         self._stopped = True
         self._engine.stop()
 
+    def _next_smem(self, label):
+        sms = self._by_label[label]
+        i = self._rr.get(label, 0)
+        self._rr[label] = (i + 1) % len(sms)  # num_recv SharedMems are used round-robin
+        return sms[i]
+
     def wait(self, timeout_usec=0):
         if not self._started or self._stopped:
             raise RuntimeError("Context.wait() outside start()/stop()")
+        # game_start / game_end notifications (batchsize 1, game.py:398-405) come first
+        poll = getattr(self._engine, "poll_event", None)
+        while poll is not None:
+            ev = poll()
+            if ev is None:
+                break
+            label, fields = ev
+            if label not in self._by_label:
+                continue  # the script did not ask for this label
+            sm = self._next_smem(label)
+            for k, val in fields.items():
+                if k in sm._fields:
+                    sm[k].view()[:1] = val
+            sm._eff = 1
+            self._cur = sm
+            return sm
         label = "actor_black"
         sms = self._by_label.get(label)
         if not sms:
             raise RuntimeError("no SharedMem allocated for label 'actor_black'")
-        i = self._rr.get(label, 0)
-        self._rr[label] = (i + 1) % len(sms)  # num_recv SharedMems are used round-robin
-        sm = sms[i]
+        sm = self._next_smem(label)
         n, feats = self._engine.next_batch(sm.getSharedMemOptions().batchsize())
         dst = sm["s"].view()
         dst[:n].copy_(feats, non_blocking=False)
@@ -235,11 +255,21 @@ class Context:
         sm = self._cur
         if sm is None:
             raise RuntimeError("Context.step() without a pending wait()")
+        if sm.getSharedMemOptions().label() in ("game_start", "game_end"):
+            self._cur = None  # notifications carry no reply
+            return
         n = sm._eff
         pi = sm["pi"].view()[:n]
         v = sm["V"].view()[:n]
         self._engine.reply(pi, v)
         self._cur = None
+
+
+class WinRateStats:  # common/game_stats.h:21-68 as exposed to Python (selfplay.py:161-166)
+    def __init__(self, black_wins, white_wins):
+        self.black_wins = int(black_wins)
+        self.white_wins = int(white_wins)
+        self.total_games = self.black_wins + self.white_wins
 
 
 class _Client:
@@ -286,6 +316,12 @@ class SelfPlayEngine:
         self.board_size = selfplay.N
         self.num_action = selfplay.N * selfplay.N + 1
         self.resign_thres = selfplay.resign_thres
+        import collections
+
+        self._events = collections.deque()
+        self.model_version = -1
+        for _ in range(selfplay.G):  # every game thread announces its first game (game_start label)
+            self._events.append(("game_start", {"black_ver": self.model_version, "white_ver": -1}))
         self._wave = None  # (features tensor [n,...], n, offset, pi buffer, v buffer)
         self._wave_idx = 0
         self._in_move = False
@@ -299,8 +335,10 @@ class SelfPlayEngine:
 
     def win_stats(self):
         r = self.sp.results
-        return {"black_wins": sum(1 for fv, _, _ in r if fv > 0), "white_wins": sum(1 for fv, _, _ in r if fv <= 0),
-                "total_games": len(r)}
+        return WinRateStats(sum(1 for fv, _, _ in r if fv > 0), sum(1 for fv, _, _ in r if fv <= 0))
+
+    def poll_event(self):
+        return self._events.popleft() if self._events else None
 
     def _advance_until_leaves(self):
         import torch
@@ -332,7 +370,11 @@ class SelfPlayEngine:
         sp = self.sp
         res = sp.mcts.results()
         sp.resign_thres = self.resign_thres
+        before = sp.games_finished
         sp.finish_move(res, self._info)
+        for _ in range(sp.games_finished - before):  # finish_game -> game_end, restart -> game_start
+            self._events.append(("game_end", {}))
+            self._events.append(("game_start", {"black_ver": self.model_version, "white_ver": -1}))
         self._in_move = False
 
     def next_batch(self, max_n):

@@ -34,6 +34,11 @@ class StubEngine:
     def stop(self):
         self.started = False
 
+    def win_stats(self):
+        from elf_b200 import compat
+
+        return compat.WinRateStats(0, 0)
+
     def next_batch(self, max_n):
         if self.cur is None or self.off >= self.cur.shape[0]:
             n = self.waves[self.w % 2]
@@ -47,6 +52,11 @@ class StubEngine:
 
     def reply(self, pi, v):
         self.replies.append((pi.clone(), v.clone()))
+
+    events = None
+
+    def poll_event(self):
+        return self.events.pop(0) if self.events else None
 
 
 def _load_reference_gcwrapper():
@@ -109,3 +119,38 @@ def test_compat_objects_have_the_pybind_names():
     with pytest.raises(RuntimeError):
         ctx.wait()  # before start()
     assert isinstance(ctx.version(), str)
+
+
+def test_game_start_and_game_end_labels_reach_their_callbacks():
+    """selfplay-mode desc (game.py:375-405): actor_black/actor_white + game_start/game_end with
+    batchsize 1; notifications are delivered through the same wait/step pump."""
+    from elf_b200 import compat
+
+    ref = _load_reference_gcwrapper()
+    eng = StubEngine()
+    eng.events = [("game_start", {"black_ver": 7, "white_ver": -1}), ("game_end", {})]
+    GC = compat.GameContext(eng, batchsize=4)
+    desc = {
+        "actor_black": dict(input=["s"], reply=["pi", "V", "a", "rv"], batchsize=4, timeout_usec=10),
+        "actor_white": dict(input=["s"], reply=["pi", "V", "a", "rv"], batchsize=4, timeout_usec=10),
+        "game_end": dict(batchsize=1),
+        "game_start": dict(batchsize=1, input=["black_ver", "white_ver"], reply=None),
+    }
+    gcw = ref.GCWrapper(GC, 4, desc, num_recv=2, gpu=None, use_numpy=False, params=GC.getParams())
+    log = []
+    n_actor = [0]
+
+    def actor(batch):
+        n = batch["s"].shape[0]
+        n_actor[0] += 1
+        return dict(pi=torch.zeros(n, 82), V=torch.zeros(n), a=torch.zeros(n, dtype=torch.int64), rv=torch.zeros(n, dtype=torch.int64))
+
+    gcw.reg_callback("actor_black", actor)
+    gcw.reg_callback("actor_white", actor)
+    assert gcw.reg_callback_if_exists("game_start", lambda b: log.append(("start", int(b["black_ver"][0]), int(b["white_ver"][0]))))
+    assert gcw.reg_callback_if_exists("game_end", lambda b: log.append(("end", b.GC.getClient().getGameStats().getWinRateStats().total_games)))
+    gcw.start()
+    for _ in range(3):
+        gcw.run()
+    gcw.stop()
+    assert log == [("start", 7, -1), ("end", 0)] and n_actor[0] == 1

@@ -63,5 +63,5 @@ def test_wait_step_pump_plays_games(device_mode):
     ctx.stop()
     assert sp.games_finished >= G and sp.moves_played >= 11 * G
     assert (sp.mcts.errors() == 0).all()
-    assert GC.getClient().getGameStats().getWinRateStats()["total_games"] == sp.games_finished
+    assert GC.getClient().getGameStats().getWinRateStats().total_games == sp.games_finished
     sp.close()
