@@ -239,10 +239,11 @@ class Context:
             sm._eff = 1
             self._cur = sm
             return sm
-        label = "actor_black"
+        nl = getattr(self._engine, "next_label", None)
+        label = nl() if nl is not None else "actor_black"  # which AI's leaves come next
         sms = self._by_label.get(label)
         if not sms:
-            raise RuntimeError("no SharedMem allocated for label 'actor_black'")
+            raise RuntimeError(f"no SharedMem allocated for label '{label}'")
         sm = self._next_smem(label)
         n, feats = self._engine.next_batch(sm.getSharedMemOptions().batchsize())
         dst = sm["s"].view()
@@ -340,6 +341,13 @@ class SelfPlayEngine:
     def poll_event(self):
         return self._events.popleft() if self._events else None
 
+    def _phases(self, info):
+        sp = self.sp
+        if sp.mcts2 is None:
+            return [(sp.mcts, "actor_black", None)]
+        black = info[:, 1] == 1
+        return [(sp.mcts, "actor_black", black.astype(np.uint8)), (sp.mcts2, "actor_white", (~black).astype(np.uint8))]
+
     def _advance_until_leaves(self):
         import torch
 
@@ -347,28 +355,41 @@ class SelfPlayEngine:
         while True:
             if not self._in_move:
                 self._info = sp.gb.info()
-                sp.mcts.begin_move()
+                self._plan = self._phases(self._info)
+                self._phase = 0
+                self._res = []
+                self._plan[0][0].begin_move(self._plan[0][2])
                 self._wave_idx = 0
                 self._in_move = True
-            if self._wave_idx >= sp.mcts.waves_per_move:
-                self._finish_move()
+            mc, label, _ = self._plan[self._phase]
+            if self._wave_idx >= mc.waves_per_move:
+                self._res.append(mc.results())
+                self._phase += 1
+                if self._phase == len(self._plan):
+                    self._finish_move()
+                else:
+                    self._plan[self._phase][0].begin_move(self._plan[self._phase][2])
+                    self._wave_idx = 0
                 continue
-            s = sp.mcts.select()
+            s = mc.select()
             self._wave_idx += 1
             n = s.shape[0]
             if n == 0:
-                sp.mcts.expand_backup(None, None)
+                mc.expand_backup(None, None)
                 continue
             sp.gb.synchronize()
             dev = s.device
-            self._wave = {"s": s, "n": n, "off": 0, "got": 0,
+            self._wave = {"s": s, "n": n, "off": 0, "got": 0, "mc": mc, "label": label,
                           "pi": torch.empty((n, self.num_action), dtype=torch.float32, device=dev),
                           "v": torch.empty((n,), dtype=torch.float32, device=dev)}
             return
 
     def _finish_move(self):
         sp = self.sp
-        res = sp.mcts.results()
+        if len(self._res) == 1:
+            res = self._res[0]
+        else:
+            res = sp.merge_results(self._info[:, 1] == 1, self._res[0], self._res[1])
         sp.resign_thres = self.resign_thres
         before = sp.games_finished
         sp.finish_move(res, self._info)
@@ -376,6 +397,13 @@ class SelfPlayEngine:
             self._events.append(("game_end", {}))
             self._events.append(("game_start", {"black_ver": self.model_version, "white_ver": -1}))
         self._in_move = False
+
+    def next_label(self):
+        if self._wave is None or self._wave["off"] >= self._wave["n"]:
+            if self._wave is not None and self._wave["got"] < self._wave["n"]:
+                raise RuntimeError("wait() called again before step() answered the previous batch")
+            self._advance_until_leaves()
+        return self._wave["label"]
 
     def next_batch(self, max_n):
         if self._wave is None or self._wave["off"] >= self._wave["n"]:
@@ -399,4 +427,4 @@ class SelfPlayEngine:
         w["got"] += k
         if w["got"] >= w["n"]:
             torch.cuda.current_stream(w["pi"].device).synchronize()
-            self.sp.mcts.expand_backup(w["pi"], w["v"])
+            w["mc"].expand_backup(w["pi"], w["v"])

@@ -37,7 +37,7 @@ class MctsBatch:
         self._torch = torch
         self.device = torch.device("cuda", go_batch.device)
         # the leaf feature batch handed to the network: lives on the device, written in place
-        self.feat = torch.empty((self.max_leaves, 18, n, n), dtype=torch.float32, device=self.device)
+        self.feat = torch.zeros((self.max_leaves, 18, n, n), dtype=torch.float32, device=self.device)
         self._stream = torch.cuda.ExternalStream(go_batch.stream, device=self.device)
 
     def close(self):

@@ -20,11 +20,15 @@ from .mcts import MctsBatch
 class SelfPlay:
     def __init__(self, actor, num_games=4096, board_size=19, device=0, policy_distri_cutoff=20,
                  resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0,
-                 record_games=False, **mcts_opts):
+                 record_games=False, actor_white=None, **mcts_opts):
         self.gb = GoBatch(num_games, board_size=board_size, device=device)
         mcts_opts.setdefault("komi", komi)
         self.mcts = MctsBatch(self.gb, **mcts_opts)
         self.actor = actor
+        # evaluation matches (GoGameSelfPlay::_ai2, game_selfplay.cc:366-367): a second AI with its own
+        # tree plays white; both trees follow every move (MCTSAI_T::advanceMoves)
+        self.actor_white = actor_white
+        self.mcts2 = MctsBatch(self.gb, **mcts_opts) if actor_white is not None else None
         self.G = num_games
         self.N = board_size
         self.komi = komi
@@ -46,7 +50,18 @@ class SelfPlay:
 
     def close(self):
         self.mcts.close()
+        if self.mcts2 is not None:
+            self.mcts2.close()
         self.gb.close()
+
+    @staticmethod
+    def merge_results(black_to_move, res_b, res_w):
+        """root statistics of the AI that is to move in each game"""
+        out = {}
+        for k in res_b:
+            m = black_to_move if res_b[k].ndim == 1 else black_to_move[:, None]
+            out[k] = np.where(m, res_b[k], res_w[k])
+        return out
 
     def _choose(self, res, info):
         """mcts_make_diverse_move: sample ~ visits while ply <= cutoff, else most visited."""
@@ -62,7 +77,12 @@ class SelfPlay:
     def step(self):
         """one move of every game; returns the number of moves played"""
         info = self.gb.info()
-        res = self.mcts.act(self.actor)
+        if self.mcts2 is None:
+            res = self.mcts.act(self.actor)
+        else:
+            black = info[:, 1] == 1
+            res = self.merge_results(black, self.mcts.act(self.actor, active=black.astype(np.uint8)),
+                                     self.mcts2.act(self.actor_white, active=(~black).astype(np.uint8)))
         return self.finish_move(res, info)
 
     def finish_move(self, res, info):
@@ -79,6 +99,8 @@ class SelfPlay:
         ok = self.gb.forward(acts)
         assert ok[~resign].all(), "MCTS proposed an illegal move"
         self.mcts.advance(acts)
+        if self.mcts2 is not None:
+            self.mcts2.advance(acts)
         self.moves_played += int((~resign).sum())
         info2 = self.gb.info()
         done = resign | (info2[:, 9] == 1)
@@ -100,6 +122,8 @@ class SelfPlay:
             m = done.astype(np.uint8)
             self.gb.reset(m)
             self.mcts.reset(m)
+            if self.mcts2 is not None:
+                self.mcts2.reset(m)
             self.never_resign[done] = self.rng.random(int(done.sum())) < self.never_resign_ratio
             self.games_finished += int(done.sum())
         return int((~resign).sum())

@@ -65,3 +65,47 @@ def test_wait_step_pump_plays_games(device_mode):
     assert (sp.mcts.errors() == 0).all()
     assert GC.getClient().getGameStats().getWinRateStats().total_games == sp.games_finished
     sp.close()
+
+
+def test_two_models_route_to_actor_black_and_actor_white():
+    """evaluation match (GoGameSelfPlay::_ai2): black's and white's searches keep separate trees
+    and their leaves arrive under the labels actor_black / actor_white."""
+    import elf_b200
+    from elf_b200 import compat
+    from elf_b200.model import Actor, PolicyValueNet
+
+    torch.manual_seed(1)
+    n, G, BS = 9, 8, 32
+    nets = {lab: Actor(PolicyValueNet(n, num_block=1, dim=8).cuda(), batchsize=BS, dtype=torch.float32, channels_last=False)
+            for lab in ("actor_black", "actor_white")}
+    sp = elf_b200.selfplay.SelfPlay(nets["actor_black"], actor_white=nets["actor_white"], num_games=G, board_size=n,
+                                    policy_distri_cutoff=0, num_rollouts=16, num_rollouts_per_batch=4, move_cutoff=10,
+                                    seed=2, rotation_flip=0)
+    GC = compat.GameContext(compat.SelfPlayEngine(sp), batchsize=BS)
+    ctx = GC.ctx()
+    keys = ["s", "pi", "V", "a", "rv"]
+    bufs, counts = {}, {"actor_black": 0, "actor_white": 0}
+    for lab in ("actor_black", "actor_white"):
+        o = ctx.createSharedMemOptions(lab, BS)
+        for _ in range(2):
+            sm = ctx.allocateSharedMem(o, keys)
+            bufs[sm.getSharedMemOptions().idx()] = {k: _alloc(sm[k], True) for k in keys}
+    ctx.start()
+    it = 0
+    while sp.games_finished < G and it < 3000:
+        sm = ctx.wait()
+        lab = sm.getSharedMemOptions().label()
+        k = sm.effective_batchsize()
+        b = bufs[sm.getSharedMemOptions().idx()]
+        out = nets[lab]({"s": b["s"][:k]})
+        b["pi"][:k].copy_(out["pi"])
+        b["V"][:k].copy_(out["V"])
+        torch.cuda.synchronize()
+        ctx.step()
+        counts[lab] += k
+        it += 1
+    ctx.stop()
+    assert counts["actor_black"] > 0 and counts["actor_white"] > 0
+    assert sp.games_finished >= G
+    assert (sp.mcts.errors() == 0).all() and (sp.mcts2.errors() == 0).all()
+    sp.close()
