@@ -3,10 +3,10 @@
 // Kernels (all templated on the board size N in {9, 19}; one game per N-lane warp segment):
 //   k_reset     clear selected games
 //   k_step      GoState::forward for a batch: validate, play, superko, next legal mask
-//   k_export_*  host-facing views (legal/stones/eyes by action index, info words)
-//   k_score     simple_tt_scoring
+//   k_export    host-facing views (legal/stones/eyes by action index, info words, tt score)
 //   k_features  BoardFeature::extractAGZ, float32 [G][18][N][N]
-//   k_playout   whole random-policy games with the position held in registers
+//   k_playout   whole random-policy games with the position (and the incremental safe/atari group
+//               masks) held in registers; to-terminal and steady-state ("stream") modes
 //
 // HBM layout (structure of arrays, G games):
 //   cur   uint64 [G][N]      current position, row y = black_row | white_row << 32

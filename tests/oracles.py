@@ -90,15 +90,6 @@ def load_ref(n):
 class _Base:
     """One game state with the GoState-like observer set used by the tests."""
 
-    def snapshot(self):
-        n = self.n
-        return {
-            "hash": self.hash(),
-            "info": self.info(),
-            "stones": self.stones(),
-            "legal": self.legal(),
-        }
-
 
 class Oracle(_Base):
     def __init__(self, n=19, lib=None):
