@@ -399,3 +399,28 @@ def test_gpu_search_with_a_real_network_matches_reference():
         mc.advance(acts)
     assert worst <= 1, worst
     print("real-network parity: worst visit deviation", worst)
+
+
+def test_node_pool_exhaustion_drops_the_tree_and_keeps_searching():
+    """bounded node pool (documented deviation): when a game's pool cannot hold one more move's
+    worth of nodes the persistent tree is dropped for that game (counter in errors()[1]) and the
+    search carries on from a fresh root; rollouts are all accounted for and no other game is hurt."""
+    import elf_b200
+
+    n, G = 9, 6
+    gb = elf_b200.GoBatch(G, board_size=n)
+    R, B = 32, 4
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, num_rollouts=R, num_rollouts_per_batch=B, nodes_per_game=R + 8)
+    actor = fake_actor(mc, n)
+    drops = 0
+    for mv in range(6):
+        res = mc.act(actor)
+        tv = res["total_visits"]
+        assert ((tv == R - B) | (tv >= R)).all()  # fresh root (first wave expands it) or reused tree
+        a = res["best_action"]
+        assert gb.forward(a).all()
+        mc.advance(a)
+        e = mc.errors()
+        assert e[0] == 0 and e[2] == 0
+        drops = int(e[1])
+    assert drops > 0  # the small pool must have forced at least one drop

@@ -21,6 +21,9 @@ SCENARIOS = {
                            opts=dict(num_rollouts=800, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1, c_puct=1.5)),
     "9_endgame": dict(n=9, G=6, moves=12, open_plies=60,
                       opts=dict(num_rollouts=160, num_rollouts_per_batch=4, virtual_loss=2, persistent_tree=1, c_puct=1.5)),
+    "9_root_uqz_noprior": dict(n=9, G=3, moves=6, open_plies=30,
+                               opts=dict(num_rollouts=80, num_rollouts_per_batch=5, virtual_loss=3, persistent_tree=1, c_puct=1.0,
+                                         root_unexplored_q_zero=1)),
     "9_uqz_pass": dict(n=9, G=4, moves=10, open_plies=50,
                        opts=dict(num_rollouts=120, num_rollouts_per_batch=6, virtual_loss=1, persistent_tree=1, c_puct=2.0,
                                  unexplored_q_zero=1, ply_pass_enabled=40, remove_pass_if_dangerous=0)),
