@@ -40,15 +40,20 @@ def opening(n, G, open_plies, make):
     return states
 
 
-def run_search(sc, make_state, make_mcts):
+def run_search(sc, make_state, make_mcts, forced=None):
+    """search `moves` moves in each of G games; the move played is the searcher's own choice or,
+    when `forced` (a list in the same order as the returned results) is given, that action -- used to
+    keep two implementations on the same trajectory when they break a most-visited TIE differently
+    (the reference resolves ties by unordered_map order, tree_search_base.h:237-294)"""
     states = opening(sc["n"], sc["G"], sc["open_plies"], make_state)
     ms = [make_mcts() for _ in range(sc["G"])]
     out = []
     for _ in range(sc["moves"]):
         for s, m in zip(states, ms):
             r = m.act(s)
+            a = r["best_action"] if forced is None else forced[len(out)]
             out.append(r)
-            s.forward(r["best_action"])
+            s.forward(a)
     return out, sum(m.num_evals() for m in ms)
 
 
@@ -59,10 +64,12 @@ def test_restatement_equals_reference(name, oracle_lib):
     if not oracles.have_ref(n):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
     a, ea = run_search(sc, lambda: oracles.Ref(n), lambda: oracles.RefMcts(n, **sc["opts"]))
-    b, eb = run_search(sc, lambda: oracles.Oracle(n, oracle_lib), lambda: oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]))
+    b, eb = run_search(sc, lambda: oracles.Oracle(n, oracle_lib), lambda: oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]),
+                       forced=[r["best_action"] for r in a])
     assert ea == eb
     for i, (ra, rb) in enumerate(zip(a, b)):
-        assert ra["best_action"] == rb["best_action"], i
+        # same most-visited count (the chosen action itself may differ on an exact tie)
+        assert ra["visits"][ra["best_action"]] == rb["visits"][rb["best_action"]], i
         np.testing.assert_array_equal(ra["visits"], rb["visits"], err_msg=f"step {i}")
         np.testing.assert_array_equal(ra["prior"], rb["prior"], err_msg=f"step {i}")
         np.testing.assert_allclose(ra["wsum"], rb["wsum"], rtol=0, atol=1e-4)
@@ -76,11 +83,12 @@ def test_restatement_equals_golden(name, oracle_lib):
     gold = json.load(open(path))
     sc = SCENARIOS[name]
     n = sc["n"]
-    b, eb = run_search(sc, lambda: oracles.Oracle(n, oracle_lib), lambda: oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]))
+    b, eb = run_search(sc, lambda: oracles.Oracle(n, oracle_lib), lambda: oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]),
+                       forced=[st["best_action"] for st in gold["steps"]])
     assert eb == gold["num_evals"]
     assert len(b) == len(gold["steps"])
     for r, gsv in zip(b, gold["steps"]):
-        assert r["best_action"] == gsv["best_action"]
+        assert r["visits"][r["best_action"]] == gsv["visits"][str(gsv["best_action"])]
         assert r["total_visits"] == gsv["total_visits"]
         vis = {int(a): int(v) for a, v in zip(np.flatnonzero(r["visits"] >= 0), r["visits"][r["visits"] >= 0])}
         assert vis == {int(k): v for k, v in gsv["visits"].items()}
