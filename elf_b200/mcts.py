@@ -42,7 +42,10 @@ class MctsBatch:
 
     def close(self):
         if getattr(self, "_m", None):
-            self._lib.elfb200_mcts_destroy(self._m)
+            # the search handle points into the board context: if that is already gone (interpreter
+            # shutdown can finalise objects in any order) the handle must not be touched any more
+            if getattr(self.gb, "_ctx", None):
+                self._lib.elfb200_mcts_destroy(self._m)
             self._m = None
 
     def __del__(self):
