@@ -405,6 +405,44 @@ def cpu_mcts_rollouts(seconds, rollouts, per_batch):
     return {"moves": sum(done), "seconds": dt, "cores": cores}
 
 
+def cpu_mcts_with_net(seconds, rollouts, per_batch, actor, device):
+    """the reference search (oracle/_ref, one search thread per game, one game
+    per host thread) driving the SAME GPU network through a callback -- what the reference's own
+    batching can extract from the net when it only has the host cores to run the search on."""
+    import torch
+
+    from tests import oracles
+
+    cores = effective_cores()
+    if not oracles.have_ref(BOARD):
+        return None
+    done = [0] * cores
+    evals = [0] * cores
+    t0 = time.perf_counter()
+    deadline = t0 + seconds
+
+    def work(tid):
+        def cb(feats, hashes):
+            with torch.no_grad():
+                out = actor({"s": torch.from_numpy(np.ascontiguousarray(feats)).to(device)})
+            evals[tid] += len(hashes)
+            return out["pi"].float().cpu().numpy(), out["V"].float().reshape(-1).cpu().numpy()
+
+        st = oracles.Ref(BOARD)
+        m = oracles.RefMcts(BOARD, num_rollouts=rollouts, num_rollouts_per_batch=per_batch, virtual_loss=1,
+                            persistent_tree=1, c_puct=1.5, seed=tid, callback=cb)
+        while time.perf_counter() < deadline and not st.terminated():
+            r = m.act(st)
+            st.forward(r["best_action"])
+            done[tid] += 1
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    return {"moves": sum(done), "seconds": dt, "cores": cores, "evals": sum(evals)}
+
+
 def run_mcts(args):
     import torch
 
@@ -519,6 +557,13 @@ def run_mcts(args):
         }
         if not args.fake_net:
             line["weight_broadcast_s"] = t_bcast
+        if world == 1 and not args.no_cpu_baseline and not args.fake_net:
+            cn = cpu_mcts_with_net(min(args.cpu_seconds, 20.0), R, B, actor, dev)
+            if cn:
+                line["cpu_baseline_same_net"] = {
+                    "value": cn["moves"] / cn["seconds"], "unit": "moves/s", "cores": cn["cores"], "kind": "reference",
+                    "nn_positions_per_s": cn["evals"] / cn["seconds"],
+                    "sample": f"reference TreeSearchT on {cn['cores']} host threads (one game each, {B} leaves per NN call) driving the same GPU network: {cn['moves']} moves in {cn['seconds']:.1f} s"}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_mcts_rollouts(min(args.cpu_seconds, 15.0), R, B)
             if cb:
