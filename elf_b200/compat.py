@@ -363,7 +363,6 @@ class SelfPlayEngine:
                 self._in_move = True
             mc, label, _ = self._plan[self._phase]
             if self._wave_idx >= mc.waves_per_move:
-                self._res.append(mc.results())
                 self._phase += 1
                 if self._phase == len(self._plan):
                     self._finish_move()
@@ -386,13 +385,9 @@ class SelfPlayEngine:
 
     def _finish_move(self):
         sp = self.sp
-        if len(self._res) == 1:
-            res = self._res[0]
-        else:
-            res = sp.merge_results(self._info[:, 1] == 1, self._res[0], self._res[1])
         sp.resign_thres = self.resign_thres
         before = sp.games_finished
-        sp.finish_move(res, self._info)
+        sp.finish_move(self._info)
         for _ in range(sp.games_finished - before):  # finish_game -> game_end, restart -> game_start
             self._events.append(("game_end", {}))
             self._events.append(("game_start", {"black_ver": self.model_version, "white_ver": -1}))

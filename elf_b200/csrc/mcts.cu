@@ -713,6 +713,97 @@ __global__ void __launch_bounds__(BLOCK)
 }
 
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float rng_u01(uint64_t key, uint32_t& ctr);  // defined with the root noise below
+
+// Move choice for every game: GoGameSelfPlay::mcts_make_diverse_move / shouldResign
+// (common/game_selfplay.cc:80-95,387-391; game_utils.h:15-54) on the root statistics.
+//   ply <= policy_distri_cutoff : sample the move from the visit distribution
+//       (MCTSPolicy::sampleAction -> elf_utils::sample_multinomial, elf/utils/utils.h:158-181:
+//        rd uniform in [0, sum N), first edge whose running sum exceeds rd);
+//   otherwise                   : the most visited edge (first maximum in edge order);
+//   resign (action -1)          : the side to move's value (best edge W/N, root V if unvisited) is
+//       below -1 + resign_thres, ply >= 50, and the game is not one of the never-resign games.
+// The uniform comes from a counter-based generator (seed, game, ply): same distribution as the
+// reference's per-game mt19937, different stream.  One warp per game.
+template <int N>
+__global__ void __launch_bounds__(BLOCK)
+    k_choose(DevState st, TreeDev tr, int cutoff, float resign_thres, const uint8_t* __restrict__ never_resign,
+             uint64_t seed, int32_t* __restrict__ action_out, float* __restrict__ value_out) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= st.G) return;
+  const int root = tr.root[g];
+  if (!tr.active[g] || root == NONE16) {
+    if (lane == 0) {
+      action_out[g] = -2;  // not searched this move
+      if (value_out) value_out[g] = 0.f;
+    }
+    return;
+  }
+  const size_t nb = (size_t)g * tr.C;
+  const NodeHdr h = load_hdr(&tr.hdr[nb + root]);
+  const BoardMeta meta = load_meta(&st.meta[g]);
+  const float4* es = tr.estat + (nb + root) * tr.E;
+  const uint32_t* el = tr.elink + (nb + root) * tr.E;
+  // most visited + total
+  int bestn = -1, besti = 0x7FFFFFFF, tot = 0;
+  for (int i = lane; i < h.n_edges; i += 32) {
+    const int n = __float_as_int(es[i].y);
+    tot += n;
+    if (n > bestn) {
+      bestn = n;
+      besti = i;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const int on = __shfl_xor_sync(FULL, bestn, d), oi = __shfl_xor_sync(FULL, besti, d);
+    if (on > bestn || (on == bestn && oi < besti)) {
+      bestn = on;
+      besti = oi;
+    }
+    tot += __shfl_xor_sync(FULL, tot, d);
+  }
+  int pick = besti;
+  if ((int)meta.ply <= cutoff && tot > 0) {
+    uint32_t ctr = 0;
+    const uint64_t key = pp_splitmix64(seed ^ ((uint64_t)g << 24) ^ (uint64_t)meta.ply ^ (st.hash[g] << 1));
+    const float rd = rng_u01(key, ctr) * (float)tot;
+    // running sums in edge order: chunked warp scan
+    int base = 0, found = 0x7FFFFFFF;
+    for (int i0 = 0; i0 < h.n_edges && found == 0x7FFFFFFF; i0 += 32) {
+      const int i = i0 + lane;
+      int v = i < h.n_edges ? __float_as_int(es[i].y) : 0;
+      int incl = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const bool hit = i < h.n_edges && rd < (float)(base + incl);
+      const unsigned bal = __ballot_sync(FULL, hit);
+      if (bal) found = i0 + __ffs(bal) - 1;
+      base += __shfl_sync(FULL, incl, 31);
+    }
+    pick = found != 0x7FFFFFFF ? found : (int)h.n_edges - 1;  // sample_multinomial's fall-through
+  }
+  if (lane == 0) {
+    float q = h.V;  // MCTSGoAI::getValue (go/mcts/mcts.h:358-365)
+    if (besti != 0x7FFFFFFF && tot > 0) {
+      const float4 e = es[besti];
+      q = e.z / (float)__float_as_int(e.y);
+    }
+    const float side = meta.next == S_BLACK ? q : -q;  // GoStateExt::shouldResign, go_state_ext.h:207-214
+    const bool nr = never_resign && never_resign[g];
+    const bool resign = !nr && side < -1.0f + resign_thres && (int)meta.ply >= 50;
+    int a = -1;
+    if (!resign) a = (h.n_edges > 0 && pick != 0x7FFFFFFF) ? (int)(el[pick] & 0xFFFFu) : -2;
+    action_out[g] = a;
+    if (value_out) value_out[g] = q;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // SearchTreeT::treeAdvance (tree_search_node.h:420-436): keep the subtree under the played move,
 // free everything else.  One warp per game; BFS over the kept subtree marks it, one sweep frees
 // the rest and rebuilds the free stack.
@@ -1223,6 +1314,32 @@ int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host) {
   k_advance<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->d_actions, m->so.persistent);
   c->launches++;
   CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_choose(elfb200_mcts* m, int policy_distri_cutoff, float resign_thres,
+                        const uint8_t* never_resign_host, uint64_t seed, int32_t* actions_host,
+                        float* values_host) {
+  if (!m || !actions_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t G = c->G;
+  const uint8_t* nr = nullptr;
+  if (never_resign_host) {
+    memcpy(c->h_pin, never_resign_host, G);
+    CK(cudaMemcpyAsync(m->d_mask, c->h_pin, G, cudaMemcpyHostToDevice, c->stream));
+    nr = m->d_mask;
+  }
+  DISPATCH_N(c,
+             (k_choose<19><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, policy_distri_cutoff, resign_thres,
+                                                                      nr, seed, m->d_best, m->d_bestq)),
+             (k_choose<9><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, policy_distri_cutoff, resign_thres,
+                                                                     nr, seed, m->d_best, m->d_bestq)));
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(actions_host, m->d_best, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (values_host) CK(cudaMemcpyAsync(values_host, m->d_bestq, G * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ELFB200_OK;
 }

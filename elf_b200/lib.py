@@ -63,6 +63,7 @@ SIGNATURES = {
     "elfb200_mcts_expand_backup": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_mcts_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
     "elfb200_mcts_advance": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_choose": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_float, vp, ctypes.c_uint64, vp, vp]),
     "elfb200_mcts_errors": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_root_priors": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_eval_count": (ctypes.c_int64, [vp]),

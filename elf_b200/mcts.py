@@ -101,6 +101,18 @@ class MctsBatch:
             self._m, best.ctypes.data, visits.ctypes.data, rootv.ctypes.data, bestq.ctypes.data, tot.ctypes.data))
         return {"best_action": best, "visits": visits, "root_value": rootv, "best_q": bestq, "total_visits": tot}
 
+    def choose(self, policy_distri_cutoff, resign_thres, never_resign=None, seed=0):
+        """device-side move choice (sample ~ visits while ply <= cutoff, else most visited; -1 =
+        resign, -2 = not searched); returns (actions int32[G], values float32[G])"""
+        G = self.gb.num_games
+        a = np.empty(G, np.int32)
+        v = np.empty(G, np.float32)
+        nr = None if never_resign is None else np.ascontiguousarray(never_resign, dtype=np.uint8)
+        _l.check(self._lib, self._lib.elfb200_mcts_choose(
+            self._m, int(policy_distri_cutoff), float(resign_thres), nr.ctypes.data if nr is not None else None,
+            int(seed) & 0xFFFFFFFFFFFFFFFF, a.ctypes.data, v.ctypes.data))
+        return a, v
+
     def advance(self, actions):
         a = np.ascontiguousarray(actions, dtype=np.int32)
         _l.check(self._lib, self._lib.elfb200_mcts_advance(self._m, a.ctypes.data))
@@ -136,6 +148,11 @@ class MctsBatch:
     def act(self, actor, active=None):
         """Run one full search (all waves) with ``actor(batch) -> {"pi", "V"}`` as the network
         callback and return the root statistics.  The callback sees ``batch["s"]`` on the GPU."""
+        self.search(actor, active)
+        return self.results()
+
+    def search(self, actor, active=None):
+        """the search of ``act`` without fetching the root tables (use ``choose`` / ``results``)"""
         torch = self._torch
         self.begin_move(active)
         pad = int(getattr(actor, "batchsize", 0) or 0)
@@ -156,4 +173,3 @@ class MctsBatch:
                 self.expand_backup(pi, v)
             else:
                 self.expand_backup(None, None)
-        return self.results()

@@ -37,6 +37,8 @@ class SelfPlay:
         self.never_resign_ratio = never_resign_ratio
         self.move_cutoff = move_cutoff
         self.rng = np.random.default_rng(seed)
+        self._seed = int(seed)
+        self._move_counter = 0
         self.never_resign = self.rng.random(num_games) < never_resign_ratio
         self.moves_played = 0
         self.games_finished = 0
@@ -63,39 +65,40 @@ class SelfPlay:
             out[k] = np.where(m, res_b[k], res_w[k])
         return out
 
-    def _choose(self, res, info):
-        """mcts_make_diverse_move: sample ~ visits while ply <= cutoff, else most visited."""
-        acts = res["best_action"].copy()
-        ply = info[:, 0]
-        for g in np.flatnonzero(ply <= self.policy_distri_cutoff):
-            v = np.maximum(res["visits"][g], 0).astype(np.float64)
-            tot = v.sum()
-            if tot > 0:
-                acts[g] = int(self.rng.choice(len(v), p=v / tot))
-        return acts
-
     def step(self):
         """one move of every game; returns the number of moves played"""
         info = self.gb.info()
         if self.mcts2 is None:
-            res = self.mcts.act(self.actor)
+            self.mcts.search(self.actor)
         else:
             black = info[:, 1] == 1
-            res = self.merge_results(black, self.mcts.act(self.actor, active=black.astype(np.uint8)),
-                                     self.mcts2.act(self.actor_white, active=(~black).astype(np.uint8)))
-        return self.finish_move(res, info)
+            self.mcts.search(self.actor, active=black.astype(np.uint8))
+            self.mcts2.search(self.actor_white, active=(~black).astype(np.uint8))
+        return self.finish_move(info)
 
-    def finish_move(self, res, info):
-        """everything GoGameSelfPlay::act does after the search returned (game_selfplay.cc:372-429);
-        ``info`` are the games' info words from before the search, ``res`` the root statistics"""
-        acts = self._choose(res, info)
-        # resign check (game_selfplay.cc:387-391, go_state_ext.h:207-214)
-        val = np.where(info[:, 1] == 1, res["best_q"], -res["best_q"])
-        resign = (~self.never_resign) & (val < -1.0 + self.resign_thres) & (info[:, 0] >= 50)
-        acts[resign] = -1
+    def finish_move(self, info, res=None):
+        """everything GoGameSelfPlay::act does after the search returned (game_selfplay.cc:372-429):
+        move choice and resign check on the device (``elfb200_mcts_choose``), ``GoState::forward``,
+        tree advance, game end / restart.  ``info`` are the games' info words from before the search;
+        ``res`` (root tables) is only needed, and fetched, when games are being recorded."""
+        self._move_counter += 1
+        seed = (self._seed << 20) ^ self._move_counter
+        nr = self.never_resign.astype(np.uint8)
+        acts, vals = self.mcts.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
+        if self.mcts2 is not None:
+            black = info[:, 1] == 1
+            a2, v2 = self.mcts2.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
+            acts = np.where(black, acts, a2)
+            vals = np.where(black, vals, v2)
+        resign = acts == -1
+        assert (acts != -2).all(), "a game was not searched"
         if self.recorders is not None:
+            if res is None:
+                res = self.mcts.results()
+                if self.mcts2 is not None:
+                    res = self.merge_results(info[:, 1] == 1, res, self.mcts2.results())
             for g in range(self.G):
-                self.recorders[g].on_move(int(info[g, 0]), int(acts[g]), res["visits"][g], float(res["best_q"][g]))
+                self.recorders[g].on_move(int(info[g, 0]), int(acts[g]), res["visits"][g], float(vals[g]))
         ok = self.gb.forward(acts)
         assert ok[~resign].all(), "MCTS proposed an illegal move"
         self.mcts.advance(acts)

@@ -83,6 +83,16 @@ int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float
  * best_q float[G] (MCTSGoAI::getValue), total_visits int32[G]. */
 int elfb200_mcts_results(elfb200_mcts* m, int32_t* best_action_host, int32_t* visits_host,
                          float* root_value_host, float* best_q_host, int32_t* total_visits_host);
+/* The move every game plays after the search: GoGameSelfPlay::mcts_make_diverse_move +
+ * GoStateExt::shouldResign (common/game_selfplay.cc:80-95,387-391, game_utils.h:15-54).  While
+ * ply <= policy_distri_cutoff the move is sampled from the root visit distribution
+ * (sample_multinomial, elf/utils/utils.h:158-181), afterwards it is the most visited one; a game
+ * resigns (action -1) when the side to move's predicted value is below -1 + resign_thres at
+ * ply >= 50 unless never_resign[g] != 0 (NULL = all games may resign).  actions int32[G]
+ * (-2 = game was not searched), values float[G] = MCTSGoAI::getValue (may be NULL). */
+int elfb200_mcts_choose(elfb200_mcts* m, int policy_distri_cutoff, float resign_thres,
+                        const uint8_t* never_resign_host, uint64_t seed, int32_t* actions_host,
+                        float* values_host);
 /* SearchTreeT::treeAdvance for the move just played in each game (actions[g] < 0: untouched). */
 int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host);
 /* float[G][N*N+1]: current prior of every root edge by action (-1 where the root has no such

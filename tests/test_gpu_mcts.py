@@ -426,3 +426,49 @@ def test_node_pool_exhaustion_drops_the_tree_and_keeps_searching():
         assert e[0] == 0 and e[2] == 0
         drops = int(e[1])
     assert drops > 0  # the small pool must have forced at least one drop
+
+
+def test_device_move_choice_sampling_argmax_and_resign():
+    """elfb200_mcts_choose: sample_multinomial over root visits while ply <= cutoff (empirical
+    frequencies follow N/sum N), most visited afterwards, resignation rule of ResignCheck."""
+    import elf_b200
+
+    n, G = 9, 512
+    gb = elf_b200.GoBatch(G, board_size=n)      # 512 identical games (empty board)
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, num_rollouts=64, num_rollouts_per_batch=4)
+    res = mc.act(fake_actor(mc, n))
+    v = res["visits"][0]
+    assert (res["visits"] == v).all()           # identical games -> identical root tables
+    # beyond the cutoff: the most visited move, for every game
+    a, val = mc.choose(policy_distri_cutoff=0, resign_thres=0.05, seed=1)
+    assert (a == res["best_action"]).all()
+    np.testing.assert_allclose(val, res["best_q"], rtol=0, atol=1e-6)
+    # within the cutoff: sampled ~ visits (different games draw different moves)
+    counts = np.zeros(n * n + 1)
+    for seed in range(8):
+        a, _ = mc.choose(policy_distri_cutoff=5, resign_thres=0.05, seed=seed)
+        assert (v[a] > 0).all()                 # only visited edges can be drawn
+        counts += np.bincount(a, minlength=n * n + 1)
+    p = np.maximum(v, 0) / np.maximum(v, 0).sum()
+    big = p > 0.03
+    np.testing.assert_allclose(counts[big] / counts.sum(), p[big], rtol=0.25)
+    assert len(np.unique(a)) > 3
+    # resign: needs ply >= 50 and value below -1 + thres; with thres = 2 every value qualifies
+    a, _ = mc.choose(policy_distri_cutoff=0, resign_thres=2.0, seed=1)
+    assert (a == res["best_action"]).all()      # ply 1 < 50: nobody resigns
+    gb2 = elf_b200.GoBatch(4, board_size=n)
+    os_ = [oracles.Oracle(n) for _ in range(4)]
+    rng = np.random.default_rng(0)
+    for _ in range(52):
+        acts = np.empty(4, np.int32)
+        for g, s in enumerate(os_):
+            idx = np.flatnonzero(s.legal() & (1 - s.true_eyes(int(s.info()[1]))))
+            acts[g] = int(rng.choice(idx)) if len(idx) else n * n
+            s.forward(acts[g])
+        gb2.forward(acts)
+    mc2 = elf_b200.MctsBatch(gb2, rotation_flip=0, num_rollouts=32, num_rollouts_per_batch=4)
+    mc2.act(fake_actor(mc2, n))
+    a, _ = mc2.choose(policy_distri_cutoff=0, resign_thres=2.0, never_resign=np.array([0, 1, 0, 1], np.uint8), seed=1)
+    assert a[0] == -1 and a[2] == -1 and a[1] >= 0 and a[3] >= 0
+    a, _ = mc2.choose(policy_distri_cutoff=0, resign_thres=0.0, seed=1)
+    assert (a >= 0).all()                        # value can never be below -1
