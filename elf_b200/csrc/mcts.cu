@@ -447,6 +447,48 @@ __global__ void __launch_bounds__(384) k_leaf_features(DevState st, TreeDev tr, 
 }
 
 // ---------------------------------------------------------------------------------------
+// Warp-wide bitonic sort of 32*R 64-bit keys held R per lane (key index i = lane*R + r), ascending.
+// Compare-exchange distances below R stay inside a lane's registers (fully unrolled, static
+// indices); larger distances exchange whole registers with the partner lane via SHFL.
+template <int R>
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[R], int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32 * R; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= R) {  // partner lane, same register
+        const int lj = j / R;
+        const bool lower = (lane & lj) == 0;
+        const bool asc = k >= 32 * R ? true : ((lane & (k / R)) == 0);
+        const bool keep_min = lower == asc;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint64_t mine = key[r];
+          const uint32_t olo = __shfl_xor_sync(FULL, (uint32_t)mine, lj);
+          const uint32_t ohi = __shfl_xor_sync(FULL, (uint32_t)(mine >> 32), lj);
+          const uint64_t other = ((uint64_t)ohi << 32) | olo;
+          const bool mine_small = mine < other;
+          key[r] = (mine_small == keep_min) ? mine : other;
+        }
+      } else {  // inside the lane
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & j) == 0) {
+            const int q = r | j;
+            // ascending block iff bit k of the global index is clear
+            const bool asc = k < R ? ((r & k) == 0) : (k >= 32 * R ? true : ((lane & (k / R)) == 0));
+            const uint64_t a0 = key[r], a1 = key[q];
+            const bool sw = (a0 > a1) == asc;
+            key[r] = sw ? a1 : a0;
+            key[q] = sw ? a0 : a1;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Expansion: MCTSActor::post_nn_result / remove_pass_if_dangerous / pi2response / normalize
 // (go/mcts/mcts.h:209-332) + NodeT::setEvaluation (tree_search_node.h:176-203).  One warp per
 // claimed leaf; the candidate list is bitonic-sorted in shared memory by descending probability.
@@ -485,7 +527,11 @@ __global__ void __launch_bounds__(BLOCK)
   __syncwarp();
   uint64_t* key = s_key[wib];
   const float* pr = pi + (size_t)slot * (P + 1);
-  for (int a = L.lane; a < SORTN; a += 32) {
+  constexpr int R = SORTN / 32;  // keys per lane
+  uint64_t kr[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int a = L.lane + 32 * r;  // any assignment of candidates to slots will do before sorting
     uint64_t k = ~0ull;
     if (a <= P) {
       int act;
@@ -502,25 +548,13 @@ __global__ void __launch_bounds__(BLOCK)
       // probabilities are non-negative floats: their bit patterns order like the values
       if (ok) k = ((uint64_t)(0xFFFFFFFFu - __float_as_uint(pr[a])) << 32) | (uint32_t)act;
     }
-    key[a] = k;
+    kr[r] = k;
   }
+  // ascending on the composite key == descending probability, then action
+  warp_bitonic_sort<R>(kr, L.lane);
+#pragma unroll
+  for (int r = 0; r < R; ++r) key[L.lane * R + r] = kr[r];
   __syncwarp();
-  // bitonic sort ascending on the composite key == descending probability, then action
-  for (int k2 = 2; k2 <= SORTN; k2 <<= 1) {
-    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-      for (int t = L.lane; t < SORTN / 2; t += 32) {
-        const int i = ((t & ~(j2 - 1)) << 1) | (t & (j2 - 1));
-        const int p2 = i | j2;
-        const bool up = (i & k2) == 0;
-        const uint64_t a0 = key[i], a1 = key[p2];
-        if ((a0 > a1) == up) {
-          key[i] = a1;
-          key[p2] = a0;
-        }
-      }
-      __syncwarp();
-    }
-  }
   // count valid, sequential float sum in sorted order (normalize, mcts.h:244-254)
   int nvalid = 0;
   for (int a = L.lane; a < SORTN; a += 32) nvalid += key[a] != ~0ull;
