@@ -481,10 +481,10 @@ def test_selfplay_soak_tree_reuse_over_many_moves():
     import torch
     import elf_b200
 
-    n, G = 9, 64
+    n, G = 9, 32
     sp = elf_b200.selfplay.SelfPlay(None, num_games=G, board_size=n, policy_distri_cutoff=6, resign_thres=0.05,
                                     never_resign_ratio=0.5, num_rollouts=32, num_rollouts_per_batch=4, seed=4,
-                                    rotation_flip=1, record_games=True)
+                                    rotation_flip=1, record_games=True, move_cutoff=45)
 
     def actor(batch):
         h, _, _ = sp.mcts.leaf_info()
@@ -495,7 +495,7 @@ def test_selfplay_soak_tree_reuse_over_many_moves():
 
     sp.actor = actor
     moves = 0
-    for _ in range(260):
+    for _ in range(100):
         moves += sp.step()
     assert sp.games_finished >= G            # every slot finished at least one game on average
     assert moves == sp.moves_played
