@@ -92,3 +92,28 @@ def test_restatement_equals_golden(name, oracle_lib):
         assert r["total_visits"] == gsv["total_visits"]
         vis = {int(a): int(v) for a, v in zip(np.flatnonzero(r["visits"] >= 0), r["visits"][r["visits"] >= 0])}
         assert vis == {int(k): v for k, v in gsv["visits"].items()}
+
+
+def test_restatement_equals_reference_on_random_option_sets(oracle_lib):
+    """fuzz over the search options (rollouts, batch, virtual loss, c_puct, FPU switches, pass
+    rules, tree persistence) and opening lengths: the C restatement must reproduce the reference
+    search's root tables exactly in every configuration."""
+    if not oracles.have_ref(9):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(2026)
+    for case in range(14):
+        opts = dict(
+            num_rollouts=int(rng.integers(8, 90)), num_rollouts_per_batch=int(rng.integers(1, 9)),
+            virtual_loss=int(rng.integers(0, 4)), persistent_tree=int(rng.integers(0, 2)),
+            c_puct=float(rng.choice([0.5, 0.85, 1.5, 2.5, 5.0])), unexplored_q_zero=int(rng.integers(0, 2)),
+            root_unexplored_q_zero=int(rng.integers(0, 2)), ply_pass_enabled=int(rng.choice([0, 30, 70])),
+            remove_pass_if_dangerous=int(rng.integers(0, 2)), komi=float(rng.choice([5.5, 6.5, 7.5])))
+        sc = dict(n=9, G=2, moves=4, open_plies=int(rng.integers(0, 75)), opts=opts)
+        a, ea = run_search(sc, lambda: oracles.Ref(9), lambda: oracles.RefMcts(9, **opts))
+        b, eb = run_search(sc, lambda: oracles.Oracle(9, oracle_lib), lambda: oracles.OracleMcts(9, lib=oracle_lib, **opts),
+                           forced=[r["best_action"] for r in a])
+        assert ea == eb, (case, opts)
+        for i, (ra, rb) in enumerate(zip(a, b)):
+            np.testing.assert_array_equal(ra["visits"], rb["visits"], err_msg=f"case {case} step {i} {opts}")
+            np.testing.assert_array_equal(ra["prior"], rb["prior"], err_msg=f"case {case} step {i}")
+            assert ra["root_value"] == rb["root_value"]
