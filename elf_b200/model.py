@@ -92,6 +92,21 @@ class Actor:
         return {"pi": torch.cat(pis) if len(pis) > 1 else pis[0], "V": torch.cat(vs) if len(vs) > 1 else vs[0]}
 
 
+def load_reference_state_dict(model, state_dict):
+    """Load weights saved from the reference's ``Model_PolicyValue`` (``df_model3.py``): its tower lives
+    one level deeper (``resnet.resnet.<i>...`` because ``GoResNet`` wraps the ``nn.Sequential``) and
+    DataParallel / DDP wrappers prefix ``module.``; everything else has the same names here.
+    Returns (missing, unexpected) like ``load_state_dict(strict=False)``."""
+    sd = state_dict.get("state_dict", state_dict)
+    out = {}
+    for k, v in sd.items():
+        k = k.replace("module.", "")
+        if k.startswith("resnet.resnet."):
+            k = "resnet." + k[len("resnet.resnet."):]
+        out[k] = v
+    return model.load_state_dict(out, strict=False)
+
+
 def broadcast_weights(model, src=0):
     """NCCL broadcast of the frozen weights from rank ``src`` (the only collective of the path)."""
     import torch.distributed as dist

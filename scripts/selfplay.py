@@ -44,7 +44,7 @@ def main():
     import torch
 
     import elf_b200
-    from elf_b200.model import Actor, PolicyValueNet, broadcast_weights
+    from elf_b200.model import Actor, PolicyValueNet, broadcast_weights, load_reference_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -59,8 +59,7 @@ def main():
     net = PolicyValueNet(args.board, num_block=args.blocks, dim=args.dim).to(f"cuda:{local}")
     if args.load and rank == 0:
         sd = torch.load(args.load, map_location=f"cuda:{local}")
-        sd = sd.get("state_dict", sd)
-        missing, unexpected = net.load_state_dict(sd, strict=False)
+        missing, unexpected = load_reference_state_dict(net, sd)
         print(f"[selfplay] loaded {args.load}: {len(missing)} missing / {len(unexpected)} unexpected keys", file=sys.stderr)
     broadcast_weights(net)
     actor = Actor(net, batchsize=args.nn_batch)
