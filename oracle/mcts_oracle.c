@@ -44,6 +44,7 @@ typedef struct {
   int flip;
   Edge* edges;
   int n_edges;
+  int n_touched; /* edges [0, n_touched) have been selected at least once (prefix property check) */
   int parent, parent_edge;
   int alive;
 } Node;
@@ -58,6 +59,8 @@ typedef struct MctsOracle {
   int root;
   int next_move_number;
   long n_evals;
+  long prefix_violations; /* times the arg-max over [0, n_touched] differed from the full arg-max */
+  long prefix_checks;
 } MctsOracle;
 
 static int add_node(MctsOracle* m, float parent_q, int parent, int parent_edge) {
@@ -142,6 +145,12 @@ void mo_free(MctsOracle* m) {
 }
 
 long mo_num_evals(const MctsOracle* m) { return m->n_evals; }
+
+/* The CUDA search only scans the selected prefix of the prior-sorted edges plus the first
+ * never-selected one (k_select); this restatement scans everything, like the reference, and counts
+ * how often the two would disagree (must be 0 unless two priors tie exactly). */
+long mo_prefix_violations(const MctsOracle* m) { return m->prefix_violations; }
+long mo_prefix_checks(const MctsOracle* m) { return m->prefix_checks; }
 
 /* ---- evaluation: MCTSActor::evaluate for one state (go/mcts/mcts.h:73-121,185-332) ---- */
 typedef struct {
@@ -233,8 +242,9 @@ static void batch_rollouts(MctsOracle* m) {
       if (m->uqz || (m->ruqz && depth == 0)) nd->mean_q = 0.0f;
       /* UCT, tree_search_node.h:361-397 + getScore, tree_search_base.h:132-157 */
       const double sq = sqrt((double)(nd->num_visits + 1));
-      float best = -FLT_MAX, tuq = 0.0f;
-      int besti = -1, tv = 0;
+      float best = -FLT_MAX, tuq = 0.0f, best_prefix = -FLT_MAX;
+      int besti = -1, tv = 0, besti_prefix = -1;
+      const int lim = nd->n_touched + 1 < nd->n_edges ? nd->n_touched + 1 : nd->n_edges;
       for (int i = 0; i < nd->n_edges; ++i) {
         const Edge* e = &nd->edges[i];
         float r = nd->flip ? -e->reward : e->reward;
@@ -248,11 +258,19 @@ static void batch_rollouts(MctsOracle* m) {
           best = score;
           besti = i;
         }
+        if (i < lim && score > best_prefix) {
+          best_prefix = score;
+          besti_prefix = i;
+        }
+        if (nwl != 0 && i >= nd->n_touched) m->prefix_violations++; /* a touched edge outside the prefix */
         if (nwl != 0) {
           tuq += uq;
           tv++;
         }
       }
+      m->prefix_checks++;
+      if (besti_prefix != besti) m->prefix_violations++;
+      if (besti == nd->n_touched) nd->n_touched++;
       nd->mean_q = (nd->parent_q + tuq) / (float)(tv + 1); /* findMove, tree_search_node.h:227 */
       Edge* e = &nd->edges[besti];
       if (m->vl > 0) e->vloss += (float)m->vl; /* addVirtualLoss */

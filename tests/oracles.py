@@ -381,6 +381,14 @@ class OracleMcts:
     def num_evals(self):
         return int(self.L.mo_num_evals(self.m))
 
+    def prefix_stats(self):
+        """(violations, checks) of the selected-prefix property the CUDA select kernel relies on"""
+        self.L.mo_prefix_violations.restype = ctypes.c_long
+        self.L.mo_prefix_violations.argtypes = [vp]
+        self.L.mo_prefix_checks.restype = ctypes.c_long
+        self.L.mo_prefix_checks.argtypes = [vp]
+        return int(self.L.mo_prefix_violations(self.m)), int(self.L.mo_prefix_checks(self.m))
+
     def __del__(self):
         if getattr(self, "m", None):
             self.L.mo_free(self.m)

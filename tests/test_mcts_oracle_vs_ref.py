@@ -117,3 +117,20 @@ def test_restatement_equals_reference_on_random_option_sets(oracle_lib):
             np.testing.assert_array_equal(ra["visits"], rb["visits"], err_msg=f"case {case} step {i} {opts}")
             np.testing.assert_array_equal(ra["prior"], rb["prior"], err_msg=f"case {case} step {i}")
             assert ra["root_value"] == rb["root_value"]
+
+
+@pytest.mark.parametrize("name", sorted(SCENARIOS))
+def test_selected_prefix_property(name, oracle_lib):
+    """k_select scans only edges [0, n_touched] of the prior-sorted list.  The restatement scans all
+    edges (as the reference does) and counts every descent step whose full arg-max is not inside
+    that prefix, or that finds a selected edge outside it: must never happen."""
+    sc = SCENARIOS[name]
+    n = sc["n"]
+    states = opening(n, sc["G"], sc["open_plies"], lambda: oracles.Oracle(n, oracle_lib))
+    ms = [oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]) for _ in range(sc["G"])]
+    for _ in range(sc["moves"]):
+        for s, m in zip(states, ms):
+            s.forward(m.act(s)["best_action"])
+    viol = sum(m.prefix_stats()[0] for m in ms)
+    checks = sum(m.prefix_stats()[1] for m in ms)
+    assert checks > 500 and viol == 0, (viol, checks)
