@@ -17,6 +17,7 @@
 #include "elfgames/go/base/board.h"
 #include "elfgames/go/base/board_feature.h"
 #include "elfgames/go/base/go_state.h"
+#include "elfgames/go/sgf/sgf.h"
 
 #include "elfb200_playout_policy.h"
 
@@ -250,6 +251,58 @@ int ref_playout(
   if (out_score)
     *out_score = simple_tt_scoring(s.board());
   return t;
+}
+
+// GoState::showBoard (go_state.h:187-192): the board picture the online console prints.
+int ref_show_board(void* p, char* out, int cap) {
+  std::string s = static_cast<RefState*>(p)->showBoard();
+  if ((int)s.size() + 1 > cap)
+    return -1;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
+// Sgf::load(filename, game_string) + iteration over the main line (sgf.h:158-290, sgf.cc:27-58).
+// Per entry: actions[i] = x*N+y, N*N for pass, -1 for an off-board / unparsable coordinate;
+// players[i] = S_BLACK(1) / S_WHITE(2) / other.  header_i = {size, handi, winner, num_moves},
+// header_f = {komi, win_margin}.  Returns the number of entries on the main line (capped), or -1
+// if the reference refuses the text.
+int ref_sgf_parse(const char* text, int32_t* actions, int32_t* players, int cap, int32_t* header_i,
+                  float* header_f) {
+  Sgf sgf;
+  if (!sgf.load("<mem>", std::string(text)))
+    return -1;
+  const SgfHeader& h = sgf.getHeader();
+  header_i[0] = h.size;
+  header_i[1] = h.handi;
+  header_i[2] = (int)h.winner;
+  header_i[3] = sgf.numMoves();
+  header_f[0] = h.komi;
+  header_f[1] = h.win_margin;
+  int n = 0;
+  for (auto it = sgf.begin(); !it.done() && n < cap; ++it) {
+    SgfMove m = it.getCurrMove();
+    int a;
+    if (m.move == M_PASS)
+      a = BOARD_SIZE * BOARD_SIZE;
+    else if (m.move == M_INVALID || !ON_BOARD(X(m.move), Y(m.move)))
+      a = -1;
+    else
+      a = X(m.move) * BOARD_SIZE + Y(m.move);
+    actions[n] = a;
+    players[n] = (int)m.player;
+    ++n;
+  }
+  return n;
+}
+
+// coord2str2 (sgf.h:73-86): the GTP-style vertex the console prints for the last move.
+int ref_vertex_str(int action, char* out, int cap) {
+  std::string s = coord2str2(action_to_coord(action));
+  if ((int)s.size() + 1 > cap)
+    return -1;
+  std::memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
 }
 
 } // extern "C"

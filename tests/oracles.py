@@ -143,6 +143,43 @@ class Oracle(_Base):
         return bool(self.L.go_terminated(self.p))
 
 
+def ref_sgf_parse(text, n, cap=2048):
+    """the reference's own Sgf::load + main-line iteration (oracle/ref_shim.cc: ref_sgf_parse).
+    Returns None if the reference refuses the text, else a dict."""
+    L = load_ref(n)
+    L.ref_sgf_parse.restype = ctypes.c_int
+    L.ref_sgf_parse.argtypes = [ctypes.c_char_p, vp, vp, ctypes.c_int, vp, vp]
+    acts = np.zeros(cap, np.int32)
+    pl = np.zeros(cap, np.int32)
+    hi = np.zeros(4, np.int32)
+    hf = np.zeros(2, np.float32)
+    k = L.ref_sgf_parse(text.encode("latin-1", "replace"), acts.ctypes.data, pl.ctypes.data, cap, hi.ctypes.data,
+                        hf.ctypes.data)
+    if k < 0:
+        return None
+    return {"actions": acts[:k].tolist(), "players": pl[:k].tolist(), "size": int(hi[0]), "handi": int(hi[1]),
+            "winner": int(hi[2]), "num_moves": int(hi[3]), "komi": float(hf[0]), "win_margin": float(hf[1])}
+
+
+def ref_show_board(ref):
+    L = ref.L
+    L.ref_show_board.restype = ctypes.c_int
+    L.ref_show_board.argtypes = [vp, ctypes.c_char_p, ctypes.c_int]
+    buf = ctypes.create_string_buffer(4096)
+    k = L.ref_show_board(ref.p, buf, 4096)
+    assert k >= 0
+    return buf.value.decode()
+
+
+def ref_vertex_str(n, action):
+    L = load_ref(n)
+    L.ref_vertex_str.restype = ctypes.c_int
+    L.ref_vertex_str.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    buf = ctypes.create_string_buffer(32)
+    assert L.ref_vertex_str(int(action), buf, 32) >= 0
+    return buf.value.decode()
+
+
 class Ref(_Base):
     def __init__(self, n=19):
         self.L = load_ref(n)
