@@ -259,6 +259,11 @@ class Context:
         if sm.getSharedMemOptions().label() in ("game_start", "game_end"):
             self._cur = None  # notifications carry no reply
             return
+        if sm.getSharedMemOptions().label() == "human_actor":
+            # GoFeature::ReplyAction (common/game_feature.h:50-66): only "a" is consumed
+            self._engine.reply_action(int(sm["a"].view().reshape(-1)[0]))
+            self._cur = None
+            return
         n = sm._eff
         pi = sm["pi"].view()[:n]
         v = sm["V"].view()[:n]
@@ -307,6 +312,11 @@ class GameContext:
 
     def getClient(self):
         return _Client(self._engine)
+
+    def getGame(self, game_idx):
+        """GameContext::getGame (inference/game_context.h:59-66): the object console_lib.py asks for
+        showBoard / getNextPlayer / getLastMove / getScore / getLastScore"""
+        return self._engine.game_view(int(game_idx))
 
 
 class SelfPlayEngine:
@@ -423,3 +433,105 @@ class SelfPlayEngine:
         if w["got"] >= w["n"]:
             torch.cuda.current_stream(w["pi"].device).synchronize()
             w["mc"].expand_backup(w["pi"], w["v"])
+
+
+class OnlineEngine:
+    """mode == "online" behind compat.Context (game.py:363-374: labels ``human_actor`` with
+    batchsize 1 and ``actor_black`` with batchsize num_rollouts_per_batch).
+
+    ``wait()`` returns the ``human_actor`` SharedMem (features of the current position) whenever the
+    game waits for the operator; the reply's ``a`` is a board action or one of the special actions
+    (ACTION_SKIP lets the AI move).  While the AI is searching, ``wait()`` hands out ``actor_black``
+    batches of MCTS leaves exactly like the self-play engine."""
+
+    def __init__(self, game):
+        self.game = game
+        self.board_size = game.N
+        self.num_action = game.N * game.N + 1
+        self._gen = None
+        self._wave = None
+        self.last_status = None
+
+    @property
+    def resign_thres(self):
+        return self.game.resign_thres
+
+    @resign_thres.setter
+    def resign_thres(self, v):
+        self.game.resign_thres = float(v)
+
+    def start(self):
+        pass
+
+    def stop(self):
+        pass
+
+    def win_stats(self):
+        r = self.game.finished
+        return WinRateStats(sum(1 for fv, _, _ in r if fv > 0), sum(1 for fv, _, _ in r if fv <= 0))
+
+    def poll_event(self):
+        return None
+
+    def game_view(self, idx):
+        if idx != 0:
+            raise IndexError("online mode has exactly one game")
+        return self.game
+
+    def next_label(self):
+        return "actor_black" if self._gen is not None else "human_actor"
+
+    def next_batch(self, max_n):
+        import torch
+
+        if self._gen is None:
+            return 1, torch.from_numpy(self.game.board.features())
+        w = self._wave
+        if w["off"] >= w["n"]:
+            raise RuntimeError("wait() called again before step() answered the previous batch")
+        k = min(int(max_n), w["n"] - w["off"])
+        feats = w["s"][w["off"]:w["off"] + k]
+        w["last"] = (w["off"], k)
+        w["off"] += k
+        return k, feats
+
+    def _set_wave(self, s):
+        import torch
+
+        n = s.shape[0]
+        self._wave = {"s": s, "n": n, "off": 0, "got": 0,
+                      "pi": torch.empty((n, self.num_action), dtype=torch.float32, device=s.device),
+                      "v": torch.empty((n,), dtype=torch.float32, device=s.device)}
+
+    def reply_action(self, a):
+        self.last_status = self.game.human(a)
+        if self.last_status != "skip":
+            return
+        if int(self.game.info()[9]):  # nothing to search in a finished position
+            self.game._finish_game("illegal")
+            return
+        self._gen = self.game.ai_search()
+        try:
+            self._set_wave(next(self._gen))
+        except StopIteration:
+            self._gen = None
+            self.game.ai_finish()
+
+    def reply(self, pi, v):
+        import torch
+
+        w = self._wave
+        off, k = w["last"]
+        w["pi"][off:off + k].copy_(pi.to(torch.float32), non_blocking=False)
+        w["v"][off:off + k].copy_(v.to(torch.float32).reshape(-1), non_blocking=False)
+        w["got"] += k
+        if w["got"] < w["n"]:
+            return
+        if w["pi"].is_cuda:
+            torch.cuda.current_stream(w["pi"].device).synchronize()
+        try:
+            self._set_wave(self._gen.send((w["pi"], w["v"])))
+        except StopIteration:
+            self._gen = None
+            self._wave = None
+            self.game.ai_finish()
