@@ -225,22 +225,25 @@ class Context:
             raise RuntimeError("Context.wait() outside start()/stop()")
         # game_start / game_end notifications (batchsize 1, game.py:398-405) come first
         poll = getattr(self._engine, "poll_event", None)
-        while poll is not None:
-            ev = poll()
-            if ev is None:
-                break
-            label, fields = ev
-            if label not in self._by_label:
-                continue  # the script did not ask for this label
-            sm = self._next_smem(label)
-            for k, val in fields.items():
-                if k in sm._fields:
-                    sm[k].view()[:1] = val
-            sm._eff = 1
-            self._cur = sm
-            return sm
         nl = getattr(self._engine, "next_label", None)
-        label = nl() if nl is not None else "actor_black"  # which AI's leaves come next
+        while True:
+            while poll is not None:
+                ev = poll()
+                if ev is None:
+                    break
+                label, fields = ev
+                if label not in self._by_label:
+                    continue  # the script did not ask for this label
+                sm = self._next_smem(label)
+                for k, val in fields.items():
+                    if k in sm._fields:
+                        sm[k].view()[:1] = val
+                sm._eff = 1
+                self._cur = sm
+                return sm
+            label = nl() if nl is not None else "actor_black"  # which AI's leaves come next
+            if label is not None:
+                break  # (None: the engine queued a notification that has to go out first)
         sms = self._by_label.get(label)
         if not sms:
             raise RuntimeError(f"no SharedMem allocated for label '{label}'")
@@ -282,8 +285,14 @@ class _Client:
     def __init__(self, engine):
         self._e = engine
 
-    def setRequest(self, black_ver, white_ver, resign_thres, num_threads=1):  # distri_client.h:318-331
-        self._e.resign_thres = float(resign_thres)
+    def setRequest(self, black_ver, white_ver, resign_thres, num_threads=-1):  # distri_client.h:318-331
+        """Client::setRequest: a local MsgRequest {vers, black/white_resign_thres = thres,
+        num_game_thread_used} handed to every game through the dispatcher"""
+        sr = getattr(self._e, "set_request", None)
+        if sr is not None:
+            sr(int(black_ver), int(white_ver), float(resign_thres), int(num_threads))
+        else:
+            self._e.resign_thres = float(resign_thres)
 
     def getGameStats(self):
         return self
@@ -330,9 +339,8 @@ class SelfPlayEngine:
         import collections
 
         self._events = collections.deque()
-        self.model_version = -1
-        for _ in range(selfplay.G):  # every game thread announces its first game (game_start label)
-            self._events.append(("game_start", {"black_ver": self.model_version, "white_ver": -1}))
+        self._pending = None  # a request waiting for the next move boundary
+        self.replies = []  # RestartReply names of the requests applied so far
         self._wave = None  # (features tensor [n,...], n, offset, pi buffer, v buffer)
         self._wave_idx = 0
         self._in_move = False
@@ -348,15 +356,32 @@ class SelfPlayEngine:
         r = self.sp.results
         return WinRateStats(sum(1 for fv, _, _ in r if fv > 0), sum(1 for fv, _, _ in r if fv <= 0))
 
+    def set_request(self, black_ver, white_ver=-1, resign_thres=None, num_game_thread_used=-1, **ctrl):
+        """a MsgRequest for every game (Client::setRequest locally, or the training server's reply
+        relayed by the caller).  It takes effect between two moves -- the reference's game threads
+        look at the dispatcher every 5th move (game_selfplay.cc:273-290), here all games do at the
+        next move boundary.  ``ctrl``: white_resign_thres, never_resign_prob, player_swap, async_."""
+        self._pending = dict(black_ver=black_ver, white_ver=white_ver, black_resign_thres=resign_thres,
+                             num_game_thread_used=num_game_thread_used, **ctrl)
+
+    def _apply_pending(self):
+        if self._pending is None or self._in_move:
+            return
+        req, self._pending = self._pending, None
+        reply = self.sp.set_request(**req)
+        self.resign_thres = self.sp.resign_thres
+        self.replies.append(reply)
+        if reply in ("update_model", "update_model_async"):
+            # DispatcherCallback::OnReply (dispatcher_callback.h:46-99): ONE game_start per actionable
+            # request carries the versions to Python, which loads the models (selfplay.py:138-156)
+            self._events.append(("game_start", {"black_ver": req["black_ver"], "white_ver": req["white_ver"]}))
+
     def poll_event(self):
+        self._apply_pending()
         return self._events.popleft() if self._events else None
 
     def _phases(self, info):
-        sp = self.sp
-        if sp.mcts2 is None:
-            return [(sp.mcts, "actor_black", None)]
-        black = info[:, 1] == 1
-        return [(sp.mcts, "actor_black", black.astype(np.uint8)), (sp.mcts2, "actor_white", (~black).astype(np.uint8))]
+        return [(mc, label, active) for mc, _, label, active in self.sp.phases(info)]
 
     def _advance_until_leaves(self):
         import torch
@@ -364,6 +389,12 @@ class SelfPlayEngine:
         sp = self.sp
         while True:
             if not self._in_move:
+                if self._pending is not None:
+                    self._apply_pending()
+                    if self._events:
+                        return False  # game_start has to reach Python before the new models are asked
+                if sp.idle is not None and sp.idle.all():
+                    raise RuntimeError("every game is waiting for a request (black_ver < 0): nothing to evaluate")
                 self._info = sp.gb.info()
                 self._plan = self._phases(self._info)
                 self._phase = 0
@@ -391,23 +422,25 @@ class SelfPlayEngine:
             self._wave = {"s": s, "n": n, "off": 0, "got": 0, "mc": mc, "label": label,
                           "pi": torch.empty((n, self.num_action), dtype=torch.float32, device=dev),
                           "v": torch.empty((n,), dtype=torch.float32, device=dev)}
-            return
+            return True
 
     def _finish_move(self):
         sp = self.sp
         sp.resign_thres = self.resign_thres
         before = sp.games_finished
         sp.finish_move(self._info)
-        for _ in range(sp.games_finished - before):  # finish_game -> game_end, restart -> game_start
+        for _ in range(sp.games_finished - before):  # finish_game -> GameNotifier::OnGameEnd -> game_end
             self._events.append(("game_end", {}))
-            self._events.append(("game_start", {"black_ver": self.model_version, "white_ver": -1}))
         self._in_move = False
 
     def next_label(self):
+        """label of the next leaf batch, or None when a notification has to be delivered first"""
         if self._wave is None or self._wave["off"] >= self._wave["n"]:
             if self._wave is not None and self._wave["got"] < self._wave["n"]:
                 raise RuntimeError("wait() called again before step() answered the previous batch")
-            self._advance_until_leaves()
+            if not self._advance_until_leaves():
+                self._wave = None
+                return None
         return self._wave["label"]
 
     def next_batch(self, max_n):
@@ -431,7 +464,8 @@ class SelfPlayEngine:
         w["v"][off:off + k].copy_(v.to(torch.float32).reshape(-1), non_blocking=False)
         w["got"] += k
         if w["got"] >= w["n"]:
-            torch.cuda.current_stream(w["pi"].device).synchronize()
+            if w["pi"].is_cuda:
+                torch.cuda.current_stream(w["pi"].device).synchronize()
             w["mc"].expand_backup(w["pi"], w["v"])
 
 

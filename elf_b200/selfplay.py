@@ -20,15 +20,27 @@ from .mcts import MctsBatch
 class SelfPlay:
     def __init__(self, actor, num_games=4096, board_size=19, device=0, policy_distri_cutoff=20,
                  resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0,
-                 record_games=False, actor_white=None, **mcts_opts):
-        self.gb = GoBatch(num_games, board_size=board_size, device=device)
+                 record_games=False, actor_white=None, board=None, search=None, search_white=None, **mcts_opts):
+        # board / search / search_white: pre-built GoBatch / MctsBatch objects (or duck-typed stand-ins:
+        # the CPU tests of the host logic inject oracle-backed ones); by default they are created here
+        self.gb = board if board is not None else GoBatch(num_games, board_size=board_size, device=device)
         mcts_opts.setdefault("komi", komi)
-        self.mcts = MctsBatch(self.gb, **mcts_opts)
+        self._mcts_opts = dict(mcts_opts)
+        self.mcts = search if search is not None else MctsBatch(self.gb, **mcts_opts)
         self.actor = actor
         # evaluation matches (GoGameSelfPlay::_ai2, game_selfplay.cc:366-367): a second AI with its own
         # tree plays white; both trees follow every move (MCTSAI_T::advanceMoves)
         self.actor_white = actor_white
-        self.mcts2 = MctsBatch(self.gb, **mcts_opts) if actor_white is not None else None
+        if search_white is not None:
+            self.mcts2 = search_white
+        else:
+            self.mcts2 = MctsBatch(self.gb, **mcts_opts) if (actor_white is not None and search is None) else None
+        # server requests (MsgRequest: model versions + client control), see set_request()
+        self.request = {"black_ver": -1, "white_ver": -1, "player_swap": False, "async": False,
+                        "num_game_thread_used": -1}
+        self.protocol = False  # becomes True with the first set_request()
+        self.idle = None  # bool[G]: games that wait for a request (ModelPair::wait); None = nobody waits
+        self.swap = False  # player_swap of an evaluation match: the "white" AI plays black
         self.G = num_games
         self.N = board_size
         self.komi = komi
@@ -65,16 +77,101 @@ class SelfPlay:
             out[k] = np.where(m, res_b[k], res_w[k])
         return out
 
+    def phases(self, info):
+        """which AI searches which games this move: [(search, actor, label, active mask or None)].
+        One AI for self-play; for a match ``_ai`` (label actor_black) takes the black-to-move games
+        and ``_ai2`` (actor_white) the others -- the other way round under player_swap
+        (GoGameSelfPlay::restart swaps the two pointers, game_selfplay.cc:185-188)."""
+        act = None if self.idle is None else ~self.idle
+        if self.mcts2 is None:
+            return [(self.mcts, self.actor, "actor_black", None if act is None else act.astype(np.uint8))]
+        first = (info[:, 1] == 1) != self.swap  # games whose side to move is served by _ai's model
+        second = ~first
+        if act is not None:
+            first, second = first & act, second & act
+        return [(self.mcts, self.actor, "actor_black", first.astype(np.uint8)),
+                (self.mcts2, self.actor_white, "actor_white", second.astype(np.uint8))]
+
     def step(self):
         """one move of every game; returns the number of moves played"""
         info = self.gb.info()
-        if self.mcts2 is None:
+        if self.mcts2 is None and self.idle is None:
             self.mcts.search(self.actor)
         else:
-            black = info[:, 1] == 1
-            self.mcts.search(self.actor, active=black.astype(np.uint8))
-            self.mcts2.search(self.actor_white, active=(~black).astype(np.uint8))
+            for mc, actor, _, active in self.phases(info):
+                mc.search(actor, active=active)
         return self.finish_move(info)
+
+    # -- MsgRequest handling: GoGameSelfPlay::OnReceive (game_selfplay.cc:222-270) for all games ----
+    def set_request(self, black_ver, white_ver=-1, black_resign_thres=None, white_resign_thres=None,
+                    never_resign_prob=None, player_swap=False, async_=False, num_game_thread_used=-1):
+        """Apply a server request between two moves.  Returns the reference's RestartReply name:
+        ``only_wait`` (black_ver < 0: every game idles), ``update_model`` (versions or player_swap
+        changed, or the games were waiting: every playing game is restarted, unfinished games are
+        dropped as the reference's ``restart()`` does), ``update_model_async`` (async: the new models
+        take over mid-game) or ``update_request_only`` (same versions: only thresholds change).
+        ``num_game_thread_used`` >= 0 lets only the first that many games play
+        (DispatcherCallback::OnFirstSend, dispatcher_callback.h:27-44)."""
+        prev = self.request
+        was_protocol = self.protocol
+        new = {"black_ver": int(black_ver), "white_ver": int(white_ver), "player_swap": bool(player_swap),
+               "async": bool(async_), "num_game_thread_used": int(num_game_thread_used)}
+        is_waiting = new["black_ver"] < 0  # ModelPair::wait
+        # a SelfPlay that never saw a request plays without versions; the reference's game threads
+        # start out waiting -- in both cases the first real request is a (re)start
+        is_prev_waiting = (prev["black_ver"] < 0) if was_protocol else True
+        same_vers = (new["black_ver"], new["white_ver"]) == (prev["black_ver"], prev["white_ver"])
+        same_swap = new["player_swap"] == prev["player_swap"]
+        no_restart = (same_vers or new["async"]) and same_swap and not is_prev_waiting
+        self.request = new
+        self.protocol = True
+        # GoStateExt::setRequest (go_state_ext.h:55-65)
+        if black_resign_thres is not None:
+            w = black_resign_thres if white_resign_thres is None else white_resign_thres
+            self.resign_thres = (float(black_resign_thres) + float(w)) / 2.0
+        if never_resign_prob is not None:
+            self.never_resign_ratio = float(never_resign_prob)
+        G = self.G
+        if is_waiting:
+            self.idle = np.ones(G, bool)
+            return "only_wait"
+        used = new["num_game_thread_used"]
+        idle = np.zeros(G, bool) if used < 0 else (np.arange(G) >= used)
+        was_idle = self.idle if self.idle is not None else np.zeros(G, bool)
+        self.idle = idle if idle.any() else None
+        if new["white_ver"] >= 0 and self.mcts2 is None:  # a match needs the second AI
+            self.mcts2 = MctsBatch(self.gb, **self._mcts_opts)
+        two = new["white_ver"] >= 0
+        if not two and self.mcts2 is not None and self.actor_white is None and was_protocol:
+            # back to self-play (ModelPair::is_selfplay): _ai2 is dropped
+            self.mcts2.close() if hasattr(self.mcts2, "close") else None
+            self.mcts2 = None
+        self.swap = bool(two and new["player_swap"])
+        if not no_restart:
+            self.restart_games(~idle)
+            return "update_model"
+        # games of threads that were parked and are used again restart even if the rest carries on
+        woken = was_idle & ~idle
+        if woken.any():
+            self.restart_games(woken)
+        if not new["async"]:
+            return "update_request_only"
+        return "update_request_only" if same_vers else "update_model_async"
+
+    def restart_games(self, mask):
+        """GoGameSelfPlay::restart for the games in ``mask``: fresh boards and trees, no result"""
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        if not m.any():
+            return
+        self.gb.reset(m)
+        self.mcts.reset(m)
+        if self.mcts2 is not None:
+            self.mcts2.reset(m)
+        sel = m.astype(bool)
+        self.never_resign[sel] = self.rng.random(int(sel.sum())) < self.never_resign_ratio
+        if self.recorders is not None:
+            for g in np.flatnonzero(sel):
+                self.recorders[g].restart()
 
     def finish_move(self, info, res=None):
         """everything GoGameSelfPlay::act does after the search returned (game_selfplay.cc:372-429):
@@ -86,29 +183,37 @@ class SelfPlay:
         nr = self.never_resign.astype(np.uint8)
         acts, vals = self.mcts.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
         if self.mcts2 is not None:
-            black = info[:, 1] == 1
+            black = (info[:, 1] == 1) != self.swap  # games whose mover was searched by self.mcts (see phases)
             a2, v2 = self.mcts2.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
             acts = np.where(black, acts, a2)
             vals = np.where(black, vals, v2)
         resign = acts == -1
-        assert (acts != -2).all(), "a game was not searched"
+        if self.idle is None:
+            assert (acts != -2).all(), "a game was not searched"
+        else:
+            assert (acts[~self.idle] != -2).all(), "a game was not searched"
+            assert (acts[self.idle] == -2).all()
         if self.recorders is not None:
             if res is None:
                 res = self.mcts.results()
                 if self.mcts2 is not None:
-                    res = self.merge_results(info[:, 1] == 1, res, self.mcts2.results())
+                    res = self.merge_results((info[:, 1] == 1) != self.swap, res, self.mcts2.results())
             for g in range(self.G):
-                self.recorders[g].on_move(int(info[g, 0]), int(acts[g]), res["visits"][g], float(vals[g]))
+                if acts[g] != -2:
+                    self.recorders[g].on_move(int(info[g, 0]), int(acts[g]), res["visits"][g], float(vals[g]))
         ok = self.gb.forward(acts)
-        assert ok[~resign].all(), "MCTS proposed an illegal move"
+        played = ~resign if self.idle is None else (~resign & ~self.idle)
+        assert ok[played].all(), "MCTS proposed an illegal move"
         self.mcts.advance(acts)
         if self.mcts2 is not None:
             self.mcts2.advance(acts)
-        self.moves_played += int((~resign).sum())
+        self.moves_played += int(played.sum())
         info2 = self.gb.info()
         done = resign | (info2[:, 9] == 1)
         if self.move_cutoff > 0:
             done |= info2[:, 0] >= self.move_cutoff
+        if self.idle is not None:
+            done &= ~self.idle
         if done.any():
             final = self.gb.evaluate(self.komi)
             for g in np.flatnonzero(done):
@@ -129,4 +234,4 @@ class SelfPlay:
                 self.mcts2.reset(m)
             self.never_resign[done] = self.rng.random(int(done.sum())) < self.never_resign_ratio
             self.games_finished += int(done.sum())
-        return int((~resign).sum())
+        return int(played.sum())
