@@ -108,7 +108,7 @@ def show_board(stones, n, last_action, b_cap, w_cap, next_player):
 
 class OnlineGame:
     def __init__(self, board, search, komi=7.5, resign_thres=0.0, policy_distri_cutoff=0, move_cutoff=-1,
-                 preload_sgf=None, preload_sgf_move_to=-1, seed=0):
+                 preload_sgf=None, preload_sgf_move_to=-1, following_pass=False, seed=0):
         if board.num_games != 1:
             raise ValueError("OnlineGame drives exactly one game")
         self.board = board
@@ -118,6 +118,7 @@ class OnlineGame:
         self.resign_thres = float(resign_thres)
         self.policy_distri_cutoff = int(policy_distri_cutoff)
         self.move_cutoff = int(move_cutoff)
+        self.following_pass = bool(following_pass)
         self._seed = int(seed)
         self._moves = 0
         self.last_value = 0.0  # GoStateExt::_last_value: final value of the last finished game
@@ -255,6 +256,14 @@ class OnlineGame:
         acts, vals = self.search.choose(self.policy_distri_cutoff, self.resign_thres, None,
                                         (self._seed << 20) ^ self._moves)
         a = int(acts[0])
+        if self.following_pass and a >= 0:
+            # mcts_update_info (game_selfplay.cc:97-119): the opponent passed and we are clearly ahead
+            # (score on the board and predicted value agree) -> pass as well
+            i = self.info()
+            v, score = float(vals[0]), self.getScore()
+            good = (score > 0 and v > 0.9) if int(i[1]) == S_BLACK else (score < 0 and v < -0.9)
+            if good and int(i[4]) == self.N * self.N:
+                a = self.N * self.N
         if a == -1:  # shouldResign && ply >= 50
             self._finish_game("resign")
             return SA_RESIGN

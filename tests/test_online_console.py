@@ -187,6 +187,18 @@ def test_ai_branch(oracle_lib):
     assert g.getLastScore() == -1.0 and g.getLastMove() == "RESIGN"
 
 
+def test_following_pass(oracle_lib):
+    e5 = online.vertex2action("E5", 9)
+    for follow, v, expect_pass in ((True, 0.95, True), (True, 0.5, False), (False, 0.95, False)):
+        g = make_game(oracle_lib, following_pass=follow)
+        g.human(e5)  # black stone: black is ahead on the board
+        g.human(81)  # white passes
+        a = g.genmove(policy_actor([0, 1], value=v))
+        assert (a == 81) == expect_pass
+        if expect_pass:
+            assert g.finished[-1][2] == "two_pass" and g.getLastScore() == pytest.approx(73.5)
+
+
 def test_move_cutoff_and_terminal_position(oracle_lib):
     g = make_game(oracle_lib, move_cutoff=4)
     actor = policy_actor(list(range(30)))
