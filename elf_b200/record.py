@@ -38,7 +38,7 @@ def quantise_policy(visits_row, n):
     out = [0] * ((n + 2) * (n + 2))
     idx = np.flatnonzero(visits_row >= 0)
     v = visits_row[idx].astype(np.float32)
-    s = np.float32(v.sum(dtype=np.float32))
+    s = np.float32(np.cumsum(v, dtype=np.float32)[-1]) if len(v) else np.float32(0)  # sequential float sum, edge order
     if s <= 0:
         return out
     p = v / s
@@ -49,10 +49,29 @@ def quantise_policy(visits_row, n):
     return out
 
 
+def ts_options_json(opts=None):
+    """``TSOptions::setJsonFields`` (``src_cpp/elf/ai/tree_search/tree_search_options.h:77-215``): the
+    ``mcts_opt`` object inside ``request.vers``.  The reference's parser REQUIRES every field
+    (``JSON_LOAD`` throws on a missing one and ``Record::createBatchFromJson`` then drops the record),
+    so all of them are written.  ``opts``: keyword options of ``elfb200_mcts_options`` / MctsBatch."""
+    o = dict(opts or {})
+    return {
+        "max_num_moves": 0, "num_threads": 1, "num_rollouts_per_thread": int(o.get("num_rollouts", 100)),
+        "num_rollouts_per_batch": int(o.get("num_rollouts_per_batch", 8)), "verbose": False, "verbose_time": False,
+        "seed": int(o.get("seed", 0)) & 0x7FFFFFFF, "persistent_tree": bool(o.get("persistent_tree", 0)),
+        "pick_method": "most_visited", "log_prefix": "", "root_epsilon": float(o.get("root_epsilon", 0.0)),
+        "root_alpha": float(o.get("root_alpha", 0.0)), "virtual_loss": int(o.get("virtual_loss", 0)),
+        "alg_opt": {"use_prior": bool(o.get("use_prior", 1)), "c_puct": float(o.get("c_puct", 5.0)),
+                    "unexplored_q_zero": bool(o.get("unexplored_q_zero", 0)),
+                    "root_unexplored_q_zero": bool(o.get("root_unexplored_q_zero", 0))},
+    }
+
+
 class GameRecorder:
     """per-slot accumulation of one game's record fields"""
 
-    def __init__(self, n, thread_id, policy_distri_cutoff, policy_distri_training_for_all=False):
+    def __init__(self, n, thread_id, policy_distri_cutoff, policy_distri_training_for_all=False, mcts_opt=None):
+        self.mcts_opt = ts_options_json(mcts_opt)
         self.n = n
         self.thread_id = thread_id
         self.cutoff = policy_distri_cutoff
@@ -72,18 +91,24 @@ class GameRecorder:
         if action >= 0:
             self.moves.append(int(action))
 
-    def finish(self, final_value, never_resign, model_ver=-1, resign_thres=0.0, never_resign_prob=0.0):
+    def finish(self, final_value, never_resign, model_ver=-1, resign_thres=0.0, never_resign_prob=0.0,
+               white_ver=-1, player_swap=False, async_=False, num_game_thread_used=-1):
+        """GoStateExt::dumpRecord (go_state_ext.h:128-147): the request the game was played under
+        (MsgRequest: versions + client control), the models used (``using_models_``: every version
+        >= 0 the game saw, ascending) and the result"""
         rec = {
             "request": {
-                "vers": {"black_ver": model_ver, "white_ver": -1, "mcts_opt": {}},
-                "client_ctrl": {"client_type": 1, "num_game_thread_used": -1, "black_resign_thres": resign_thres,
-                                "white_resign_thres": resign_thres, "never_resign_prob": never_resign_prob,
-                                "player_swap": False, "async": False},
+                "vers": {"black_ver": int(model_ver), "white_ver": int(white_ver), "mcts_opt": self.mcts_opt},
+                "client_ctrl": {"client_type": 1, "num_game_thread_used": int(num_game_thread_used),
+                                "black_resign_thres": resign_thres, "white_resign_thres": resign_thres,
+                                "never_resign_prob": never_resign_prob, "player_swap": bool(player_swap),
+                                "async": bool(async_)},
             },
             "result": {
                 "num_move": len(self.moves), "reward": float(final_value),
                 "black_never_resign": bool(never_resign), "white_never_resign": bool(never_resign),
-                "using_models": [model_ver], "content": moves_to_sgf(self.moves, self.n),
+                "using_models": sorted({int(v) for v in (model_ver, white_ver) if v >= 0}),
+                "content": moves_to_sgf(self.moves, self.n),
                 "policies": self.policies, "values": self.values,
             },
             "timestamp": int(time.time()), "thread_id": self.thread_id, "seq": self.seq, "pri": 0.0, "offline": False,

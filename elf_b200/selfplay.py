@@ -60,7 +60,8 @@ class SelfPlay:
         if record_games:
             from .record import GameRecorder
 
-            self.recorders = [GameRecorder(board_size, g, policy_distri_cutoff) for g in range(num_games)]
+            self.recorders = [GameRecorder(board_size, g, policy_distri_cutoff, mcts_opt=self._mcts_opts)
+                              for g in range(num_games)]
 
     def close(self):
         self.mcts.close()
@@ -224,9 +225,12 @@ class SelfPlay:
                     why = "two_pass" if info2[g, 10] else ("superko" if info2[g, 11] else "max_step")
                 self.results.append((fv, int(info2[g, 0]), why))
                 if self.recorders is not None:
-                    self.records.append(self.recorders[g].finish(fv, bool(self.never_resign[g]),
-                                                                 resign_thres=self.resign_thres,
-                                                                 never_resign_prob=self.never_resign_ratio))
+                    q = self.request
+                    self.records.append(self.recorders[g].finish(
+                        fv, bool(self.never_resign[g]), model_ver=q["black_ver"], resign_thres=self.resign_thres,
+                        never_resign_prob=self.never_resign_ratio, white_ver=q["white_ver"],
+                        player_swap=q["player_swap"], async_=q["async"],
+                        num_game_thread_used=q["num_game_thread_used"]))
             m = done.astype(np.uint8)
             self.gb.reset(m)
             self.mcts.reset(m)

@@ -161,6 +161,56 @@ def ref_sgf_parse(text, n, cap=2048):
             "winner": int(hi[2]), "num_moves": int(hi[3]), "komi": float(hf[0]), "win_margin": float(hf[1])}
 
 
+def ref_record_roundtrip(text, n=9):
+    """Record::createFromJson + setJsonFields of the compiled reference; None if its parser throws"""
+    L = load_ref(n)
+    L.ref_record_roundtrip.restype = ctypes.c_int
+    L.ref_record_roundtrip.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    cap = 4 * len(text) + (1 << 16)
+    buf = ctypes.create_string_buffer(cap)
+    k = L.ref_record_roundtrip(text.encode(), buf, cap)
+    assert k != -2
+    return None if k < 0 else buf.value.decode()
+
+
+def ref_record_batch_count(text, n=9):
+    L = load_ref(n)
+    L.ref_record_batch_count.restype = ctypes.c_int
+    L.ref_record_batch_count.argtypes = [ctypes.c_char_p]
+    return int(L.ref_record_batch_count(text.encode()))
+
+
+def ref_quantise_policy(actions, visits, n):
+    L = load_ref(n)
+    L.ref_quantise_policy.restype = ctypes.c_int
+    L.ref_quantise_policy.argtypes = [ctypes.c_int, vp, vp, vp]
+    a = np.ascontiguousarray(actions, np.int32)
+    v = np.ascontiguousarray(visits, np.float32)
+    out = np.zeros((n + 2) * (n + 2), np.uint8)
+    k = L.ref_quantise_policy(len(a), a.ctypes.data, v.ctypes.data, out.ctypes.data)
+    assert k == out.size
+    return out
+
+
+def ref_offline_sample(record_json, move_to, d4, num_future, n):
+    """one training sample from the reference's GoStateExtOffline + GoFeature extractors"""
+    L = load_ref(n)
+    L.ref_offline_sample.restype = ctypes.c_int
+    L.ref_offline_sample.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    s = np.zeros((18, n, n), np.float32)
+    oa = np.zeros(num_future, np.int64)
+    sc = np.zeros(n * n + 1, np.float32)
+    fl = np.zeros(2, np.float32)
+    it = np.zeros(3, np.int32)
+    ver = np.zeros(1, np.int64)
+    rc = L.ref_offline_sample(record_json.encode(), int(move_to), int(d4), int(num_future), s.ctypes.data, oa.ctypes.data,
+                              sc.ctypes.data, fl.ctypes.data, it.ctypes.data, ver.ctypes.data)
+    if rc != 0:
+        return rc
+    return {"s": s, "offline_a": oa, "mcts_scores": sc, "winner": float(fl[0]), "predicted_value": float(fl[1]),
+            "move_idx": int(it[0]), "num_move": int(it[1]), "aug_code": int(it[2]), "selfplay_ver": int(ver[0])}
+
+
 def ref_show_board(ref):
     L = ref.L
     L.ref_show_board.restype = ctypes.c_int

@@ -24,9 +24,9 @@ P1 = N * N + 1
 class Boards:
     """GoBatch interface over G independent oracle games"""
 
-    def __init__(self, G, lib):
-        self.num_games, self.board_size, self.lib = G, N, lib
-        self.o = [oracles.Oracle(N, lib) for _ in range(G)]
+    def __init__(self, G, lib, n=N):
+        self.num_games, self.board_size, self.lib = G, n, lib
+        self.o = [oracles.Oracle(n, lib) for _ in range(G)]
         self.resets = np.zeros(G, int)
 
     def forward(self, actions):
@@ -38,13 +38,13 @@ class Boards:
     def evaluate(self, komi):
         return np.array([o.evaluate(komi) for o in self.o], np.float32)
 
-    def features(self):
-        return np.stack([o.features(0) for o in self.o]).astype(np.float32)
+    def features(self, d4=None):
+        return np.stack([o.features(0 if d4 is None else int(d4[g])) for g, o in enumerate(self.o)]).astype(np.float32)
 
     def reset(self, mask):
         for g in range(self.num_games):
             if mask is None or mask[g]:
-                self.o[g] = oracles.Oracle(N, self.lib)
+                self.o[g] = oracles.Oracle(self.board_size, self.lib)
                 self.resets[g] += 1
 
     def synchronize(self):
