@@ -185,10 +185,14 @@ class Context:
     def _field_dims(self, key):
         n, a = self._engine.board_size, self._engine.num_action
         bs = self._batchsize
-        table = {
+        k = int(getattr(self._engine, "num_future_actions", 1))
+        table = {  # GoFeature::registerExtractor, common/game_feature.h:159-183
             "s": ("float", [bs, 18, n, n]), "pi": ("float", [bs, a]), "V": ("float", [bs]),
             "a": ("int64_t", [bs]), "rv": ("int64_t", [bs]),
             "black_ver": ("int64_t", [bs]), "white_ver": ("int64_t", [bs]), "selfplay_ver": ("int64_t", [bs]),
+            "offline_a": ("int64_t", [bs, k]), "winner": ("float", [bs]), "predicted_value": ("float", [bs]),
+            "mcts_scores": ("float", [bs, a]), "move_idx": ("int32_t", [bs]), "aug_code": ("int32_t", [bs]),
+            "num_move": ("int32_t", [bs]),
         }
         if key not in table:
             raise KeyError(f"field '{key}' is not provided by the elf_b200 engine")
@@ -248,9 +252,16 @@ class Context:
         if not sms:
             raise RuntimeError(f"no SharedMem allocated for label '{label}'")
         sm = self._next_smem(label)
-        n, feats = self._engine.next_batch(sm.getSharedMemOptions().batchsize())
-        dst = sm["s"].view()
-        dst[:n].copy_(feats, non_blocking=False)
+        nf = getattr(self._engine, "next_fields", None)
+        if nf is not None:  # engines that fill several input fields (the `train` label)
+            n, fields = nf(sm.getSharedMemOptions().batchsize())
+            for k, val in fields.items():
+                if k in sm._fields:
+                    sm[k].view()[:n].copy_(val, non_blocking=False)
+        else:
+            n, feats = self._engine.next_batch(sm.getSharedMemOptions().batchsize())
+            dst = sm["s"].view()
+            dst[:n].copy_(feats, non_blocking=False)
         sm._eff = int(n)
         self._cur = sm
         return sm
@@ -261,6 +272,9 @@ class Context:
             raise RuntimeError("Context.step() without a pending wait()")
         if sm.getSharedMemOptions().label() in ("game_start", "game_end"):
             self._cur = None  # notifications carry no reply
+            return
+        if sm.getSharedMemOptions().label() in ("train", "train_ctrl"):
+            self._cur = None  # reply=None labels (game.py:407-418)
             return
         if sm.getSharedMemOptions().label() == "human_actor":
             # GoFeature::ReplyAction (common/game_feature.h:50-66): only "a" is consumed
@@ -569,3 +583,40 @@ class OnlineEngine:
             self._gen = None
             self._wave = None
             self.game.ai_finish()
+
+
+class TrainEngine:
+    """mode == "train" behind compat.Context: every ``wait()`` returns one ``train`` batch
+    (game.py:407-413: input s, offline_a, winner, mcts_scores, move_idx, selfplay_ver; no reply) drawn
+    from the replay records by ``elf_b200.replay.ReplayBatch`` (GoGameTrain::act for the batch)."""
+
+    def __init__(self, replay_batch):
+        self.rb = replay_batch
+        self.board_size = replay_batch.N
+        self.num_action = replay_batch.N * replay_batch.N + 1
+        self.num_future_actions = replay_batch.K
+        self.batches = 0
+
+    def start(self):
+        pass
+
+    def stop(self):
+        pass
+
+    def win_stats(self):
+        return WinRateStats(0, 0)
+
+    def poll_event(self):
+        return None
+
+    def next_label(self):
+        return "train"
+
+    def next_fields(self, max_n):
+        import torch
+
+        if max_n < self.rb.B:
+            raise RuntimeError(f"the train label's batchsize ({max_n}) is smaller than the replay batch ({self.rb.B})")
+        out = self.rb.sample()
+        self.batches += 1
+        return self.rb.B, {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in out.items()}

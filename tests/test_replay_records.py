@@ -166,3 +166,41 @@ def test_replay_19x19_with_captures(oracle_lib):
     rb = replay.ReplayBatch(B, board_size=n, num_future_actions=K, board=Boards(B, oracle_lib, n))
     rb.add_records([r])
     check_against_reference(rb, [text], [(0, 148, 5), (0, 0, 3), (0, 29, 6), (0, 97, 7)], n)
+
+
+REF_UTILS = "/root/reference/src_py/elf/utils_elf.py"
+
+
+def test_train_label_through_compat_surface(selfplay_records, oracle_lib):
+    """mode == "train": the reference's GCWrapper pumps `train` batches out of the replay engine"""
+    import importlib.util
+    import os
+
+    from elf_b200 import compat
+
+    if not os.path.exists(REF_UTILS):
+        pytest.skip("reference tree not present")
+    spec = importlib.util.spec_from_file_location("ref_utils_elf_train", REF_UTILS)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    B, K = 6, 2
+    rb = replay.ReplayBatch(B, board_size=9, num_future_actions=K, seed=9, board=Boards(B, oracle_lib))
+    rb.add_records(selfplay_records)
+    twin = replay.ReplayBatch(B, board_size=9, num_future_actions=K, seed=9, board=Boards(B, oracle_lib))
+    twin.add_records(selfplay_records)
+    GC = compat.GameContext(compat.TrainEngine(rb), batchsize=B)
+    desc = {"train": dict(input=["s", "offline_a", "winner", "mcts_scores", "move_idx", "selfplay_ver"], reply=None)}
+    gcw = ref.GCWrapper(GC, B, desc, num_recv=2, gpu=None, use_numpy=False, params=GC.getParams())
+    seen = []
+    gcw.reg_callback("train", lambda batch: seen.append({k: batch[k].clone() for k in desc["train"]["input"]}))
+    gcw.start()
+    for _ in range(3):
+        gcw.run()
+    gcw.stop()
+    assert len(seen) == 3
+    for got in seen:
+        want = twin.sample()
+        assert got["s"].shape == (B, 18, 9, 9) and got["offline_a"].shape == (B, K) and got["offline_a"].dtype == torch.int64
+        assert got["move_idx"].dtype == torch.int32 and got["mcts_scores"].shape == (B, 82)
+        for k in got:
+            np.testing.assert_array_equal(got[k].numpy(), want[k])
