@@ -83,6 +83,12 @@ class GameRecorder:
         self.moves = []
         self.policies = []
         self.values = []
+        self.models = set()  # GoStateExt::using_models_
+
+    def add_models(self, *versions):
+        """GoStateExt::addCurrentModel (go_state_ext.h:66-71): at every (re)start and at every
+        async model update"""
+        self.models.update(int(v) for v in versions if v >= 0)
 
     def on_move(self, ply_before, action, visits_row, predicted_value):
         if self.for_all or ply_before <= self.cutoff:  # mcts_make_diverse_move, game_selfplay.cc:88-93
@@ -107,7 +113,7 @@ class GameRecorder:
             "result": {
                 "num_move": len(self.moves), "reward": float(final_value),
                 "black_never_resign": bool(never_resign), "white_never_resign": bool(never_resign),
-                "using_models": sorted({int(v) for v in (model_ver, white_ver) if v >= 0}),
+                "using_models": sorted(self.models | {int(v) for v in (model_ver, white_ver) if v >= 0}),
                 "content": moves_to_sgf(self.moves, self.n),
                 "policies": self.policies, "values": self.values,
             },

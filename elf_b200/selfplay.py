@@ -157,6 +157,9 @@ class SelfPlay:
             self.restart_games(woken)
         if not new["async"]:
             return "update_request_only"
+        if self.recorders is not None:  # setAsync -> addCurrentModel: running games now span two models
+            for g in np.flatnonzero(~idle):
+                self.recorders[g].add_models(prev["black_ver"], prev["white_ver"], new["black_ver"], new["white_ver"])
         return "update_request_only" if same_vers else "update_model_async"
 
     def restart_games(self, mask):

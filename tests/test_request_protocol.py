@@ -267,3 +267,22 @@ def test_version_switch_through_compat_surface(oracle_lib):
         for _ in range(10):
             gcw.run()
     gcw.stop()
+
+
+def test_records_name_every_model_a_game_saw(oracle_lib):
+    class VisitSearch(Search):
+        def results(self):
+            return {"visits": np.where(self.pi > 0.5, 10, -1).astype(np.int32)}
+
+    b = Boards(2, oracle_lib)
+    sp = SelfPlay(net("black", []), num_games=2, board_size=N, policy_distri_cutoff=0, never_resign_ratio=0.0,
+                  move_cutoff=6, record_games=True, board=b, search=VisitSearch(b, "ai"))
+    sp.set_request(3, -1, 0.0)
+    sp.step()
+    sp.step()
+    assert sp.set_request(4, -1, 0.0, async_=True) == "update_model_async"  # new model in the middle of the games
+    while len(sp.records) < 4:
+        sp.step()
+    assert [r["result"]["using_models"] for r in sp.records] == [[3, 4], [3, 4], [4], [4]]
+    assert [r["request"]["vers"]["black_ver"] for r in sp.records] == [4] * 4
+    assert all(r["request"]["client_ctrl"]["async"] for r in sp.records)
