@@ -10,7 +10,7 @@ import pytest
 
 from tests import oracles
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
               pytest.mark.xfail(strict=False, reason="first GPU run of the online path is due in round 2")]
 
 
