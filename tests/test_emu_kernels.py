@@ -1,0 +1,247 @@
+"""The kernel SOURCES (elf_b200/csrc/*.cu, board.cuh) executed on the host SIMT emulator
+(tests/simt_emu) through the product's own C ABI, against the oracle.
+
+What this proves and what it does not: every lane's arithmetic, the predication of idle lanes, the
+warp collectives with partial masks (9x9 packs three games per warp), shared-memory staging and the
+node-pool bookkeeping are the code that runs on the GPU, executed here with 32-lane warps whose
+collectives complete only when all named lanes arrive (a lane that never arrives, or arrives with a
+different operation, aborts the test).  It does not prove anything about timing, inter-warp memory
+ordering or hardware behaviour -- the `-m gpu` tests on a B200 are the parity gate; this file keeps
+the kernels' logic under test on GPU-less machines and covers paths that have not yet had a GPU run
+(G = 1 online mode, parked games, the replay path on the board batch)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import oracles
+
+pytestmark = pytest.mark.timeout(900)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests import emu as E
+
+    try:
+        E.emu_lib()
+    except Exception as e:  # no g++ / ucontext: the emulator is a convenience, not a requirement
+        pytest.skip(f"SIMT emulator build unavailable: {e}")
+    return E
+
+
+def fake_actor(search, n):
+    def actor(batch):
+        h, _, _ = search.leaf_info()
+        pi, v = oracles.fakenet(h, n * n + 1)
+        assert batch["s"].shape[0] == len(h)
+        return {"pi": torch.from_numpy(pi), "V": torch.from_numpy(v)}
+
+    return actor
+
+
+@pytest.mark.parametrize("n,G", [(9, 5), (19, 3)])
+def test_board_kernels(emu, oracle_lib, n, G):
+    """k_reset / k_step / k_export / k_features: forward verdict, hash, legal mask, info words,
+    scores, true eyes and the 18 planes under every D4 code, with illegal and pass moves mixed in;
+    9x9 runs 3 games per warp with G = 5 leaving a partially filled warp"""
+    gb = emu.emu_batch(G, n)
+    os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+    rng = np.random.default_rng(n)
+    for t in range(90):
+        acts = np.empty(G, np.int32)
+        for g, o in enumerate(os_):
+            lg = np.flatnonzero(o.legal())
+            acts[g] = int(rng.choice(lg)) if len(lg) and rng.random() > 0.05 else n * n
+            if rng.random() < 0.05:
+                acts[g] = int(rng.integers(n * n))  # possibly illegal
+            if rng.random() < 0.03:
+                acts[g] = -1  # leave the game untouched
+        ok = gb.forward(acts)
+        for g, o in enumerate(os_):
+            if acts[g] >= 0:
+                assert bool(ok[g]) == bool(o.forward(int(acts[g]))), (t, g)
+        assert [int(x) for x in gb.getHashCode()] == [o.hash() for o in os_], t
+        if t % 6 == 0:
+            lm, info, sc, ev = gb.legal_mask(), gb.info(), gb.tt_score(), gb.evaluate(7.5)
+            eyes = gb.true_eyes(0)
+            for g, o in enumerate(os_):
+                assert (lm[g, :-1] == o.legal()).all() and lm[g, -1] == 1
+                oi = np.asarray(o.info()).copy()
+                oi[8] = 0  # ko_age is not part of the device state
+                assert (info[g] == oi).all(), (t, g, info[g], oi)
+                assert sc[g] == o.tt_score() and ev[g] == pytest.approx(o.evaluate(7.5))
+                assert (eyes[g] == o.true_eyes(int(info[g, 1]))).all()
+    d4 = np.arange(G, dtype=np.int32) % 8
+    f = gb.features(d4)
+    for g, o in enumerate(os_):
+        assert (f[g] == o.features(int(d4[g]))).all()
+    gb.reset(np.array([1] + [0] * (G - 1), np.uint8))
+    assert gb.info()[0, 0] == 1 and gb.getHashCode()[0] == 0 and gb.getHashCode()[1] == os_[1].hash()
+
+
+@pytest.mark.parametrize("n,G", [(9, 7), (19, 3)])
+def test_playout_kernel(emu, oracle_lib, n, G):
+    """k_playout (incremental safe/atari masks, Bloom-filtered superko, policy pick, checksum):
+    to-terminal and steady-state modes, per-game checksums of every intermediate position"""
+    gb = emu.emu_batch(G, n)
+    r = gb.playout(1234, first_game_id=50)
+    want = oracles.oracle_playout_many(n, 1234, 50, G, lib=oracle_lib)
+    np.testing.assert_array_equal(r["chk"], want["chk"])
+    np.testing.assert_array_equal(r["plies"], want["plies"])
+    np.testing.assert_array_equal(r["score"], want["score"])
+    assert r["total_plies"] == want["total_plies"]
+    rs = gb.playout_stream(99, first_game_id=7, plies_per_slot=300)
+    for s in range(G):
+        t, acc, games = oracles.oracle_playout_stream(n, 99, 7, s, G, 300, lib=oracle_lib)
+        assert (t, acc, games) == (int(rs["plies"][s]), int(rs["chk"][s]), int(rs["games"][s]))
+
+
+@pytest.mark.parametrize("n,G,R", [(9, 4, 96), (19, 2, 64)])
+def test_search_kernels(emu, oracle_lib, n, G, R):
+    """k_begin / k_select / k_leaf_features / k_expand / k_backup / k_results / k_advance with tree
+    reuse over several moves: root visit counts equal the search restatement's"""
+    opts = dict(num_rollouts=R, num_rollouts_per_batch=8, c_puct=1.5, virtual_loss=1, persistent_tree=1)
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, rotation_flip=0, **opts)
+    os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+    oms = [oracles.OracleMcts(n, lib=oracle_lib, **opts) for _ in range(G)]
+    rng = np.random.default_rng(1)
+    for _ in range(6):
+        acts = np.array([int(rng.choice(np.flatnonzero(o.legal()))) for o in os_], np.int32)
+        assert gb.forward(acts).all()
+        for o, a in zip(os_, acts):
+            o.forward(int(a))
+    actor = fake_actor(mc, n)
+    for _ in range(4):
+        res = mc.act(actor)
+        want = [om.act(o) for om, o in zip(oms, os_)]
+        for g in range(G):
+            np.testing.assert_array_equal(res["visits"][g], want[g]["visits"])
+            assert res["total_visits"][g] == want[g]["total_visits"]
+            assert res["root_value"][g] == pytest.approx(want[g]["root_value"], abs=1e-6)
+        acts = np.array([w["best_action"] for w in want], np.int32)
+        gb.forward(acts)
+        mc.advance(acts)
+        for o, a in zip(os_, acts):
+            o.forward(int(a))
+    assert (mc.errors() == 0).all()
+
+
+def test_leaf_features_of_the_search(emu, oracle_lib):
+    """the planes k_leaf_features writes for every leaf (history along the tree path + the game's
+    ring, random D4 per evaluation) equal the restatement's extractor on the same position"""
+    n, G = 9, 2
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, rotation_flip=1, seed=3, num_rollouts=24, num_rollouts_per_batch=4)
+    os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+    rng = np.random.default_rng(8)
+    for _ in range(12):
+        acts = np.array([int(rng.choice(np.flatnonzero(o.legal()))) for o in os_], np.int32)
+        gb.forward(acts)
+        for o, a in zip(os_, acts):
+            o.forward(int(a))
+    seen = []
+
+    def actor(batch):
+        h, g, ply = mc.leaf_info()
+        seen.append((h.copy(), g.copy(), ply.copy(), mc.leaf_d4.copy(), batch["s"].numpy().copy()))
+        pi, v = oracles.fakenet(h, n * n + 1)
+        return {"pi": torch.from_numpy(pi), "V": torch.from_numpy(v)}
+
+    mc.search(actor)
+    # the first wave's leaves are the roots: planes must be the game's own features under leaf_d4
+    h, g, ply, d4, s = seen[0]
+    assert len(h) == G and set(d4.tolist()) <= set(range(8))
+    for i in range(len(h)):
+        o = os_[int(g[i])]
+        assert int(h[i]) == o.hash() and int(ply[i]) == int(o.info()[0])
+        assert (s[i] == o.features(int(d4[i]))).all()
+    # deeper leaves: the side-to-move planes and the stone planes agree with the leaf's ply parity
+    for h, g, ply, d4, s in seen[1:]:
+        for i in range(len(h)):
+            black_to_move = int(ply[i]) % 2 == 1
+            assert s[i, 16].all() == black_to_move and s[i, 17].all() == (not black_to_move)
+            assert set(np.unique(s[i])) <= {0.0, 1.0}
+    assert len({int(x) for _, _, _, d, _ in seen for x in d}) > 1  # the D4 draw varies
+
+
+def test_online_game_g1_on_the_kernels(emu, oracle_lib):
+    """single-game online mode (OnlineGame + GtpConsole) on the real kernels: the G = 1 combination
+    with operator moves between searches -- moves equal the restatement's"""
+    from elf_b200 import console, online
+
+    n = 9
+    opts = dict(num_rollouts=64, num_rollouts_per_batch=8, c_puct=1.5, virtual_loss=1, persistent_tree=1)
+    gb = emu.emu_batch(1, n)
+    g = online.OnlineGame(gb, emu.EmuSearch(gb, rotation_flip=0, **opts), resign_thres=0.0)
+    c = console.GtpConsole(g, fake_actor(g.search, n))
+    o = oracles.Oracle(n, oracle_lib)
+    om = oracles.OracleMcts(n, lib=oracle_lib, **opts)
+    rng = np.random.default_rng(3)
+    for t in range(10):
+        who = "b" if int(o.info()[1]) == 1 else "w"
+        if t % 3 == 2:
+            a = int(rng.choice(np.flatnonzero(o.legal())))
+            assert c.execute(f"play {who} {online.action2vertex(a, n)}") == "=\n\n"
+        else:
+            a = om.act(o)["best_action"]
+            assert c.execute(f"genmove {who}") == f"= {online.action2vertex(a, n)}\n\n"
+        assert o.forward(a)
+        assert int(gb.getHashCode()[0]) == o.hash()
+    assert "Last move" in c.execute("showboard") and g.seq == 0 and (g.search.errors() == 0).all()
+    c.execute("clear_board")
+    assert gb.info()[0, 0] == 1 and g.seq == 1
+
+
+def test_selfplay_loop_with_parked_games_on_the_kernels(emu, oracle_lib):
+    """SelfPlay.step with the device-side move choice (k_choose) and a request that parks games:
+    parked games are neither searched nor moved, playing games follow the restatement"""
+    from elf_b200.selfplay import SelfPlay
+
+    n, G = 9, 4
+    opts = dict(num_rollouts=32, num_rollouts_per_batch=4, c_puct=1.5, virtual_loss=1, persistent_tree=1)
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, rotation_flip=0, **opts)
+    sp = SelfPlay(fake_actor(mc, n), num_games=G, board_size=n, policy_distri_cutoff=0, never_resign_ratio=1.0,
+                  board=gb, search=mc)
+    assert sp.set_request(1, -1, 0.05, num_game_thread_used=3) == "update_model"
+    os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+    oms = [oracles.OracleMcts(n, lib=oracle_lib, **opts) for _ in range(G)]
+    for _ in range(3):
+        want = [oms[g].act(os_[g])["best_action"] for g in range(3)]
+        assert sp.step() == 3
+        for g in range(3):
+            assert os_[g].forward(want[g])
+        h = gb.getHashCode()
+        assert [int(h[g]) for g in range(3)] == [os_[g].hash() for g in range(3)] and int(h[3]) == 0
+    assert gb.info()[:, 0].tolist() == [4, 4, 4, 1] and (mc.errors() == 0).all()
+
+
+def test_replay_batch_on_the_board_kernels(emu, oracle_lib):
+    """ReplayBatch on the real board batch (k_reset / k_step with untouched games / k_features with
+    per-sample D4) equals ReplayBatch on oracle boards"""
+    from elf_b200 import record, replay
+    from tests.test_request_protocol import Boards
+
+    n, B = 9, 5
+    rng = np.random.default_rng(6)
+    recs = []
+    for i in range(3):
+        o = oracles.Oracle(n, oracle_lib)
+        r = record.GameRecorder(n, i, 8)
+        for t in range(25 + 7 * i):
+            lg = np.flatnonzero(o.legal())
+            a = int(rng.choice(lg)) if len(lg) else n * n
+            row = np.full(n * n + 1, -1, np.int32)
+            row[rng.choice(n * n + 1, 10, replace=False)] = rng.integers(1, 99, 10)
+            r.on_move(int(o.info()[0]), a, row, 0.0)
+            o.forward(a)
+        recs.append(r.finish(1.0 if i % 2 else -1.0, False, model_ver=i))
+    a_ = replay.ReplayBatch(B, board_size=n, num_future_actions=2, board=emu.emu_batch(B, n))
+    b_ = replay.ReplayBatch(B, board_size=n, num_future_actions=2, board=Boards(B, oracle_lib))
+    a_.add_records(recs)
+    b_.add_records(recs)
+    picks = [(0, 0, 1), (1, 30, 6), (2, 37, 3), (0, 23, 7), (2, 5, 0)]
+    x, y = a_.sample(picks), b_.sample(picks)
+    for k in x:
+        np.testing.assert_array_equal(x[k], y[k])

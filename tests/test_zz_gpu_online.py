@@ -20,8 +20,8 @@ def test_online_game_matches_search_restatement(oracle_lib):
     from elf_b200 import console, online
 
     n = 9
-    opts = dict(num_rollouts=96, num_rollouts_per_batch=8, c_puct=1.5, virtual_loss=1, persistent_tree=1)
-    g = online.OnlineGame.create(board_size=n, **opts)
+    opts = dict(num_rollouts=96, num_rollouts_per_batch=8, c_puct=1.5, virtual_loss=1, persistent_tree=1)  # rotation_flip off below: the fake net is keyed by hash
+    g = online.OnlineGame.create(board_size=n, rotation_flip=0, **opts)
 
     def actor(batch):
         h, _, _ = g.search.leaf_info()
