@@ -272,6 +272,14 @@ inline void fiber_main() {
   swapcontext(&s.cur->ctx, &s.sched);
 }
 
+inline int& order_mode_ref() {  // 0 ascending, 1 reverse, 2 random; initial value from SIMT_EMU_ORDER
+  static int mode = [] {
+    const char* e = std::getenv("SIMT_EMU_ORDER");
+    return !e ? 0 : (e[0] == 'r' && e[1] == 'e') ? 1 : (e[0] == 'r' && e[1] == 'a') ? 2 : 0;
+  }();
+  return mode;
+}
+
 template <class F>
 inline void launch(const char* name, dim3 grid, dim3 block, F&& f) {
   State& s = S();
@@ -299,9 +307,24 @@ inline void launch(const char* name, dim3 grid, dim3 block, F&& f) {
       makecontext(&fb.ctx, (void (*)())fiber_main, 0);
     }
     unsigned remaining = nt;
+    // Scheduling order of the lanes between two collectives.  Hardware gives no ordering between
+    // the lanes of a warp except at __syncwarp / *_sync; code that reads what another lane wrote
+    // without such a barrier only works under one particular order.  SIMT_EMU_ORDER=reverse /
+    // random runs the lanes in a different order (a poor man's racecheck for intra-warp hazards).
+    const int order_mode = order_mode_ref();
+    static uint64_t rng_state = 0x9E3779B97F4A7C15ull;
+    std::vector<unsigned> order(nt);
+    for (unsigned t = 0; t < nt; ++t) order[t] = order_mode == 1 ? nt - 1 - t : t;
     while (remaining) {
       const uint64_t before = s.progress;
-      for (unsigned t = 0; t < nt; ++t) {
+      if (order_mode == 2) {
+        for (unsigned t = nt; t > 1; --t) {
+          rng_state = rng_state * 6364136223846793005ull + 1442695040888963407ull;
+          std::swap(order[t - 1], order[(rng_state >> 33) % t]);
+        }
+      }
+      for (unsigned oi = 0; oi < nt; ++oi) {
+        const unsigned t = order[oi];
         Fiber& fb = s.fibers[t];
         if (fb.done) continue;
         s.cur = &fb;
@@ -343,6 +366,10 @@ inline T from_bits(uint64_t b) {
 }
 
 }  // namespace simt
+
+extern "C" __attribute__((used, visibility("default"))) inline void simt_emu_set_order(int mode) {
+  simt::order_mode_ref() = mode;
+}
 
 #define threadIdx (simt::thread_idx())
 #define blockIdx (simt::block_idx())

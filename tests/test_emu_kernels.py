@@ -29,6 +29,16 @@ def emu():
     return E
 
 
+@pytest.fixture(params=["ascending", "reverse", "random"])
+def lane_order(request, emu):
+    """order in which the emulator runs the lanes of a warp between two collectives: hardware
+    promises none, so results must not depend on it (a missing __syncwarp shows up here)"""
+    L = emu.emu_lib()
+    L.simt_emu_set_order(["ascending", "reverse", "random"].index(request.param))
+    yield request.param
+    L.simt_emu_set_order(0)
+
+
 def fake_actor(search, n):
     def actor(batch):
         h, _, _ = search.leaf_info()
@@ -40,7 +50,7 @@ def fake_actor(search, n):
 
 
 @pytest.mark.parametrize("n,G", [(9, 5), (19, 3)])
-def test_board_kernels(emu, oracle_lib, n, G):
+def test_board_kernels(emu, oracle_lib, n, G, lane_order):
     """k_reset / k_step / k_export / k_features: forward verdict, hash, legal mask, info words,
     scores, true eyes and the 18 planes under every D4 code, with illegal and pass moves mixed in;
     9x9 runs 3 games per warp with G = 5 leaving a partially filled warp"""
@@ -80,7 +90,7 @@ def test_board_kernels(emu, oracle_lib, n, G):
 
 
 @pytest.mark.parametrize("n,G", [(9, 7), (19, 3)])
-def test_playout_kernel(emu, oracle_lib, n, G):
+def test_playout_kernel(emu, oracle_lib, n, G, lane_order):
     """k_playout (incremental safe/atari masks, Bloom-filtered superko, policy pick, checksum):
     to-terminal and steady-state modes, per-game checksums of every intermediate position"""
     gb = emu.emu_batch(G, n)
@@ -97,7 +107,7 @@ def test_playout_kernel(emu, oracle_lib, n, G):
 
 
 @pytest.mark.parametrize("n,G,R", [(9, 4, 96), (19, 2, 64)])
-def test_search_kernels(emu, oracle_lib, n, G, R):
+def test_search_kernels(emu, oracle_lib, n, G, R, lane_order):
     """k_begin / k_select / k_leaf_features / k_expand / k_backup / k_results / k_advance with tree
     reuse over several moves: root visit counts equal the search restatement's"""
     opts = dict(num_rollouts=R, num_rollouts_per_batch=8, c_puct=1.5, virtual_loss=1, persistent_tree=1)
