@@ -59,6 +59,18 @@ class GoBatch:
     def forward_dev(self, actions_ptr, ok_ptr=None):
         _l.check(self._lib, self._lib.elfb200_step_dev(self._ctx, actions_ptr, ok_ptr))
 
+    def replay(self, move_lists):
+        """reset every game and forward its own move list in one launch
+        (GoStateExtOffline::switchBeforeMove for the batch); ``move_lists``: G sequences of actions"""
+        assert len(move_lists) == self.num_games
+        stride = max(1, max((len(m) for m in move_lists), default=1))
+        mv = np.full((self.num_games, stride), -1, np.int16)
+        cnt = np.zeros(self.num_games, np.int32)
+        for g, m in enumerate(move_lists):
+            cnt[g] = len(m)
+            mv[g, : len(m)] = m
+        _l.check(self._lib, self._lib.elfb200_replay(self._ctx, mv.ctypes.data, stride, cnt.ctypes.data))
+
     def synchronize(self):
         _l.check(self._lib, self._lib.elfb200_synchronize(self._ctx))
 

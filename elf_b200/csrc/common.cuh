@@ -158,4 +158,7 @@ struct elfb200_ctx {
   void* h_pin = nullptr;
   size_t h_pin_bytes = 0;
   int64_t launches = 0;
+  // move lists of elfb200_replay (grown on demand)
+  int16_t* d_replay = nullptr;
+  size_t d_replay_bytes = 0;
 };

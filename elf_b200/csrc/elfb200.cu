@@ -113,6 +113,80 @@ __global__ void __launch_bounds__(BLOCK)
 }
 
 // ---------------------------------------------------------------------------------------
+// GoStateExtOffline::switchBeforeMove (common/go_state_ext.h:305-312) for all games in one launch:
+// every game starts from the empty board and forwards its own move list, moves[g][0 .. count[g]).
+// Per ply this is k_step (validate against the legal rows, play, superko, next legal rows) with the
+// position held in registers; a refused move changes nothing and the list goes on, as the reference
+// ignores forward()'s verdict there.  Games of one warp (9x9 packs three) may have different
+// lengths: the warp runs to the longest, shorter games idle with MV_NONE.
+template <int N>
+__global__ void __launch_bounds__(BLOCK)
+    k_replay(DevState st, const int16_t* __restrict__ moves, int stride, const int32_t* __restrict__ count) {
+  __shared__ uint64_t s_zob[Geo<N>::ZOB];
+  load_zobrist<N>(s_zob);
+  const Lane L = make_lane<N>();
+  bool valid;
+  const int g = warp_game<N>(L, st.G, valid);
+  const int gs = valid ? g : 0;  // safe index for idle lanes (loads only)
+
+  uint32_t b = 0, w = 0;
+  BoardMeta meta = initial_meta();
+  uint64_t hash = 0;
+  uint32_t lrow = valid ? Geo<N>::ROWMASK : 0u;  // every point of the empty board is legal
+  int nsk = 0;
+  if (valid)
+    for (int s = 0; s < 8; ++s) st.ring[((size_t)g * 8 + s) * N + L.row] = 0;
+  const int n = valid ? count[gs] : 0;
+  const int nmax = __reduce_max_sync(FULL, n);
+  uint64_t* skg = st.sk + (size_t)gs * Geo<N>::MAX_PLY;
+
+  for (int t = 0; t < nmax; ++t) {
+    const int a = (valid && t < n) ? (int)moves[(size_t)gs * stride + t] : -1;
+    const bool term = is_terminated<N>(meta);
+    int pm = MV_NONE;
+    if (valid && !term) {
+      if (a == Geo<N>::P) {
+        pm = MV_PASS;
+      } else if (a >= 0 && a < Geo<N>::P) {
+        pm = (a % N) * N + (a / N);  // a = x*N + y  ->  p = y*N + x
+      }
+    }
+    {
+      const int y = pm >= 0 ? pm / N : -1, x = pm >= 0 ? pm - y * N : 0;
+      const bool bit = (L.row == y) && ((lrow >> x) & 1u);
+      const bool is_legal = game_any<N>(bit, L);
+      if (pm >= 0 && !is_legal) pm = MV_NONE;
+    }
+    const uint64_t pre_hash = hash;
+    play_move<N>(b, w, meta, hash, pm, s_zob, L);
+    const bool sko = superko_scan<N>(skg, pm >= 0 ? nsk : 0, hash, L);
+    __syncwarp();
+    if (pm >= 0) {
+      if (sko) meta.flags |= F_SUPERKO;
+      if (valid && L.row == 0) skg[nsk] = pre_hash;
+      nsk++;
+    }
+    const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
+    const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
+    const uint32_t lnew = legal_rows<N>(own, opp, L, ko_applies, meta.ko_pt);
+    if (valid && pm != MV_NONE) {
+      lrow = lnew;
+      st.ring[((size_t)g * 8 + ((meta.ply - 2) & 7)) * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);  // go_state.cc:90-92
+    }
+    __syncwarp();
+  }
+  if (valid) {
+    st.cur[(size_t)g * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);
+    st.legal[(size_t)g * N + L.row] = lrow;
+    if (L.row == 0) {
+      st.hash[g] = hash;
+      store_meta(&st.meta[g], meta);
+      st.sk_n[g] = nsk;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 template <int N>
 __global__ void __launch_bounds__(BLOCK)
     k_export(DevState st, uint8_t* __restrict__ legal_out, uint8_t* __restrict__ stones_out,
@@ -383,7 +457,8 @@ void elfb200_destroy(elfb200_ctx* c) {
   cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->st.cur,  c->st.ring, c->st.legal, c->st.hash,   c->st.meta,   c->st.sk,
                   c->st.sk_n, c->d_actions, c->d_ok,   c->d_bytes,   c->d_words,   c->d_d4,
-                  c->d_feat,  c->d_po_sk, c->d_po_chk, c->d_po_hash, c->d_po_plies, c->d_po_score};
+                  c->d_feat,  c->d_po_sk, c->d_po_chk, c->d_po_hash, c->d_po_plies, c->d_po_score,
+                  c->d_replay};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -439,6 +514,34 @@ int elfb200_step(elfb200_ctx* c, const int32_t* actions_host, uint8_t* ok_host) 
   if (ok_host) {
     CK(cudaMemcpyAsync(ok_host, c->d_ok, c->G, cudaMemcpyDeviceToHost, c->stream));
   }
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_replay(elfb200_ctx* c, const int16_t* moves_host, int stride, const int32_t* count_host) {
+  if (!c || !moves_host || !count_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  const int max_ply = c->N == 19 ? elfb200::Geo<19>::MAX_PLY : elfb200::Geo<9>::MAX_PLY;
+  if (stride <= 0 || stride > max_ply)
+    return elfb200_fail(ELFB200_ERR_ARG, "stride %d outside [1, %d]", stride, max_ply);
+  for (int g = 0; g < c->G; ++g)
+    if (count_host[g] < 0 || count_host[g] > stride)
+      return elfb200_fail(ELFB200_ERR_ARG, "count[%d] = %d outside [0, stride = %d]", g, count_host[g], stride);
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)c->G * (size_t)stride * sizeof(int16_t);
+  if (bytes > c->d_replay_bytes) {
+    if (c->d_replay) CK(cudaFree(c->d_replay));
+    c->d_replay = nullptr;
+    c->d_replay_bytes = 0;
+    CK(cudaMalloc(&c->d_replay, bytes));
+    c->d_replay_bytes = bytes;
+  }
+  memcpy(c->h_pin, count_host, (size_t)c->G * 4);
+  CK(cudaMemcpyAsync(c->d_actions, c->h_pin, (size_t)c->G * 4, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_replay, moves_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  DISPATCH_N(c, (k_replay<19><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, c->d_replay, stride, c->d_actions)),
+             (k_replay<9><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, c->d_replay, stride, c->d_actions)));
+  c->launches++;
+  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   return ELFB200_OK;
 }

@@ -9,10 +9,10 @@ Reference: ``GoGameTrain::act`` (``src_cpp/elfgames/go/train/game_train.cc:22-53
 when the record holds no policy for it), ``move_idx``, ``num_move``, ``predicted_value``,
 ``aug_code``, ``selfplay_ver``.
 
-The reference replays each record on one CPU thread; here ``B`` samples advance in lock step on a
-``GoBatch`` of ``B`` games (one ``elfb200_step`` launch per ply, games that have reached their move
-idle) and the planes of all of them come from one ``elfb200_features`` launch.  Everything else is
-host arithmetic on the record.
+The reference replays each record on one CPU thread; here the ``B`` samples of a batch are replayed
+by one ``elfb200_replay`` launch on a ``GoBatch`` of ``B`` games (every game forwards its own move
+list, positions in registers) and the planes of all of them come from one ``elfb200_features``
+launch.  Everything else is host arithmetic on the record.
 """
 import json
 
@@ -122,11 +122,14 @@ class ReplayBatch:
         for r, m in zip(recs, move_to):
             if not (0 <= m <= len(r["moves"]) - K):
                 raise ValueError("move index outside switchRandomMove's range")
-        # switchBeforeMove for all samples at once: ply t of every record that still has to move
-        self.board.reset(None)
-        for t in range(int(move_to.max()) if B else 0):
-            acts = np.array([r["moves"][t] if t < m else -1 for r, m in zip(recs, move_to)], np.int32)
-            self.board.forward(acts)  # the reference ignores forward()'s verdict here as well
+        # switchBeforeMove for all samples at once
+        if hasattr(self.board, "replay"):  # one launch: every game forwards its own move list (k_replay)
+            self.board.replay([r["moves"][:m] for r, m in zip(recs, move_to)])
+        else:  # boards without the replay entry point: one step per ply, finished samples idle
+            self.board.reset(None)
+            for t in range(int(move_to.max()) if B else 0):
+                acts = np.array([r["moves"][t] if t < m else -1 for r, m in zip(recs, move_to)], np.int32)
+                self.board.forward(acts)  # the reference ignores forward()'s verdict here as well
         out = {
             "s": self.board.features(d4),
             "offline_a": np.zeros((B, K), np.int64),

@@ -58,6 +58,12 @@ int elfb200_reset(elfb200_ctx* ctx, const uint8_t* mask_host);
 int elfb200_step(elfb200_ctx* ctx, const int32_t* actions_host, uint8_t* ok_host);
 /* Same with device buffers, asynchronous on the context stream. */
 int elfb200_step_dev(elfb200_ctx* ctx, const int32_t* actions_dev, uint8_t* ok_dev);
+/* GoStateExtOffline::switchBeforeMove (common/go_state_ext.h:305-312), the replay step of the
+ * training loop (train/game_train.cc:22-45), for every game in ONE launch: game g is reset and
+ * moves_host[g*stride + 0 .. count_host[g]) are forwarded in order (int16 actions x*N+y, N*N =
+ * pass).  A move GoState::forward refuses is skipped and the list goes on -- the reference ignores
+ * forward()'s verdict there.  1 <= stride <= 2*N*N, 0 <= count[g] <= stride.  Synchronous. */
+int elfb200_replay(elfb200_ctx* ctx, const int16_t* moves_host, int stride, const int32_t* count_host);
 
 /* Board hash, GoState::getHashCode (go_state.h:170; set_color board.cc:38-51). uint64[G]. */
 int elfb200_get_hash(elfb200_ctx* ctx, uint64_t* hash_host);

@@ -255,3 +255,45 @@ def test_replay_batch_on_the_board_kernels(emu, oracle_lib):
     x, y = a_.sample(picks), b_.sample(picks)
     for k in x:
         np.testing.assert_array_equal(x[k], y[k])
+
+
+@pytest.mark.parametrize("n,G", [(9, 7), (19, 3)])
+def test_replay_kernel(emu, oracle_lib, n, G, lane_order):
+    """k_replay (one launch forwards every game's own move list from the empty board) leaves exactly
+    the state that the same moves leave through k_step -- position, info words, legal rows, the
+    8-position history seen by the feature kernel and the superko record (checked by playing on)"""
+    rng = np.random.default_rng(n)
+    lists, os_ = [], []
+    for g in range(G):
+        o = oracles.Oracle(n, oracle_lib)
+        mv = []
+        for _ in range(0 if g == 1 else int(rng.integers(1, 70 if n == 9 else 200))):
+            lg = np.flatnonzero(o.legal())
+            a = int(rng.choice(lg)) if len(lg) and rng.random() > 0.04 else n * n
+            if rng.random() < 0.05:
+                a = int(rng.integers(n * n))  # possibly refused: skipped, the list goes on
+            mv.append(a)
+            o.forward(a)
+        lists.append(mv)
+        os_.append(o)
+    gb = emu.emu_batch(G, n)
+    gb.forward(np.full(G, 3, np.int32))  # state that the replay has to wipe
+    gb.replay(lists)
+    ref = emu.emu_batch(G, n)
+    for t in range(max(len(m) for m in lists)):
+        ref.forward(np.array([m[t] if t < len(m) else -1 for m in lists], np.int32))
+    assert [int(h) for h in gb.getHashCode()] == [o.hash() for o in os_]
+    np.testing.assert_array_equal(gb.info(), ref.info())
+    np.testing.assert_array_equal(gb.stones(), ref.stones())
+    np.testing.assert_array_equal(gb.legal_mask(), ref.legal_mask())
+    d4 = np.arange(G, dtype=np.int32) % 8
+    np.testing.assert_array_equal(gb.features(d4), ref.features(d4))
+    for _ in range(40):
+        acts = np.array([int(rng.choice(np.flatnonzero(o.legal()))) if o.legal().any() and not o.terminated() else n * n
+                         for o in os_], np.int32)
+        ok = gb.forward(acts)
+        for g, o in enumerate(os_):
+            assert bool(ok[g]) == bool(o.forward(int(acts[g])))
+        assert [int(h) for h in gb.getHashCode()] == [o.hash() for o in os_]
+    with pytest.raises(Exception, match="stride"):
+        gb.replay([[0] * (2 * n * n + 1)] * G)
