@@ -128,6 +128,20 @@ class EmuSearch:
         _l.check(self._lib, self._lib.elfb200_mcts_errors(self._m, e.ctypes.data))
         return e
 
+    def eval_count(self):
+        return self._lib.elfb200_mcts_eval_count(self._m)
+
+    def stats(self):
+        s = np.zeros(4, np.uint64)
+        _l.check(self._lib, self._lib.elfb200_mcts_stats(self._m, s.ctypes.data))
+        return s
+
+    def timings(self, reset=False):
+        ms = np.zeros(4, np.float64)
+        w = ctypes.c_int64()
+        _l.check(self._lib, self._lib.elfb200_mcts_timings(self._m, ms.ctypes.data, ctypes.byref(w), int(reset)))
+        return ms, w.value
+
     def search(self, actor, active=None):
         self.begin_move(active)
         for _ in range(self.waves_per_move):
