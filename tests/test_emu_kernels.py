@@ -297,3 +297,50 @@ def test_replay_kernel(emu, oracle_lib, n, G, lane_order):
         assert [int(h) for h in gb.getHashCode()] == [o.hash() for o in os_]
     with pytest.raises(Exception, match="stride"):
         gb.replay([[0] * (2 * n * n + 1)] * G)
+
+
+def test_wait_step_pump_on_the_kernels(emu):
+    """the host path of tests/test_gpu_compat.py::test_wait_step_pump_plays_games (no request ever
+    set, host-memory SharedMems, a small network answering the actor_black batches) with the
+    kernels on the emulator: games are played to the move cutoff and restarted"""
+    from elf_b200 import compat
+    from elf_b200.model import Actor, PolicyValueNet
+    from elf_b200.selfplay import SelfPlay
+
+    torch.manual_seed(0)
+    n, G, BS = 9, 6, 8
+    net = Actor(PolicyValueNet(n, num_block=1, dim=8), batchsize=BS, dtype=torch.float32, channels_last=False)
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, num_rollouts=8, num_rollouts_per_batch=4, rotation_flip=1, seed=3)
+    sp = SelfPlay(None, num_games=G, board_size=n, policy_distri_cutoff=0, move_cutoff=5, seed=3, board=gb, search=mc)
+    GC = compat.GameContext(compat.SelfPlayEngine(sp), batchsize=BS)
+    ctx = GC.ctx()
+    keys = ["s", "pi", "V", "a", "rv"]
+    opts = ctx.createSharedMemOptions("actor_black", BS)
+    bufs = {}
+    for _ in range(2):
+        sm = ctx.allocateSharedMem(opts, keys)
+        b = {}
+        for k in keys:
+            f = sm[k].field()
+            dt = {"float": torch.float32, "int64_t": torch.int64, "int32_t": torch.int32}[f.type_name()]
+            b[k] = torch.zeros(*f.sz().vec(), dtype=dt)
+            sm[k].set(b[k].data_ptr(), [i * b[k].element_size() for i in b[k].stride()])
+        bufs[sm.getSharedMemOptions().idx()] = b
+    ctx.start()
+    batches = 0
+    while sp.games_finished < G and batches < 400:
+        sm = ctx.wait()
+        k = sm.effective_batchsize()
+        assert 0 < k <= BS and sm.getSharedMemOptions().label() == "actor_black"
+        b = bufs[sm.getSharedMemOptions().idx()]
+        ind = b["s"][:k, 16:18].reshape(k, 2, -1)
+        assert ((ind.sum(2) == n * n).sum(1) == 1).all()  # exactly one side-to-move plane is set
+        out = net({"s": b["s"][:k]})
+        b["pi"][:k].copy_(out["pi"])
+        b["V"][:k].copy_(out["V"])
+        ctx.step()
+        batches += 1
+    ctx.stop()
+    assert sp.games_finished >= G and sp.moves_played >= 4 * G and (mc.errors() == 0).all()
+    assert GC.getClient().getGameStats().getWinRateStats().total_games == sp.games_finished
