@@ -344,3 +344,58 @@ def test_wait_step_pump_on_the_kernels(emu):
     ctx.stop()
     assert sp.games_finished >= G and sp.moves_played >= 4 * G and (mc.errors() == 0).all()
     assert GC.getClient().getGameStats().getWinRateStats().total_games == sp.games_finished
+
+
+def test_online_engine_pump_on_the_kernels(emu, oracle_lib):
+    """mode == "online" through compat.Context with the kernels on the emulator: human_actor asks
+    for an action, ACTION_SKIP starts a search whose waves (8 leaves) arrive as actor_black batches of
+    <= 3, and the move played is the restatement's"""
+    from elf_b200 import compat, online
+
+    n = 9
+    opts = dict(num_rollouts=32, num_rollouts_per_batch=8, c_puct=1.5, virtual_loss=1, persistent_tree=1)
+    gb = emu.emu_batch(1, n)
+    search = emu.EmuSearch(gb, rotation_flip=0, **opts)
+    g = online.OnlineGame(gb, search)
+    GC = compat.GameContext(compat.OnlineEngine(g), batchsize=3)
+    ctx = GC.ctx()
+    bufs = {}
+    for label, keys, bs in (("human_actor", ["s", "pi", "a", "V"], 1), ("actor_black", ["s", "pi", "V", "a", "rv"], 3)):
+        sm = ctx.allocateSharedMem(ctx.createSharedMemOptions(label, bs), keys)
+        b = {}
+        for k in keys:
+            f = sm[k].field()
+            dt = {"float": torch.float32, "int64_t": torch.int64, "int32_t": torch.int32}[f.type_name()]
+            b[k] = torch.zeros(*f.sz().vec(), dtype=dt)
+            sm[k].set(b[k].data_ptr(), [i * b[k].element_size() for i in b[k].stride()])
+        bufs[label] = b
+    o = oracles.Oracle(n, oracle_lib)
+    om = oracles.OracleMcts(n, lib=oracle_lib, **opts)
+    script = [online.vertex2action("E5", n), online.SA_SKIP, online.vertex2action("C3", n), online.SA_SKIP, online.SA_SKIP]
+    ctx.start()
+    chunks = []
+    for cmd in script:
+        sm = ctx.wait()
+        assert sm.getSharedMemOptions().label() == "human_actor" and sm.effective_batchsize() == 1
+        assert (bufs["human_actor"]["s"][0].numpy() == o.features(0)).all()  # the operator sees the position
+        bufs["human_actor"]["a"][0] = cmd
+        ctx.step()
+        if cmd != online.SA_SKIP:
+            assert o.forward(cmd)
+            continue
+        want = om.act(o)["best_action"]
+        while GC._engine.next_label() == "actor_black":
+            sm = ctx.wait()
+            k = sm.effective_batchsize()
+            chunks.append(k)
+            # the leaves of a wave arrive in slot order; the fake net needs their hashes
+            h, _, _ = search.leaf_info()
+            base = GC._engine._wave["off"] - k
+            pi, v = oracles.fakenet(h[base:base + k], n * n + 1)
+            bufs["actor_black"]["pi"][:k] = torch.from_numpy(pi)
+            bufs["actor_black"]["V"][:k] = torch.from_numpy(v)
+            ctx.step()
+        assert o.forward(want) and int(gb.getHashCode()[0]) == o.hash()
+    ctx.stop()
+    assert max(chunks) == 3 and len(chunks) > 12 and (search.errors() == 0).all()
+    assert GC.getGame(0).getNextPlayer() in "BW" and "Last move" in GC.getGame(0).showBoard()
