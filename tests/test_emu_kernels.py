@@ -399,3 +399,50 @@ def test_online_engine_pump_on_the_kernels(emu, oracle_lib):
     ctx.stop()
     assert max(chunks) == 3 and len(chunks) > 12 and (search.errors() == 0).all()
     assert GC.getGame(0).getNextPlayer() in "BW" and "Last move" in GC.getGame(0).showBoard()
+
+
+def test_search_option_fuzz(emu, oracle_lib):
+    """random search options (rollouts not a multiple of the batch, batch 1..16, virtual loss 0..3,
+    tree reuse on/off, priors off, FPU switches, pass rules, komi), random openings, 1..4 games,
+    terminated games left inactive: root visit tables equal the restatement's in every case"""
+    n = 9
+    rng = np.random.default_rng(7)
+    for case in range(8):
+        opts = dict(
+            num_rollouts=int(rng.integers(8, 90)), num_rollouts_per_batch=int(rng.integers(1, 17)),
+            virtual_loss=int(rng.integers(0, 4)), persistent_tree=int(rng.integers(0, 2)),
+            c_puct=float(rng.choice([0.5, 0.85, 1.5, 2.5, 5.0])), unexplored_q_zero=int(rng.integers(0, 2)),
+            root_unexplored_q_zero=int(rng.integers(0, 2)), ply_pass_enabled=int(rng.choice([0, 30, 70])),
+            remove_pass_if_dangerous=int(rng.integers(0, 2)), komi=float(rng.choice([5.5, 6.5, 7.5])),
+            use_prior=int(rng.random() > 0.15))
+        G, open_plies = int(rng.integers(1, 5)), int(rng.integers(0, 75))
+        emu.emu_lib().simt_emu_set_order(case % 3)
+        gb = emu.emu_batch(G, n)
+        mc = emu.EmuSearch(gb, rotation_flip=0, **opts)
+        os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+        oms = [oracles.OracleMcts(n, lib=oracle_lib, **opts) for _ in range(G)]
+        for _ in range(open_plies):
+            acts = np.array([int(rng.choice(np.flatnonzero(o.legal()))) if o.legal().any() and not o.terminated() else n * n
+                             for o in os_], np.int32)
+            gb.forward(acts)
+            for o, a in zip(os_, acts):
+                o.forward(int(a))
+        actor = fake_actor(mc, n)
+        for mv in range(3):
+            live = np.array([not o.terminated() for o in os_])
+            if not live.any():
+                break
+            res = mc.act(actor, active=live.astype(np.uint8))
+            acts = np.full(G, -1, np.int32)
+            for g in np.flatnonzero(live):
+                w = oms[g].act(os_[g])
+                np.testing.assert_array_equal(res["visits"][g], w["visits"], err_msg=f"case {case} move {mv} {opts}")
+                assert res["total_visits"][g] == w["total_visits"]
+                acts[g] = w["best_action"]
+            gb.forward(acts)
+            mc.advance(acts)
+            for o, a in zip(os_, acts):
+                if a >= 0:
+                    o.forward(int(a))
+        assert (mc.errors() == 0).all(), (case, opts)
+    emu.emu_lib().simt_emu_set_order(0)
