@@ -112,7 +112,11 @@ class ReplayBatch:
         return picks
 
     # -- one `train` batch ---------------------------------------------------------------------------
-    def sample(self, picks=None):
+    def sample(self, picks=None, s_out=None):
+        """one ``train`` batch as a dict of arrays.  ``s_out``: optional float32 torch tensor
+        ``[B, 18, N, N]`` (contiguous) on the boards' device: the feature kernel then writes the planes
+        straight into it (``elfb200_features_dev``) and ``out["s"]`` is that tensor -- the 26 KB per
+        position never cross PCIe; all other fields are small host arrays."""
         n, B, K, A = self.N, self.B, self.K, self.N * self.N + 1
         picks = self.draw() if picks is None else list(picks)
         assert len(picks) == B
@@ -130,8 +134,17 @@ class ReplayBatch:
             for t in range(int(move_to.max()) if B else 0):
                 acts = np.array([r["moves"][t] if t < m else -1 for r, m in zip(recs, move_to)], np.int32)
                 self.board.forward(acts)  # the reference ignores forward()'s verdict here as well
+        if s_out is not None:
+            import torch
+
+            assert tuple(s_out.shape) == (B, 18, n, n) and s_out.dtype == torch.float32 and s_out.is_contiguous()
+            d4_dev = torch.as_tensor(d4, device=s_out.device)
+            if s_out.is_cuda:
+                torch.cuda.current_stream(s_out.device).synchronize()  # d4_dev is ready, s_out is free
+            self.board.features_dev(s_out.data_ptr(), d4_dev.data_ptr())
+            self.board.synchronize()
         out = {
-            "s": self.board.features(d4),
+            "s": s_out if s_out is not None else self.board.features(d4),
             "offline_a": np.zeros((B, K), np.int64),
             "winner": np.array([r["winner"] for r in recs], np.float32),
             "mcts_scores": np.zeros((B, A), np.float32),

@@ -255,6 +255,11 @@ def test_replay_batch_on_the_board_kernels(emu, oracle_lib):
     x, y = a_.sample(picks), b_.sample(picks)
     for k in x:
         np.testing.assert_array_equal(x[k], y[k])
+    # planes written by the feature kernel straight into the caller's tensor
+    dst = torch.full((B, 18, n, n), -1.0)
+    z = a_.sample(picks, s_out=dst)
+    assert z["s"] is dst
+    np.testing.assert_array_equal(dst.numpy(), y["s"])
 
 
 @pytest.mark.parametrize("n,G", [(9, 7), (19, 3)])

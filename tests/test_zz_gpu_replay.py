@@ -78,3 +78,10 @@ def test_replay_batch_equals_oracle_boards(oracle_lib):
         x, y = a_.sample(), b_.sample()
         for k in x:
             np.testing.assert_array_equal(x[k], y[k])
+    import torch
+
+    dst = torch.full((B, 18, n, n), -1.0, device="cuda")
+    z, y = a_.sample(s_out=dst), b_.sample()
+    assert z["s"] is dst
+    np.testing.assert_array_equal(dst.cpu().numpy(), y["s"])
+    np.testing.assert_array_equal(z["offline_a"], y["offline_a"])
