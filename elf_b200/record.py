@@ -67,6 +67,42 @@ def ts_options_json(opts=None):
     }
 
 
+def request_json(black_ver, white_ver=-1, mcts_opt=None, black_resign_thres=0.0, white_resign_thres=0.0,
+                 never_resign_prob=0.0, player_swap=False, async_=False, num_game_thread_used=-1, client_type=1):
+    """``MsgRequest::setJsonFields`` (``common/record.h:113-135``): what the training server sends to a
+    client (``ModelPair`` vers + ``ClientCtrl``), as a dict"""
+    return {
+        "vers": {"black_ver": int(black_ver), "white_ver": int(white_ver), "mcts_opt": ts_options_json(mcts_opt)
+                 if not (isinstance(mcts_opt, dict) and "alg_opt" in mcts_opt) else mcts_opt},
+        "client_ctrl": {"client_type": int(client_type), "num_game_thread_used": int(num_game_thread_used),
+                        "black_resign_thres": float(black_resign_thres), "white_resign_thres": float(white_resign_thres),
+                        "never_resign_prob": float(never_resign_prob), "player_swap": bool(player_swap),
+                        "async": bool(async_)},
+    }
+
+
+def parse_request(msg):
+    """a MsgRequest (dict or JSON text, ``MsgRequest::createFromJson``) -> keyword arguments of
+    ``SelfPlay.set_request`` plus ``mcts_opt`` (the TSOptions object, kept for the records).
+    ``player_swap`` is optional for self-play requests and ``async`` is optional altogether, as in
+    ``ClientCtrl::createFromJson`` (record.h:52-69)."""
+    if isinstance(msg, (str, bytes)):
+        msg = json.loads(msg)
+    v, c = msg["vers"], msg["client_ctrl"]
+    for k in ("black_ver", "white_ver", "mcts_opt"):
+        if k not in v:
+            raise KeyError(f"{k}cannot not be found!")  # the reference's message, typo included
+    selfplay = v["black_ver"] >= 0 and v["white_ver"] == -1
+    if not selfplay and "player_swap" not in c:
+        raise KeyError("player_swapcannot not be found!")
+    return {
+        "black_ver": int(v["black_ver"]), "white_ver": int(v["white_ver"]),
+        "black_resign_thres": float(c["black_resign_thres"]), "white_resign_thres": float(c["white_resign_thres"]),
+        "never_resign_prob": float(c["never_resign_prob"]), "player_swap": bool(c.get("player_swap", False)),
+        "async_": bool(c.get("async", False)), "num_game_thread_used": int(c["num_game_thread_used"]),
+    }, v["mcts_opt"]
+
+
 class GameRecorder:
     """per-slot accumulation of one game's record fields"""
 

@@ -162,6 +162,19 @@ class SelfPlay:
                 self.recorders[g].add_models(prev["black_ver"], prev["white_ver"], new["black_ver"], new["white_ver"])
         return "update_request_only" if same_vers else "update_model_async"
 
+    def set_request_msg(self, msg):
+        """``set_request`` from the server's MsgRequest (dict or JSON text).  The search options in
+        ``vers.mcts_opt`` are recorded with the games; the running search keeps the options it was
+        created with (the reference re-creates its AI from them at restart, game_selfplay.cc:165-182)."""
+        from .record import parse_request
+
+        kw, mcts_opt = parse_request(msg)
+        reply = self.set_request(**kw)
+        if self.recorders is not None:
+            for r in self.recorders:
+                r.mcts_opt = mcts_opt
+        return reply
+
     def restart_games(self, mask):
         """GoGameSelfPlay::restart for the games in ``mask``: fresh boards and trees, no result"""
         m = np.ascontiguousarray(mask, dtype=np.uint8)

@@ -45,6 +45,20 @@ int ref_record_roundtrip(const char* text, char* out, int cap) {
   }
 }
 
+// MsgRequest::createFromJson + setJsonFields (record.h:113-135): the server's request message.
+int ref_request_roundtrip(const char* text, char* out, int cap) {
+  try {
+    MsgRequest r = MsgRequest::createFromJson(json::parse(std::string(text)));
+    std::string s = r.setJsonFields();
+    if ((int)s.size() + 1 > cap)
+      return -2;
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return (int)s.size();
+  } catch (...) {
+    return -1;
+  }
+}
+
 // MCTSPolicy::normalize (tree_search_base.h:193-203) + GoStateExt::addMCTSPolicy
 // (go_state_ext.h:168-190) on `n` (action, visit count) pairs given in edge order; out = the u8
 // policy indexed by the reference Coord, BOUND_COORD entries.  Returns BOUND_COORD.

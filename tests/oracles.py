@@ -173,6 +173,16 @@ def ref_record_roundtrip(text, n=9):
     return None if k < 0 else buf.value.decode()
 
 
+def ref_request_roundtrip(text, n=9):
+    """MsgRequest::createFromJson + setJsonFields of the compiled reference; None if it throws"""
+    L = load_ref(n)
+    L.ref_request_roundtrip.restype = ctypes.c_int
+    L.ref_request_roundtrip.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+    buf = ctypes.create_string_buffer(1 << 16)
+    k = L.ref_request_roundtrip(text.encode(), buf, 1 << 16)
+    return None if k < 0 else buf.value.decode()
+
+
 def ref_record_batch_count(text, n=9):
     L = load_ref(n)
     L.ref_record_batch_count.restype = ctypes.c_int

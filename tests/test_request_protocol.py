@@ -286,3 +286,52 @@ def test_records_name_every_model_a_game_saw(oracle_lib):
     assert [r["result"]["using_models"] for r in sp.records] == [[3, 4], [3, 4], [4], [4]]
     assert [r["request"]["vers"]["black_ver"] for r in sp.records] == [4] * 4
     assert all(r["request"]["client_ctrl"]["async"] for r in sp.records)
+
+
+@pytest.mark.skipif(not oracles.have_ref(9), reason="oracle/_ref not built")
+def test_request_message_format_against_reference(oracle_lib):
+    """the server's MsgRequest JSON: what record.request_json writes is what the reference's own
+    MsgRequest::createFromJson reads (and writes back), and parse_request + set_request_msg consume
+    what the reference writes"""
+    import json
+
+    from elf_b200 import record
+
+    msg = record.request_json(7, 5, mcts_opt=dict(num_rollouts=1600, c_puct=0.85, virtual_loss=2, persistent_tree=1),
+                              black_resign_thres=0.04, white_resign_thres=0.08, never_resign_prob=0.1, player_swap=True,
+                              async_=True, num_game_thread_used=3)
+    back = oracles.ref_request_roundtrip(json.dumps(msg))
+    assert back is not None
+    back = json.loads(back)
+    assert back["vers"]["mcts_opt"]["num_rollouts_per_thread"] == 1600 and back["vers"]["mcts_opt"]["alg_opt"]["c_puct"] == pytest.approx(0.85)
+    assert back["client_ctrl"]["player_swap"] is True and back["client_ctrl"]["async"] is True
+    kw, opt = record.parse_request(json.dumps(back))  # the reference's own serialisation
+    assert kw == dict(black_ver=7, white_ver=5, black_resign_thres=pytest.approx(0.04), white_resign_thres=pytest.approx(0.08),
+                      never_resign_prob=pytest.approx(0.1), player_swap=True, async_=True, num_game_thread_used=3)
+    assert opt["virtual_loss"] == 2
+    # fields the reference treats as optional / mandatory
+    m2 = json.loads(json.dumps(record.request_json(3)))
+    del m2["client_ctrl"]["async"], m2["client_ctrl"]["player_swap"]  # a self-play request may omit both
+    assert oracles.ref_request_roundtrip(json.dumps(m2)) is not None and record.parse_request(m2)[0]["player_swap"] is False
+    m3 = json.loads(json.dumps(record.request_json(3, 2)))
+    del m3["client_ctrl"]["player_swap"]  # an evaluation request may not
+    assert oracles.ref_request_roundtrip(json.dumps(m3)) is None
+    with pytest.raises(KeyError):
+        record.parse_request(m3)
+    # applied to the engine: versions, thresholds, the parked games, and mcts_opt into the records
+    class VisitSearch(Search):
+        def results(self):
+            return {"visits": np.where(self.pi > 0.5, 10, -1).astype(np.int32)}
+
+    b = Boards(3, oracle_lib)
+    sp = SelfPlay(net("black", []), num_games=3, board_size=N, policy_distri_cutoff=0, never_resign_ratio=0.0,
+                  move_cutoff=4, record_games=True, board=b, search=VisitSearch(b, "ai"))
+    assert sp.set_request_msg(json.dumps(record.request_json(9, mcts_opt=dict(num_rollouts=400), black_resign_thres=0.02,
+                                                             white_resign_thres=0.06, num_game_thread_used=2))) == "update_model"
+    assert sp.resign_thres == pytest.approx(0.04) and sp.idle.tolist() == [False, False, True]
+    while len(sp.records) < 2:
+        sp.step()
+    r = sp.records[0]
+    assert r["request"]["vers"]["black_ver"] == 9 and r["request"]["vers"]["mcts_opt"]["num_rollouts_per_thread"] == 400
+    assert r["request"]["client_ctrl"]["num_game_thread_used"] == 2 and r["result"]["using_models"] == [9]
+    assert oracles.ref_record_roundtrip(json.dumps(r)) is not None
