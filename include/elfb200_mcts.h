@@ -48,7 +48,12 @@ typedef struct {
   int32_t root_unexplored_q_zero;  /* SearchAlgoOptions::root_unexplored_q_zero */
   int32_t ply_pass_enabled;        /* MCTSActorParams::ply_pass_enabled */
   int32_t remove_pass_if_dangerous;/* MCTSActorParams::remove_pass_if_dangerous */
-  int32_t rotation_flip;           /* MCTSActorParams::rotation_flip: random D4 per evaluation */
+  int32_t rotation_flip;           /* MCTSActorParams::rotation_flip: random D4 per evaluation (default 1).
+                                    * The planes of each leaf are written under its D4 code and the returned
+                                    * pi is read back through the inverse, exactly as the reference does, so a
+                                    * network sees nothing unusual.  A callback that computes pi from the leaf
+                                    * HASH instead of the planes (test nets) must set 0 or permute through
+                                    * elfb200_mcts_leaf_info's d4 output. */
   int32_t seed;
   int32_t nodes_per_game;          /* node-pool slots per game; 0 = 2*rollouts + 256 */
   float c_puct;                    /* SearchAlgoOptions::c_puct */
