@@ -31,6 +31,8 @@
 #include <cstring>
 #include <deque>
 #include <functional>
+#include <string>
+#include <utility>
 #include <vector>
 
 // ---- qualifiers ---------------------------------------------------------------------------------
@@ -132,6 +134,21 @@ inline void yield() {
   swapcontext(&s.cur->ctx, &s.sched);
 }
 
+// per-kernel counts of completed warp collectives by operation (one count per warp-wide collective)
+struct Counters {
+  uint64_t n[32] = {0};
+};
+inline std::vector<std::pair<std::string, Counters>>& counters() {
+  static std::vector<std::pair<std::string, Counters>> c;
+  return c;
+}
+inline Counters& counters_for(const char* kernel) {
+  for (auto& kv : counters())
+    if (kv.first == kernel) return kv.second;
+  counters().emplace_back(kernel, Counters());
+  return counters().back().second;
+}
+
 inline void complete(Slot& sl, uint32_t need) {
   // all needed lanes are here: compute every lane's result
   uint64_t* out = sl.out[sl.gen & 1];
@@ -200,6 +217,7 @@ inline void complete(Slot& sl, uint32_t need) {
     }
     out[l] = r;
   }
+  counters_for(S().kernel).n[op]++;
   sl.arrived = 0;
   sl.op = -1;
   sl.gen++;
@@ -366,6 +384,24 @@ inline T from_bits(uint64_t b) {
 }
 
 }  // namespace simt
+
+// collective counters: text dump "kernel op count" per line into buf; reset afterwards if asked
+extern "C" __attribute__((used, visibility("default"))) inline int simt_emu_counters(char* buf, int cap, int reset) {
+  static const char* names[] = {"syncwarp", "shfl_idx", "shfl_up", "shfl_down", "shfl_xor", "ballot", "any", "all",
+                                "redux_add", "redux_min", "redux_max", "redux_xor", "redux_and", "redux_or",
+                                "redux_add_u", "redux_min_u", "redux_max_u", "match_any"};
+  int len = 0;
+  for (auto& kv : simt::counters())
+    for (int op = 0; op < 18; ++op)
+      if (kv.second.n[op]) {
+        const int k = std::snprintf(buf + len, cap > len ? cap - len : 0, "%s %s %llu\n", kv.first.c_str(), names[op],
+                                    (unsigned long long)kv.second.n[op]);
+        if (k < 0 || len + k >= cap) return -1;
+        len += k;
+      }
+  if (reset) simt::counters().clear();
+  return len;
+}
 
 extern "C" __attribute__((used, visibility("default"))) inline void simt_emu_set_order(int mode) {
   simt::order_mode_ref() = mode;
