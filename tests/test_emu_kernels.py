@@ -451,3 +451,53 @@ def test_search_option_fuzz(emu, oracle_lib):
                     o.forward(int(a))
         assert (mc.errors() == 0).all(), (case, opts)
     emu.emu_lib().simt_emu_set_order(0)
+
+
+def test_two_model_pump_on_the_kernels(emu):
+    """host path of tests/test_gpu_compat.py::test_two_models_route_to_actor_black_and_actor_white
+    with the kernels on the emulator: two trees over one board batch, leaves of black-to-move games
+    under actor_black, of white-to-move games under actor_white"""
+    from elf_b200 import compat
+    from elf_b200.model import Actor, PolicyValueNet
+    from elf_b200.selfplay import SelfPlay
+
+    torch.manual_seed(1)
+    n, G, BS = 9, 4, 16
+    nets = {lab: Actor(PolicyValueNet(n, num_block=1, dim=8), batchsize=BS, dtype=torch.float32, channels_last=False)
+            for lab in ("actor_black", "actor_white")}
+    gb = emu.emu_batch(G, n)
+    opts = dict(num_rollouts=8, num_rollouts_per_batch=4, rotation_flip=0)
+    sp = SelfPlay(nets["actor_black"], actor_white=nets["actor_white"], num_games=G, board_size=n, policy_distri_cutoff=0,
+                  move_cutoff=6, seed=2, board=gb, search=emu.EmuSearch(gb, **opts), search_white=emu.EmuSearch(gb, **opts))
+    GC = compat.GameContext(compat.SelfPlayEngine(sp), batchsize=BS)
+    ctx = GC.ctx()
+    keys = ["s", "pi", "V", "a", "rv"]
+    bufs, counts = {}, {"actor_black": 0, "actor_white": 0}
+    for lab in counts:
+        o = ctx.createSharedMemOptions(lab, BS)
+        sm = ctx.allocateSharedMem(o, keys)
+        b = {}
+        for k in keys:
+            f = sm[k].field()
+            dt = {"float": torch.float32, "int64_t": torch.int64, "int32_t": torch.int32}[f.type_name()]
+            b[k] = torch.zeros(*f.sz().vec(), dtype=dt)
+            sm[k].set(b[k].data_ptr(), [i * b[k].element_size() for i in b[k].stride()])
+        bufs[sm.getSharedMemOptions().idx()] = b
+    ctx.start()
+    it = 0
+    while sp.games_finished < G and it < 300:
+        sm = ctx.wait()
+        lab, k = sm.getSharedMemOptions().label(), sm.effective_batchsize()
+        b = bufs[sm.getSharedMemOptions().idx()]
+        _, games, _ = GC._engine._wave["mc"].leaf_info()  # the wave's leaves belong to games whose ROOT mover matches the label
+        root_black = gb.info()[games, 1] == 1
+        assert root_black.all() if lab == "actor_black" else (~root_black).all()
+        out = nets[lab]({"s": b["s"][:k]})
+        b["pi"][:k].copy_(out["pi"])
+        b["V"][:k].copy_(out["V"])
+        ctx.step()
+        counts[lab] += k
+        it += 1
+    ctx.stop()
+    assert counts["actor_black"] > 0 and counts["actor_white"] > 0 and sp.games_finished >= G
+    assert (sp.mcts.errors() == 0).all() and (sp.mcts2.errors() == 0).all()
