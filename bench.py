@@ -347,7 +347,11 @@ def run_ours(args):
                        "plies_per_slot": PLIES,
                        "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"games sharded x{world}, no collective"},
             "e2e": {"value": e2e_plies / e2e_s, "unit": "moves/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": 24 * G, "note": "inputs are 3 scalars (seed, first id, plies per slot) passed as kernel params"},
+                    "d2h_bytes_per_step": 24 * G,
+                    "note": "elfb200_playout_stream() from the host, results read back every step; this workload's inputs are 3 scalars "
+                            "(seed, first id, plies per slot) passed as kernel params, so there is nothing to copy in.  The host-driven "
+                            "flavour of the same path -- one elfb200_step() per ply with HOST action and accept buffers -- is in host_driven",
+                    "host_driven": step_api if isinstance(step_api, dict) else {"unmeasured": str(step_api)}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("k_playout<19>") if BOARD == 19 else None, "peak_source": peak_src,
