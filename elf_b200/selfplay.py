@@ -20,12 +20,16 @@ from .mcts import MctsBatch
 class SelfPlay:
     def __init__(self, actor, num_games=4096, board_size=19, device=0, policy_distri_cutoff=20,
                  resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0,
-                 record_games=False, actor_white=None, board=None, search=None, search_white=None, **mcts_opts):
+                 record_games=False, actor_white=None, board=None, search=None, search_white=None,
+                 white_mcts_opts=None, **mcts_opts):
         # board / search / search_white: pre-built GoBatch / MctsBatch objects (or duck-typed stand-ins:
         # the CPU tests of the host logic inject oracle-backed ones); by default they are created here
         self.gb = board if board is not None else GoBatch(num_games, board_size=board_size, device=device)
         mcts_opts.setdefault("komi", komi)
         self._mcts_opts = dict(mcts_opts)
+        # the second AI may search differently (GameOptions::white_puct / white_mcts_rollout_per_batch /
+        # white_mcts_rollout_per_thread, game_selfplay.cc:175-182): overrides on top of the common options
+        self._white_opts = {**mcts_opts, **(white_mcts_opts or {})}
         self.mcts = search if search is not None else MctsBatch(self.gb, **mcts_opts)
         self.actor = actor
         # evaluation matches (GoGameSelfPlay::_ai2, game_selfplay.cc:366-367): a second AI with its own
@@ -34,7 +38,7 @@ class SelfPlay:
         if search_white is not None:
             self.mcts2 = search_white
         else:
-            self.mcts2 = MctsBatch(self.gb, **mcts_opts) if (actor_white is not None and search is None) else None
+            self.mcts2 = MctsBatch(self.gb, **self._white_opts) if (actor_white is not None and search is None) else None
         # server requests (MsgRequest: model versions + client control), see set_request()
         self.request = {"black_ver": -1, "white_ver": -1, "player_swap": False, "async": False,
                         "num_game_thread_used": -1}
@@ -141,7 +145,7 @@ class SelfPlay:
         was_idle = self.idle if self.idle is not None else np.zeros(G, bool)
         self.idle = idle if idle.any() else None
         if new["white_ver"] >= 0 and self.mcts2 is None:  # a match needs the second AI
-            self.mcts2 = MctsBatch(self.gb, **self._mcts_opts)
+            self.mcts2 = MctsBatch(self.gb, **self._white_opts)
         two = new["white_ver"] >= 0
         if not two and self.mcts2 is not None and self.actor_white is None and was_protocol:
             # back to self-play (ModelPair::is_selfplay): _ai2 is dropped
