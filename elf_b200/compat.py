@@ -346,6 +346,8 @@ class SelfPlayEngine:
     """The engine behind compat.Context: SelfPlay's move loop cut at the network round trip."""
 
     def __init__(self, selfplay):
+        if any(getattr(selfplay, "policy_only", {}).values()):
+            raise NotImplementedError("policy-only colours are driven by SelfPlay.step(), not by the wait/step pump")
         self.sp = selfplay
         self.board_size = selfplay.N
         self.num_action = selfplay.N * selfplay.N + 1

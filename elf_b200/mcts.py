@@ -151,12 +151,14 @@ class MctsBatch:
         self.search(actor, active)
         return self.results()
 
-    def search(self, actor, active=None):
-        """the search of ``act`` without fetching the root tables (use ``choose`` / ``results``)"""
+    def search(self, actor, active=None, waves=None):
+        """the search of ``act`` without fetching the root tables (use ``choose`` / ``results``).
+        ``waves``: run only that many waves (1 on a fresh tree = evaluate and expand the root only,
+        TreeSearchT::runPolicyOnly, tree_search.h:387-408); default: the whole move"""
         torch = self._torch
         self.begin_move(active)
         pad = int(getattr(actor, "batchsize", 0) or 0)
-        for _ in range(self.waves_per_move):
+        for _ in range(self.waves_per_move if waves is None else int(waves)):
             s = self.select()
             if s.shape[0] > 0:
                 if pad > 1:

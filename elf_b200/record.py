@@ -127,7 +127,7 @@ class GameRecorder:
         self.models.update(int(v) for v in versions if v >= 0)
 
     def on_move(self, ply_before, action, visits_row, predicted_value):
-        if self.for_all or ply_before <= self.cutoff:  # mcts_make_diverse_move, game_selfplay.cc:88-93
+        if visits_row is not None and (self.for_all or ply_before <= self.cutoff):  # mcts_make_diverse_move, game_selfplay.cc:88-93
             self.policies.append(quantise_policy(visits_row, self.n))
         self.values.append(float(predicted_value))  # addPredictedValue
         if action >= 0:

@@ -21,7 +21,8 @@ class SelfPlay:
     def __init__(self, actor, num_games=4096, board_size=19, device=0, policy_distri_cutoff=20,
                  resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0,
                  record_games=False, actor_white=None, board=None, search=None, search_white=None,
-                 white_mcts_opts=None, **mcts_opts):
+                 white_mcts_opts=None, black_use_policy_network_only=False, white_use_policy_network_only=False,
+                 **mcts_opts):
         # board / search / search_white: pre-built GoBatch / MctsBatch objects (or duck-typed stand-ins:
         # the CPU tests of the host logic inject oracle-backed ones); by default they are created here
         self.gb = board if board is not None else GoBatch(num_games, board_size=board_size, device=device)
@@ -42,6 +43,9 @@ class SelfPlay:
         # server requests (MsgRequest: model versions + client control), see set_request()
         self.request = {"black_ver": -1, "white_ver": -1, "player_swap": False, "async": False,
                         "num_game_thread_used": -1}
+        # GameOptions::black/white_use_policy_network_only (game_selfplay.cc:360-371): that colour moves by
+        # the network policy alone (MCTSAI_T::actPolicyOnly), no search
+        self.policy_only = {1: bool(black_use_policy_network_only), 2: bool(white_use_policy_network_only)}
         self.protocol = False  # becomes True with the first set_request()
         self.idle = None  # bool[G]: games that wait for a request (ModelPair::wait); None = nobody waits
         self.swap = False  # player_swap of an evaluation match: the "white" AI plays black
@@ -100,12 +104,60 @@ class SelfPlay:
     def step(self):
         """one move of every game; returns the number of moves played"""
         info = self.gb.info()
+        if self.policy_only[1] or self.policy_only[2]:
+            return self.finish_move(info, chosen=self._search_with_policy_only(info))
         if self.mcts2 is None and self.idle is None:
             self.mcts.search(self.actor)
         else:
             for mc, actor, _, active in self.phases(info):
                 mc.search(actor, active=active)
         return self.finish_move(info)
+
+    def _search_with_policy_only(self, info):
+        """the search phase when one colour moves by policy only: those games get their root
+        evaluated if it is not yet (TreeSearchT::runPolicyOnly) and play the arg-max prior (rank
+        criterion PRIOR, first maximum in edge order); the other games search as usual.  Returns the
+        chosen (actions, values) for finish_move.  The predicted value of a policy-only move is the
+        root's network value (MCTSGoAI::getValue falls back to it for an unvisited best edge)."""
+        G = self.G
+        acts = np.full(G, -2, np.int32)
+        vals = np.zeros(G, np.float32)
+        po_colour = np.array([self.policy_only[int(c)] for c in info[:, 1]], bool)
+        nr = self.never_resign.astype(np.uint8)
+        seed = (self._seed << 20) ^ (self._move_counter + 1)
+        for mc, actor, _, active in self.phases(info):
+            act = np.ones(G, bool) if active is None else np.asarray(active).astype(bool)
+            a_po, a_ts = act & po_colour, act & ~po_colour
+            if a_ts.any():
+                mc.search(actor, active=a_ts.astype(np.uint8))
+                a, v = mc.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
+                acts[a_ts], vals[a_ts] = a[a_ts], v[a_ts]
+            if a_po.any():
+                # roots that are already expanded (left by the other colour's search in a shared tree)
+                # are used as they are; the others are evaluated once.  begin_move() may drop a tree
+                # whose node pool is short, which turns an expanded root into a fresh one.
+                pr = mc.root_priors()
+                fresh = a_po & (pr.max(1) < 0)
+                old = a_po & ~fresh
+                if old.any():
+                    mc.begin_move(old.astype(np.uint8))
+                    pr = mc.root_priors()
+                    dropped = old & (pr.max(1) < 0)
+                    rv = mc.results()["root_value"]
+                    keep = old & ~dropped
+                    vals[keep] = rv[keep]
+                    fresh |= dropped
+                if fresh.any():
+                    mc.search(actor, active=fresh.astype(np.uint8), waves=1)
+                    pr = mc.root_priors()
+                    rv = mc.results()["root_value"]
+                    vals[fresh] = rv[fresh]
+                acts[a_po] = pr[a_po].argmax(1)
+                side = np.where(info[:, 1] == 1, vals, -vals)  # GoStateExt::shouldResign
+                resign = a_po & (side < -1.0 + self.resign_thres) & (info[:, 0] >= 50) & ~self.never_resign
+                acts[resign] = -1
+        self._policy_only_moves = po_colour & (acts >= 0)
+        return acts, vals
 
     # -- MsgRequest handling: GoGameSelfPlay::OnReceive (game_selfplay.cc:222-270) for all games ----
     def set_request(self, black_ver, white_ver=-1, black_resign_thres=None, white_resign_thres=None,
@@ -194,7 +246,7 @@ class SelfPlay:
             for g in np.flatnonzero(sel):
                 self.recorders[g].restart()
 
-    def finish_move(self, info, res=None):
+    def finish_move(self, info, res=None, chosen=None):
         """everything GoGameSelfPlay::act does after the search returned (game_selfplay.cc:372-429):
         move choice and resign check on the device (``elfb200_mcts_choose``), ``GoState::forward``,
         tree advance, game end / restart.  ``info`` are the games' info words from before the search;
@@ -202,8 +254,11 @@ class SelfPlay:
         self._move_counter += 1
         seed = (self._seed << 20) ^ self._move_counter
         nr = self.never_resign.astype(np.uint8)
-        acts, vals = self.mcts.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
-        if self.mcts2 is not None:
+        if chosen is not None:
+            acts, vals = chosen
+        else:
+            acts, vals = self.mcts.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
+        if chosen is None and self.mcts2 is not None:
             black = (info[:, 1] == 1) != self.swap  # games whose mover was searched by self.mcts (see phases)
             a2, v2 = self.mcts2.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
             acts = np.where(black, acts, a2)
@@ -221,7 +276,9 @@ class SelfPlay:
                     res = self.merge_results((info[:, 1] == 1) != self.swap, res, self.mcts2.results())
             for g in range(self.G):
                 if acts[g] != -2:
-                    self.recorders[g].on_move(int(info[g, 0]), int(acts[g]), res["visits"][g], float(vals[g]))
+                    po = chosen is not None and bool(self._policy_only_moves[g])  # no MCTS policy to record
+                    self.recorders[g].on_move(int(info[g, 0]), int(acts[g]), None if po else res["visits"][g],
+                                              float(vals[g]))
         ok = self.gb.forward(acts)
         played = ~resign if self.idle is None else (~resign & ~self.idle)
         assert ok[played].all(), "MCTS proposed an illegal move"

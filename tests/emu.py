@@ -142,9 +142,9 @@ class EmuSearch:
         _l.check(self._lib, self._lib.elfb200_mcts_timings(self._m, ms.ctypes.data, ctypes.byref(w), int(reset)))
         return ms, w.value
 
-    def search(self, actor, active=None):
+    def search(self, actor, active=None, waves=None):
         self.begin_move(active)
-        for _ in range(self.waves_per_move):
+        for _ in range(self.waves_per_move if waves is None else int(waves)):
             s = self.select()
             if s.shape[0] > 0:
                 r = actor({"s": s})

@@ -501,3 +501,54 @@ def test_two_model_pump_on_the_kernels(emu):
     ctx.stop()
     assert counts["actor_black"] > 0 and counts["actor_white"] > 0 and sp.games_finished >= G
     assert (sp.mcts.errors() == 0).all() and (sp.mcts2.errors() == 0).all()
+
+
+@pytest.mark.parametrize("two_models", [False, True])
+def test_policy_only_colour_on_the_kernels(emu, oracle_lib, two_models):
+    """white_use_policy_network_only (GoGameSelfPlay::act -> actPolicyOnly): white plays the arg-max
+    of the network policy over its legal moves without searching (one root evaluation at most), black
+    searches as usual; with one shared tree white's root is usually already expanded by black's search"""
+    from elf_b200.selfplay import SelfPlay
+
+    n, G = 9, 3
+    opts = dict(num_rollouts=32, num_rollouts_per_batch=4, c_puct=1.5, virtual_loss=1, persistent_tree=1)
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, rotation_flip=0, **opts)
+    mc2 = emu.EmuSearch(gb, rotation_flip=0, **opts) if two_models else None
+    calls = []
+
+    def make_actor(search, tag):
+        inner = fake_actor(search, n)
+
+        def actor(batch):
+            calls.append((tag, batch["s"].shape[0]))
+            return inner(batch)
+
+        return actor
+
+    sp = SelfPlay(make_actor(mc, "b"), actor_white=make_actor(mc2, "w") if two_models else None, num_games=G, board_size=n,
+                  policy_distri_cutoff=0, never_resign_ratio=1.0, white_use_policy_network_only=True, record_games=True,
+                  board=gb, search=mc, search_white=mc2)
+    os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+    oms = [oracles.OracleMcts(n, lib=oracle_lib, **opts) for _ in range(G)]
+    for mv in range(6):
+        black = mv % 2 == 0
+        want = []
+        for g, o in enumerate(os_):
+            if black:
+                want.append(oms[g].act(o)["best_action"])
+            else:
+                pi, _ = oracles.fakenet(np.array([o.hash()], np.uint64), n * n + 1)
+                legal = np.append(o.legal().astype(bool), True)
+                want.append(int(np.where(legal, pi[0], -1.0).argmax()))
+        del calls[:]
+        assert sp.step() == G
+        if not black:  # at most one root evaluation per game, nothing else
+            assert sum(k for _, k in calls) <= G and all(t == ("w" if two_models else "b") for t, _ in calls)
+        for o, a in zip(os_, want):
+            assert o.forward(a)
+        assert [int(h) for h in gb.getHashCode()] == [o.hash() for o in os_], (mv, want)
+    # records: MCTS policies only for the searched (black) moves while ply <= cutoff (0 here: none), values for all
+    sp.move_cutoff = 1
+    sp.step()
+    assert len(sp.records) == G and all(len(r["result"]["values"]) == 7 for r in sp.records)
