@@ -622,3 +622,121 @@ class TrainEngine:
         out = self.rb.sample()
         self.batches += 1
         return self.rb.B, {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in out.items()}
+
+
+# ---- option objects and GameContext(ContextOptions, GameOptions) ---------------------------------------
+class _Bag:
+    """attribute bag with the reference struct's field names and defaults (pybind REGISTER_PYBIND_FIELDS)"""
+
+    _defaults = {}
+
+    def __init__(self, **kw):
+        for k, v in self._defaults.items():
+            setattr(self, k, v() if callable(v) else v)
+        for k, v in kw.items():
+            if k not in self._defaults:
+                raise AttributeError(f"{type(self).__name__} has no field '{k}'")
+            setattr(self, k, v)
+
+    def info(self):
+        return "\n".join(f"{k}: {getattr(self, k)}" for k in self._defaults)
+
+
+class SearchAlgoOptions(_Bag):  # elf/ai/tree_search/tree_search_options.h:23-27
+    _defaults = dict(use_prior=True, c_puct=5.0, unexplored_q_zero=False, root_unexplored_q_zero=False)
+
+
+class TSOptions(_Bag):  # tree_search_options.h:77-96
+    _defaults = dict(max_num_moves=0, num_threads=16, num_rollouts_per_thread=100, num_rollouts_per_batch=8,
+                     verbose=False, verbose_time=False, seed=0, persistent_tree=False, root_epsilon=0.0,
+                     root_alpha=0.0, log_prefix="", pick_method="most_visited", alg_opt=SearchAlgoOptions,
+                     virtual_loss=0)
+
+
+class ContextOptions(_Bag):  # elf/legacy/python_options_utils_cpp.h:19-47
+    _defaults = dict(num_games=1, batchsize=0, T=1, job_id="", mcts_options=TSOptions)
+
+    def print(self):
+        print(self.info())
+
+
+class GameOptions(_Bag):  # elfgames/go/common/go_game_specific.h:20-128 (fields the engine or the scripts touch)
+    _defaults = dict(
+        seed=0, num_games_per_thread=-1, mode="selfplay", use_mcts=False, use_mcts_ai2=False,
+        black_use_policy_network_only=False, white_use_policy_network_only=False, data_aug=-1,
+        start_ratio_pre_moves=0.5, ratio_pre_moves=0.0, move_cutoff=-1, policy_distri_cutoff=20,
+        policy_distri_training_for_all=False, resign_thres=0.05, resign_thres_lower_bound=1e-9,
+        resign_thres_upper_bound=0.50, resign_prob_never=0.1, resign_target_fp_rate=0.05, resign_target_hist_size=2500,
+        num_reset_ranking=5000, preload_sgf="", preload_sgf_move_to=-1, use_df_feature=False, q_min_size=10,
+        q_max_size=1000, num_reader=50, komi=7.5, ply_pass_enabled=0, white_puct=-1.0, white_mcts_rollout_per_batch=-1,
+        white_mcts_rollout_per_thread=-1, eval_num_games=400, eval_thres=0.55, client_max_delay_sec=1200,
+        selfplay_init_num=5000, selfplay_update_num=1000, selfplay_async=False, following_pass=False,
+        cheat_eval_new_model_wins_half=False, cheat_selfplay_random_result=False, keep_prev_selfplay=False,
+        eval_num_threads=1, expected_num_clients=-1, list_files=list, server_addr="", server_id="", port=0,
+        verbose=False, print_result=False, dump_record_prefix="", num_future_actions=1)
+
+
+def search_kwargs(ts, rollouts_per_thread=None, per_batch=None, c_puct=None):
+    """TSOptions -> elfb200_mcts_options.  The reference runs ``num_threads`` search threads of
+    ``num_rollouts_per_thread`` rollouts each on one tree; the GPU search does the same total number
+    of rollouts as one deterministic sequence of waves."""
+    rpt = ts.num_rollouts_per_thread if not rollouts_per_thread or rollouts_per_thread <= 0 else rollouts_per_thread
+    return dict(
+        num_rollouts=int(max(1, ts.num_threads) * rpt),
+        num_rollouts_per_batch=int(ts.num_rollouts_per_batch if not per_batch or per_batch <= 0 else per_batch),
+        virtual_loss=int(ts.virtual_loss), persistent_tree=int(bool(ts.persistent_tree)),
+        use_prior=int(bool(ts.alg_opt.use_prior)), c_puct=float(ts.alg_opt.c_puct if not c_puct or c_puct <= 0 else c_puct),
+        unexplored_q_zero=int(bool(ts.alg_opt.unexplored_q_zero)),
+        root_unexplored_q_zero=int(bool(ts.alg_opt.root_unexplored_q_zero)),
+        root_epsilon=float(ts.root_epsilon), root_alpha=float(ts.root_alpha))
+
+
+def game_context(co, opt, board_size=19, device=0, factories=None):
+    """``go.GameContext(co, opt)`` (train/game_context.h:37-85, inference/game_context.h:31-66): build the
+    engine the options describe and return the GameContext the scripts pump.
+
+    ``co`` / ``opt``: ContextOptions / GameOptions -- these classes or the reference's pybind objects
+    (only attributes are read).  ``opt.mode``: "selfplay" (SelfPlay + SelfPlayEngine), "online"
+    (OnlineGame + OnlineEngine) or "train" / "offline_train" (ReplayBatch + TrainEngine; the caller
+    feeds records with ``GC._engine.rb.add_records``).  ``board_size`` is a compile-time constant of
+    the reference (BOARD9x9).  ``factories``: {"selfplay"|"online"|"replay": callable(**kwargs)} to
+    substitute the constructors (tests)."""
+    f = dict(factories or {})
+    ts = co.mcts_options
+    common = search_kwargs(ts)
+    common.update(komi=float(opt.komi), ply_pass_enabled=int(opt.ply_pass_enabled))
+    if opt.mode == "selfplay":
+        from .selfplay import SelfPlay
+
+        kw = dict(
+            actor=None, num_games=int(co.num_games), board_size=board_size, device=device,
+            policy_distri_cutoff=int(opt.policy_distri_cutoff), resign_thres=float(opt.resign_thres),
+            never_resign_ratio=float(opt.resign_prob_never), move_cutoff=int(opt.move_cutoff),
+            seed=int(opt.seed), record_games=True,
+            black_use_policy_network_only=bool(opt.black_use_policy_network_only),
+            white_use_policy_network_only=bool(opt.white_use_policy_network_only),
+            white_mcts_opts={k: v for k, v in search_kwargs(ts, opt.white_mcts_rollout_per_thread,
+                                                             opt.white_mcts_rollout_per_batch, opt.white_puct).items()
+                             if v != common.get(k)},
+            **common)
+        if kw["black_use_policy_network_only"] or kw["white_use_policy_network_only"]:
+            raise NotImplementedError("policy-only colours are driven by SelfPlay.step(), not by the wait/step pump")
+        sp = f.get("selfplay", SelfPlay)(**kw)
+        return GameContext(SelfPlayEngine(sp), batchsize=int(co.batchsize))
+    if opt.mode == "online":
+        from .online import OnlineGame
+
+        kw = dict(board_size=board_size, device=device, komi=float(opt.komi), resign_thres=float(opt.resign_thres),
+                  policy_distri_cutoff=int(opt.policy_distri_cutoff), move_cutoff=int(opt.move_cutoff),
+                  preload_sgf=opt.preload_sgf or None, preload_sgf_move_to=int(opt.preload_sgf_move_to),
+                  following_pass=bool(opt.following_pass), seed=int(opt.seed), **{k: v for k, v in common.items() if k != "komi"})
+        game = f.get("online", OnlineGame.create)(**kw)
+        return GameContext(OnlineEngine(game), batchsize=int(co.batchsize))
+    if opt.mode in ("train", "offline_train"):
+        from .replay import ReplayBatch
+
+        kw = dict(num_states=int(co.batchsize), board_size=board_size, device=device,
+                  num_future_actions=int(opt.num_future_actions), seed=int(opt.seed))
+        rb = f.get("replay", ReplayBatch)(**kw)
+        return GameContext(TrainEngine(rb), batchsize=int(co.batchsize))
+    raise ValueError("Unknown mode! " + str(opt.mode))  # "options.mode not recognized!" (distri_client.h:294)

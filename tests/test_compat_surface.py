@@ -154,3 +154,67 @@ def test_game_start_and_game_end_labels_reach_their_callbacks():
         gcw.run()
     gcw.stop()
     assert log == [("start", 7, -1), ("end", 0)] and n_actor[0] == 1
+
+
+def test_game_context_from_reference_options():
+    """go.GameContext(co, opt): the reference's option structs (same field names and defaults) are
+    turned into the engine's constructor arguments"""
+    from elf_b200 import compat
+
+    co, opt = compat.ContextOptions(), compat.GameOptions()
+    assert (co.mcts_options.num_threads, co.mcts_options.num_rollouts_per_thread, co.mcts_options.alg_opt.c_puct) == (16, 100, 5.0)
+    assert (opt.policy_distri_cutoff, opt.resign_thres, opt.komi, opt.white_puct, opt.preload_sgf_move_to) == (20, 0.05, 7.5, -1.0, -1)
+    with pytest.raises(AttributeError):
+        compat.GameOptions(no_such_field=1)
+    # what src_py/elf/context_utils.py:89-112 and src_py/elfgames/go/game.py:264-345 set for start_selfplay.sh
+    co.num_games, co.batchsize = 32, 128
+    m = co.mcts_options
+    m.num_threads, m.num_rollouts_per_thread, m.num_rollouts_per_batch, m.virtual_loss, m.persistent_tree = 8, 100, 8, 1, True
+    m.alg_opt.c_puct, m.alg_opt.unexplored_q_zero = 1.5, True
+    opt.mode, opt.policy_distri_cutoff, opt.resign_thres, opt.move_cutoff, opt.seed = "selfplay", 30, 0.01, 200, 5
+    opt.white_puct, opt.white_mcts_rollout_per_thread = 0.85, 50
+    got = {}
+
+    class FakeSelfPlay:
+        def __init__(self, **kw):
+            got.update(kw)
+            self.N, self.G, self.resign_thres, self.policy_only = kw["board_size"], kw["num_games"], kw["resign_thres"], {}
+
+    GC = compat.game_context(co, opt, board_size=9, factories={"selfplay": FakeSelfPlay})
+    assert isinstance(GC, compat.GameContext) and GC.getParams()["board_size"] == 9
+    assert got["num_games"] == 32 and got["num_rollouts"] == 800 and got["num_rollouts_per_batch"] == 8
+    assert got["c_puct"] == 1.5 and got["virtual_loss"] == 1 and got["persistent_tree"] == 1 and got["unexplored_q_zero"] == 1
+    assert got["policy_distri_cutoff"] == 30 and got["resign_thres"] == 0.01 and got["move_cutoff"] == 200 and got["seed"] == 5
+    assert got["never_resign_ratio"] == 0.1 and got["komi"] == 7.5 and got["actor"] is None
+    assert got["white_mcts_opts"] == {"c_puct": 0.85, "num_rollouts": 400}  # only what differs for the second AI
+    # online and train modes
+    opt.mode, opt.preload_sgf, opt.preload_sgf_move_to, opt.following_pass = "online", "g.sgf", 12, True
+
+    class FakeGame:
+        N, resign_thres = 9, 0.0
+
+    def fake_online(**kw):
+        got.clear()
+        got.update(kw)
+        return FakeGame()
+
+    GC = compat.game_context(co, opt, board_size=9, factories={"online": fake_online})
+    assert isinstance(GC._engine, compat.OnlineEngine)
+    assert (got["preload_sgf"], got["preload_sgf_move_to"], got["following_pass"], got["num_rollouts"]) == ("g.sgf", 12, True, 800)
+    opt.mode, opt.num_future_actions = "train", 3
+
+    class FakeReplay:
+        def __init__(self, **kw):
+            got.clear()
+            got.update(kw)
+            self.N, self.K, self.B = kw["board_size"], kw["num_future_actions"], kw["num_states"]
+
+    GC = compat.game_context(co, opt, board_size=9, factories={"replay": FakeReplay})
+    assert isinstance(GC._engine, compat.TrainEngine) and got["num_states"] == 128 and got["num_future_actions"] == 3
+    assert GC.ctx().allocateSharedMem(GC.ctx().createSharedMemOptions("train", 128), ["offline_a"])["offline_a"].field().sz().vec() == [128, 3]
+    opt.mode = "bogus"
+    with pytest.raises(ValueError, match="Unknown mode"):
+        compat.game_context(co, opt)
+    opt.mode, opt.white_use_policy_network_only = "selfplay", True
+    with pytest.raises(NotImplementedError):
+        compat.game_context(co, opt, factories={"selfplay": FakeSelfPlay})

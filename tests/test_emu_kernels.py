@@ -552,3 +552,51 @@ def test_policy_only_colour_on_the_kernels(emu, oracle_lib, two_models):
     sp.move_cutoff = 1
     sp.step()
     assert len(sp.records) == G and all(len(r["result"]["values"]) == 7 for r in sp.records)
+
+
+def test_game_context_from_options_on_the_kernels(emu):
+    """compat.game_context(ContextOptions, GameOptions) -> engine -> wait/step pump, with the engine
+    built on the emulated kernels: the option mapping produces a search that actually runs"""
+    from elf_b200 import compat, lib as _l
+    from elf_b200.selfplay import SelfPlay
+
+    n = 9
+    co, opt = compat.ContextOptions(), compat.GameOptions()
+    co.num_games, co.batchsize = 3, 8
+    m = co.mcts_options
+    m.num_threads, m.num_rollouts_per_thread, m.num_rollouts_per_batch, m.virtual_loss, m.persistent_tree = 2, 8, 4, 1, True
+    m.alg_opt.c_puct = 1.5
+    opt.mode, opt.policy_distri_cutoff, opt.move_cutoff = "selfplay", 0, 4
+    built = {}
+
+    def factory(**kw):
+        fields = {f[0] for f in _l.MctsOptions._fields_}
+        gb = emu.emu_batch(kw["num_games"], kw["board_size"])
+        mk = {k: v for k, v in kw.items() if k in fields and k != "seed"}
+        built["search"] = emu.EmuSearch(gb, **mk)
+        return SelfPlay(board=gb, search=built["search"], **kw)
+
+    GC = compat.game_context(co, opt, board_size=n, factories={"selfplay": factory})
+    assert built["search"].options.num_rollouts == 16 and built["search"].waves_per_move == 4
+    assert built["search"].options.c_puct == 1.5 and built["search"].options.komi == 7.5
+    ctx = GC.ctx()
+    sm = ctx.allocateSharedMem(ctx.createSharedMemOptions("actor_black", 8), ["s", "pi", "V", "a", "rv"])
+    bufs = {}
+    for k in ("s", "pi", "V", "a", "rv"):
+        f = sm[k].field()
+        dt = {"float": torch.float32, "int64_t": torch.int64, "int32_t": torch.int32}[f.type_name()]
+        bufs[k] = torch.zeros(*f.sz().vec(), dtype=dt)
+        sm[k].set(bufs[k].data_ptr(), [i * bufs[k].element_size() for i in bufs[k].stride()])
+    ctx.start()
+    sp = GC._engine.sp
+    it = 0
+    while sp.games_finished < 3 and it < 200:
+        s = ctx.wait()
+        k = s.effective_batchsize()
+        bufs["pi"][:k] = torch.rand(k, n * n + 1)
+        bufs["V"][:k] = 0.0
+        ctx.step()
+        it += 1
+    ctx.stop()
+    assert sp.games_finished >= 3 and len(sp.records) == sp.games_finished  # selfplay mode keeps the records
+    assert sp.records[0]["request"]["vers"]["mcts_opt"]["num_rollouts_per_thread"] == 16
