@@ -715,6 +715,8 @@ def game_context(co, opt, board_size=19, device=0, factories=None):
             seed=int(opt.seed), record_games=True,
             black_use_policy_network_only=bool(opt.black_use_policy_network_only),
             white_use_policy_network_only=bool(opt.white_use_policy_network_only),
+            policy_distri_training_for_all=bool(opt.policy_distri_training_for_all),
+            num_games_per_thread=int(opt.num_games_per_thread),
             white_mcts_opts={k: v for k, v in search_kwargs(ts, opt.white_mcts_rollout_per_thread,
                                                              opt.white_mcts_rollout_per_batch, opt.white_puct).items()
                              if v != common.get(k)},

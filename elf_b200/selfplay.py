@@ -22,7 +22,7 @@ class SelfPlay:
                  resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0,
                  record_games=False, actor_white=None, board=None, search=None, search_white=None,
                  white_mcts_opts=None, black_use_policy_network_only=False, white_use_policy_network_only=False,
-                 **mcts_opts):
+                 policy_distri_training_for_all=False, num_games_per_thread=-1, **mcts_opts):
         # board / search / search_white: pre-built GoBatch / MctsBatch objects (or duck-typed stand-ins:
         # the CPU tests of the host logic inject oracle-backed ones); by default they are created here
         self.gb = board if board is not None else GoBatch(num_games, board_size=board_size, device=device)
@@ -68,8 +68,13 @@ class SelfPlay:
         if record_games:
             from .record import GameRecorder
 
-            self.recorders = [GameRecorder(board_size, g, policy_distri_cutoff, mcts_opt=self._mcts_opts)
-                              for g in range(num_games)]
+            self.recorders = [GameRecorder(board_size, g, policy_distri_cutoff, policy_distri_training_for_all,
+                                           mcts_opt=self._mcts_opts) for g in range(num_games)]
+        # GameOptions::num_games_per_thread (GoStateExt::finished, go_state_ext.h:229-232): a game slot
+        # stops after that many games (-1: never); stopped slots idle like parked ones
+        self.num_games_per_thread = int(num_games_per_thread)
+        self.games_per_slot = np.zeros(num_games, np.int64)
+        self.stopped = np.zeros(num_games, bool)
 
     def close(self):
         self.mcts.close()
@@ -195,6 +200,7 @@ class SelfPlay:
         used = new["num_game_thread_used"]
         idle = np.zeros(G, bool) if used < 0 else (np.arange(G) >= used)
         was_idle = self.idle if self.idle is not None else np.zeros(G, bool)
+        idle = idle | self.stopped  # slots that have played their num_games_per_thread stay out
         self.idle = idle if idle.any() else None
         if new["white_ver"] >= 0 and self.mcts2 is None:  # a match needs the second AI
             self.mcts2 = MctsBatch(self.gb, **self._white_opts)
@@ -315,4 +321,9 @@ class SelfPlay:
                 self.mcts2.reset(m)
             self.never_resign[done] = self.rng.random(int(done.sum())) < self.never_resign_ratio
             self.games_finished += int(done.sum())
+            if self.num_games_per_thread > 0:
+                self.games_per_slot[done] += 1
+                self.stopped |= self.games_per_slot >= self.num_games_per_thread
+                if self.stopped.any():
+                    self.idle = self.stopped.copy() if self.idle is None else (self.idle | self.stopped)
         return int(played.sum())

@@ -335,3 +335,24 @@ def test_request_message_format_against_reference(oracle_lib):
     assert r["request"]["vers"]["black_ver"] == 9 and r["request"]["vers"]["mcts_opt"]["num_rollouts_per_thread"] == 400
     assert r["request"]["client_ctrl"]["num_game_thread_used"] == 2 and r["result"]["using_models"] == [9]
     assert oracles.ref_record_roundtrip(json.dumps(r)) is not None
+
+
+def test_num_games_per_thread_and_policy_for_all(oracle_lib):
+    """a slot stops after num_games_per_thread games (GoStateExt::finished); with
+    policy_distri_training_for_all every move's MCTS policy is recorded, not only those up to the cutoff"""
+    class VisitSearch(Search):
+        def results(self):
+            return {"visits": np.where(self.pi > 0.5, 10, -1).astype(np.int32)}
+
+    b = Boards(2, oracle_lib)
+    sp = SelfPlay(net("black", []), num_games=2, board_size=N, policy_distri_cutoff=1, never_resign_ratio=0.0,
+                  move_cutoff=5, record_games=True, policy_distri_training_for_all=True, num_games_per_thread=2,
+                  board=b, search=VisitSearch(b, "ai"))
+    moved = [sp.step() for _ in range(12)]
+    assert moved[:8] == [2] * 8 and moved[8:] == [0] * 4  # 2 games x 4 moves per slot, then every slot has stopped
+    assert sp.games_finished == 4 and sp.stopped.all() and sp.idle.all()
+    assert all(len(r["result"]["policies"]) == 4 for r in sp.records)  # for_all: one policy per move
+    with pytest.raises(RuntimeError, match="waiting"):  # nothing left for the pump either
+        from elf_b200 import compat as _c
+        eng = _c.SelfPlayEngine(sp)
+        eng.next_label()
