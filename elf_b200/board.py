@@ -100,6 +100,13 @@ class GoBatch:
     def terminated(self):
         return self.info()[:, 9].astype(bool)
 
+    def showBoard(self, game=0):
+        """GoState::showBoard (go_state.h:187-192) of one game: the reference's board picture"""
+        from .online import show_board
+
+        i = self.info()[game]
+        return show_board(self.stones()[game], self.board_size, int(i[4]), int(i[2]), int(i[3]), int(i[1]))
+
     def stones(self):
         n = self.board_size
         o = np.empty((self.num_games, n * n), np.uint8)

@@ -85,6 +85,14 @@ def test_board_kernels(emu, oracle_lib, n, G, lane_order):
     f = gb.features(d4)
     for g, o in enumerate(os_):
         assert (f[g] == o.features(int(d4[g]))).all()
+    if oracles.have_ref(n) and lane_order == "ascending":  # GoState::showBoard of the compiled reference
+        r = oracles.Ref(n)
+        for a in (3, n + 4, n * n, 2 * n + 1):
+            r.forward(a)
+        gb2 = emu.emu_batch(2, n)
+        for a in (3, n + 4, n * n, 2 * n + 1):
+            gb2.forward(np.array([a, -1], np.int32))
+        assert gb2.showBoard(0) == oracles.ref_show_board(r)
     gb.reset(np.array([1] + [0] * (G - 1), np.uint8))
     assert gb.info()[0, 0] == 1 and gb.getHashCode()[0] == 0 and gb.getHashCode()[1] == os_[1].hash()
 
