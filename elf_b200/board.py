@@ -146,8 +146,15 @@ class GoBatch:
         _l.check(self._lib, self._lib.elfb200_features(self._ctx, d.ctypes.data if d is not None else None, o.ctypes.data))
         return o
 
-    def features_dev(self, out_ptr, d4_ptr=None):
-        _l.check(self._lib, self._lib.elfb200_features_dev(self._ctx, d4_ptr, out_ptr))
+    def features_dev(self, out_ptr, d4_ptr=None, fmt=_l.FEAT_F32_NCHW, cpad=0):
+        """planes of every game straight into device memory at ``out_ptr``: float32 ``[G,18,N,N]``
+        or, in the 16-bit channels-last formats (``lib.FEAT_F16_NHWC`` / ``FEAT_BF16_NHWC``),
+        ``[G,N,N,cpad]``.  Asynchronous on the context stream."""
+        _l.check(self._lib, self._lib.elfb200_features_dev_ex(self._ctx, d4_ptr, out_ptr, fmt, cpad))
+
+    def set_feature_store(self, mode):
+        """1 = feature tiles leave shared memory by one bulk (TMA) store (default), 0 = vector stores"""
+        _l.check(self._lib, self._lib.elfb200_set_feature_store(self._ctx, int(mode)))
 
     # -- random-policy playouts (BASELINE configs 1/2/5) ------------------------------------
     def playout(self, seed, first_game_id=0, max_plies=None):

@@ -115,6 +115,150 @@ __device__ __forceinline__ void write_agz_planes(const uint64_t (*rows)[N], int 
   }
 }
 
+
+// ---- feature output formats -----------------------------------------------------------------------
+// FEAT_F32_NCHW is the GoFeature tensor contract (float32 [n][18][N][N], game_feature.h:159-206).
+// The 16-bit NHWC formats are the fast mode for a network that runs in half precision with
+// channels-last convolutions: [n][N][N][cpad] with the 18 planes in channels 0..17 and zeros above
+// (cpad a multiple of 8: 16 bytes per 8 channels), so the network's input cast/permute pass
+// disappears.  Values are exactly 0.0 / 1.0 in every format.
+enum : int { FEAT_F32_NCHW = 0, FEAT_F16_NHWC = 1, FEAT_BF16_NHWC = 2 };
+
+// Shared -> global bulk copy (TMA engine, `cp.async.bulk`): one thread hands the whole staged tile
+// to the copy engine instead of every thread issuing stores.  `bytes` a multiple of 16, both
+// addresses 16-byte aligned.
+__device__ __forceinline__ void async_proxy_fence() {
+#if !defined(ELFB200_SIMT_EMU)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+#if defined(ELFB200_SIMT_EMU)
+  memcpy(gdst, ssrc, bytes);
+#else
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the CTA may retire once smem was read
+#endif
+}
+
+// Flush a staged tile: every thread has written its part of `ssrc` (generic-proxy stores).
+//   tma != 0: fence the writes towards the async proxy, barrier, thread 0 issues ONE bulk store;
+//   tma == 0: barrier, then coalesced 16-byte vector stores by all threads.
+// vec8 != 0 (unaligned tail of a float32 batch): 8-byte vectors instead of 16.
+__device__ __forceinline__ void flush_tile(void* gdst, const void* ssrc, uint32_t bytes, int tma, int vec8 = 0) {
+  if (tma && !vec8) {
+    async_proxy_fence();
+    __syncthreads();
+    if (threadIdx.x == 0) bulk_store_s2g(gdst, ssrc, bytes);
+  } else if (!vec8) {
+    __syncthreads();
+    const uint4* s4 = reinterpret_cast<const uint4*>(ssrc);
+    uint4* g4 = reinterpret_cast<uint4*>(gdst);
+    for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) g4[i] = s4[i];
+  } else {
+    __syncthreads();
+    const uint2* s2 = reinterpret_cast<const uint2*>(ssrc);
+    uint2* g2 = reinterpret_cast<uint2*>(gdst);
+    for (uint32_t i = threadIdx.x; i < bytes / 8; i += blockDim.x) g2[i] = s2[i];
+  }
+}
+
+// The 18 planes of one position as 16-bit channels-last cells: cell (tx,ty) -> cpad halves at
+// sbuf + cell*cpad.  `one` is the bit pattern of 1.0 (0x3C00 half, 0x3F80 bfloat16).
+template <int N>
+__device__ __forceinline__ void write_agz_nhwc16(const uint64_t (*rows)[N], int hn, int next, int d4, uint32_t one,
+                                                 int cpad, uint16_t* __restrict__ sbuf) {
+  constexpr int P = Geo<N>::P;
+  for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
+    const int tx = cell / N, ty = cell - tx * N;
+    int x, y;
+    d4_inverse(N, d4, tx, ty, x, y);
+    const bool black_first = next == S_BLACK;
+    uint32_t bits = black_first ? (1u << 16) : (1u << 17);  // bit c = plane c of this cell
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (t < hn) {
+        const uint64_t r = rows[t][y];
+        const uint32_t bl = ((uint32_t)r >> x) & 1u, wh = ((uint32_t)(r >> 32) >> x) & 1u;
+        bits |= (black_first ? bl : wh) << (2 * t);
+        bits |= (black_first ? wh : bl) << (2 * t + 1);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(sbuf + (size_t)cell * cpad);
+    for (int k = 0; k < cpad / 8; ++k) {
+      const uint32_t b8 = k < 4 ? (bits >> (8 * k)) & 0xFFu : 0u;
+      uint4 v;
+      v.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
+      v.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
+      v.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
+      v.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
+      dst[k] = v;
+    }
+  }
+}
+
+// Dynamic shared memory of the feature kernels (the SIMT emulator has no dynamic smem: a static
+// buffer of the largest tile stands in).
+constexpr int FEAT_CPAD_MAX = 32;
+template <int N>
+struct FeatTile {
+  static constexpr int F32_PAIR_BYTES = 2 * 18 * Geo<N>::P * 4;           // two positions: a 16-byte multiple
+  static constexpr int NHWC_BYTES_MAX = Geo<N>::P * FEAT_CPAD_MAX * 2;
+  static constexpr int BYTES = F32_PAIR_BYTES > NHWC_BYTES_MAX ? F32_PAIR_BYTES : NHWC_BYTES_MAX;
+};
+#if defined(ELFB200_SIMT_EMU)
+#define ELFB200_FEAT_SMEM(N) __align__(16) __shared__ unsigned char feat_smem[FeatTile<N>::BYTES]
+#else
+#define ELFB200_FEAT_SMEM(N) extern __shared__ __align__(16) unsigned char feat_smem[]
+#endif
+
+// One CTA of a feature kernel: float32 NCHW -> the CTA stages TWO consecutive positions (25,992 B each
+// at 19x19: only a pair is a 16-byte multiple) and flushes them with one bulk store; 16-bit NHWC ->
+// one position per CTA.  `gather(slot, rows, hn, next, d4)` is called by ALL threads of the CTA and
+// fills rows[t][y] (t < 8 history positions, newest first) for output slot `slot`.
+template <int N, class Gather>
+__device__ __forceinline__ void features_cta(Gather gather, int n_pos, void* __restrict__ out, int fmt, int cpad,
+                                             int tma, int align8) {
+  constexpr int P = Geo<N>::P, TOTAL = 18 * P;
+  ELFB200_FEAT_SMEM(N);
+  __shared__ uint64_t rows[2][8][N];
+  if (fmt == FEAT_F32_NCHW) {
+    const int first = blockIdx.x * 2;
+    if (first >= n_pos) return;
+    const int here = min(2, n_pos - first);
+    float* buf = reinterpret_cast<float*>(feat_smem);
+    for (int p = 0; p < here; ++p) {
+      int hn, next, d4;
+      gather(first + p, rows[p], hn, next, d4);
+      __syncthreads();
+      write_agz_planes<N>(rows[p], hn, next, d4, buf + p * TOTAL);
+    }
+    float* dst = reinterpret_cast<float*>(out) + (size_t)first * TOTAL;
+    if (here == 2 && !align8)
+      flush_tile(dst, buf, 2 * TOTAL * 4, tma);
+    else
+      flush_tile(dst, buf, here * TOTAL * 4, 0, 1);  // odd tail / 8-byte aligned destination
+  } else {
+    const int slot = blockIdx.x;
+    if (slot >= n_pos) return;
+    int hn, next, d4;
+    gather(slot, rows[0], hn, next, d4);
+    __syncthreads();
+    uint16_t* buf = reinterpret_cast<uint16_t*>(feat_smem);
+    write_agz_nhwc16<N>(rows[0], hn, next, d4, fmt == FEAT_F16_NHWC ? 0x3C00u : 0x3F80u, cpad, buf);
+    flush_tile(reinterpret_cast<uint16_t*>(out) + (size_t)slot * P * cpad, buf, (uint32_t)(P * cpad * 2), tma);
+  }
+}
+
+template <int N>
+inline size_t feature_smem_bytes(int fmt, int cpad) {
+  return fmt == FEAT_F32_NCHW ? (size_t)FeatTile<N>::F32_PAIR_BYTES : (size_t)Geo<N>::P * cpad * 2;
+}
+inline int feature_grid(int n_pos, int fmt) { return fmt == FEAT_F32_NCHW ? (n_pos + 1) / 2 : n_pos; }
+
 }  // namespace elfb200
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -148,6 +292,7 @@ struct elfb200_ctx {
   int32_t* d_words = nullptr;   // G * 12 export buffer
   int32_t* d_d4 = nullptr;
   float* d_feat = nullptr;      // lazily allocated G*18*P floats
+  int feat_tma = 1;             // feature tiles leave shared memory by one bulk (TMA) store; 0 = vector stores
   // playout outputs
   uint64_t* d_po_sk = nullptr;
   uint64_t* d_po_chk = nullptr;

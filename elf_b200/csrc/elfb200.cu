@@ -243,23 +243,29 @@ __global__ void __launch_bounds__(BLOCK)
 }
 
 // ---------------------------------------------------------------------------------------
-// BoardFeature::extractAGZ (board_feature.cc:247-290).  One CTA per position; the 8 history
-// positions are staged in shared memory and every thread owns one output cell of all 18 planes
-// (write_agz_planes, common.cuh).
+// BoardFeature::extractAGZ (board_feature.cc:247-290).  The 8 history positions of a game come
+// from its ring; staging, formats and the bulk store are features_cta's (common.cuh).
+template <int N>
+struct RingGather {
+  DevState st;
+  const int32_t* d4codes;
+  __device__ __forceinline__ void operator()(int g, uint64_t (*rows)[N], int& hn, int& next, int& d4) const {
+    const BoardMeta meta = load_meta(&st.meta[g]);
+    hn = min(8, (int)meta.ply - 1);
+    next = meta.next;
+    d4 = d4codes ? d4codes[g] : 0;
+    for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
+      const int t = i / N, y = i - t * N;
+      rows[t][y] = t < hn ? st.ring[((size_t)g * 8 + ((meta.ply - 2 - t) & 7)) * N + y] : 0ull;
+    }
+  }
+};
+
 template <int N>
 __global__ void __launch_bounds__(384)
-    k_features(DevState st, const int32_t* __restrict__ d4codes, float* __restrict__ out) {
-  constexpr int P = Geo<N>::P;
-  __shared__ uint64_t rows[8][N];
-  const int g = blockIdx.x;
-  const BoardMeta meta = load_meta(&st.meta[g]);
-  const int hn = min(8, (int)meta.ply - 1);
-  for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
-    const int t = i / N, y = i - t * N;
-    rows[t][y] = t < hn ? st.ring[((size_t)g * 8 + ((meta.ply - 2 - t) & 7)) * N + y] : 0ull;
-  }
-  __syncthreads();
-  write_agz_planes<N>(rows, hn, meta.next, d4codes ? d4codes[g] : 0, out + (size_t)g * 18 * P);
+    k_features(DevState st, const int32_t* __restrict__ d4codes, void* __restrict__ out, int fmt, int cpad, int tma,
+               int align8) {
+  features_cta<N>(RingGather<N>{st, d4codes}, st.G, out, fmt, cpad, tma, align8);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -425,6 +431,8 @@ int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out)
   c->device = device;
   const size_t N = board_size, G = num_games, P = N * N, MAXPLY = 2 * P;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  // the float32 feature tile (two positions, 51,984 B at 19x19) is above the 48 KB default
+  CK(cudaFuncSetAttribute(k_features<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, FeatTile<19>::BYTES));
   CK(cudaMalloc(&c->st.cur, G * N * 8));
   CK(cudaMalloc(&c->st.ring, G * 8 * N * 8));
   CK(cudaMalloc(&c->st.legal, G * N * 4));
@@ -643,13 +651,45 @@ int elfb200_evaluate(elfb200_ctx* c, float komi, float* value_host) {
   return ELFB200_OK;
 }
 
-int elfb200_features_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) {
+static int check_feature_args(const void* out, int format, int cpad, int* align8) {
+  if (format < FEAT_F32_NCHW || format > FEAT_BF16_NHWC) return elfb200_fail(ELFB200_ERR_ARG, "unknown feature format %d", format);
+  const uintptr_t a = (uintptr_t)out;
+  *align8 = 0;
+  if (format == FEAT_F32_NCHW) {
+    if (a & 7) return elfb200_fail(ELFB200_ERR_ARG, "feature buffer must be 8-byte aligned");
+    *align8 = (a & 15) ? 1 : 0;
+  } else {
+    if (cpad < 24 || cpad > FEAT_CPAD_MAX || (cpad & 7))
+      return elfb200_fail(ELFB200_ERR_ARG, "channel padding must be 24 or 32 (got %d)", cpad);
+    if (a & 15) return elfb200_fail(ELFB200_ERR_ARG, "16-bit NHWC feature buffer must be 16-byte aligned");
+  }
+  return ELFB200_OK;
+}
+
+int elfb200_features_dev_ex(elfb200_ctx* c, const int32_t* d4_dev, void* out_dev, int format, int cpad) {
   if (!c || !out_dev) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  int align8 = 0;
+  int rc = check_feature_args(out_dev, format, cpad, &align8);
+  if (rc) return rc;
   CK(cudaSetDevice(c->device));
-  DISPATCH_N(c, (k_features<19><<<c->G, 384, 0, c->stream>>>(c->st, d4_dev, out_dev)),
-             (k_features<9><<<c->G, 96, 0, c->stream>>>(c->st, d4_dev, out_dev)));
+  const int grid = feature_grid(c->G, format);
+  DISPATCH_N(c,
+             (k_features<19><<<grid, 384, feature_smem_bytes<19>(format, cpad), c->stream>>>(
+                 c->st, d4_dev, out_dev, format, cpad, c->feat_tma, align8)),
+             (k_features<9><<<grid, 96, feature_smem_bytes<9>(format, cpad), c->stream>>>(
+                 c->st, d4_dev, out_dev, format, cpad, c->feat_tma, align8)));
   c->launches++;
   CK(cudaGetLastError());
+  return ELFB200_OK;
+}
+
+int elfb200_features_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) {
+  return elfb200_features_dev_ex(c, d4_dev, out_dev, FEAT_F32_NCHW, 0);
+}
+
+int elfb200_set_feature_store(elfb200_ctx* c, int mode) {
+  if (!c || mode < 0 || mode > 1) return elfb200_fail(ELFB200_ERR_ARG, "mode must be 0 (vector stores) or 1 (bulk store)");
+  c->feat_tma = mode;
   return ELFB200_OK;
 }
 

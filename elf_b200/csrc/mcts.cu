@@ -122,8 +122,60 @@ __device__ __forceinline__ int pop_free(const TreeDev& tr, int g) {  // lane 0 o
 }
 
 // ---------------------------------------------------------------------------------------
+// Free the subtree below `top` (inclusive): BFS through the child links, every node goes back on the
+// game's free stack.  Whole warp; `q` is the game's BFS scratch.
+__device__ __forceinline__ void free_subtree(const TreeDev& tr, size_t nb, int g, int top, int lane) {
+  uint16_t* q = tr.bfs_q + nb;
+  int head = 0, tail = 1;
+  if (lane == 0) q[0] = (uint16_t)top;
+  __syncwarp();
+  while (head < tail) {
+    const int node = q[head++];
+    const int ne = tr.hdr[nb + node].status == NS_VISITED ? (int)tr.hdr[nb + node].n_edges : 0;
+    const uint32_t* el = tr.elink + (nb + node) * tr.E;
+    for (int i0 = 0; i0 < ne; i0 += 32) {
+      const int i = i0 + lane;
+      const int child = i < ne ? (int)(el[i] >> 16) : (int)NONE16;
+      const bool has = child != NONE16;
+      const uint32_t bal = __ballot_sync(FULL, has);
+      if (has) q[tail + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)child;
+      tail += __popc(bal);
+    }
+    __syncwarp();
+  }
+  // q[0 .. tail) is the subtree: release it
+  int n = tr.free_n[g];
+  __syncwarp();
+  for (int i = lane; i < tail; i += 32) {
+    const int node = q[i];
+    tr.hdr[nb + node].status = NS_FREE;
+    tr.hdr[nb + node].flags = 0;
+    tr.free_list[nb + n + i] = (uint16_t)node;
+  }
+  __syncwarp();
+  if (lane == 0) tr.free_n[g] = n + tail;
+  __syncwarp();
+}
+
+__device__ __forceinline__ void reset_game_pool(const TreeDev& tr, size_t nb, int g, int lane) {
+  for (int i = lane; i < tr.C; i += 32) {
+    tr.free_list[nb + i] = (uint16_t)(tr.C - 1 - i);
+    tr.hdr[nb + i].status = NS_FREE;
+    tr.hdr[nb + i].flags = 0;
+  }
+  __syncwarp();
+  if (lane == 0) tr.free_n[g] = tr.C;
+  __syncwarp();
+}
+
 // Root set-up: SearchTreeT::allocateRoot + TreeSearchT::setRootNodeState (tree_search_node.h:555,
 // tree_search.h:478-493).  One warp per game.
+//
+// Bounded pool (the reference's heap is not): when fewer than `rollouts_needed` slots are free the
+// persistent tree is PRUNED, not dropped -- the subtrees under the root's least-visited children
+// are recycled (fewest visits first, later edge first among equals) until this move's rollouts fit.
+// The root edge keeps its statistics (N, W) and only loses the child link, so a later descent
+// through it re-creates and re-evaluates the child.  Counter errors[3] (benign).
 template <int N>
 __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int rollouts_needed) {
   const Lane L = make_lane_single<N>();
@@ -131,18 +183,49 @@ __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int ro
   if (g >= st.G || !tr.active[g]) return;
   const size_t nb = (size_t)g * tr.C;
   int root = tr.root[g];
-  // not enough room for this move's new nodes: drop the persistent tree (documented deviation;
-  // the reference's heap is unbounded)
-  if (tr.free_n[g] < rollouts_needed + 1) {
-    if (L.lane == 0) atomicAdd(&tr.errors[1], 1);
-    for (int i = L.lane; i < tr.C; i += 32) {
-      tr.free_list[nb + i] = (uint16_t)(tr.C - 1 - i);
-      tr.hdr[nb + i].status = NS_FREE;
-    }
-    __syncwarp();
-    if (L.lane == 0) tr.free_n[g] = tr.C;
+  if (root != NONE16 && tr.hash[nb + root] != st.hash[g]) {
+    // "TreeSearch::Root state is not the same as the input state" (tree_search.h:488-492): the
+    // reference throws; here the stale tree is discarded, the search restarts from the board, and
+    // the counter lets the host raise (MctsBatch.begin_move does).
+    if (L.lane == 0) atomicAdd(&tr.errors[0], 1);
+    reset_game_pool(tr, nb, g, L.lane);
     root = NONE16;
-    __syncwarp();
+  }
+  if (root != NONE16 && tr.free_n[g] < rollouts_needed + 1) {
+    if (L.lane == 0) atomicAdd(&tr.errors[3], 1);
+    const int ne = tr.hdr[nb + root].status == NS_VISITED ? (int)tr.hdr[nb + root].n_edges : 0;
+    float4* es = tr.estat + (nb + root) * tr.E;
+    uint32_t* el = tr.elink + (nb + root) * tr.E;
+    while (tr.free_n[g] < rollouts_needed + 1) {
+      // least-visited root edge that still has a child
+      int bestn = 0x7FFFFFFF, besti = -1;
+      for (int i = L.lane; i < ne; i += 32) {
+        if ((el[i] >> 16) != NONE16) {
+          const int n = __float_as_int(es[i].y);
+          if (n <= bestn) {
+            bestn = n;
+            besti = i;
+          }
+        }
+      }
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const int on = __shfl_xor_sync(FULL, bestn, d), oi = __shfl_xor_sync(FULL, besti, d);
+        if (on < bestn || (on == bestn && oi > besti)) {
+          bestn = on;
+          besti = oi;
+        }
+      }
+      if (besti < 0) break;  // the root alone: C >= rollouts + 2 guarantees room
+      const int child = (int)(el[besti] >> 16);
+      __syncwarp();
+      if (L.lane == 0) {
+        el[besti] = (el[besti] & 0xFFFFu) | ((uint32_t)NONE16 << 16);
+        es[besti].w = __uint_as_float((__float_as_uint(es[besti].w) & 0xFFFFu) | ((uint32_t)NONE16 << 16));
+      }
+      __syncwarp();
+      free_subtree(tr, nb, g, child, L.lane);
+    }
   }
   if (root == NONE16) {
     int id = 0;
@@ -169,9 +252,6 @@ __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int ro
       tr.anc[nb + id] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
       tr.root[g] = (uint16_t)id;
     }
-  } else if (L.lane == 0) {
-    // "TreeSearch::Root state is not the same as the input state" (tree_search.h:488-492)
-    if (tr.hash[nb + root] != st.hash[g]) atomicAdd(&tr.errors[0], 1);
   }
 }
 
@@ -397,53 +477,62 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
 
 // ---------------------------------------------------------------------------------------
 // BoardFeature::extractAGZ for every claimed leaf: the 8-position history is the leaf, its
-// ancestors up to the root, then the game's own ring (go_state.cc:90-92).  One CTA per leaf.
+// ancestors up to the root, then the game's own ring (go_state.cc:90-92).  Staging, output formats
+// and the bulk store are features_cta's (common.cuh); the grid may be larger than the number of
+// claimed leaves (device-side count), so a wave needs no host round trip before this launch.
 template <int N>
-__global__ void __launch_bounds__(384) k_leaf_features(DevState st, TreeDev tr, float* __restrict__ out) {
-  constexpr int P = Geo<N>::P;
-  constexpr int TOTAL = 18 * P;
-  __shared__ uint64_t rows[8][N];
-  __shared__ int s_src[8];  // >=0: node local id, <0: -(ring slot)-1, INT_MIN: none
-  const int slot = blockIdx.x;
-  if (slot >= *tr.eval_count) return;
-  const int g = tr.eval_game[slot];
-  const int leaf = tr.eval_node[slot];
-  const size_t nb = (size_t)g * tr.C;
-  const BoardMeta meta = load_meta(&tr.meta[nb + leaf]);
-  const int hn = min(8, (int)meta.ply - 1);
-  if (threadIdx.x < 8) {
-    // history slot t: the leaf (t = 0), its t-th ancestor while still inside the current tree,
-    // then the game's own ring (the root is ring slot (ply_root-2)&7, go_state.cc:90-92)
-    const int t = threadIdx.x;
-    const int pr = st.meta[g].ply;            // ply of the root == ply of the game
-    const int depth = (int)meta.ply - pr;     // leaf depth below the root
-    int src = INT_MIN;
-    if (t < hn) {
-      if (t == 0) {
-        src = leaf;
-      } else if (t <= depth) {
-        const uint4 a4 = tr.anc[nb + leaf];
-        const uint32_t w = (t - 1) < 2 ? a4.x : (t - 1) < 4 ? a4.y : (t - 1) < 6 ? a4.z : a4.w;
-        src = (int)((w >> (((t - 1) & 1) * 16)) & 0xFFFFu);
-      } else {
-        src = -(((pr - 2 - (t - depth)) & 7)) - 1;
+struct LeafGather {
+  DevState st;
+  TreeDev tr;
+  int* s_src;  // shared, 8 ints: >=0 node local id, <0: -(ring slot)-1, INT_MIN: none
+  __device__ __forceinline__ void operator()(int slot, uint64_t (*rows)[N], int& hn, int& next, int& d4) const {
+    const int g = tr.eval_game[slot];
+    const int leaf = tr.eval_node[slot];
+    const size_t nb = (size_t)g * tr.C;
+    const BoardMeta meta = load_meta(&tr.meta[nb + leaf]);
+    hn = min(8, (int)meta.ply - 1);
+    next = meta.next;
+    d4 = tr.eval_d4[slot];
+    __syncthreads();  // s_src may still be read for the CTA's previous position
+    if (threadIdx.x < 8) {
+      // history slot t: the leaf (t = 0), its t-th ancestor while still inside the current tree,
+      // then the game's own ring (the root is ring slot (ply_root-2)&7, go_state.cc:90-92)
+      const int t = threadIdx.x;
+      const int pr = st.meta[g].ply;            // ply of the root == ply of the game
+      const int depth = (int)meta.ply - pr;     // leaf depth below the root
+      int src = INT_MIN;
+      if (t < hn) {
+        if (t == 0) {
+          src = leaf;
+        } else if (t <= depth) {
+          const uint4 a4 = tr.anc[nb + leaf];
+          const uint32_t w = (t - 1) < 2 ? a4.x : (t - 1) < 4 ? a4.y : (t - 1) < 6 ? a4.z : a4.w;
+          src = (int)((w >> (((t - 1) & 1) * 16)) & 0xFFFFu);
+        } else {
+          src = -(((pr - 2 - (t - depth)) & 7)) - 1;
+        }
       }
+      s_src[t] = src;
     }
-    s_src[t] = src;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
+      const int t = i / N, y = i - t * N;
+      const int src = s_src[t];
+      uint64_t v = 0;
+      if (src >= 0)
+        v = tr.pos[(nb + src) * N + y];
+      else if (src != INT_MIN)
+        v = st.ring[((size_t)g * 8 + (-src - 1)) * N + y];
+      rows[t][y] = v;
+    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
-    const int t = i / N, y = i - t * N;
-    const int src = s_src[t];
-    uint64_t v = 0;
-    if (src >= 0)
-      v = tr.pos[(nb + src) * N + y];
-    else if (src != INT_MIN)
-      v = st.ring[((size_t)g * 8 + (-src - 1)) * N + y];
-    rows[t][y] = v;
-  }
-  __syncthreads();
-  write_agz_planes<N>(rows, hn, meta.next, tr.eval_d4[slot], out + (size_t)slot * TOTAL);
+};
+
+template <int N>
+__global__ void __launch_bounds__(384)
+    k_leaf_features(DevState st, TreeDev tr, void* __restrict__ out, int fmt, int cpad, int tma, int align8) {
+  __shared__ int s_src[8];
+  features_cta<N>(LeafGather<N>{st, tr, s_src}, *tr.eval_count, out, fmt, cpad, tma, align8);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -619,6 +708,7 @@ __global__ void __launch_bounds__(BLOCK) k_backup(int G, TreeDev tr, int virtual
   __shared__ int s_cnt[WARPS][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) tr.stats[4] += (unsigned long long)*tr.eval_count;  // evaluations so far
   if (g >= G || !tr.active[g]) return;
   const size_t nb = (size_t)g * tr.C;
   const int B = tr.B, E = tr.E;
@@ -1053,13 +1143,19 @@ struct elfb200_mcts {
   float* d_priors = nullptr;
   // per-kernel device timing (CUDA events on the context stream), accumulated on the host
   cudaEvent_t ev[7] = {};  // sel0 sel1 feat0 feat1 exp0 exp1 bak1
-  bool pending_feat = false, pending_eb = false;
+  bool pending_sel = false, pending_feat = false, pending_eb = false;
+  bool used_async = false;  // a wave ran without the host reading its leaf count
   double acc_ms[4] = {0, 0, 0, 0};  // select, features, expand, backup
   int64_t acc_waves = 0;
 };
 
 static void flush_timings(elfb200_mcts* m) {  // caller has synchronised the stream
   float ms = 0.f;
+  if (m->pending_sel) {
+    if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->acc_ms[0] += ms;
+    m->acc_waves++;
+    m->pending_sel = false;
+  }
   if (m->pending_feat) {
     if (cudaEventElapsedTime(&ms, m->ev[2], m->ev[3]) == cudaSuccess) m->acc_ms[1] += ms;
     m->pending_feat = false;
@@ -1138,8 +1234,9 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   CK(cudaMalloc(&t.bfs_q, GC * 2));
   CK(cudaMalloc(&t.errors, 16));
   CK(cudaMemsetAsync(t.errors, 0, 16, c->stream));
-  CK(cudaMalloc(&t.stats, 32));
-  CK(cudaMemsetAsync(t.stats, 0, 32, c->stream));
+  CK(cudaMalloc(&t.stats, 64));
+  CK(cudaMemsetAsync(t.stats, 0, 64, c->stream));
+  CK(cudaFuncSetAttribute(k_leaf_features<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, FeatTile<19>::BYTES));
   CK(cudaMemsetAsync(t.hdr, 0, GC * sizeof(NodeHdr), c->stream));
   CK(cudaMemsetAsync(t.active, 1, G, c->stream));
   CK(cudaMemsetAsync(t.eval_count, 0, 4, c->stream));
@@ -1239,10 +1336,21 @@ int elfb200_mcts_begin_move(elfb200_mcts* m, const uint8_t* active_host) {
   return ELFB200_OK;
 }
 
-int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves) {
-  if (!m || !feat_dev || !n_leaves) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad, int32_t* n_leaves) {
+  if (!m || !feat_dev) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   elfb200_ctx* c = m->ctx;
+  int align8 = 0;
+  if (format < FEAT_F32_NCHW || format > FEAT_BF16_NHWC) return elfb200_fail(ELFB200_ERR_ARG, "unknown feature format %d", format);
+  if (format != FEAT_F32_NCHW && (cpad < 24 || cpad > FEAT_CPAD_MAX || (cpad & 7)))
+    return elfb200_fail(ELFB200_ERR_ARG, "channel padding must be 24 or 32 (got %d)", cpad);
+  if ((uintptr_t)feat_dev & 15) return elfb200_fail(ELFB200_ERR_ARG, "leaf feature buffer must be 16-byte aligned");
   CK(cudaSetDevice(c->device));
+  if (m->pending_sel || m->pending_feat || m->pending_eb) {
+    // the event pairs are reused every wave: read the previous wave's before re-recording them
+    // (only reached in the asynchronous mode; the synchronous mode flushed after its own sync)
+    CK(cudaEventSynchronize(m->ev[6]));
+    flush_timings(m);
+  }
   CK(cudaMemsetAsync(m->tr.eval_count, 0, 4, c->stream));
   CK(cudaEventRecord(m->ev[0], c->stream));
   DISPATCH_N(c, (k_select<19><<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, m->wave)),
@@ -1250,29 +1358,53 @@ int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves) {
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(m->ev[1], c->stream));
-  int32_t* hp = (int32_t*)c->h_pin;
-  CK(cudaMemcpyAsync(hp, m->tr.eval_count, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  {
-    flush_timings(m);  // previous wave's features / expand / backup are complete by now
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]) == cudaSuccess) m->acc_ms[0] += ms;
-    m->acc_waves++;
+  m->pending_sel = true;
+  int n = -1;  // unknown to the host: the feature / expand grids cover all G*B slots and the kernels
+               // stop at the device-side count
+  if (n_leaves) {
+    int32_t* hp = (int32_t*)c->h_pin;
+    CK(cudaMemcpyAsync(hp, m->tr.eval_count, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    flush_timings(m);  // this wave's select and the previous wave's features / expand / backup are complete
+    n = hp[0];
+    m->n_eval_total += n;
+    *n_leaves = n;
+  } else {
+    m->used_async = true;
   }
-  const int n = hp[0];
   m->last_eval_count = n;
-  m->n_eval_total += n;
-  *n_leaves = n;
-  if (n > 0) {
+  if (n != 0) {
+    const int npos = n > 0 ? n : c->G * m->tr.B;
+    const int grid = feature_grid(npos, format);
     CK(cudaEventRecord(m->ev[2], c->stream));
-    DISPATCH_N(c, (k_leaf_features<19><<<n, 384, 0, c->stream>>>(c->st, m->tr, feat_dev)),
-               (k_leaf_features<9><<<n, 96, 0, c->stream>>>(c->st, m->tr, feat_dev)));
+    DISPATCH_N(c,
+               (k_leaf_features<19><<<grid, 384, feature_smem_bytes<19>(format, cpad), c->stream>>>(
+                   c->st, m->tr, feat_dev, format, cpad, c->feat_tma, align8)),
+               (k_leaf_features<9><<<grid, 96, feature_smem_bytes<9>(format, cpad), c->stream>>>(
+                   c->st, m->tr, feat_dev, format, cpad, c->feat_tma, align8)));
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m->ev[3], c->stream));
     m->pending_feat = true;
   }
   m->wave++;
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves) {
+  if (!n_leaves) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  return elfb200_mcts_select_ex(m, feat_dev, FEAT_F32_NCHW, 0, n_leaves);
+}
+
+int elfb200_mcts_leaf_count(elfb200_mcts* m, int32_t* n_leaves) {
+  if (!m || !n_leaves) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  int32_t* hp = (int32_t*)c->h_pin;
+  CK(cudaMemcpyAsync(hp, m->tr.eval_count, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n_leaves = hp[0];
+  m->last_eval_count = hp[0];  // known to the host from here on: leaf_info and the expansion grid use it
   return ELFB200_OK;
 }
 
@@ -1301,10 +1433,11 @@ int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float
   CK(cudaSetDevice(c->device));
   const int n = m->last_eval_count;
   CK(cudaEventRecord(m->ev[4], c->stream));
-  if (n > 0) {
+  if (n != 0) {
     if (!pi_dev || !value_dev) return elfb200_fail(ELFB200_ERR_ARG, "pi/value is NULL with %d leaves pending", n);
-    DISPATCH_N(c, (k_expand<19><<<warp_grid(n), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)),
-               (k_expand<9><<<warp_grid(n), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)));
+    const int nw = n > 0 ? n : c->G * m->tr.B;  // n < 0: count known to the device only
+    DISPATCH_N(c, (k_expand<19><<<warp_grid(nw), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)),
+               (k_expand<9><<<warp_grid(nw), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)));
     c->launches++;
     CK(cudaGetLastError());
   }
@@ -1401,7 +1534,16 @@ int elfb200_mcts_errors(elfb200_mcts* m, int32_t* counters_host4) {
   return ELFB200_OK;
 }
 
-int64_t elfb200_mcts_eval_count(const elfb200_mcts* m) { return m ? m->n_eval_total : 0; }
+int64_t elfb200_mcts_eval_count(const elfb200_mcts* m) {
+  if (!m) return 0;
+  if (!m->used_async) return m->n_eval_total;
+  // waves ran without a host read of the count: the device keeps the total (k_backup)
+  unsigned long long v = 0;
+  if (cudaSetDevice(m->ctx->device) != cudaSuccess || cudaStreamSynchronize(m->ctx->stream) != cudaSuccess ||
+      cudaMemcpy(&v, m->tr.stats + 4, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return -1;
+  return (int64_t)v;
+}
 
 int elfb200_mcts_timings(elfb200_mcts* m, double* ms_host4, int64_t* waves, int reset) {
   if (!m || !ms_host4) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");

@@ -6,6 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libelfb200.so")
 
 INFO_FIELDS = 12
+FEAT_F32_NCHW, FEAT_F16_NHWC, FEAT_BF16_NHWC = 0, 1, 2  # ELFB200_FEAT_* (include/elfb200.h)
 
 
 class ElfB200Error(RuntimeError):
@@ -44,6 +45,8 @@ SIGNATURES = {
     "elfb200_evaluate": (ctypes.c_int, [vp, ctypes.c_float, vp]),
     "elfb200_features": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_features_dev": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_features_dev_ex": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int]),
+    "elfb200_set_feature_store": (ctypes.c_int, [vp, ctypes.c_int]),
     "elfb200_playout": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp, vp, vp, vp, vp]),
     "elfb200_playout_launch": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]),
     "elfb200_playout_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
@@ -60,6 +63,8 @@ SIGNATURES = {
     "elfb200_mcts_reset": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_begin_move": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_select": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_mcts_select_ex": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp]),
+    "elfb200_mcts_leaf_count": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_leaf_info": (ctypes.c_int, [vp, vp, vp, vp, vp]),
     "elfb200_mcts_expand_backup": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_mcts_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),

@@ -14,11 +14,23 @@ from . import lib as _l
 
 
 class MctsBatch:
-    def __init__(self, go_batch, **opts):
+    """``feature_format``: "f32" = the GoFeature contract, ``batch["s"]`` float32 ``[n,18,N,N]``
+    (default); "f16" / "bf16" = the fast mode for a half-precision channels-last network: the leaf
+    batch is written as ``batch["s_nhwc"]`` ``[n,N,N,cpad]`` (planes in channels 0..17, zeros above),
+    which ``elf_b200.model.FusedActor`` consumes without a cast/permute pass.
+    ``strict_root``: raise when a persistent root does not match the board it is asked to search
+    (the reference throws, tree_search.h:488-492); off = count it in ``errors()[0]`` and carry on
+    with the tree rebuilt from the board."""
+
+    def __init__(self, go_batch, feature_format="f32", cpad=24, strict_root=True, **opts):
         import torch
 
         self.gb = go_batch
         self._lib = _l.load_library()
+        if feature_format not in ("f32", "f16", "bf16"):
+            raise ValueError("feature_format must be f32, f16 or bf16")
+        self.feature_format, self.cpad, self.strict_root = feature_format, int(cpad), bool(strict_root)
+        self._mismatches = 0
         o = _l.MctsOptions()
         _l.check(self._lib, self._lib.elfb200_mcts_default_options(ctypes.byref(o)))
         for k, v in opts.items():
@@ -37,8 +49,16 @@ class MctsBatch:
         self._torch = torch
         self.device = torch.device("cuda", go_batch.device)
         # the leaf feature batch handed to the network: lives on the device, written in place
-        self.feat = torch.zeros((self.max_leaves, 18, n, n), dtype=torch.float32, device=self.device)
+        if feature_format == "f32":
+            self._fmt = _l.FEAT_F32_NCHW
+            self.feat = torch.zeros((self.max_leaves, 18, n, n), dtype=torch.float32, device=self.device)
+        else:
+            self._fmt = _l.FEAT_F16_NHWC if feature_format == "f16" else _l.FEAT_BF16_NHWC
+            dt = torch.float16 if feature_format == "f16" else torch.bfloat16
+            self.feat = torch.zeros((self.max_leaves, n, n, self.cpad), dtype=dt, device=self.device)
+        self.feat_key = "s" if feature_format == "f32" else "s_nhwc"
         self._stream = torch.cuda.ExternalStream(go_batch.stream, device=self.device)
+        self._keep = None  # network replies still being read by kernels on the context stream
 
     def close(self):
         if getattr(self, "_m", None):
@@ -61,14 +81,30 @@ class MctsBatch:
     def begin_move(self, active=None):
         a = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
         _l.check(self._lib, self._lib.elfb200_mcts_begin_move(self._m, a.ctypes.data if a is not None else None))
+        if self.strict_root:
+            bad = int(self.errors()[0])
+            if bad != self._mismatches:
+                n, self._mismatches = bad - self._mismatches, bad
+                raise _l.ElfB200Error(
+                    f"TreeSearch::Root state is not the same as the input state in {n} game(s): the board moved "
+                    "without advance()/reset() of the search (the stale trees were discarded)")
 
-    def select(self):
-        """one wave of descents; returns the CUDA feature tensor view [n, 18, N, N] of the leaves
-        that need the network (n may be 0)"""
+    def select(self, wait=True):
+        """one wave of descents; returns the CUDA feature tensor view of the leaves that need the
+        network (``[n,18,N,N]`` float32, or ``[n,N,N,cpad]`` in the 16-bit formats; n may be 0).
+        ``wait=False``: nothing is read back and the host does not wait -- the view covers all
+        ``max_leaves`` rows (rows past the device-side count are stale, their replies are ignored);
+        ``leaf_count()`` fetches the count later."""
         n = ctypes.c_int32()
-        _l.check(self._lib, self._lib.elfb200_mcts_select(self._m, self.feat.data_ptr(), ctypes.byref(n)))
-        self._n = n.value
-        return self.feat[: n.value]
+        _l.check(self._lib, self._lib.elfb200_mcts_select_ex(self._m, self.feat.data_ptr(), self._fmt, self.cpad,
+                                                             ctypes.byref(n) if wait else None))
+        self._n = n.value if wait else -1
+        return self.feat[: n.value] if wait else self.feat
+
+    def leaf_count(self):
+        n = ctypes.c_int32()
+        _l.check(self._lib, self._lib.elfb200_mcts_leaf_count(self._m, ctypes.byref(n)))
+        return n.value
 
     def leaf_info(self):
         n = self._n
@@ -83,10 +119,14 @@ class MctsBatch:
     def expand_backup(self, pi, v):
         """pi: CUDA float32 [n, N*N+1], v: CUDA float32 [n] (contiguous), produced on any stream
         the caller has synchronised with the context stream."""
-        if self._n > 0:
+        if self._n != 0:
             assert pi.is_cuda and v.is_cuda and pi.dtype == self._torch.float32 and v.dtype == self._torch.float32
-            assert pi.is_contiguous() and v.is_contiguous() and pi.shape[0] >= self._n
+            assert pi.is_contiguous() and v.is_contiguous()
+            assert pi.shape[0] >= (self._n if self._n > 0 else self.max_leaves)
             _l.check(self._lib, self._lib.elfb200_mcts_expand_backup(self._m, pi.data_ptr(), v.data_ptr()))
+            # the kernels read pi / v on the context stream, which the caching allocator knows nothing
+            # about: keep the tensors alive until the next wave has been ordered behind them
+            self._keep = (pi, v)
         else:
             _l.check(self._lib, self._lib.elfb200_mcts_expand_backup(self._m, None, None))
 
@@ -151,27 +191,54 @@ class MctsBatch:
         self.search(actor, active)
         return self.results()
 
+    def wave(self, actor):
+        """one wave: descents, the network on the claimed leaves, expansion and backup.  The host
+        waits once (for the leaf count); network and search kernels are ordered by stream events."""
+        self.wave_finish(self.wave_eval(actor, self.wave_select()))
+
+    # -- the three pieces of a wave (elf_b200.pipeline.WavePipeline interleaves them across batches) --
+    def wave_select(self):
+        """descents + leaf features; returns the (padded) feature view for the network or None"""
+        pad = int(getattr(self, "_pad", 0) or 0)
+        s = self.select()  # waits for the context stream to learn the leaf count
+        if s.shape[0] == 0:
+            return None
+        if pad > 1:
+            # static NN shapes: round the batch up to a multiple of the actor's batch size
+            # (rows past n are stale features; their replies are never read)
+            s = self.feat[: min(-(-s.shape[0] // pad) * pad, self.max_leaves)]
+        return s
+
+    def wave_eval(self, actor, s, nn_stream=None):
+        """enqueue the network on ``nn_stream`` (default: torch's current stream) behind the feature
+        kernel; returns (pi, v, event) or None"""
+        if s is None:
+            return None
+        torch = self._torch
+        st = nn_stream if nn_stream is not None else torch.cuda.current_stream(self.device)
+        st.wait_stream(self._stream)  # the network after the features
+        with torch.cuda.stream(st), torch.no_grad():
+            reply = actor({self.feat_key: s})
+            pi = reply["pi"].to(torch.float32).contiguous()
+            v = reply["V"].to(torch.float32).reshape(-1).contiguous()
+            ev = torch.cuda.Event()
+            ev.record(st)
+        return pi, v, ev
+
+    def wave_finish(self, reply):
+        """expansion + backup on the context stream, behind the network's event; does not wait"""
+        if reply is None:
+            self.expand_backup(None, None)
+            return
+        pi, v, ev = reply
+        self._stream.wait_event(ev)
+        self.expand_backup(pi, v)
+
     def search(self, actor, active=None, waves=None):
         """the search of ``act`` without fetching the root tables (use ``choose`` / ``results``).
         ``waves``: run only that many waves (1 on a fresh tree = evaluate and expand the root only,
         TreeSearchT::runPolicyOnly, tree_search.h:387-408); default: the whole move"""
-        torch = self._torch
         self.begin_move(active)
-        pad = int(getattr(actor, "batchsize", 0) or 0)
+        self._pad = int(getattr(actor, "batchsize", 0) or 0)
         for _ in range(self.waves_per_move if waves is None else int(waves)):
-            s = self.select()
-            if s.shape[0] > 0:
-                if pad > 1:
-                    # static NN shapes: round the batch up to a multiple of the actor's batch size
-                    # (rows past n are stale features; their replies are never read)
-                    n_pad = min(-(-s.shape[0] // pad) * pad, self.max_leaves)
-                    s = self.feat[:n_pad]
-                self.gb.synchronize()  # features written on the context stream
-                with torch.no_grad():
-                    reply = actor({"s": s})
-                pi = reply["pi"].to(torch.float32).contiguous()
-                v = reply["V"].to(torch.float32).reshape(-1).contiguous()
-                torch.cuda.current_stream(self.device).synchronize()
-                self.expand_backup(pi, v)
-            else:
-                self.expand_backup(None, None)
+            self.wave(actor)

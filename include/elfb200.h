@@ -87,6 +87,19 @@ int elfb200_evaluate(elfb200_ctx* ctx, float komi, float* value_host);
  * d4[g] (board_feature.h:88-95; NULL = identity): float32 [G][18][N][N]. */
 int elfb200_features(elfb200_ctx* ctx, const int32_t* d4_host, float* out_host);
 int elfb200_features_dev(elfb200_ctx* ctx, const int32_t* d4_dev, float* out_dev);
+/* Feature formats.  ELFB200_FEAT_F32_NCHW is the GoFeature tensor contract "s"
+ * (common/game_feature.h:159-206).  The 16-bit channels-last formats are a fast mode for a network
+ * that runs in half precision: [n][N][N][cpad] halves (binary16 / bfloat16), planes 0..17 in
+ * channels 0..17, zeros above; cpad = 24 or 32.  Values are exactly 0 or 1 in every format. */
+#define ELFB200_FEAT_F32_NCHW 0
+#define ELFB200_FEAT_F16_NHWC 1
+#define ELFB200_FEAT_BF16_NHWC 2
+/* elfb200_features_dev with an explicit format.  out_dev: 16-byte aligned (float32: 8-byte aligned
+ * is accepted, e.g. an odd row of a larger tensor, at the price of narrower stores). */
+int elfb200_features_dev_ex(elfb200_ctx* ctx, const int32_t* d4_dev, void* out_dev, int format, int cpad);
+/* How staged feature tiles leave shared memory: 1 = one bulk (TMA) store per tile (default),
+ * 0 = 16-byte vector stores by all threads.  Same bytes either way; a tuning/diagnostic knob. */
+int elfb200_set_feature_store(elfb200_ctx* ctx, int mode);
 
 /* The deterministic random-playout workload (include/elfb200_playout_policy.h; BASELINE
  * configs 1/2/5): game g plays game id first_game_id+g from the empty board until

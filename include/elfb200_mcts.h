@@ -78,6 +78,16 @@ int elfb200_mcts_begin_move(elfb200_mcts* m, const uint8_t* active_host);
 /* One wave of descents.  Writes the feature planes of the *n_leaves leaves that need the network
  * to feat_dev (device, capacity elfb200_mcts_max_leaves * 18*N*N floats). */
 int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves);
+/* elfb200_mcts_select with an explicit feature format (ELFB200_FEAT_*, elfb200.h): the 16-bit
+ * channels-last formats let a half-precision network read the leaf batch without a cast/permute
+ * pass.  feat_dev: 16-byte aligned, capacity elfb200_mcts_max_leaves positions.
+ * n_leaves == NULL selects the ASYNCHRONOUS mode: nothing is copied back and the host does not
+ * wait; the feature and expansion kernels run on a grid for all G*B slots and stop at the
+ * device-side count, so the caller evaluates all elfb200_mcts_max_leaves rows (rows past the count
+ * are stale and ignored) or asks for the count later with elfb200_mcts_leaf_count. */
+int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad, int32_t* n_leaves);
+/* Number of leaves the last select claimed (waits for the context stream). */
+int elfb200_mcts_leaf_count(elfb200_mcts* m, int32_t* n_leaves);
 /* Hash / game index / ply / D4 code of the pending leaves (host, each may be NULL); test & debug aid. */
 int elfb200_mcts_leaf_info(elfb200_mcts* m, uint64_t* hash_host, int32_t* game_host, int32_t* ply_host,
                            int32_t* d4_host);
@@ -103,7 +113,11 @@ int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host);
 /* float[G][N*N+1]: current prior of every root edge by action (-1 where the root has no such
  * edge), after any exploration noise (NodeT::enhanceExploration, tree_search_node.h:132-155). */
 int elfb200_mcts_root_priors(elfb200_mcts* m, float* priors_host);
-/* int32[4]: root-hash mismatches, node-pool drops/overflows, depth overflows, reserved. */
+/* int32[4]: [0] root-hash mismatches (the reference throws "Root state is not the same as the input
+ * state", tree_search.h:488-492; here the stale tree is discarded and rebuilt from the board),
+ * [1] node-pool exhaustion during a descent (rollout cut short), [2] descents cut at 128 plies
+ * below the root, [3] moves whose persistent tree had to be pruned to fit the pool (least-visited
+ * root subtrees recycled; benign). */
 int elfb200_mcts_errors(elfb200_mcts* m, int32_t* counters_host4);
 int64_t elfb200_mcts_eval_count(const elfb200_mcts* m);
 /* uint64[4] running totals: descent steps (nodes visited by PUCT), edge records actually read

@@ -39,9 +39,10 @@ class EmuSearch:
     """MctsBatch's interface (begin_move / select / leaf_info / expand_backup / results / choose /
     advance / reset / search / act) over the emulated C ABI with CPU torch tensors"""
 
-    def __init__(self, gb, **opts):
+    def __init__(self, gb, feature_format="f32", cpad=24, strict_root=True, **opts):
         import torch
 
+        self.feature_format, self.cpad, self.strict_root, self._mismatches = feature_format, int(cpad), strict_root, 0
         self._torch = torch
         self.gb = gb
         self._lib = L = emu_lib()
@@ -57,7 +58,14 @@ class EmuSearch:
         n = gb.board_size
         self.waves_per_move = L.elfb200_mcts_waves_per_move(self._m)
         self.max_leaves = L.elfb200_mcts_max_leaves(self._m)
-        self.feat = torch.zeros((self.max_leaves, 18, n, n), dtype=torch.float32)
+        if feature_format == "f32":
+            self._fmt = _l.FEAT_F32_NCHW
+            self.feat = torch.zeros((self.max_leaves, 18, n, n), dtype=torch.float32)
+        else:
+            self._fmt = _l.FEAT_F16_NHWC if feature_format == "f16" else _l.FEAT_BF16_NHWC
+            self.feat = torch.zeros((self.max_leaves, n, n, self.cpad),
+                                    dtype=torch.float16 if feature_format == "f16" else torch.bfloat16)
+        self.feat_key = "s" if feature_format == "f32" else "s_nhwc"
         self.device = torch.device("cpu")
         self._n = 0
 
@@ -73,12 +81,23 @@ class EmuSearch:
     def begin_move(self, active=None):
         a = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
         _l.check(self._lib, self._lib.elfb200_mcts_begin_move(self._m, a.ctypes.data if a is not None else None))
+        if self.strict_root:
+            bad = int(self.errors()[0])
+            if bad != self._mismatches:
+                self._mismatches = bad
+                raise _l.ElfB200Error("TreeSearch::Root state is not the same as the input state")
 
-    def select(self):
+    def select(self, wait=True):
         k = ctypes.c_int32()
-        _l.check(self._lib, self._lib.elfb200_mcts_select(self._m, self.feat.data_ptr(), ctypes.byref(k)))
-        self._n = k.value
-        return self.feat[: k.value]
+        _l.check(self._lib, self._lib.elfb200_mcts_select_ex(self._m, self.feat.data_ptr(), self._fmt, self.cpad,
+                                                             ctypes.byref(k) if wait else None))
+        self._n = k.value if wait else -1
+        return self.feat[: k.value] if wait else self.feat
+
+    def leaf_count(self):
+        k = ctypes.c_int32()
+        _l.check(self._lib, self._lib.elfb200_mcts_leaf_count(self._m, ctypes.byref(k)))
+        return k.value
 
     def leaf_info(self):
         n = self._n
@@ -89,10 +108,10 @@ class EmuSearch:
         return h, g, p
 
     def expand_backup(self, pi, v):
-        if self._n > 0:
+        if self._n != 0:
             pi = pi.to(self._torch.float32).contiguous()
             v = v.to(self._torch.float32).reshape(-1).contiguous()
-            assert pi.shape[0] >= self._n
+            assert pi.shape[0] >= (self._n if self._n > 0 else self.max_leaves)
             _l.check(self._lib, self._lib.elfb200_mcts_expand_backup(self._m, pi.data_ptr(), v.data_ptr()))
         else:
             _l.check(self._lib, self._lib.elfb200_mcts_expand_backup(self._m, None, None))
@@ -147,7 +166,7 @@ class EmuSearch:
         for _ in range(self.waves_per_move if waves is None else int(waves)):
             s = self.select()
             if s.shape[0] > 0:
-                r = actor({"s": s})
+                r = actor({self.feat_key: s})
                 self.expand_backup(r["pi"], r["V"])
             else:
                 self.expand_backup(None, None)

@@ -500,3 +500,18 @@ def oracle_playout_stream(n, seed, first, slot, num_slots, budget, lib=None):
     games = ctypes.c_int32()
     t = L.go_playout_stream(n, seed, first, slot, num_slots, budget, ctypes.byref(acc), ctypes.byref(games))
     return t, acc.value, games.value
+
+
+def feature_net(x, num_actions):
+    """deterministic test net computed FROM THE PLANES (not the leaf hash): x float [m,18,N,N] ->
+    (pi float32 [m,A], v float32 [m]).  Rows are independent and evaluated in float64 on the CPU, so
+    the answer for a position does not depend on the batch it arrives in."""
+    x = np.asarray(x, np.float64).reshape(len(x), -1)
+    rng = np.random.default_rng(x.shape[1] * 1000003 + num_actions)
+    W = rng.standard_normal((x.shape[1], num_actions)) * 0.05
+    w2 = rng.standard_normal(x.shape[1]) * 0.02
+    z = x @ W
+    z -= z.max(1, keepdims=True)
+    p = np.exp(z)
+    p /= p.sum(1, keepdims=True)
+    return p.astype(np.float32), np.tanh(x @ w2).astype(np.float32)

@@ -608,3 +608,99 @@ def test_game_context_from_options_on_the_kernels(emu):
     ctx.stop()
     assert sp.games_finished >= 3 and len(sp.records) == sp.games_finished  # selfplay mode keeps the records
     assert sp.records[0]["request"]["vers"]["mcts_opt"]["num_rollouts_per_thread"] == 16
+
+
+@pytest.mark.parametrize("n", [9, 19])
+def test_fast_feature_formats_async_waves_prune_and_mismatch(emu, n):
+    """round-2 kernel paths on the emulator: 16-bit NHWC leaf features equal the float32 ones, waves
+    without a host read-back (fixed grids, device-side leaf count) give the same search, a short node
+    pool prunes least-visited root subtrees instead of dropping the tree, a stale root is reported"""
+    G, R, B = 4, 16, 4
+    opts = dict(num_rollouts=R, num_rollouts_per_batch=B, rotation_flip=1, seed=7)
+
+    def make(**kw):
+        gb = emu.emu_batch(G, n)
+        rng = np.random.default_rng(2)
+        os_ = [oracles.Oracle(n) for _ in range(G)]
+        for _ in range(9):  # more than 8 plies: the history gather crosses from the tree into the ring
+            acts = np.array([int(rng.choice(np.flatnonzero(o.legal()))) for o in os_], np.int32)
+            for o, a in zip(os_, acts):
+                o.forward(int(a))
+            assert gb.forward(acts).all()
+        return gb, emu.EmuSearch(gb, **opts, **kw)
+
+    def actor_for(mc, log=None):
+        def actor(batch):
+            h, _, _ = mc.leaf_info()
+            key = "s" if "s" in batch else "s_nhwc"
+            x = batch[key]
+            if log is not None:
+                xx = x[: len(h)].float()
+                log.append(xx.numpy().copy() if key == "s" else xx.permute(0, 3, 1, 2)[:, :18].numpy().copy())
+                if key != "s":
+                    assert (xx[..., 18:] == 0).all()
+            pi, v = oracles.fakenet(h, n * n + 1)
+            P, V = torch.zeros(x.shape[0], n * n + 1), torch.zeros(x.shape[0])
+            P[: len(h)], V[: len(h)] = torch.from_numpy(pi), torch.from_numpy(v)
+            return {"pi": P, "V": V}
+        return actor
+
+    gb0, m0 = make()
+    log0 = []
+    r0 = m0.act(actor_for(m0, log0))
+    for fmt, cpad in (("f16", 24), ("bf16", 32)):
+        gb1, m1 = make(feature_format=fmt, cpad=cpad)
+        log1 = []
+        r1 = m1.act(actor_for(m1, log1))
+        assert len(log0) == len(log1)
+        for a, b in zip(log0, log1):
+            np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(r0["visits"], r1["visits"])
+    # asynchronous waves
+    gb2, m2 = make()
+    act2 = actor_for(m2)
+    m2.begin_move()
+    for _ in range(m2.waves_per_move):
+        s = m2.select(wait=False)
+        assert s.shape[0] == m2.max_leaves
+        m2._n = m2.leaf_count()      # the fake net needs the hashes of the claimed leaves only
+        rep = act2({"s": s})
+        m2.expand_backup(rep["pi"], rep["V"])
+    r2 = m2.results()
+    np.testing.assert_array_equal(r0["visits"], r2["visits"])
+    assert m2.eval_count() == m0.eval_count()
+    # fully asynchronous waves (no count on the host at all: fixed grids everywhere) with a net that
+    # reads the planes, against the same net through the synchronous path
+    def plane_actor(batch):
+        x = batch["s"] if "s" in batch else batch["s_nhwc"].float().permute(0, 3, 1, 2)[:, :18]
+        pi, v = oracles.feature_net(x.float().numpy(), n * n + 1)
+        return {"pi": torch.from_numpy(pi), "V": torch.from_numpy(v)}
+
+    gb4, m4 = make()
+    r4 = m4.act(plane_actor)
+    gb5, m5 = make(feature_format="f16")
+    m5.begin_move()
+    for _ in range(m5.waves_per_move):
+        rep = plane_actor({"s_nhwc": m5.select(wait=False)})
+        m5.expand_backup(rep["pi"], rep["V"])
+    r5 = m5.results()
+    np.testing.assert_array_equal(r4["visits"], r5["visits"])
+    assert m5.eval_count() == m4.eval_count() and (m5.errors() == 0).all()
+    # stale root: the board moves without advance()
+    a = r0["best_action"]
+    assert gb0.forward(a).all()
+    with pytest.raises(Exception, match="Root state is not the same"):
+        m0.act(actor_for(m0))
+    r = m0.act(actor_for(m0))
+    assert (r["total_visits"] == R - B).all() and m0.errors()[0] == G
+    # short pool: prune, never overflow
+    gb3 = emu.emu_batch(G, n)
+    m3 = emu.EmuSearch(gb3, num_rollouts=R, num_rollouts_per_batch=B, rotation_flip=0, nodes_per_game=R + 6)
+    act3 = actor_for(m3)
+    for _ in range(6):
+        r = m3.act(act3)
+        assert ((r["total_visits"] == R - B) | (r["total_visits"] >= R)).all()
+        assert gb3.forward(r["best_action"]).all()
+        m3.advance(r["best_action"])
+    e = m3.errors()
+    assert e[0] == 0 and e[1] == 0 and e[2] == 0 and e[3] > 0, e

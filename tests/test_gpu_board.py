@@ -27,13 +27,17 @@ def _random_candidate(rng, o, avoid_eyes=True):
     return int(rng.choice(idx))
 
 
+@pytest.mark.parametrize("against", ["port", "reference"])
 @pytest.mark.parametrize("n,G,plies", [(19, 64, 600), (9, 96, 200)])
-def test_step_parity_every_ply(n, G, plies, oracle_lib):
+def test_step_parity_every_ply(n, G, plies, against, oracle_lib):
     """GoState::forward for a batch: after EVERY ply compare hash, info words, stones, legal
-    mask, and periodically score / eyes / features with the oracle."""
+    mask, and periodically score / eyes / features with the oracle -- the C restatement and the
+    compiled UNMODIFIED reference (oracle/_ref) alike."""
+    if against == "reference" and not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built")
     rng = np.random.default_rng(1234 + n)
     gb = _gobatch(G, n)
-    os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+    os_ = [oracles.Oracle(n, oracle_lib) if against == "port" else oracles.Ref(n) for _ in range(G)]
     for t in range(plies):
         acts = np.empty(G, np.int32)
         exp_ok = np.empty(G, bool)
@@ -248,4 +252,100 @@ def test_config5_small_board_stress(oracle_lib):
     for slot in (0, 5, 16383):
         t, acc, games = oracles.oracle_playout_stream(n, 9, 0, slot, G, 300, lib=oracle_lib)
         assert (acc, games) == (int(s["chk"][slot]), int(s["games"][slot]))
+    gb.close()
+
+
+def _ref_playouts_all_threads(n, seed, first, count):
+    """`count` playouts of the compiled reference (oracle/_ref: ref_playout drives the unmodified
+    GoState), spread over the host threads (ctypes releases the GIL during the call)"""
+    import ctypes
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    L = oracles.load_ref(n)
+    chk = np.zeros(count, np.uint64)
+    plies = np.zeros(count, np.int32)
+    score = np.zeros(count, np.int32)
+
+    def work(lo, hi):
+        c, s = ctypes.c_uint64(), ctypes.c_int32()
+        for i in range(lo, hi):
+            plies[i] = L.ref_playout(seed, first + i, 2 * n * n, None, None, None, ctypes.byref(c), ctypes.byref(s))
+            chk[i], score[i] = c.value, s.value
+
+    nt = max(1, min(64, len(os.sched_getaffinity(0))))
+    step = -(-count // (nt * 8))
+    with ThreadPoolExecutor(nt) as ex:
+        list(ex.map(lambda lo: work(lo, min(lo + step, count)), range(0, count, step)))
+    return chk, plies, score
+
+
+@pytest.mark.parametrize("n,G,batches", [(19, 4096, 3), (9, 16384, 1)])
+def test_ten_thousand_playouts_bit_exact_vs_compiled_reference(n, G, batches):
+    """north_star parity bar: >= 10k random playouts, GAME BY GAME against the reference C++ itself
+    (not the restatement): the per-game checksum folds hash, both capture counts, side to move and the
+    full legal mask of EVERY position, so equality means those were bit-identical at every ply; plus
+    ply count and final Tromp-Taylor score.  19x19: 3 x 4096 = 12,288 games (BASELINE config 2's batch,
+    three times); 9x9: 16,384 games (config 5's batch)."""
+    if not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built")
+    gb = _gobatch(G, n)
+    total = 0
+    for b in range(batches):
+        first = 5_000_000 + b * G
+        res = gb.playout(seed=2024, first_game_id=first)
+        chk, plies, score = _ref_playouts_all_threads(n, 2024, first, G)
+        bad = np.flatnonzero((res["chk"] != chk) | (res["plies"] != plies) | (res["score"] != score))
+        assert bad.size == 0, f"{bad.size} of {G} games differ from the reference, first: game id {first + int(bad[0])}"
+        total += int(plies.sum())
+    print(f"{batches * G} playouts ({total} positions) bit-exact vs the compiled reference, {n}x{n}")
+    gb.close()
+
+
+@pytest.mark.parametrize("n,G", [(19, 37), (9, 50)])
+def test_feature_formats_and_store_modes(n, G):
+    """the feature writer's fast formats and both ways a staged tile leaves shared memory (bulk/TMA
+    store, vector stores) produce the planes of elfb200_features (oracle-checked above): float32
+    NCHW incl. an odd batch and an 8-byte-aligned destination, binary16 / bfloat16 NHWC with 24 or 32
+    channels (zeros above plane 17)"""
+    import torch
+
+    from elf_b200 import lib as L
+
+    gb = _gobatch(G, n)
+    rng = np.random.default_rng(n)
+    os_ = [oracles.Oracle(n) for _ in range(G)]
+    for t in range(70):
+        acts = np.array([_random_candidate(rng, o) for o in os_], np.int32)
+        for o, a in zip(os_, acts):
+            o.forward(int(a))
+        gb.forward(acts)
+    d4 = rng.integers(0, 8, G).astype(np.int32)
+    want = gb.features(d4)  # host copy of the float32 planes
+    for g in (0, G // 2, G - 1):
+        np.testing.assert_array_equal(want[g], os_[g].features(int(d4[g])))
+    dev = torch.device("cuda", gb.device)
+    stream = torch.cuda.ExternalStream(gb.stream, device=dev)
+    d4_dev = torch.from_numpy(d4).to(dev)
+    for mode in (1, 0):
+        gb.set_feature_store(mode)
+        out = torch.full((G + 1, 18, n, n), -7.0, device=dev)
+        gb.features_dev(out.data_ptr(), d4_dev.data_ptr())
+        gb.synchronize()
+        np.testing.assert_array_equal(out[:G].cpu().numpy(), want)
+        assert (out[G] == -7.0).all()  # odd batch: the tail tile must not spill
+        out.fill_(-7.0)
+        gb.features_dev(out[1:].data_ptr(), d4_dev.data_ptr())  # destination only 8-byte aligned
+        gb.synchronize()
+        np.testing.assert_array_equal(out[1:].cpu().numpy(), want)
+        assert (out[0] == -7.0).all()
+        for fmt, dt in ((L.FEAT_F16_NHWC, torch.float16), (L.FEAT_BF16_NHWC, torch.bfloat16)):
+            for cpad in (24, 32):
+                o16 = torch.full((G + 1, n, n, cpad), 5.0, dtype=dt, device=dev)
+                gb.features_dev(o16.data_ptr(), d4_dev.data_ptr(), fmt, cpad)
+                gb.synchronize()
+                got = o16[:G].float().permute(0, 3, 1, 2).cpu().numpy()
+                np.testing.assert_array_equal(got[:, :18], want, err_msg=f"mode {mode} fmt {fmt} cpad {cpad}")
+                assert (got[:, 18:] == 0).all() and (o16[G] == 5.0).all()
+    del stream
     gb.close()

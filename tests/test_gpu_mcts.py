@@ -403,10 +403,11 @@ def test_gpu_search_with_a_real_network_matches_reference():
     print("real-network parity: worst visit deviation", worst)
 
 
-def test_node_pool_exhaustion_drops_the_tree_and_keeps_searching():
+def test_node_pool_exhaustion_prunes_the_tree_and_keeps_searching():
     """bounded node pool (documented deviation): when a game's pool cannot hold one more move's
-    worth of nodes the persistent tree is dropped for that game (counter in errors()[1]) and the
-    search carries on from a fresh root; rollouts are all accounted for and no other game is hurt."""
+    worth of nodes, the subtrees under the root's least-visited children are recycled (counter in
+    errors()[3]); the root keeps its edge statistics, the search carries on, rollouts are all
+    accounted for, the pool never overflows during a descent (errors()[1] stays 0)."""
     import elf_b200
 
     n, G = 9, 6
@@ -414,8 +415,8 @@ def test_node_pool_exhaustion_drops_the_tree_and_keeps_searching():
     R, B = 32, 4
     mc = elf_b200.MctsBatch(gb, rotation_flip=0, num_rollouts=R, num_rollouts_per_batch=B, nodes_per_game=R + 8)
     actor = fake_actor(mc, n)
-    drops = 0
-    for mv in range(6):
+    prunes = 0
+    for mv in range(8):
         res = mc.act(actor)
         tv = res["total_visits"]
         assert ((tv == R - B) | (tv >= R)).all()  # fresh root (first wave expands it) or reused tree
@@ -423,9 +424,181 @@ def test_node_pool_exhaustion_drops_the_tree_and_keeps_searching():
         assert gb.forward(a).all()
         mc.advance(a)
         e = mc.errors()
-        assert e[0] == 0 and e[2] == 0
-        drops = int(e[1])
-    assert drops > 0  # the small pool must have forced at least one drop
+        assert e[0] == 0 and e[1] == 0 and e[2] == 0, e
+        prunes = int(e[3])
+    assert prunes > 0  # the small pool must have forced at least one pruning
+    mc.close()
+    gb.close()
+
+
+def test_root_mismatch_raises_like_the_reference():
+    """TreeSearchT::setRootNodeState throws when the persistent root is not the position it is asked
+    to search (tree_search.h:488-492).  Here: the board moves without advance() -> begin_move raises,
+    the stale tree is gone and the next search starts from the board."""
+    import elf_b200
+    from elf_b200.lib import ElfB200Error
+
+    n, G = 9, 3
+    gb = elf_b200.GoBatch(G, board_size=n)
+    mc = elf_b200.MctsBatch(gb, rotation_flip=0, num_rollouts=16, num_rollouts_per_batch=4)
+    actor = fake_actor(mc, n)
+    res = mc.act(actor)
+    assert gb.forward(res["best_action"]).all()  # no mc.advance(): the trees are stale now
+    with pytest.raises(ElfB200Error, match="Root state is not the same"):
+        mc.act(actor)
+    res = mc.act(actor)  # rebuilt from the board
+    assert (res["total_visits"] == 16 - 4).all() and mc.errors()[0] == G
+    mc.close()
+    gb.close()
+
+
+@pytest.mark.parametrize("n", [9, 19])
+def test_fast_feature_formats_async_waves_and_pipeline(n):
+    """the same search four ways -- float32 features with a host wait per wave (baseline), binary16
+    NHWC leaf features, waves without any host read-back (device-side leaf count), and two half
+    batches interleaved by WavePipeline -- gives identical root statistics; the NHWC leaf batch equals
+    the float32 one position by position."""
+    import torch
+
+    import elf_b200
+    from elf_b200.pipeline import WavePipeline
+
+    G, R, B = 8, 24, 4
+    opts = dict(num_rollouts=R, num_rollouts_per_batch=B, rotation_flip=1, seed=3)
+
+    def opening(gb, lo=0):
+        rng = np.random.default_rng(1)
+        os_ = [oracles.Oracle(n) for _ in range(G)]
+        for _ in range(10):
+            acts = np.array([int(rng.choice(np.flatnonzero(o.legal()))) for o in os_], np.int32)
+            for o, a in zip(os_, acts):
+                o.forward(int(a))
+            gb.forward(acts[lo:lo + gb.num_games])
+
+    def net(feat_f32, hashes):  # deterministic in the position, independent of the batch layout
+        pi, v = oracles.fakenet(hashes, n * n + 1)
+        return torch.from_numpy(pi), torch.from_numpy(v)
+
+    def make(G_, lo=0, **kw):
+        gb = elf_b200.GoBatch(G_, board_size=n)
+        opening(gb, lo)
+        return gb, elf_b200.MctsBatch(gb, **opts, **kw)
+
+    def actor_for(mc, log=None):
+        def actor(batch):
+            h, _, _ = mc.leaf_info()
+            key = "s" if "s" in batch else "s_nhwc"
+            if log is not None:
+                x = batch[key][: len(h)]
+                log.append(x.float().cpu().numpy() if key == "s" else x.float().permute(0, 3, 1, 2)[:, :18].cpu().numpy())
+            pi, v = net(None, h)
+            full = batch[key].shape[0]
+            P = torch.zeros(full, n * n + 1)
+            V = torch.zeros(full)
+            P[: len(h)], V[: len(h)] = pi, v
+            return {"pi": P.to(mc.device), "V": V.to(mc.device)}
+        return actor
+
+    # note: the d4 code of an evaluation depends on (seed, game index, wave, node, hash): the halves of
+    # the pipeline run are therefore compared with rotation-independent quantities (the fake net is
+    # keyed by the hash and answers in NN action space, so visits differ with d4) -> rotation off there
+    gb0, m0 = make(G)
+    log0 = []
+    r0 = m0.act(actor_for(m0, log0))
+    gb1, m1 = make(G, feature_format="f16", cpad=24)
+    log1 = []
+    r1 = m1.act(actor_for(m1, log1))
+    assert len(log0) == len(log1)
+    for a, b in zip(log0, log1):
+        np.testing.assert_array_equal(a, b)
+    for k in ("visits", "best_action", "root_value", "total_visits"):
+        np.testing.assert_array_equal(r0[k], r1[k])
+    for m, g in ((m0, gb0), (m1, gb1)):
+        assert (m.errors() == 0).all()
+        m.close()
+        g.close()
+    # waves without any host read-back (fixed grids, device-side leaf count) with a net that reads the
+    # planes, against the same net through the synchronous path
+    def plane_actor(mc):
+        def actor(batch):
+            x = batch["s"] if "s" in batch else batch["s_nhwc"].float().permute(0, 3, 1, 2)[:, :18]
+            pi, v = oracles.feature_net(x.float().cpu().numpy(), n * n + 1)
+            return {"pi": torch.from_numpy(pi).to(mc.device), "V": torch.from_numpy(v).to(mc.device)}
+        return actor
+
+    gb2, m2 = make(G)
+    r2 = m2.act(plane_actor(m2))
+    gb3, m3 = make(G, feature_format="bf16", cpad=32)
+    act3 = plane_actor(m3)
+    m3.begin_move()
+    for _ in range(m3.waves_per_move):
+        s = m3.select(wait=False)
+        assert s.shape[0] == m3.max_leaves
+        m3.gb.synchronize()
+        rep = act3({"s_nhwc": s})
+        torch.cuda.synchronize()
+        m3.expand_backup(rep["pi"], rep["V"])
+    r3 = m3.results()
+    for k in ("visits", "best_action", "root_value", "total_visits"):
+        np.testing.assert_array_equal(r2[k], r3[k])
+    assert m3.eval_count() == m2.eval_count()
+    for m, g in ((m2, gb2), (m3, gb3)):
+        assert (m.errors() == 0).all()
+        m.close()
+        g.close()
+    # two halves through the pipeline == the two halves searched one after the other
+    opts["rotation_flip"] = 0
+    res_seq, res_pipe = [], []
+    for mode in ("seq", "pipe"):
+        parts = [make(G // 2, lo) for lo in (0, G // 2)]
+        if mode == "seq":
+            for gb, mc in parts:
+                res_seq.append(mc.act(actor_for(mc)))
+        else:
+            class Routed:  # one callable for both parts, routed by the tensor it is handed
+                batchsize = 0
+
+                def __call__(self, batch):
+                    for gb, mc in parts:
+                        if batch["s"].data_ptr() == mc.feat.data_ptr():
+                            return actor_for(mc)(batch)
+                    raise AssertionError("unknown batch")
+            pipe = WavePipeline([mc for _, mc in parts], Routed())
+            pipe.search()
+            res_pipe = [mc.results() for _, mc in parts]
+        for gb, mc in parts:
+            assert (mc.errors() == 0).all()
+            mc.close()
+            gb.close()
+    for a, b in zip(res_seq, res_pipe):
+        for k in ("visits", "best_action", "root_value", "total_visits"):
+            np.testing.assert_array_equal(a[k], b[k])
+
+
+def test_fused_actor_matches_module():
+    """FusedActor on the GPU (cuDNN fused conv+bias(+add)+ReLU, CUDA graph for full batches, eager for
+    the tail, float32 NCHW and binary16 NHWC inputs) against the float32 module"""
+    import torch
+
+    from elf_b200.model import FusedActor, PolicyValueNet
+    from tests.test_fused_actor import randomise_bn
+
+    torch.manual_seed(1)
+    dev = torch.device("cuda")
+    m = PolicyValueNet(9, num_block=3, dim=32).to(dev).eval()
+    randomise_bn(m)
+    fa = FusedActor(m, batchsize=8, dtype=torch.float16, cuda_graph=True)
+    x = (torch.rand(21, 18, 9, 9, device=dev) > 0.6).float()
+    with torch.no_grad():
+        ref = m(x)
+    for _ in range(2):  # replay twice: static buffers are reused
+        out = fa({"s": x})
+        assert (out["pi"] - ref["pi"]).abs().max().item() < 5e-3
+        assert (out["V"] - ref["V"].reshape(-1)).abs().max().item() < 2e-2
+    xn = torch.zeros(21, 9, 9, fa.cpad, dtype=torch.float16, device=dev)
+    xn[..., :18] = x.permute(0, 2, 3, 1).half()
+    out2 = fa({"s_nhwc": xn})
+    assert torch.equal(out2["pi"], out["pi"]) and torch.equal(out2["V"], out["V"])
 
 
 def test_device_move_choice_sampling_argmax_and_resign():

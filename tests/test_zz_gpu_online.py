@@ -1,17 +1,15 @@
 """Online mode with the real engine (GoBatch of one game + MctsBatch): the moves `genmove` plays
 must be the ones the search restatement (oracle/mcts_oracle.c) chooses on the same positions.
 
-This file was written after the round's last GPU session: the host logic is covered on CPU
-(tests/test_online_console.py) and every kernel it launches is covered by tests/test_gpu_mcts.py,
-but the combination (G = 1, human moves interleaved with searches) has not yet run on a GPU,
-hence the non-strict xfail marker; drop it after the first green run."""
+The host logic is also covered on CPU (tests/test_online_console.py); this is the G = 1 combination
+(human moves interleaved with searches) on the device (first green hardware run: round 1's final
+GPU test pass)."""
 import numpy as np
 import pytest
 
 from tests import oracles
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="first GPU run of the online path is due in round 2")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 def test_online_game_matches_search_restatement(oracle_lib):

@@ -1,17 +1,15 @@
 """elfb200_replay / ReplayBatch on the GPU board batch.
 
-Written after the round's last GPU session: k_replay is k_step's body in a loop (same device
-functions), its logic is covered on the SIMT emulator (tests/test_emu_kernels.py::test_replay_kernel,
-three lane orders) and ReplayBatch's arithmetic is pinned on the compiled reference
-(tests/test_replay_records.py); what has not happened yet is a run on hardware, hence the non-strict
-xfail marker -- drop it after the first green run."""
+k_replay is k_step's body in a loop (same device functions); its logic is also covered on the SIMT
+emulator (tests/test_emu_kernels.py::test_replay_kernel, three lane orders) and ReplayBatch's
+arithmetic is pinned on the compiled reference (tests/test_replay_records.py).  First green
+hardware run: round 1's final GPU test pass."""
 import numpy as np
 import pytest
 
 from tests import oracles
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="first GPU run of the replay kernel is due in round 2")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 @pytest.mark.parametrize("n,G", [(9, 100), (19, 64)])
