@@ -1,20 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- the driver's measurement contract for the board hot path.
+"""bench.py -- the driver's measurement contract for the self-play hot path.
 
-Workload (BASELINE.json configs[1]): 4096 concurrent 19x19 games per GPU, random-policy playouts
-(include/elfb200_playout_policy.h) from the empty board to GoState::terminated().  One "step" =
-one such batch (about 1.86 M plies).  Metric: moves/sec (plies/sec), whole job over all ranks.
+Default workload (BASELINE.json configs[2]; with N GPUs configs[3]): 4096 concurrent 19x19 self-play
+games in total (4096/N per GPU), 800 MCTS rollouts per move in waves of 8 per game, random-init
+20-block x 256-channel policy/value net in fp16 at NN batch 256, puct 1.5, virtual loss 1, persistent
+tree.  One "step" = one search wave of every game in steady state (8 rollouts per game: descents,
+leaf features, network, expansion, backup); a move is 100 waves, so
+    moves/sec = steps/sec x games x 8 / 800.
+Move boundaries that fall inside the timed region (choice, GoState::forward, tree advance) are
+timed with it.
 
   python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, sm_100a)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path, host cores
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU search driving the
+                                                           # same GPU network, all host threads
+  python bench.py --workload playout ...                   # configs[1]/[4]: random-policy playouts only
 
-`value`   device-timed (CUDA events on the library's stream), inputs resident, max over ranks.
-`e2e`     the same metric through the public C-ABI call elfb200_playout() with HOST result
-          buffers (launch + D2H of checksum/plies/score/hash every step), wall clock.
-`roofline` dominant kernel k_playout: SURVEY 8d algorithmic bytes (step 264 B + legal mask 184 B
-          per game-ply) / CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
-`cpu_baseline` the compiled reference (oracle/_ref; else the oracle port) on all host cores for a
-          bounded sample of the same workload (rank 0, N=1 only).
+`value`    device-timed (CUDA events spanning all streams), fast path: leaf features stay on the GPU
+           as fp16 NHWC, two half batches interleaved so the network stream never drains.
+`e2e`      the same metric through the reference's tensor boundary with HOST buffers: float32 "s"
+           lands in pinned host memory, the callback moves it to the GPU, pi/V return through pinned
+           host memory (src_py/elf/utils_elf.py:39-47,378-405), wall clock.
+`roofline` our HBM-bound kernel of this workload, k_leaf_features (26,792 B/position),
+           timed alone; `rooflines` lists the other kernels, the select kernel with its measured DRAM
+           bytes next to the 8d formula.  `board_step` is the playout workload with its own roofline.
+`cpu_baseline` the compiled reference search (oracle/_ref) on the host cores driving the same network.
 """
 import argparse
 import ctypes
@@ -124,7 +133,7 @@ def cpu_playouts(seconds=None, games_per_thread=None, first_id=10_000_000):
     return {"moves": sum(moves), "seconds": dt, "cores": cores, "kind": kind, "games": sum(games)}
 
 
-def run_reference(args):
+def run_reference_playout(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -204,7 +213,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_ours(args):
+def run_playout(args):
     import torch
 
     import elf_b200
@@ -277,6 +286,7 @@ def run_ours(args):
         e2e_plies += r["total_plies"]
     barrier()
     e2e_s = time.perf_counter() - t0
+    hb_h2d, hb_d2h = hb.h2d / Ke, hb.d2h / Ke
 
     # ---- secondary: one batch of G games played to terminal (includes the ragged tail) -----------
     tt_ms, tt_plies = 0.0, 0
@@ -376,95 +386,28 @@ def run_ours(args):
 
 
 # --------------------------------------------------------------------------------------------
-# secondary workload: BASELINE configs[2] -- MCTS self-play (the network is PyTorch/cuDNN plumbing;
-# our kernels are select / leaf features / expand / backup).  `--workload mcts`.
+# headline workload: BASELINE configs[2]/[3] -- MCTS self-play.  The network is PyTorch/cuDNN plumbing
+# (elf_b200.model.FusedActor); our kernels are select / leaf features / expand / backup / choose /
+# step / advance.
 # --------------------------------------------------------------------------------------------
-def cpu_mcts_rollouts(seconds, rollouts, per_batch):
-    """reference TreeSearchT (oracle/_ref) with the deterministic fake net on every host thread:
-    rollouts/s without any network cost."""
-    from tests import oracles
-
-    cores = effective_cores()
-    if not oracles.have_ref(BOARD):
-        return None
-    done = [0] * cores
-    t0 = time.perf_counter()
-    deadline = t0 + seconds
-
-    def work(tid):
-        st = oracles.Ref(BOARD)
-        m = oracles.RefMcts(BOARD, num_rollouts=rollouts, num_rollouts_per_batch=per_batch, virtual_loss=1,
-                            persistent_tree=1, c_puct=1.5, seed=tid)
-        while time.perf_counter() < deadline:
-            r = m.act(st)
-            st.forward(r["best_action"])
-            done[tid] += 1
-            if st.terminated():
-                break
-
-    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    dt = time.perf_counter() - t0
-    return {"moves": sum(done), "seconds": dt, "cores": cores}
+ROLLOUTS, PER_BATCH, NN_BATCH = 800, 8, 256
+ISSUE_SLOTS_PER_S = 148 * 4  # x SM clock: warp instructions the chip can issue per second
 
 
-def cpu_mcts_with_net(seconds, rollouts, per_batch, actor, device):
-    """the reference search (oracle/_ref, one search thread per game, one game
-    per host thread) driving the SAME GPU network through a callback -- what the reference's own
-    batching can extract from the net when it only has the host cores to run the search on."""
+def load_profile_numbers():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+def make_network(args, dev):
+    """the 20x256 policy/value net of configs[2] (random init, fixed seed) behind the model-interface
+    callback; returns (actor, description, module)"""
     import torch
 
-    from tests import oracles
+    from elf_b200.model import FusedActor, PolicyValueNet
 
-    cores = effective_cores()
-    if not oracles.have_ref(BOARD):
-        return None
-    done = [0] * cores
-    evals = [0] * cores
-    t0 = time.perf_counter()
-    deadline = t0 + seconds
-
-    def work(tid):
-        def cb(feats, hashes):
-            with torch.no_grad():
-                out = actor({"s": torch.from_numpy(np.ascontiguousarray(feats)).to(device)})
-            evals[tid] += len(hashes)
-            return out["pi"].float().cpu().numpy(), out["V"].float().reshape(-1).cpu().numpy()
-
-        st = oracles.Ref(BOARD)
-        m = oracles.RefMcts(BOARD, num_rollouts=rollouts, num_rollouts_per_batch=per_batch, virtual_loss=1,
-                            persistent_tree=1, c_puct=1.5, seed=tid, callback=cb)
-        while time.perf_counter() < deadline and not st.terminated():
-            r = m.act(st)
-            st.forward(r["best_action"])
-            done[tid] += 1
-
-    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
-    [t.start() for t in th]
-    [t.join() for t in th]
-    dt = time.perf_counter() - t0
-    return {"moves": sum(done), "seconds": dt, "cores": cores, "evals": sum(evals)}
-
-
-def run_mcts(args):
-    import torch
-
-    import elf_b200
-    from elf_b200.model import Actor, PolicyValueNet, broadcast_weights
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    G, R, B = args.games, args.rollouts, args.per_batch
-    dev = torch.device("cuda", local)
     torch.manual_seed(1234)
     if args.fake_net:
         P1 = BOARD * BOARD + 1
@@ -472,115 +415,562 @@ def run_mcts(args):
         vals = torch.rand(4096, device=dev) * 2 - 1
 
         def actor(batch):
-            n = batch["s"].shape[0]
+            n = (batch["s"] if "s" in batch else batch["s_nhwc"]).shape[0]
             idx = torch.arange(n, device=dev) % 4096
             return {"pi": table[idx], "V": vals[idx]}
-        net_desc = "fake (table lookup, engine-only timing)"
-    else:
-        model = PolicyValueNet(BOARD, num_block=args.blocks, dim=args.dim).to(dev)
-        t_b0 = time.perf_counter()
-        broadcast_weights(model)  # frozen weights from rank 0: the only collective of the path
-        torch.cuda.synchronize()
-        t_bcast = time.perf_counter() - t_b0
-        actor = Actor(model, batchsize=args.nn_batch)
-        net_desc = f"random-init resnet {args.blocks}x{args.dim}, fp16 weights, channels_last, NN batch {args.nn_batch}"
-    sp = elf_b200.selfplay.SelfPlay(actor, num_games=G, board_size=BOARD, device=local, policy_distri_cutoff=0,
-                                    resign_thres=0.0, never_resign_ratio=1.0, num_rollouts=R,
-                                    num_rollouts_per_batch=B, virtual_loss=1, persistent_tree=1, c_puct=1.5,
-                                    rotation_flip=1, seed=rank)
-    ext = torch.cuda.ExternalStream(sp.gb.stream, device=dev)
+        return actor, "fake (table lookup: engine-only timing, BASELINE.md config 3a)", None
+    torch.backends.cudnn.benchmark = True
+    model = PolicyValueNet(BOARD, num_block=args.blocks, dim=args.dim).to(dev).eval()
+    return None, (f"random-init resnet {args.blocks}x{args.dim} (df_model3.Model_PolicyValue), fp16, BatchNorm folded, "
+                  f"cuDNN fused conv+bias(+add)+ReLU, NN batch {args.nn_batch} replayed as a CUDA graph"), model
+
+
+def random_opening(gb, plies, rng):
+    """`plies` uniformly random legal non-pass moves in every game (host-chosen from the legal masks)"""
+    import numpy as np
+
+    for _ in range(plies):
+        lg = gb.legal_mask()[:, :-1].astype(np.float64)
+        lg += 1e-9  # a game without a legal point would pass below
+        lg /= lg.sum(1, keepdims=True)
+        c = lg.cumsum(1)
+        a = (c < rng.random((lg.shape[0], 1))).sum(1).astype(np.int32)
+        a = np.minimum(a, lg.shape[1] - 1)
+        ok = gb.forward(a)
+        if not ok.all():  # the epsilon picked an illegal point somewhere: those games pass instead
+            a2 = np.where(ok, -1, BOARD * BOARD).astype(np.int32)
+            gb.forward(a2)
+
+
+class HostBoundary:
+    """The reference's tensor boundary around the model callback (utils_elf.py:39-47,378-405): the
+    feature batch lands in PINNED HOST memory, the callback moves it to the GPU, and the replies go back
+    through pinned host memory.  Used for the `e2e` reading; counts the bytes it moves."""
+
+    def __init__(self, actor, rows, n, dev):
+        import torch
+
+        self.actor, self.dev = actor, dev
+        self.batchsize = getattr(actor, "batchsize", 0)
+        self.s = torch.empty((rows, 18, n, n), dtype=torch.float32, pin_memory=True)
+        self.pi = torch.empty((rows, n * n + 1), dtype=torch.float32, pin_memory=True)
+        self.v = torch.empty((rows,), dtype=torch.float32, pin_memory=True)
+        self.h2d = self.d2h = 0
+
+    def __call__(self, batch):
+        import torch
+
+        s = batch["s"]
+        m = s.shape[0]
+        self.s[:m].copy_(s, non_blocking=True)  # D2H: what GoFeature's extractor + SharedMem do in the reference
+        torch.cuda.current_stream(self.dev).synchronize()
+        x = self.s[:m].to(self.dev, non_blocking=True)  # H2D: the callback's .cuda()
+        out = self.actor({"s": x})
+        self.pi[:m].copy_(out["pi"], non_blocking=True)  # D2H: reply tensors are host tensors
+        self.v[:m].copy_(out["V"].reshape(-1), non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        self.d2h += m * (18 * s.shape[2] * s.shape[3] + self.pi.shape[1] + 1) * 4
+        self.h2d += m * (18 * s.shape[2] * s.shape[3] + self.pi.shape[1] + 1) * 4
+        return {"pi": self.pi[:m].to(self.dev, non_blocking=True), "V": self.v[:m].to(self.dev, non_blocking=True)}
+
+
+class SelfPlayEngine:
+    """G games on one GPU as `parts` SelfPlay batches driven wave by wave through a WavePipeline"""
+
+    def __init__(self, actor, G, parts, local, rank, feature_format):
+        import numpy as np
+
+        import elf_b200
+        from elf_b200.pipeline import WavePipeline
+
+        sizes = [G // parts + (1 if i < G % parts else 0) for i in range(parts)]
+        self.sp = [elf_b200.selfplay.SelfPlay(
+            actor, num_games=g, board_size=BOARD, device=local, policy_distri_cutoff=0, resign_thres=0.0,
+            never_resign_ratio=1.0, num_rollouts=ROLLOUTS, num_rollouts_per_batch=PER_BATCH, virtual_loss=1,
+            persistent_tree=1, c_puct=1.5, rotation_flip=1, seed=rank * 16 + i, feature_format=feature_format)
+            for i, g in enumerate(sizes) if g > 0]
+        rng = np.random.default_rng(99 + rank)
+        for sp in self.sp:
+            random_opening(sp.gb, 16, rng)
+        self.actor = actor
+        self.pipe = WavePipeline([sp.mcts for sp in self.sp], actor)
+        self.wpm = self.pipe.waves_per_move
+        self.wave_in_move = 0
+        self.moves = 0
+        self.infos = None
+
+    def _begin(self):
+        self.infos = [sp.gb.info() for sp in self.sp]
+        self.pipe.begin_move()
+        self.wave_in_move = 0
+
+    def step(self, pipelined=True, actor=None):
+        """one wave of every game; at a move boundary also the move itself"""
+        if self.infos is None:
+            self._begin()
+        if pipelined:
+            self.pipe.waves(1)
+        else:
+            self.pipe.drain()
+            for sp in self.sp:
+                sp.mcts._pad = int(getattr(actor or self.actor, "batchsize", 0) or 0)
+                sp.mcts.wave(actor or self.actor)
+        self.wave_in_move += 1
+        if self.wave_in_move == self.wpm:
+            self.pipe.drain()
+            for sp, info in zip(self.sp, self.infos):
+                self.moves += sp.finish_move(info)
+            self._begin()
+
+    def set_feature_format(self, fmt):
+        self.pipe.drain()
+        for sp in self.sp:
+            sp.mcts.set_feature_format(fmt)
+
+    def launches(self):
+        return sum(sp.gb.launch_count() for sp in self.sp)
+
+    def evals(self):
+        return sum(sp.mcts.eval_count() for sp in self.sp)
+
+    def errors(self):
+        import numpy as np
+
+        return np.sum([sp.mcts.errors() for sp in self.sp], axis=0)
+
+    def streams(self):
+        import torch
+
+        return [torch.cuda.ExternalStream(sp.gb.stream, device=self.pipe.device) for sp in self.sp] + [self.pipe.nn_stream]
+
+    def close(self):
+        self.pipe.drain()
+        for sp in self.sp:
+            sp.close()
+
+
+def device_span(streams, fn):
+    """run fn() and return the device time (ms) from 'all streams idle' to 'all streams done'"""
+    import torch
+
+    torch.cuda.synchronize()
+    cur = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    for st in streams:
+        st.wait_event(e0)
+    fn()
+    for st in streams:
+        cur.wait_stream(st)
+    e1.record(cur)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512):
+    """BASELINE's second metric, "board-step GB/s vs roofline": the configs[1] playout workload (4096
+    concurrent games, steady state) timed on its own, with the HBM formula AND the issue-slot roof"""
+    import torch
+
+    import elf_b200
+
+    gb = elf_b200.GoBatch(G, board_size=BOARD, device=local)
+    stream = torch.cuda.ExternalStream(gb.stream, device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    for w in range(warmup):
+        gb.playout_stream_launch(SEED, 10_000_000 + w * G, plies)
+    gb.synchronize()
+    ms, tot = 0.0, 0
+    for s in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            flush.fill_(s & 0xFF)
+            a.record(stream)
+        gb.playout_stream_launch(SEED, s * G, plies)
+        with torch.cuda.stream(stream):
+            b.record(stream)
+        gb.synchronize()
+        ms += a.elapsed_time(b)
+        tot += gb.playout_results()["total_plies"]
+    gb.close()
+    peak, peak_src = measured_peaks()
+    prof = load_profile_numbers().get(f"k_playout<{BOARD}>", {})
+    rate = tot / (ms / 1e3)
+    algo = ALGO_BYTES_PER_PLY if BOARD == 19 else 224
+    out = {"value": rate, "unit": "moves/s", "workload": f"configs[1]: {G} concurrent {BOARD}x{BOARD} games, random-policy playouts, "
+           f"steady state ({plies} plies per slot per step, finished games restart)", "ms_per_step": ms / steps, "steps": steps,
+           "roofline": {"bound": "hbm", "achieved": algo * rate / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": algo * rate / 1e9 / peak, "traffic": prof.get("dram_bytes_per_launch"),
+                        "peak_source": peak_src, "kernel": f"k_playout<{BOARD}>", "algorithmic_bytes_per_ply": algo,
+                        "note": "SURVEY 8d byte formula; the position lives in registers, DRAM is idle -- the honest roof is issue_roof"}}
+    wi = prof.get("warp_inst_per_ply")
+    if wi:
+        try:
+            ghz = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"] / 1e3
+        except Exception:
+            ghz = 1.965
+        roof = ISSUE_SLOTS_PER_S * ghz * 1e9 / wi
+        out["issue_roof"] = {"warp_inst_per_ply": wi, "plies_per_s_at_full_issue": roof, "frac": rate / roof,
+                             "note": "148 SMs x 4 schedulers x SM clock / (warp instructions per game-ply from the committed ncu capture)"}
+    return out
+
+
+def run_selfplay(args):
+    import numpy as np
+    import torch
+
+    from elf_b200.model import FusedActor, broadcast_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(ext):
-        for _ in range(args.warmup):
-            sp.step()
-        sp.mcts.timings(reset=True)
-        st0 = sp.mcts.stats().astype(np.int64)
-        ev0 = sp.mcts.eval_count()
-        l0 = sp.gb.launch_count()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
+    G_total = args.games
+    G = G_total // world + (1 if rank < G_total % world else 0)  # games sharded, total fixed (configs[3]: 512/GPU at 8)
+    actor, net_desc, model = make_network(args, dev)
+    t_bcast = 0.0
+    if model is not None:
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(ext)
         t0 = time.perf_counter()
-        moves = 0
-        for _ in range(args.steps):
-            moves += sp.step()
-        e1.record(ext)
-        barrier()
-        wall = time.perf_counter() - t0
-        dev_ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
-        ms, waves = sp.mcts.timings()
-        st = sp.mcts.stats().astype(np.int64) - st0
-        evals = sp.mcts.eval_count() - ev0
-        launches = sp.gb.launch_count() - l0
+        broadcast_weights(model)  # frozen weights from rank 0: the only collective of the path
+        torch.cuda.synchronize()
+        t_bcast = time.perf_counter() - t0
+        actor = FusedActor(model, batchsize=args.nn_batch, dtype=torch.float16, cuda_graph=True)
+    eng = SelfPlayEngine(actor, G, args.parts, local, rank, "f32" if args.fake_net else "f16")
+    streams = eng.streams()
+    K, W = args.steps, args.warmup
+
+    for _ in range(W):
+        eng.step()
+    eng.pipe.drain()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0, ev0, mv0 = eng.launches(), eng.evals(), eng.moves
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = device_span(streams, lambda: ([eng.step() for _ in range(K)], eng.pipe.drain()))
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches, evals, real_moves = eng.launches() - l0, eng.evals() - ev0, eng.moves - mv0
+
+    # ---- e2e: the same waves through the host-buffer tensor boundary (float32 "s"), wall clock --------
+    eng.set_feature_format("f32")
+    Ke = min(K, args.e2e_steps)
+    hb = HostBoundary(actor, max(sp.mcts.max_leaves for sp in eng.sp), BOARD, dev)
+    eng.step(pipelined=False, actor=hb)  # warm (pinned buffers, eager shapes)
+    hb.h2d = hb.d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        eng.step(pipelined=False, actor=hb)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- kernel timings, alone (no overlap with the network): CUDA events inside the library ---------
+    kern = None
+    if rank == 0:
+        kern = {}
+        for fmt in ("f32", "f16"):
+            if args.fake_net and fmt != "f32":
+                continue
+            eng.set_feature_format(fmt)
+            for sp in eng.sp:
+                sp.mcts.timings(reset=True)
+            st0 = np.sum([sp.mcts.stats().astype(np.int64) for sp in eng.sp], axis=0)
+            e0 = eng.evals()
+            for _ in range(3):
+                eng.step(pipelined=False)
+            eng.pipe.drain()
+            ms = np.sum([sp.mcts.timings()[0] for sp in eng.sp], axis=0)
+            waves = eng.sp[0].mcts.timings()[1]
+            st = np.sum([sp.mcts.stats().astype(np.int64) for sp in eng.sp], axis=0) - st0
+            kern[fmt] = {"ms": ms, "waves": waves, "stats": st, "evals": eng.evals() - e0}
+    errs = eng.errors()
+    eng.close()
+    del eng, hb
+    torch.cuda.empty_cache()
+
+    board = board_step_probe(local) if rank == 0 and not args.no_board_step else None
+
+    # ---- reduce over ranks (MAX of times, SUM of counters) ----------------------------------------------
     if dist is not None:
-        t = torch.tensor([dev_ms, wall], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, wall, e2e_s, t_bcast], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall = t.tolist()
-        c = torch.tensor([moves, launches], dtype=torch.int64, device=dev)
+        dev_ms, wall, e2e_s, t_bcast = t.tolist()
+        c = torch.tensor([launches, evals, real_moves, int(errs[1]), int(errs[3])], dtype=torch.int64, device=dev)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        moves, launches = c.tolist()
+        launches, evals, real_moves, e1, e3 = c.tolist()
+        errs = [int(errs[0]), e1, int(errs[2]), e3]
     if rank == 0:
         peak, peak_src = measured_peaks()
-        E = BOARD * BOARD + 1
-        sel_bytes = int(st[0]) * (32 + 4) + int(st[3]) * 16  # header + E_n*16 + vl write (full scan)
-        sel_bytes_read = int(st[0]) * (32 + 4) + int(st[1]) * 16  # what the prefix scan actually reads
-        feat_bytes = evals * 26792
-        sel_gbs = sel_bytes / (ms[0] / 1e3) / 1e9 if ms[0] > 0 else 0.0
-        feat_gbs = feat_bytes / (ms[1] / 1e3) / 1e9 if ms[1] > 0 else 0.0
+        prof = load_profile_numbers()
+        moves_per_step = G_total * PER_BATCH / ROLLOUTS
+        value = K * moves_per_step / (dev_ms / 1e3)
         line = {
-            "metric": "self-play moves/sec (MCTS, 19x19)", "value": moves / (dev_ms / 1e3), "unit": "moves/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 search / fp16 net",
-            "data": "synthetic",
-            "config": {"workload": f"configs[2]-shaped: {G} games/GPU x {R} rollouts/move, {B} rollouts/wave, puct 1.5, vloss 1, persistent tree",
-                       "net": net_desc, "games_per_gpu": G, "rollouts": R, "l2": "node pool >> L2 (7.4 KB/node)",
-                       "parallelism": f"games sharded x{world}, NCCL weight broadcast only"},
-            "e2e": {"value": moves / wall, "unit": "moves/s", "h2d_bytes_per_step": 4 * G + G,
-                    "d2h_bytes_per_step": int(G * (E * 4 + 16 + 48 * 2)),
-                    "note": "through SelfPlay.step(): actions H2D, root tables + info D2H each move; leaf features never leave the GPU"},
-            "gpu_launches": int(launches),
-            "kernels_ms_per_wave": {"select": ms[0] / max(waves, 1), "leaf_features": ms[1] / max(waves, 1),
-                                    "expand": ms[2] / max(waves, 1), "backup": ms[3] / max(waves, 1)},
-            "waves": int(waves), "nn_evals": int(evals), "rollouts_per_s": (int(waves) * B * G * world) / (dev_ms / 1e3),
-            "roofline": {"bound": "hbm", "achieved": sel_gbs, "peak": peak, "unit": "GB/s", "frac": sel_gbs / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "k_select<19>",
-                         "algorithmic_bytes": sel_bytes, "bytes_read_by_prefix_scan": sel_bytes_read,
-                         "nodes_visited": int(st[0]), "edges_scanned": int(st[1]), "edges_stored": int(st[3]),
-                         "note": "achieved uses the SURVEY 8d full-scan byte formula; the kernel reads only the selected prefix of each node's edges (same arg-max), so achieved can exceed what DRAM delivers",
-                         "leaf_features_GBps": feat_gbs},
+            "metric": "self-play moves/sec (MCTS, 19x19)", "value": value, "unit": "moves/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 search statistics / fp16 network", "data": "synthetic",
+            "config": {
+                "workload": (f"configs[{2 if world == 1 else 3}]: {G_total} concurrent {BOARD}x{BOARD} self-play games in total "
+                             f"({G_total // world} per GPU), {ROLLOUTS} MCTS rollouts/move in waves of {PER_BATCH}, puct 1.5, "
+                             f"virtual loss 1, persistent tree, NN batch {args.nn_batch}; step = one wave of every game "
+                             f"(= {moves_per_step:.2f} moves), steady state after 16 random opening plies"),
+                "net": net_desc, "games_total": G_total, "games_per_gpu": G_total // world, "rollouts_per_move": ROLLOUTS,
+                "rollouts_per_wave": PER_BATCH, "nn_batch": args.nn_batch, "board": BOARD, "parts_per_gpu": args.parts,
+                "l2": "inputs larger than L2: the node pool is %.1f GB per GPU and a wave's leaf batch %.0f MB" % (
+                    (G_total // world) * (2 * ROLLOUTS + 256) * 7.4e3 / 1e9, (G_total // world) * PER_BATCH * 17328 / 1e6),
+                "parallelism": f"games sharded x{world}, NCCL weight broadcast only"},
+            "e2e": {"value": Ke * moves_per_step / e2e_s, "unit": "moves/s", "steps": Ke,
+                    "h2d_bytes_per_step": int(hb_h2d), "d2h_bytes_per_step": int(hb_d2h),
+                    "note": "same waves through the reference's tensor boundary with HOST buffers: float32 s -> pinned host -> GPU -> "
+                            "network -> pi/V -> pinned host -> GPU (rank 0's bytes per step), wall clock, no overlap between parts"},
+            "gpu_launches": int(launches), "nn_evals": int(evals), "nn_positions_per_s": evals / (dev_ms / 1e3),
+            "moves_completed_in_timed_region": int(real_moves),
+            "weight_broadcast_s": t_bcast, "wall_s_timed_region": wall,
+            "host_gap_ms_per_step": max(0.0, (wall * 1e3 - dev_ms) / K),
+            "search_errors": {"root_mismatch": int(errs[0]), "pool_overflow": int(errs[1]), "depth_cut": int(errs[2]),
+                              "tree_prunes": int(errs[3])},
             "clocks": clocks,
         }
-        if not args.fake_net:
-            line["weight_broadcast_s"] = t_bcast
+        if kern:
+            line.update(kernel_rooflines(kern, prof, peak, peak_src, args.parts))
+        if board is not None:
+            line["board_step"] = board
         if world == 1 and not args.no_cpu_baseline and not args.fake_net:
-            cn = cpu_mcts_with_net(min(args.cpu_seconds, 20.0), R, B, actor, dev)
-            if cn:
-                line["cpu_baseline_same_net"] = {
-                    "value": cn["moves"] / cn["seconds"], "unit": "moves/s", "cores": cn["cores"], "kind": "reference",
-                    "nn_positions_per_s": cn["evals"] / cn["seconds"],
-                    "sample": f"reference TreeSearchT on {cn['cores']} host threads (one game each, {B} leaves per NN call) driving the same GPU network: {cn['moves']} moves in {cn['seconds']:.1f} s"}
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_mcts_rollouts(min(args.cpu_seconds, 15.0), R, B)
-            if cb:
-                line["cpu_baseline"] = {"value": cb["moves"] / cb["seconds"], "unit": "moves/s", "cores": cb["cores"],
-                                        "kind": "reference",
-                                        "sample": f"reference TreeSearchT, {R} rollouts/move, 1 search thread per game, fake net (no NN cost), {cb['moves']} moves in {cb['seconds']:.1f} s on {cb['cores']} threads"}
+            cb = ref_selfplay(actor, dev, steps=args.cpu_steps, warmup=1)
+            line["cpu_baseline"] = cb
         emit(line)
-    sp.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
+
+def kernel_rooflines(kern, prof, peak, peak_src, parts):
+    """roofline objects from the kernels timed alone (3 waves, CUDA events in the library)"""
+    out = {"rooflines": {}}
+    k32 = kern["f32"]
+    w = max(int(k32["waves"]), 1)
+    ms, st, ev = k32["ms"], k32["stats"], k32["evals"]
+    feat_bytes = 26792  # SURVEY 8d: 8 history pairs 768 B + meta 32 B + 18 planes float32 25,992 B
+    feat_gbs = ev * feat_bytes / (ms[1] / 1e3) / 1e9 if ms[1] > 0 else 0.0
+    traffic = prof.get("k_leaf_features<19>", {}).get("dram_bytes_per_launch")
+    out["roofline"] = {"bound": "hbm", "achieved": feat_gbs, "peak": peak, "unit": "GB/s", "frac": feat_gbs / peak,
+                       "traffic": traffic, "peak_source": peak_src, "kernel": "k_leaf_features<19> (float32 NCHW, the GoFeature contract)",
+                       "algorithmic_bytes_per_position": feat_bytes, "positions_per_launch": ev / w / parts,
+                       "ms_per_launch": ms[1] / w, "note": "timed alone over 3 waves; per-launch figures are per part"}
+    sel_formula = int(st[0]) * (32 + 4) + int(st[3]) * 16  # SURVEY 8d: header + E_n*16 + vl write (full scan)
+    sel_prefix = int(st[0]) * (32 + 4) + int(st[1]) * 16   # what the prefix scan touches
+    sel_ms = ms[0]
+    sel = {"bound": "hbm", "kernel": "k_select<19>", "unit": "GB/s", "peak": peak,
+           "formula_GBps": sel_formula / (sel_ms / 1e3) / 1e9, "prefix_scan_GBps": sel_prefix / (sel_ms / 1e3) / 1e9,
+           "ms_per_wave": sel_ms / w, "nodes_visited": int(st[0]), "edges_scanned": int(st[1]), "edges_stored": int(st[3])}
+    dsel = prof.get("k_select<19>", {}).get("dram_bytes_per_launch")
+    if dsel and prof.get("k_select<19>", {}).get("launch_ms"):
+        p = prof["k_select<19>"]
+        sel["measured_dram_GBps"] = p["dram_bytes_per_launch"] / (p["launch_ms"] / 1e3) / 1e9
+        sel["achieved"] = sel["measured_dram_GBps"]
+        sel["frac"] = sel["measured_dram_GBps"] / peak
+        sel["note"] = ("frac is MEASURED DRAM bytes / time from the committed ncu capture (profiles/), not the 8d full-scan "
+                       "formula: the kernel reads only the selected prefix of each node's edges and is bound by the "
+                       "dependent-load latency of the descent, not by bandwidth")
+    else:
+        sel["achieved"] = sel["prefix_scan_GBps"]
+        sel["frac"] = sel["prefix_scan_GBps"] / peak
+        sel["note"] = "no ncu DRAM capture found: frac uses the bytes the prefix scan touches"
+    out["rooflines"]["k_select"] = sel
+    out["rooflines"]["k_expand"] = {"ms_per_wave": ms[2] / w, "bound": "issue (sort network)",
+                                    "algorithmic_GBps": ev * (1448 + 56 + 20 * 250) / (ms[2] / 1e3) / 1e9 if ms[2] > 0 else 0.0}
+    out["rooflines"]["k_backup"] = {"ms_per_wave": ms[3] / w, "bound": "latency (pointer chase)"}
+    if "f16" in kern:
+        k16 = kern["f16"]
+        b16 = 768 + 32 + 361 * 24 * 2
+        g16 = k16["evals"] * b16 / (k16["ms"][1] / 1e3) / 1e9 if k16["ms"][1] > 0 else 0.0
+        out["rooflines"]["k_leaf_features_f16_nhwc"] = {
+            "bound": "hbm", "achieved": g16, "peak": peak, "unit": "GB/s", "frac": g16 / peak,
+            "algorithmic_bytes_per_position": b16, "ms_per_wave": k16["ms"][1] / max(int(k16["waves"]), 1),
+            "note": "the format the timed region uses: fp16 NHWC, 24 channels (17,328 B written per position)"}
+    out["kernels_ms_per_wave"] = {"select": ms[0] / w, "leaf_features_f32": ms[1] / w, "expand": ms[2] / w, "backup": ms[3] / w}
+    return out
+
+
+# ---- the reference arm: the compiled reference search on the host cores, same GPU network ---------------
+def ref_selfplay(actor, dev, steps, warmup, slice_rollouts=80):
+    """BASELINE.md config 3b.  T host threads, one reference game + one reference TreeSearchT
+    (oracle/_ref: MCTSAI_T::act, 1 search thread, 8 rollouts per batch, puct 1.5, virtual loss 1,
+    persistent tree) each; every wave's 8 leaves go to the SAME GPU network through the callback.
+    A step = every game advances its search by `slice_rollouts` rollouts (a tenth of a move; ten
+    slices accumulate on the persistent root, then the move is played), so moves = rollouts / 800.
+    Two ways of feeding the network are timed and the better one is the baseline:
+      one_call_per_wave : each thread calls the network with its own 8 leaves (what a lone game thread sees)
+      batched           : a collector gathers the waiting threads' leaves into one call of up to 256 rows,
+                          as elf::Batcher does for the reference's game threads (broadcast.h:51-141); more
+                          game threads than cores, since they block on the network."""
+    import queue
+
+    import numpy as np
+    import torch
+
+    from tests import oracles
+
+    if not oracles.have_ref(BOARD):
+        return {"unavailable": "oracle/_ref not built"}
+    cores = effective_cores()
+    P1 = BOARD * BOARD + 1
+    lock = threading.Lock()
+
+    def net(feats):  # feats: float32 numpy [m,18,N,N] -> pi [m,P1], v [m]; pads to a power of two (static shapes)
+        m = feats.shape[0]
+        mp = 8
+        while mp < m:
+            mp *= 2
+        x = torch.zeros((mp, 18, BOARD, BOARD), dtype=torch.float32, pin_memory=dev.type == "cuda")
+        x[:m] = torch.from_numpy(feats)
+        with lock, torch.no_grad():
+            out = actor({"s": x.to(dev, non_blocking=True)})
+            pi, v = out["pi"][:m].float().cpu().numpy(), out["V"].reshape(-1)[:m].float().cpu().numpy()
+        return pi, v
+
+    results = {}
+    for mode, T in (("one_call_per_wave", cores), ("batched", min(8 * cores, 256))):
+        evals = [0] * T
+        q = queue.Queue()
+        stop = threading.Event()
+
+        def collector():
+            while not stop.is_set():
+                try:
+                    first = q.get(timeout=0.05)
+                except queue.Empty:
+                    continue
+                items, rows = [first], first[0].shape[0]
+                while rows < NN_BATCH:
+                    try:
+                        it = q.get_nowait()
+                    except queue.Empty:
+                        break
+                    items.append(it)
+                    rows += it[0].shape[0]
+                pi, v = net(np.concatenate([it[0] for it in items]))
+                o = 0
+                for f, box, ev in items:
+                    k = f.shape[0]
+                    box.append((pi[o:o + k], v[o:o + k]))
+                    o += k
+                    ev.set()
+
+        start, done = threading.Barrier(T + 1), threading.Barrier(T + 1)
+        nsteps = warmup + steps
+
+        def work(tid):
+            def cb(feats, hashes):
+                evals[tid] += len(hashes)
+                if mode == "one_call_per_wave":
+                    return net(np.ascontiguousarray(feats))
+                box, ev = [], threading.Event()
+                q.put((np.array(feats, copy=True), box, ev))
+                ev.wait()
+                return box[0]
+
+            rng = np.random.default_rng(1000 + tid)
+            st = oracles.Ref(BOARD)
+            for _ in range(16):
+                st.forward(int(rng.choice(np.flatnonzero(st.legal()))))
+            m = oracles.RefMcts(BOARD, num_rollouts=slice_rollouts, num_rollouts_per_batch=PER_BATCH, virtual_loss=1,
+                                persistent_tree=1, c_puct=1.5, seed=tid, callback=cb)
+            slices = 0
+            for _ in range(nsteps):
+                start.wait()
+                r = m.act(st)
+                slices += 1
+                if slices * slice_rollouts >= ROLLOUTS:
+                    if not st.terminated():
+                        st.forward(r["best_action"])
+                    slices = 0
+                done.wait()
+
+        th = [threading.Thread(target=work, args=(i,), daemon=True) for i in range(T)]
+        col = threading.Thread(target=collector, daemon=True)
+        [t.start() for t in th]
+        col.start()
+        tot, ev0 = 0.0, 0
+        for s in range(nsteps):
+            if s == warmup:
+                ev0 = sum(evals)
+            t0 = time.perf_counter()
+            start.wait()
+            done.wait()
+            if s >= warmup:
+                tot += time.perf_counter() - t0
+        stop.set()
+        [t.join() for t in th]
+        col.join()
+        moves = steps * T * slice_rollouts / ROLLOUTS
+        results[mode] = {"value": moves / tot, "unit": "moves/s", "game_threads": T, "ms_per_step": 1e3 * tot / steps,
+                         "nn_positions_per_s": (sum(evals) - ev0) / tot}
+    best = max(results, key=lambda k: results[k]["value"])
+    return {"value": results[best]["value"], "unit": "moves/s", "cores": cores, "kind": "reference", "mode": best,
+            "modes": results, "ms_per_step": results[best]["ms_per_step"],
+            "sample": (f"reference TreeSearchT (oracle/_ref), {steps} steps x {results[best]['game_threads']} game threads x "
+                       f"{slice_rollouts} rollouts (= {slice_rollouts / ROLLOUTS:.2f} move each) on {cores} host cores, "
+                       f"driving the same GPU network; better of {list(results)}")}
+
+
+def run_reference_selfplay(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    from elf_b200.model import FusedActor
+
+    if not torch.cuda.is_available():
+        emit({"impl": "reference", "unavailable": "config 3b drives the GPU network from the reference search: no CUDA device here"})
+        return 0
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    _, net_desc, model = make_network(args, dev)
+    actor = FusedActor(model, batchsize=args.nn_batch, dtype=torch.float16, cuda_graph=True)
+    cb = ref_selfplay(actor, dev, steps=args.steps, warmup=max(1, args.warmup))
+    if "unavailable" in cb:
+        emit({"impl": "reference", "unavailable": cb["unavailable"]})
+        return 0
+    world = args.gpus
+    line = {
+        "impl": "reference", "metric": "self-play moves/sec (MCTS, 19x19)", "value": cb["value"], "unit": "moves/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 search statistics / fp16 network", "data": "synthetic",
+        "config": {"workload": (f"configs[{2 if world == 1 else 3}]: {BOARD}x{BOARD} self-play, {ROLLOUTS} MCTS rollouts/move in waves of "
+                                f"{PER_BATCH}, puct 1.5, virtual loss 1, persistent tree, NN batch <= {args.nn_batch}; the reference keeps as "
+                                f"many games in flight as its host threads can drive (not {args.games}); step = every game thread "
+                                f"advances its search by 80 rollouts (0.1 move)"),
+                   "net": net_desc, "games_total": args.games, "rollouts_per_move": ROLLOUTS, "rollouts_per_wave": PER_BATCH,
+                   "nn_batch": args.nn_batch, "board": BOARD,
+                   "parallelism": "host threads of rank 0's process; the network runs on its GPU"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    emit(line)
+    return 0
 
 _REAL_STDOUT = None
 
@@ -600,29 +990,34 @@ def main():
     os.dup2(2, 1)  # fd 1 -> stderr for native libraries and stray prints
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--plies-per-slot", type=int, default=512)
-    ap.add_argument("--workload", default="playout", choices=["playout", "mcts"])
-    ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--workload", default="selfplay", choices=["selfplay", "playout"])
+    ap.add_argument("--games", type=int, default=GAMES_PER_GPU,
+                    help="selfplay: games in TOTAL over all GPUs (4096); playout: games per GPU")
     ap.add_argument("--board", type=int, default=19, choices=[9, 19])
-    ap.add_argument("--rollouts", type=int, default=64)
-    ap.add_argument("--per-batch", type=int, default=8)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-steps", type=int, default=6, help="steps of the reference search in our line's cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-board-step", action="store_true")
+    ap.add_argument("--plies-per-slot", type=int, default=512)
+    ap.add_argument("--parts", type=int, default=2, help="selfplay: half batches interleaved per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--blocks", type=int, default=20)
     ap.add_argument("--dim", type=int, default=256)
-    ap.add_argument("--nn-batch", type=int, default=256)
+    ap.add_argument("--nn-batch", type=int, default=NN_BATCH)
     ap.add_argument("--fake-net", action="store_true")
     args = ap.parse_args()
     BOARD = args.board
-    if args.workload == "mcts" and args.impl == "ours":
-        return run_mcts(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    if args.workload == "playout":
+        if args.steps == 20:
+            args.steps = 30
+        return run_reference_playout(args) if args.impl == "reference" else run_playout(args)
+    if BOARD != 19:
+        raise SystemExit("the self-play workload is 19x19 (configs[2]/[3]); use --workload playout --board 9 for configs[4]")
+    return run_reference_selfplay(args) if args.impl == "reference" else run_selfplay(args)
 
 
 if __name__ == "__main__":

@@ -49,6 +49,20 @@ class MctsBatch:
         self._torch = torch
         self.device = torch.device("cuda", go_batch.device)
         # the leaf feature batch handed to the network: lives on the device, written in place
+        self.set_feature_format(feature_format, cpad)
+        self._stream = torch.cuda.ExternalStream(go_batch.stream, device=self.device)
+        self._keep = None  # network replies still being read by kernels on the context stream
+
+    def set_feature_format(self, feature_format, cpad=None):
+        """switch the leaf-batch format between moves/waves (re-allocates the feature tensor)"""
+        torch = self._torch
+        if feature_format not in ("f32", "f16", "bf16"):
+            raise ValueError("feature_format must be f32, f16 or bf16")
+        self.gb.synchronize()
+        self.feature_format = feature_format
+        self.cpad = self.cpad if cpad is None else int(cpad)
+        n = self.gb.board_size
+        self.feat = None
         if feature_format == "f32":
             self._fmt = _l.FEAT_F32_NCHW
             self.feat = torch.zeros((self.max_leaves, 18, n, n), dtype=torch.float32, device=self.device)
@@ -57,8 +71,6 @@ class MctsBatch:
             dt = torch.float16 if feature_format == "f16" else torch.bfloat16
             self.feat = torch.zeros((self.max_leaves, n, n, self.cpad), dtype=dt, device=self.device)
         self.feat_key = "s" if feature_format == "f32" else "s_nhwc"
-        self._stream = torch.cuda.ExternalStream(go_batch.stream, device=self.device)
-        self._keep = None  # network replies still being read by kernels on the context stream
 
     def close(self):
         if getattr(self, "_m", None):

@@ -65,7 +65,7 @@ def main():
         report(f"fused fp16 graph NN batch {nb}", 4096, timeit(lambda: fa({"s": x}), 3))
     # fp16 NHWC input handed in directly (what k_leaf_features' fast mode will write)
     fa = FusedActor(model, batchsize=256, dtype=torch.float16, cuda_graph=True)
-    xh = torch.rand(4096, 19, 19, 18, device=dev).half()
+    xh = torch.rand(4096, 19, 19, fa.cpad, device=dev).half()
     report("fused fp16 graph, NHWC fp16 input", 4096, timeit(lambda: fa({"s_nhwc": xh}), 3))
     # two streams, two graphs: do concurrent batch-256 chunks overlap better?
     fa2 = FusedActor(model, batchsize=256, dtype=torch.float16, cuda_graph=True)

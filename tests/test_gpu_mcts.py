@@ -486,11 +486,14 @@ def test_fast_feature_formats_async_waves_and_pipeline(n):
 
     def actor_for(mc, log=None):
         def actor(batch):
-            h, _, _ = mc.leaf_info()
+            h, gi, _ = mc.leaf_info()
             key = "s" if "s" in batch else "s_nhwc"
             if log is not None:
                 x = batch[key][: len(h)]
-                log.append(x.float().cpu().numpy() if key == "s" else x.float().permute(0, 3, 1, 2)[:, :18].cpu().numpy())
+                x = x.float().cpu().numpy() if key == "s" else x.float().permute(0, 3, 1, 2)[:, :18].cpu().numpy()
+                # leaf slots are handed out by an atomic counter: their order is not reproducible between
+                # runs on hardware, so a wave's batch is keyed by (game, position hash)
+                log.append({(int(g_), int(h_)): x[i] for i, (g_, h_) in enumerate(zip(gi, h))})
             pi, v = net(None, h)
             full = batch[key].shape[0]
             P = torch.zeros(full, n * n + 1)
@@ -510,7 +513,9 @@ def test_fast_feature_formats_async_waves_and_pipeline(n):
     r1 = m1.act(actor_for(m1, log1))
     assert len(log0) == len(log1)
     for a, b in zip(log0, log1):
-        np.testing.assert_array_equal(a, b)
+        assert a.keys() == b.keys()
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
     for k in ("visits", "best_action", "root_value", "total_visits"):
         np.testing.assert_array_equal(r0[k], r1[k])
     for m, g in ((m0, gb0), (m1, gb1)):
