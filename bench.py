@@ -286,7 +286,6 @@ def run_playout(args):
         e2e_plies += r["total_plies"]
     barrier()
     e2e_s = time.perf_counter() - t0
-    hb_h2d, hb_d2h = hb.h2d / Ke, hb.d2h / Ke
 
     # ---- secondary: one batch of G games played to terminal (includes the ragged tail) -----------
     tt_ms, tt_plies = 0.0, 0
@@ -651,9 +650,15 @@ def run_selfplay(args):
         torch.cuda.synchronize()
         t_bcast = time.perf_counter() - t0
         actor = FusedActor(model, batchsize=args.nn_batch, dtype=torch.float16, cuda_graph=True)
+    def note(msg):
+        if rank == 0:
+            print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+    note(f"network ready ({net_desc}); building {G} games in {args.parts} part(s)")
     eng = SelfPlayEngine(actor, G, args.parts, local, rank, "f32" if args.fake_net else "f16")
     streams = eng.streams()
     K, W = args.steps, args.warmup
+    note("engine ready, warm-up")
 
     for _ in range(W):
         eng.step()
@@ -669,6 +674,7 @@ def run_selfplay(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     launches, evals, real_moves = eng.launches() - l0, eng.evals() - ev0, eng.moves - mv0
+    note(f"timed region: {K} steps in {dev_ms:.1f} ms device / {wall * 1e3:.1f} ms wall, {evals} evaluations")
 
     # ---- e2e: the same waves through the host-buffer tensor boundary (float32 "s"), wall clock --------
     eng.set_feature_format("f32")
@@ -682,6 +688,8 @@ def run_selfplay(args):
         eng.step(pipelined=False, actor=hb)
     barrier()
     e2e_s = time.perf_counter() - t0
+    hb_h2d, hb_d2h = hb.h2d / Ke, hb.d2h / Ke
+    note(f"e2e (host-buffer boundary): {Ke} steps in {e2e_s * 1e3:.1f} ms wall")
 
     # ---- kernel timings, alone (no overlap with the network): CUDA events inside the library ---------
     kern = None
@@ -707,6 +715,7 @@ def run_selfplay(args):
     del eng, hb
     torch.cuda.empty_cache()
 
+    note("kernel timings done; board-step probe")
     board = board_step_probe(local) if rank == 0 and not args.no_board_step else None
 
     # ---- reduce over ranks (MAX of times, SUM of counters) ----------------------------------------------
@@ -754,6 +763,7 @@ def run_selfplay(args):
         if board is not None:
             line["board_step"] = board
         if world == 1 and not args.no_cpu_baseline and not args.fake_net:
+            note("cpu_baseline: reference search on the host cores")
             cb = ref_selfplay(actor, dev, steps=args.cpu_steps, warmup=1)
             line["cpu_baseline"] = cb
         emit(line)

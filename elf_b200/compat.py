@@ -346,8 +346,6 @@ class SelfPlayEngine:
     """The engine behind compat.Context: SelfPlay's move loop cut at the network round trip."""
 
     def __init__(self, selfplay):
-        if any(getattr(selfplay, "policy_only", {}).values()):
-            raise NotImplementedError("policy-only colours are driven by SelfPlay.step(), not by the wait/step pump")
         self.sp = selfplay
         self.board_size = selfplay.N
         self.num_action = selfplay.N * selfplay.N + 1
@@ -397,7 +395,16 @@ class SelfPlayEngine:
         return self._events.popleft() if self._events else None
 
     def _phases(self, info):
-        return [(mc, label, active) for mc, _, label, active in self.sp.phases(info)]
+        """[(search, label, active, waves or None, post or None)] for this move; with a policy-only
+        colour (GameOptions::black/white_use_policy_network_only) the plan is SelfPlay.policy_only_plan's"""
+        sp = self.sp
+        self._chosen = None
+        if any(getattr(sp, "policy_only", {}).values()):
+            G = sp.G
+            self._chosen = (np.full(G, -2, np.int32), np.zeros(G, np.float32))
+            return [(mc, label, active, waves, post)
+                    for mc, _, label, active, waves, post in sp.policy_only_plan(info, *self._chosen)]
+        return [(mc, label, active, None, None) for mc, _, label, active in sp.phases(info)]
 
     def _advance_until_leaves(self):
         import torch
@@ -418,8 +425,10 @@ class SelfPlayEngine:
                 self._plan[0][0].begin_move(self._plan[0][2])
                 self._wave_idx = 0
                 self._in_move = True
-            mc, label, _ = self._plan[self._phase]
-            if self._wave_idx >= mc.waves_per_move:
+            mc, label, _, waves, post = self._plan[self._phase]
+            if self._wave_idx >= (mc.waves_per_move if waves is None else waves):
+                if post is not None:
+                    post()
                 self._phase += 1
                 if self._phase == len(self._plan):
                     self._finish_move()
@@ -444,7 +453,9 @@ class SelfPlayEngine:
         sp = self.sp
         sp.resign_thres = self.resign_thres
         before = sp.games_finished
-        sp.finish_move(self._info)
+        if self._chosen is not None:
+            sp._policy_only_moves = sp._po_colour & (self._chosen[0] >= 0)
+        sp.finish_move(self._info, chosen=self._chosen)
         for _ in range(sp.games_finished - before):  # finish_game -> GameNotifier::OnGameEnd -> game_end
             self._events.append(("game_end", {}))
         self._in_move = False
@@ -721,8 +732,6 @@ def game_context(co, opt, board_size=19, device=0, factories=None):
                                                              opt.white_mcts_rollout_per_batch, opt.white_puct).items()
                              if v != common.get(k)},
             **common)
-        if kw["black_use_policy_network_only"] or kw["white_use_policy_network_only"]:
-            raise NotImplementedError("policy-only colours are driven by SelfPlay.step(), not by the wait/step pump")
         sp = f.get("selfplay", SelfPlay)(**kw)
         return GameContext(SelfPlayEngine(sp), batchsize=int(co.batchsize))
     if opt.mode == "online":

@@ -118,50 +118,61 @@ class SelfPlay:
                 mc.search(actor, active=active)
         return self.finish_move(info)
 
-    def _search_with_policy_only(self, info):
-        """the search phase when one colour moves by policy only: those games get their root
-        evaluated if it is not yet (TreeSearchT::runPolicyOnly) and play the arg-max prior (rank
-        criterion PRIOR, first maximum in edge order); the other games search as usual.  Returns the
-        chosen (actions, values) for finish_move.  The predicted value of a policy-only move is the
-        root's network value (MCTSGoAI::getValue falls back to it for an unvisited best edge)."""
+    def policy_only_plan(self, info, acts, vals):
+        """The search phases of a move in which one colour moves by policy only, as a list of
+        ``(search, actor, label, active mask, waves, post)``: run ``waves`` waves (None = a whole
+        move's, 0 = none) for the games in ``active``, then call ``post()``, which fills ``acts`` /
+        ``vals`` for those games.  Policy-only games get their root evaluated if it is not yet
+        (TreeSearchT::runPolicyOnly, tree_search.h:387-408) and play the arg-max prior (rank criterion
+        PRIOR, first maximum in edge order); the other games search as usual.  The predicted value of a
+        policy-only move is the root's network value (MCTSGoAI::getValue falls back to it for an
+        unvisited best edge).  Shared by ``step()`` and the wait/step pump of ``compat``."""
         G = self.G
-        acts = np.full(G, -2, np.int32)
-        vals = np.zeros(G, np.float32)
         po_colour = np.array([self.policy_only[int(c)] for c in info[:, 1]], bool)
         nr = self.never_resign.astype(np.uint8)
         seed = (self._seed << 20) ^ (self._move_counter + 1)
-        for mc, actor, _, active in self.phases(info):
+        plan = []
+        for mc, actor, label, active in self.phases(info):
             act = np.ones(G, bool) if active is None else np.asarray(active).astype(bool)
             a_po, a_ts = act & po_colour, act & ~po_colour
             if a_ts.any():
-                mc.search(actor, active=a_ts.astype(np.uint8))
-                a, v = mc.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
-                acts[a_ts], vals[a_ts] = a[a_ts], v[a_ts]
+                def post_ts(mc=mc, sel=a_ts):
+                    a, v = mc.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
+                    acts[sel], vals[sel] = a[sel], v[sel]
+                plan.append((mc, actor, label, a_ts.astype(np.uint8), None, post_ts))
             if a_po.any():
                 # roots that are already expanded (left by the other colour's search in a shared tree)
-                # are used as they are; the others are evaluated once.  begin_move() may drop a tree
-                # whose node pool is short, which turns an expanded root into a fresh one.
-                pr = mc.root_priors()
-                fresh = a_po & (pr.max(1) < 0)
+                # are used as they are; the others are evaluated once
+                fresh = a_po & (mc.root_priors().max(1) < 0)
+
+                def post_po(mc=mc, sel=None):
+                    pr = mc.root_priors()
+                    rv = mc.results()["root_value"]
+                    vals[sel] = rv[sel]
+                    acts[sel] = pr[sel].argmax(1)
+                    side = np.where(info[:, 1] == 1, vals, -vals)  # GoStateExt::shouldResign
+                    resign = sel & (side < -1.0 + self.resign_thres) & (info[:, 0] >= 50) & ~self.never_resign
+                    acts[resign] = -1
                 old = a_po & ~fresh
                 if old.any():
-                    mc.begin_move(old.astype(np.uint8))
-                    pr = mc.root_priors()
-                    dropped = old & (pr.max(1) < 0)
-                    rv = mc.results()["root_value"]
-                    keep = old & ~dropped
-                    vals[keep] = rv[keep]
-                    fresh |= dropped
+                    plan.append((mc, actor, label, old.astype(np.uint8), 0, lambda f=post_po, m=old: f(sel=m)))
                 if fresh.any():
-                    mc.search(actor, active=fresh.astype(np.uint8), waves=1)
-                    pr = mc.root_priors()
-                    rv = mc.results()["root_value"]
-                    vals[fresh] = rv[fresh]
-                acts[a_po] = pr[a_po].argmax(1)
-                side = np.where(info[:, 1] == 1, vals, -vals)  # GoStateExt::shouldResign
-                resign = a_po & (side < -1.0 + self.resign_thres) & (info[:, 0] >= 50) & ~self.never_resign
-                acts[resign] = -1
-        self._policy_only_moves = po_colour & (acts >= 0)
+                    plan.append((mc, actor, label, fresh.astype(np.uint8), 1, lambda f=post_po, m=fresh: f(sel=m)))
+        self._po_colour = po_colour
+        return plan
+
+    def _search_with_policy_only(self, info):
+        """the search phase when one colour moves by policy only (see policy_only_plan); returns the
+        chosen (actions, values) for finish_move"""
+        acts = np.full(self.G, -2, np.int32)
+        vals = np.zeros(self.G, np.float32)
+        for mc, actor, _, active, waves, post in self.policy_only_plan(info, acts, vals):
+            if waves == 0:
+                mc.begin_move(active)  # marks the games whose root statistics post() reads
+            else:
+                mc.search(actor, active=active, waves=waves)
+            post()
+        self._policy_only_moves = self._po_colour & (acts >= 0)
         return acts, vals
 
     # -- MsgRequest handling: GoGameSelfPlay::OnReceive (game_selfplay.cc:222-270) for all games ----

@@ -215,6 +215,7 @@ def test_game_context_from_reference_options():
     opt.mode = "bogus"
     with pytest.raises(ValueError, match="Unknown mode"):
         compat.game_context(co, opt)
+    # policy-only colours go through the same pump (tests/test_dropin_shim.py plays such games)
     opt.mode, opt.white_use_policy_network_only = "selfplay", True
-    with pytest.raises(NotImplementedError):
-        compat.game_context(co, opt, factories={"selfplay": FakeSelfPlay})
+    GC = compat.game_context(co, opt, factories={"selfplay": FakeSelfPlay})
+    assert isinstance(GC._engine, compat.SelfPlayEngine) and got["white_use_policy_network_only"] is True
