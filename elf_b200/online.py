@@ -174,11 +174,18 @@ class OnlineGame:
         return self.last_value
 
     # -- game boundaries -------------------------------------------------------------------------
+    def _restart_game(self):
+        """what finish_game does at the end (game_selfplay.cc:121-149: _ai->endGame + _state_ext.restart()):
+        an empty board and tree.  The SGF preload is NOT repeated and the SGF iterator stays where it
+        was -- both belong to GoGameSelfPlay::restart(), which only runs when a request arrives."""
+        self.board.reset(None)
+        self.search.reset(None)
+        self.seq += 1
+
     def _restart(self, first=False):
+        """GoGameSelfPlay::restart (game_selfplay.cc:186-219): fresh state, then the SGF preload"""
         if not first:
-            self.board.reset(None)
-            self.search.reset(None)
-            self.seq += 1
+            self._restart_game()
         path, move_to = self._preload
         if path:  # game_selfplay.cc:202-219
             self._sgf = _sgf.Sgf.load(path, self.N) if isinstance(path, str) else path
@@ -206,7 +213,7 @@ class OnlineGame:
             self._last_move_of_finished = int(i[4])
         self.last_value = fv
         self.finished.append((fv, int(i[0]), reason))
-        self._restart()
+        self._restart_game()
         return fv
 
     # -- the human branch of act() ----------------------------------------------------------------

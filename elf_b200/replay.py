@@ -87,8 +87,13 @@ class ReplayBatch:
         n = self.N
         for r in records:
             res = r["result"]
+            moves = _sgf.sgfstr2actions(res["content"], n)
+            if any(a < 0 or a > n * n for a in moves):
+                # a malformed vertex parses to M_INVALID in the reference and GoState::forward(M_INVALID)
+                # throws there (go_state.cc:74-77); reject the record up front instead of replaying it
+                raise ValueError("record contains an invalid move: " + res["content"][:60])
             self.records.append({
-                "moves": _sgf.sgfstr2actions(res["content"], n),
+                "moves": moves,
                 "winner": 1.0 if res["reward"] > 0 else -1.0,
                 "policies": res.get("policies", []),
                 "values": res.get("values", []),
@@ -134,6 +139,10 @@ class ReplayBatch:
             for t in range(int(move_to.max()) if B else 0):
                 acts = np.array([r["moves"][t] if t < m else -1 for r, m in zip(recs, move_to)], np.int32)
                 self.board.forward(acts)  # the reference ignores forward()'s verdict here as well
+        # the reference's extractors index the labels with _state.getPly() - 1 (game_feature.h:75-139),
+        # i.e. the number of moves the board ACCEPTED, not the sampled move_to: a refused move in a record
+        # (forward()'s verdict is ignored by switchBeforeMove) shifts the labels with the position
+        move_idx = self.board.info()[:, 0].astype(np.int64) - 1
         if s_out is not None:
             import torch
 
@@ -148,14 +157,15 @@ class ReplayBatch:
             "offline_a": np.zeros((B, K), np.int64),
             "winner": np.array([r["winner"] for r in recs], np.float32),
             "mcts_scores": np.zeros((B, A), np.float32),
-            "move_idx": move_to.astype(np.int32),
+            "move_idx": move_idx.astype(np.int32),
             "num_move": np.array([len(r["moves"]) for r in recs], np.int32),
             "predicted_value": np.array([r["values"][m] if m < len(r["values"]) else 0.0
-                                         for r, m in zip(recs, move_to)], np.float32),
+                                         for r, m in zip(recs, move_idx)], np.float32),
             "aug_code": d4.copy(),
             "selfplay_ver": np.array([r["ver"] for r in recs], np.int64),
         }
-        for b, (r, m, code) in enumerate(zip(recs, move_to, d4)):
+        for b, (r, m, code) in enumerate(zip(recs, move_idx, d4)):
+            m = int(m)
             for k in range(K):  # extractOfflineAction
                 out["offline_a"][b, k] = board_to_nn_action(r["moves"][m + k], n, int(code))
             sc = out["mcts_scores"][b]

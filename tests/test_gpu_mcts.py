@@ -685,3 +685,142 @@ def test_selfplay_soak_tree_reuse_over_many_moves():
     for rec in sp.records[:20]:
         assert rec["result"]["num_move"] == rec["result"]["content"].count(";")
     sp.close()
+
+
+@pytest.mark.parametrize("n", [9, 19])
+def test_gpu_selfplay_records_are_accepted_by_the_reference_parser(n):
+    """row f1 on the device: records written by GPU self-play (real search, real visit tables) go
+    through the compiled reference's own Record::createFromJson / setJsonFields (oracle/_ref,
+    ref_offline_shim.cc; JSON_LOAD throws on any missing field) and come back field for field; the
+    batch parser keeps all of them; the u8-quantised policies equal GoStateExt::addMCTSPolicy's on
+    the same visit counts; and replaying a record's moves on reference boards reproduces the game."""
+    import json
+
+    import torch
+
+    import elf_b200
+    from elf_b200 import record
+    from elf_b200.model import Actor, PolicyValueNet
+    from tests.test_replay_records import same
+
+    if not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built")
+    torch.manual_seed(2)
+    G = 12 if n == 9 else 6
+    net = PolicyValueNet(n, num_block=1, dim=16).cuda()
+    cutoff = 6
+    sp = elf_b200.selfplay.SelfPlay(Actor(net, batchsize=64, dtype=torch.float32, channels_last=False), num_games=G,
+                                    board_size=n, policy_distri_cutoff=cutoff, num_rollouts=24, num_rollouts_per_batch=4,
+                                    move_cutoff=14 if n == 9 else 10, seed=4, record_games=True, resign_thres=0.0)
+    tables = []  # (game, ply, visits) of every searched move, as the recorder saw them
+    orig = sp.mcts.results
+
+    def spy():
+        r = orig()
+        info = sp.gb.info()
+        for g in range(G):
+            tables.append((g, int(info[g, 0]), r["visits"][g].copy()))
+        return r
+    sp.mcts.results = spy
+    while sp.games_finished < G:
+        sp.step()
+    recs = sp.records
+    assert len(recs) >= G
+    text = record.dumps(recs)
+    assert oracles.ref_record_batch_count(text, n) == len(recs)
+    for rec in recs:
+        back = oracles.ref_record_roundtrip(json.dumps(rec), n)
+        assert back is not None, "the reference's Record::createFromJson rejected a GPU self-play record"
+        same(rec, json.loads(back))
+        res = rec["result"]
+        # the game replays on the REFERENCE board: every recorded move is legal there, in order
+        st = oracles.Ref(n)
+        from elf_b200.sgf import sgfstr2actions
+
+        moves = sgfstr2actions(res["content"], n)
+        for a in moves:
+            assert st.forward(int(a))
+        assert int(st.info()[0]) - 1 == res["num_move"] == len(moves)
+        assert len(res["policies"]) == min(cutoff, res["num_move"])
+    # quantisation on real visit tables == the reference's MCTSPolicy::normalize + addMCTSPolicy
+    checked = 0
+    for g, ply, vis in tables[:: max(1, len(tables) // 40)]:
+        acts = np.flatnonzero(vis >= 0)
+        if vis[acts].sum() == 0:
+            continue
+        want = oracles.ref_quantise_policy(acts, vis[acts].astype(np.float32), n)
+        np.testing.assert_array_equal(np.asarray(record.quantise_policy(vis, n), np.uint8), want)
+        checked += 1
+    assert checked > 10
+    assert (sp.mcts.errors() == 0).all()
+    sp.close()
+
+
+def test_shim_modules_drive_the_real_engine(monkeypatch):
+    """the drop-in modules (elf_b200/shim: `_elf`, `_elfgames_go`) on the device, called the way the
+    reference's game.py / GCWrapper call them (the reference tree itself is not on the GPU box;
+    tests/test_dropin_shim.py runs its unmodified files on the same modules):
+    go.ContextOptions / go.GameOptions -> go.GameContext(co, opt) -> ctx().createSharedMemOptions /
+    allocateSharedMem -> AnyP.field()/set(ptr, strides) -> start / wait / step / stop."""
+    import os
+    import sys
+
+    import torch
+
+    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "elf_b200", "shim")
+    monkeypatch.syspath_prepend(shim)
+    monkeypatch.setenv("ELFB200_BOARD", "9")
+    for m in ("_elf", "_elfgames_go"):
+        sys.modules.pop(m, None)
+    import _elf
+    import _elfgames_go as go
+
+    monkeypatch.setattr(go, "BOARD_SIZE", 9)
+    n, bs = 9, 16
+    co = go.ContextOptions()
+    co.num_games, co.batchsize = 8, bs
+    ts = co.mcts_options
+    ts.num_threads, ts.num_rollouts_per_thread, ts.num_rollouts_per_batch = 1, 16, 4
+    ts.persistent_tree, ts.virtual_loss = True, 1
+    ts.alg_opt.use_prior, ts.alg_opt.c_puct = True, 1.5
+    opt = go.GameOptions()
+    opt.mode, opt.use_mcts, opt.move_cutoff, opt.policy_distri_cutoff, opt.resign_thres = "selfplay", True, 10, 4, 0.0
+    GC = go.GameContext(co, opt)
+    params = GC.getParams()
+    assert params["num_action"] == 82 and params["ACTION_PASS"] == -99
+    ctx = GC.ctx()
+    assert isinstance(ctx, _elf.Context)
+    keep = {}
+    smem = {}
+    for label, keys in (("actor_black", ["s", "pi", "V", "a", "rv"]), ("game_end", []), ("game_start", ["black_ver", "white_ver"])):
+        o = ctx.createSharedMemOptions(label, bs if label == "actor_black" else 1)
+        o.setTimeout(10)
+        sm = ctx.allocateSharedMem(o, keys)
+        for k in keys:  # what Allocator._alloc does (utils_elf.py:32-57)
+            f = sm[k].field()
+            dt = {"float": torch.float32, "int64_t": torch.int64, "int32_t": torch.int32}[f.type_name()]
+            t = torch.zeros(f.sz().vec(), dtype=dt).pin_memory()
+            sm[k].set(t.data_ptr(), [s_ * t.element_size() for s_ in t.stride()])
+            keep[(label, k)] = t
+        smem[label] = sm
+    ctx.start()
+    ends, batches = 0, 0
+    for _ in range(4000):
+        sm = ctx.wait(0)
+        label = sm.getSharedMemOptions().label()
+        if label == "actor_black":
+            k = sm.effective_batchsize()
+            s = keep[(label, "s")][:k]
+            assert 0 < k <= bs and set(np.unique(s.numpy())) <= {0.0, 1.0}
+            pi, v = oracles.feature_net(s.numpy(), 82)
+            keep[(label, "pi")][:k] = torch.from_numpy(pi)
+            keep[(label, "V")][:k] = torch.from_numpy(v)
+            batches += 1
+        elif label == "game_end":
+            ends += 1
+        ctx.step(_elf.ReplyStatus.SUCCESS)
+        if ends >= 8:
+            break
+    ctx.stop()
+    wr = GC.getClient().getGameStats().getWinRateStats()
+    assert ends >= 8 and batches > 20 and wr.total_games >= 8

@@ -219,7 +219,9 @@ def test_sgf_preload_and_follow(oracle_lib, tmp_path):
     got = [g.genmove(actor) for _ in range(52)]
     assert got == rec.actions()[10:62] and len(actor.calls) == 52
     assert g.genmove(actor) is None and g.finished[-1][2] == "max_step"  # record exhausted
-    assert g.info()[0] == 11  # restarted and preloaded again
+    # finish_game -> _state_ext.restart(): an EMPTY board; the preload is not repeated and the SGF
+    # iterator stays exhausted (both belong to GoGameSelfPlay::restart, game_selfplay.cc:202-219)
+    assert g.info()[0] == 1 and g._sgf_pos == len(rec.actions())
     with pytest.raises(RuntimeError):
         bad = tmp_path / "bad.sgf"
         bad.write_text("(;SZ[9];B[aa];W[aa])")
