@@ -233,6 +233,8 @@ def run_playout(args):
 
     G = args.games
     gb = elf_b200.GoBatch(G, board_size=BOARD, device=local)
+    if args.playout_layout:
+        gb.set_playout_layout(args.playout_layout)
     stream = torch.cuda.ExternalStream(gb.stream, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
 
@@ -364,7 +366,7 @@ def run_playout(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("k_playout<19>") if BOARD == 19 else None, "peak_source": peak_src,
-                         "kernel": f"k_playout<{BOARD}>", "algorithmic_bytes_per_ply": algo,
+                         "kernel": f"k_playout{2 if args.playout_layout else ''}<{BOARD}>", "algorithmic_bytes_per_ply": algo,
                          "note": "position and group masks live in registers, the superko record in L2: DRAM is idle and the kernel is bound by the integer ALU pipe (profiles/r1_playout_F.md)"},
             "clocks": clocks, "wall_s_timed_region": t_wall, "parity_spot_check": parity, "step_api": step_api,
             "batch_to_terminal": {"value": tt_plies / (tt_ms / 1e3) * 1.0, "unit": "moves/s (this rank)",
@@ -566,7 +568,7 @@ def device_span(streams, fn):
     return e0.elapsed_time(e1)
 
 
-def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512):
+def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512, layout=0):
     """BASELINE's second metric, "board-step GB/s vs roofline": the configs[1] playout workload (4096
     concurrent games, steady state) timed on its own, with the HBM formula AND the issue-slot roof"""
     import torch
@@ -574,6 +576,8 @@ def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512):
     import elf_b200
 
     gb = elf_b200.GoBatch(G, board_size=BOARD, device=local)
+    if layout:
+        gb.set_playout_layout(layout)
     stream = torch.cuda.ExternalStream(gb.stream, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
     for w in range(warmup):
@@ -593,15 +597,17 @@ def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512):
         tot += gb.playout_results()["total_plies"]
     gb.close()
     peak, peak_src = measured_peaks()
-    prof = load_profile_numbers().get(f"k_playout<{BOARD}>", {})
+    kname = f"k_playout{2 if layout else ''}<{BOARD}>"
+    prof = load_profile_numbers().get(kname, {})
     rate = tot / (ms / 1e3)
     algo = ALGO_BYTES_PER_PLY if BOARD == 19 else 224
     out = {"value": rate, "unit": "moves/s", "workload": f"configs[1]: {G} concurrent {BOARD}x{BOARD} games, random-policy playouts, "
            f"steady state ({plies} plies per slot per step, finished games restart)", "ms_per_step": ms / steps, "steps": steps,
            "roofline": {"bound": "hbm", "achieved": algo * rate / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": algo * rate / 1e9 / peak, "traffic": prof.get("dram_bytes_per_launch"),
-                        "peak_source": peak_src, "kernel": f"k_playout<{BOARD}>", "algorithmic_bytes_per_ply": algo,
-                        "note": "SURVEY 8d byte formula; the position lives in registers, DRAM is idle -- the honest roof is issue_roof"}}
+                        "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_ply": algo,
+                        "note": "SURVEY 8d byte formula; the position lives in registers, DRAM is idle -- the honest roof is issue_roof"},
+           "lane_layout": "two board rows per lane, three games per warp" if layout else "one board row per lane, one game per warp"}
     wi = prof.get("warp_inst_per_ply")
     if wi:
         try:
@@ -716,7 +722,7 @@ def run_selfplay(args):
     torch.cuda.empty_cache()
 
     note("kernel timings done; board-step probe")
-    board = board_step_probe(local) if rank == 0 and not args.no_board_step else None
+    board = board_step_probe(local, layout=args.playout_layout) if rank == 0 and not args.no_board_step else None
 
     # ---- reduce over ranks (MAX of times, SUM of counters) ----------------------------------------------
     if dist is not None:
@@ -1012,6 +1018,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-board-step", action="store_true")
     ap.add_argument("--plies-per-slot", type=int, default=512)
+    ap.add_argument("--playout-layout", type=int, default=0, choices=[0, 1],
+                    help="playout kernel: 0 = one board row per lane, 1 = two rows per lane (19x19, three games per warp)")
     ap.add_argument("--parts", type=int, default=2, help="selfplay: half batches interleaved per GPU")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--blocks", type=int, default=20)

@@ -152,6 +152,10 @@ class GoBatch:
         ``[G,N,N,cpad]``.  Asynchronous on the context stream."""
         _l.check(self._lib, self._lib.elfb200_features_dev_ex(self._ctx, d4_ptr, out_ptr, fmt, cpad))
 
+    def set_playout_layout(self, layout):
+        """0 = one board row per lane (default), 1 = two rows per lane (19x19: three games per warp)"""
+        _l.check(self._lib, self._lib.elfb200_set_playout_layout(self._ctx, int(layout)))
+
     def set_feature_store(self, mode):
         """1 = feature tiles leave shared memory by one bulk (TMA) store (default), 0 = vector stores"""
         _l.check(self._lib, self._lib.elfb200_set_feature_store(self._ctx, int(mode)))

@@ -292,6 +292,7 @@ struct elfb200_ctx {
   int32_t* d_words = nullptr;   // G * 12 export buffer
   int32_t* d_d4 = nullptr;
   float* d_feat = nullptr;      // lazily allocated G*18*P floats
+  int playout_layout = 0;       // k_playout: 0 = one board row per lane, 1 = two rows per lane (19x19, three games per warp)
   int feat_tma = 1;             // feature tiles leave shared memory by one bulk (TMA) store; 0 = vector stores
   // playout outputs
   uint64_t* d_po_sk = nullptr;
@@ -302,6 +303,12 @@ struct elfb200_ctx {
   // pinned staging
   void* h_pin = nullptr;
   size_t h_pin_bytes = 0;
+  // zero-copy window of the host-driven step API: actions int32[G] then accept flags uint8[G], pinned
+  // and MAPPED into the device address space -- k_step reads the actions and writes the flags over
+  // PCIe itself, so a GoState::forward for the whole batch is one launch and one wait, no copies
+  void* h_map = nullptr;
+  int32_t* d_map_actions = nullptr;
+  uint8_t* d_map_ok = nullptr;
   int64_t launches = 0;
   // move lists of elfb200_replay (grown on demand)
   int16_t* d_replay = nullptr;

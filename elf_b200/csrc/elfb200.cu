@@ -21,6 +21,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "board2.cuh"
 
 namespace elfb200 {
 
@@ -382,6 +383,115 @@ __global__ void __launch_bounds__(PLAYOUT_WARPS * 32)
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// k_playout in the two-rows-per-lane layout (board2.cuh): three 19x19 games per warp, 30 of 32 lanes
+// busy.  Same workload, same outputs, same checksums as k_playout (elfb200_set_playout_layout picks).
+template <int N>
+__global__ void __launch_bounds__(PLAYOUT_WARPS * 32)
+    k_playout2(int G, uint64_t seed, uint64_t first_id, int max_plies, int stream_plies,
+               uint64_t* __restrict__ sk, uint64_t* __restrict__ out_chk, int32_t* __restrict__ out_plies,
+               int32_t* __restrict__ out_score, uint64_t* __restrict__ out_hash) {
+  constexpr int GPW = Geo2<N>::GPW, LPG = Geo2<N>::LPG;
+  __shared__ uint64_t s_zob[Geo<N>::ZOB];
+  __shared__ uint32_t s_bloom[PLAYOUT_WARPS][GPW][128];  // see k_playout
+  load_zobrist<N>(s_zob);
+  const Lane2 L = make_lane2<N>();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int g = warp * GPW + L.sub;
+  const bool valid = L.active && g < G;
+  uint64_t gid = first_id + (uint64_t)g;
+  uint64_t* skg = sk + (size_t)(valid ? g : 0) * Geo<N>::MAX_PLY;
+  uint32_t* bloom = s_bloom[threadIdx.x >> 5][L.sub];
+  if (L.active)
+    for (int i = L.li; i < 128; i += LPG) bloom[i] = 0u;
+  __syncwarp();
+
+  P2 b = zero2(), w = zero2(), safe = zero2(), atari = zero2();
+  BoardMeta meta = initial_meta();
+  uint64_t hash = 0, chk = 0, acc = 0;
+  int nsk = 0, t = 0, ts = 0, ngames = 0;
+  const bool stream = stream_plies > 0;
+  const bool has_hi = 2 * L.li + 1 < N;
+
+  while (true) {
+    const bool over = is_terminated<N>(meta) || t >= max_plies;
+    bool term;
+    if (stream) {
+      const bool budget_out = ts >= stream_plies;
+      const bool restart = valid && over && !budget_out;
+      if (__any_sync(FULL, restart)) {
+        if (restart) {  // finish this game, start the slot's next one
+          acc = pp_splitmix64(acc ^ pp_fold_final(chk, hash, meta.ply));
+          ngames++;
+          gid += (uint64_t)G;
+          b = w = safe = atari = zero2();
+          meta = initial_meta();
+          hash = chk = 0;
+          nsk = t = 0;
+          for (int i = L.li; i < 128; i += LPG) bloom[i] = 0u;
+        }
+        __syncwarp();
+      }
+      term = !valid || budget_out;
+    } else {
+      term = !valid || over;
+    }
+    if (__all_sync(FULL, term)) break;
+    const P2 own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
+    const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
+    const P2 legal = legal_rows_cached<N>(own, opp, safe, atari, L, ko_applies, meta.ko_pt);
+    const P2 cand = legal & ~true_eye_rows<N>(own, opp, L);
+    const int n = game_sum(popc2(cand), L);
+    uint64_t rt = 0;
+    if (L.active) {
+      rt = pp_row_term((uint32_t)(2 * L.li), legal.lo);
+      if (has_hi) rt ^= pp_row_term((uint32_t)(2 * L.li + 1), legal.hi);
+    }
+    const uint64_t rx = game_xor64<N>(rt, L);
+    const uint64_t chk2 = pp_fold3(chk, hash, rx, meta.b_cap, meta.w_cap, meta.next);
+    const int k = n > 0 ? (int)pp_pick(seed, gid, meta.ply, (uint32_t)n) : 0;
+    const int p = select_kth_action_order<N>(cand, k, L);
+    const int pm = term ? MV_NONE : (n > 0 ? p : MV_PASS);
+    const uint64_t pre_hash = hash;
+    play_move_cached<N>(b, w, meta, hash, pm, s_zob, L, safe, atari);
+    const uint32_t q1 = (uint32_t)hash & 4095u, q2 = (uint32_t)(hash >> 12) & 4095u;
+    const bool maybe = pm >= 0 && ((bloom[q1 >> 5] >> (q1 & 31)) & (bloom[q2 >> 5] >> (q2 & 31)) & 1u);
+    bool sko = false;
+    if (__any_sync(FULL, maybe)) sko = superko_scan<N>(skg, maybe ? nsk : 0, hash, L);
+    __syncwarp();
+    if (pm >= 0) {
+      if (sko) meta.flags |= F_SUPERKO;
+      if (L.li == 0 && L.active) {
+        skg[nsk] = pre_hash;
+        const uint32_t i1 = (uint32_t)pre_hash & 4095u, i2 = (uint32_t)(pre_hash >> 12) & 4095u;
+        bloom[i1 >> 5] |= 1u << (i1 & 31);
+        bloom[i2 >> 5] |= 1u << (i2 & 31);
+      }
+      nsk++;
+    }
+    if (!term) {
+      chk = chk2;
+      t++;
+      ts++;
+    }
+    __syncwarp();
+  }
+  chk = pp_fold_final(chk, hash, meta.ply);
+  const int score = tt_score<N>(b, w, L);
+  if (valid && L.li == 0) {
+    if (stream) {
+      if (out_chk) out_chk[g] = pp_splitmix64(acc ^ chk);
+      if (out_plies) out_plies[g] = ts;
+      if (out_score) out_score[g] = ngames + 1;
+    } else {
+      if (out_chk) out_chk[g] = chk;
+      if (out_plies) out_plies[g] = t;
+      if (out_score) out_score[g] = score;
+    }
+    if (out_hash) out_hash[g] = hash;
+  }
+}
+
 }  // namespace elfb200
 
 // =========================================================================================
@@ -429,6 +539,8 @@ int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out)
   c->N = board_size;
   c->G = num_games;
   c->device = device;
+  // any failure below releases what was allocated so far (elfb200_destroy tolerates a partly built context)
+  auto build = [&]() -> int {
   const size_t N = board_size, G = num_games, P = N * N, MAXPLY = 2 * P;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   // the float32 feature tile (two positions, 51,984 B at 19x19) is above the 48 KB default
@@ -453,16 +565,26 @@ int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out)
   CK(cudaMalloc(&c->d_po_score, G * 4));
   c->h_pin_bytes = G * (P + 1) > G * 64 ? G * (P + 1) : G * 64;
   CK(cudaMallocHost(&c->h_pin, c->h_pin_bytes));
+  CK(cudaHostAlloc(&c->h_map, G * 5, cudaHostAllocMapped));
+  CK(cudaHostGetDevicePointer(&c->d_map_actions, c->h_map, 0));
+  c->d_map_ok = reinterpret_cast<uint8_t*>(c->d_map_actions) + G * 4;
+  return elfb200_reset(c, nullptr);
+  };
+  const int rc = build();
+  if (rc) {
+    const std::string why = g_err;  // elfb200_destroy must not lose the message
+    elfb200_destroy(c);
+    g_err = why;
+    return rc;
+  }
   *out = c;
-  int rc = elfb200_reset(c, nullptr);
-  if (rc) return rc;
   return ELFB200_OK;
 }
 
 void elfb200_destroy(elfb200_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
   void* ptrs[] = {c->st.cur,  c->st.ring, c->st.legal, c->st.hash,   c->st.meta,   c->st.sk,
                   c->st.sk_n, c->d_actions, c->d_ok,   c->d_bytes,   c->d_words,   c->d_d4,
                   c->d_feat,  c->d_po_sk, c->d_po_chk, c->d_po_hash, c->d_po_plies, c->d_po_score,
@@ -470,7 +592,8 @@ void elfb200_destroy(elfb200_ctx* c) {
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pin) cudaFreeHost(c->h_pin);
-  cudaStreamDestroy(c->stream);
+  if (c->h_map) cudaFreeHost(c->h_map);
+  if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
@@ -515,14 +638,13 @@ int elfb200_step_dev(elfb200_ctx* c, const int32_t* actions_dev, uint8_t* ok_dev
 int elfb200_step(elfb200_ctx* c, const int32_t* actions_host, uint8_t* ok_host) {
   if (!c || !actions_host) return elfb200_fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
   CK(cudaSetDevice(c->device));
-  memcpy(c->h_pin, actions_host, (size_t)c->G * 4);
-  CK(cudaMemcpyAsync(c->d_actions, c->h_pin, (size_t)c->G * 4, cudaMemcpyHostToDevice, c->stream));
-  int rc = elfb200_step_dev(c, c->d_actions, c->d_ok);
+  // host buffers, no copy engine: the actions go into the mapped pinned window, k_step reads them and
+  // writes the accept flags there over PCIe (16 KB + 4 KB at 4096 games), one launch, one wait
+  memcpy(c->h_map, actions_host, (size_t)c->G * 4);
+  int rc = elfb200_step_dev(c, c->d_map_actions, c->d_map_ok);
   if (rc) return rc;
-  if (ok_host) {
-    CK(cudaMemcpyAsync(ok_host, c->d_ok, c->G, cudaMemcpyDeviceToHost, c->stream));
-  }
   CK(cudaStreamSynchronize(c->stream));
+  if (ok_host) memcpy(ok_host, reinterpret_cast<const uint8_t*>(c->h_map) + (size_t)c->G * 4, c->G);
   return ELFB200_OK;
 }
 
@@ -687,6 +809,13 @@ int elfb200_features_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) 
   return elfb200_features_dev_ex(c, d4_dev, out_dev, FEAT_F32_NCHW, 0);
 }
 
+int elfb200_set_playout_layout(elfb200_ctx* c, int layout) {
+  if (!c || layout < 0 || layout > 1) return elfb200_fail(ELFB200_ERR_ARG, "layout must be 0 (row per lane) or 1 (two rows per lane)");
+  if (layout == 1 && c->N != 19) return elfb200_fail(ELFB200_ERR_ARG, "the two-rows-per-lane layout is 19x19 only");
+  c->playout_layout = layout;
+  return ELFB200_OK;
+}
+
 int elfb200_set_feature_store(elfb200_ctx* c, int mode) {
   if (!c || mode < 0 || mode > 1) return elfb200_fail(ELFB200_ERR_ARG, "mode must be 0 (vector stores) or 1 (bulk store)");
   c->feat_tma = mode;
@@ -716,6 +845,14 @@ static int playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id,
   if (max_plies <= 0) return elfb200_fail(ELFB200_ERR_ARG, "max_plies must be positive");
   if (stream_plies < 0) return elfb200_fail(ELFB200_ERR_ARG, "plies_per_slot must be positive");
   CK(cudaSetDevice(c->device));
+  if (c->N == 19 && c->playout_layout == 1) {
+    const int pgrid2 = ((c->G + Geo2<19>::GPW - 1) / Geo2<19>::GPW + PLAYOUT_WARPS - 1) / PLAYOUT_WARPS;
+    k_playout2<19><<<pgrid2, PLAYOUT_WARPS * 32, 0, c->stream>>>(c->G, seed, first_game_id, max_plies, stream_plies, c->d_po_sk,
+                                                               c->d_po_chk, c->d_po_plies, c->d_po_score, c->d_po_hash);
+    c->launches++;
+    CK(cudaGetLastError());
+    return ELFB200_OK;
+  }
   const int gpw = 32 / c->N;
   const int pgrid = ((c->G + gpw - 1) / gpw + PLAYOUT_WARPS - 1) / PLAYOUT_WARPS;
   DISPATCH_N(c,

@@ -1205,6 +1205,8 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   elfb200_mcts* m = new elfb200_mcts();
   m->ctx = c;
   m->opt = *opt;
+  // any failure below releases what was allocated so far (elfb200_mcts_destroy tolerates a partly built handle)
+  auto build = [&]() -> int {
   const int B = opt->num_rollouts_per_batch;
   m->waves_per_move = (opt->num_rollouts + B - 1) / B;  // for (idx = 0; idx < R; idx += B)
   int C = opt->nodes_per_game > 0 ? opt->nodes_per_game : 2 * m->waves_per_move * B + 256;
@@ -1269,6 +1271,15 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+  };
+  const int rc = build();
+  if (rc) {
+    const std::string why = elfb200_last_error();
+    elfb200_mcts_destroy(m);
+    elfb200_fail(rc, "%s", why.c_str());
+    return rc;
+  }
   *out = m;
   return ELFB200_OK;
 }

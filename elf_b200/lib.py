@@ -47,6 +47,7 @@ SIGNATURES = {
     "elfb200_features_dev": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_features_dev_ex": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int]),
     "elfb200_set_feature_store": (ctypes.c_int, [vp, ctypes.c_int]),
+    "elfb200_set_playout_layout": (ctypes.c_int, [vp, ctypes.c_int]),
     "elfb200_playout": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, vp, vp, vp, vp, vp]),
     "elfb200_playout_launch": (ctypes.c_int, [vp, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]),
     "elfb200_playout_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),

@@ -128,6 +128,10 @@ int elfb200_playout_stream(elfb200_ctx* ctx, uint64_t seed, uint64_t first_game_
                            uint64_t* last_hash_host, int64_t* total_plies);
 int elfb200_playout_stream_launch(elfb200_ctx* ctx, uint64_t seed, uint64_t first_game_id, int plies_per_slot);
 
+/* Lane layout of the playout kernel: 0 = one board row per lane (one 19x19 game per warp, the
+ * default), 1 = two rows per lane (three 19x19 games per warp; 19x19 only).  Same results either way. */
+int elfb200_set_playout_layout(elfb200_ctx* ctx, int layout);
+
 /* Number of kernels this library has launched since creation (bench gpu_launches). */
 int64_t elfb200_launch_count(const elfb200_ctx* ctx);
 

@@ -503,6 +503,9 @@ template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)std
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { *p = (T*)std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
 inline cudaError_t cudaFree(void* p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaFreeHost(void* p) { std::free(p); return cudaSuccess; }
+enum { cudaHostAllocMapped = 2 };
+template <class T> inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { *p = (T*)std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
+template <class T> inline cudaError_t cudaHostGetDevicePointer(T** d, void* h, unsigned) { *d = (T*)h; return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }

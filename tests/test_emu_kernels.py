@@ -97,11 +97,14 @@ def test_board_kernels(emu, oracle_lib, n, G, lane_order):
     assert gb.info()[0, 0] == 1 and gb.getHashCode()[0] == 0 and gb.getHashCode()[1] == os_[1].hash()
 
 
-@pytest.mark.parametrize("n,G", [(9, 7), (19, 3)])
-def test_playout_kernel(emu, oracle_lib, n, G, lane_order):
+@pytest.mark.parametrize("n,G,layout", [(9, 7, 0), (19, 3, 0), (19, 7, 1), (19, 2, 1)])
+def test_playout_kernel(emu, oracle_lib, n, G, layout, lane_order):
     """k_playout (incremental safe/atari masks, Bloom-filtered superko, policy pick, checksum):
-    to-terminal and steady-state modes, per-game checksums of every intermediate position"""
+    to-terminal and steady-state modes, per-game checksums of every intermediate position; layout 1 =
+    k_playout2, two board rows per lane, three 19x19 games per warp (G = 7: two full warps and a warp
+    with one game; G = 2: a warp with an empty third slot)"""
     gb = emu.emu_batch(G, n)
+    gb.set_playout_layout(layout)
     r = gb.playout(1234, first_game_id=50)
     want = oracles.oracle_playout_many(n, 1234, 50, G, lib=oracle_lib)
     np.testing.assert_array_equal(r["chk"], want["chk"])

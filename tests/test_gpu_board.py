@@ -85,11 +85,13 @@ def test_step_parity_every_ply(n, G, plies, against, oracle_lib):
     gb.close()
 
 
-@pytest.mark.parametrize("n,G", [(19, 256), (9, 300)])
-def test_playout_matches_oracle(n, G, oracle_lib):
+@pytest.mark.parametrize("n,G,layout", [(19, 256, 0), (9, 300, 0), (19, 257, 1)])
+def test_playout_matches_oracle(n, G, layout, oracle_lib):
     """whole device-resident playouts: per-game checksum (hash, captures, legal mask of every
-    position), ply count, final score and hash identical to the oracle's."""
+    position), ply count, final score and hash identical to the oracle's.  layout 1 = k_playout2 (two
+    board rows per lane, three games per warp; 257 games leave a partly filled last warp)."""
     gb = _gobatch(G, n)
+    gb.set_playout_layout(layout)
     res = gb.playout(seed=77, first_game_id=1000)
     exp = oracles.oracle_playout_many(n, 77, 1000, G, lib=oracle_lib)
     np.testing.assert_array_equal(res["plies"], exp["plies"])
@@ -219,11 +221,12 @@ def test_full_size_playout_properties(oracle_lib):
     gb.close()
 
 
-@pytest.mark.parametrize("n,G,budget", [(19, 512, 700), (9, 510, 400), (19, 64, 37)])
-def test_stream_playout_matches_oracle(n, G, budget, oracle_lib):
+@pytest.mark.parametrize("n,G,budget,layout", [(19, 512, 700, 0), (9, 510, 400, 0), (19, 64, 37, 0), (19, 511, 700, 1)])
+def test_stream_playout_matches_oracle(n, G, budget, layout, oracle_lib):
     """steady-state mode: every slot plays exactly `budget` plies across consecutive games; the
     per-slot fold of game checksums, the ply count and the number of games equal the oracle's."""
     gb = _gobatch(G, n)
+    gb.set_playout_layout(layout)
     res = gb.playout_stream(seed=5, first_game_id=70, plies_per_slot=budget)
     assert (res["plies"] == budget).all() and res["total_plies"] == budget * G
     for slot in np.linspace(0, G - 1, 40).astype(int):
@@ -280,8 +283,8 @@ def _ref_playouts_all_threads(n, seed, first, count):
     return chk, plies, score
 
 
-@pytest.mark.parametrize("n,G,batches", [(19, 4096, 3), (9, 16384, 1)])
-def test_ten_thousand_playouts_bit_exact_vs_compiled_reference(n, G, batches):
+@pytest.mark.parametrize("n,G,batches,layout", [(19, 4096, 3, 0), (9, 16384, 1, 0), (19, 4096, 3, 1)])
+def test_ten_thousand_playouts_bit_exact_vs_compiled_reference(n, G, batches, layout):
     """north_star parity bar: >= 10k random playouts, GAME BY GAME against the reference C++ itself
     (not the restatement): the per-game checksum folds hash, both capture counts, side to move and the
     full legal mask of EVERY position, so equality means those were bit-identical at every ply; plus
@@ -290,9 +293,10 @@ def test_ten_thousand_playouts_bit_exact_vs_compiled_reference(n, G, batches):
     if not oracles.have_ref(n):
         pytest.skip("oracle/_ref not built")
     gb = _gobatch(G, n)
+    gb.set_playout_layout(layout)  # 1: the two-rows-per-lane kernel (k_playout2)
     total = 0
     for b in range(batches):
-        first = 5_000_000 + b * G
+        first = 5_000_000 + (b + 3 * layout) * G
         res = gb.playout(seed=2024, first_game_id=first)
         chk, plies, score = _ref_playouts_all_threads(n, 2024, first, G)
         bad = np.flatnonzero((res["chk"] != chk) | (res["plies"] != plies) | (res["score"] != score))
