@@ -89,33 +89,6 @@ __device__ __forceinline__ void d4_inverse(int N, int d4, int tx, int ty, int& x
   }
 }
 
-template <int N>
-__device__ __forceinline__ void write_agz_planes(const uint64_t (*rows)[N], int hn, int next, int d4,
-                                                 float* __restrict__ out) {
-  constexpr int P = Geo<N>::P;
-  for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
-    const int tx = cell / N, ty = cell - tx * N;
-    int x, y;
-    d4_inverse(N, d4, tx, ty, x, y);
-    const bool black_first = next == S_BLACK;  // even planes = side to move (board_feature.cc:268-281)
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      float mine = 0.f, theirs = 0.f;
-      if (t < hn) {
-        const uint64_t r = rows[t][y];
-        const float bl = (float)(((uint32_t)r >> x) & 1u), wh = (float)(((uint32_t)(r >> 32) >> x) & 1u);
-        mine = black_first ? bl : wh;
-        theirs = black_first ? wh : bl;
-      }
-      out[(2 * t) * P + cell] = mine;
-      out[(2 * t + 1) * P + cell] = theirs;
-    }
-    out[16 * P + cell] = black_first ? 1.0f : 0.0f;
-    out[17 * P + cell] = black_first ? 0.0f : 1.0f;
-  }
-}
-
-
 // ---- feature output formats -----------------------------------------------------------------------
 // FEAT_F32_NCHW is the GoFeature tensor contract (float32 [n][18][N][N], game_feature.h:159-206).
 // The 16-bit NHWC formats are the fast mode for a network that runs in half precision with
@@ -147,117 +120,155 @@ __device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uin
 // Flush a staged tile: every thread has written its part of `ssrc` (generic-proxy stores).
 //   tma != 0: fence the writes towards the async proxy, barrier, thread 0 issues ONE bulk store;
 //   tma == 0: barrier, then coalesced 16-byte vector stores by all threads.
-// vec8 != 0 (unaligned tail of a float32 batch): 8-byte vectors instead of 16.
-__device__ __forceinline__ void flush_tile(void* gdst, const void* ssrc, uint32_t bytes, int tma, int vec8 = 0) {
-  if (tma && !vec8) {
+__device__ __forceinline__ void flush_tile(void* gdst, const void* ssrc, uint32_t bytes, int tma) {
+  if (tma) {
     async_proxy_fence();
     __syncthreads();
     if (threadIdx.x == 0) bulk_store_s2g(gdst, ssrc, bytes);
-  } else if (!vec8) {
+  } else {
     __syncthreads();
     const uint4* s4 = reinterpret_cast<const uint4*>(ssrc);
     uint4* g4 = reinterpret_cast<uint4*>(gdst);
     for (uint32_t i = threadIdx.x; i < bytes / 16; i += blockDim.x) g4[i] = s4[i];
-  } else {
-    __syncthreads();
-    const uint2* s2 = reinterpret_cast<const uint2*>(ssrc);
-    uint2* g2 = reinterpret_cast<uint2*>(gdst);
-    for (uint32_t i = threadIdx.x; i < bytes / 8; i += blockDim.x) g2[i] = s2[i];
   }
 }
 
-// The 18 planes of one position as 16-bit channels-last cells: cell (tx,ty) -> cpad halves at
-// sbuf + cell*cpad.  `one` is the bit pattern of 1.0 (0x3C00 half, 0x3F80 bfloat16).
-template <int N>
-__device__ __forceinline__ void write_agz_nhwc16(const uint64_t (*rows)[N], int hn, int next, int d4, uint32_t one,
-                                                 int cpad, uint16_t* __restrict__ sbuf) {
-  constexpr int P = Geo<N>::P;
-  for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
-    const int tx = cell / N, ty = cell - tx * N;
-    int x, y;
-    d4_inverse(N, d4, tx, ty, x, y);
-    const bool black_first = next == S_BLACK;
-    uint32_t bits = black_first ? (1u << 16) : (1u << 17);  // bit c = plane c of this cell
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      if (t < hn) {
-        const uint64_t r = rows[t][y];
-        const uint32_t bl = ((uint32_t)r >> x) & 1u, wh = ((uint32_t)(r >> 32) >> x) & 1u;
-        bits |= (black_first ? bl : wh) << (2 * t);
-        bits |= (black_first ? wh : bl) << (2 * t + 1);
-      }
-    }
-    uint4* dst = reinterpret_cast<uint4*>(sbuf + (size_t)cell * cpad);
-    for (int k = 0; k < cpad / 8; ++k) {
-      const uint32_t b8 = k < 4 ? (bits >> (8 * k)) & 0xFFu : 0u;
-      uint4 v;
-      v.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
-      v.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
-      v.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
-      v.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
-      dst[k] = v;
-    }
-  }
-}
-
-// Dynamic shared memory of the feature kernels (the SIMT emulator has no dynamic smem: a static
-// buffer of the largest tile stands in).
+// Dynamic shared memory of the feature kernels: the staging tile of the 16-bit NHWC formats (the
+// float32 format stores straight from registers).  The SIMT emulator has no dynamic smem: a static
+// buffer of the largest tile stands in.
 constexpr int FEAT_CPAD_MAX = 32;
-template <int N>
-struct FeatTile {
-  static constexpr int F32_PAIR_BYTES = 2 * 18 * Geo<N>::P * 4;           // two positions: a 16-byte multiple
-  static constexpr int NHWC_BYTES_MAX = Geo<N>::P * FEAT_CPAD_MAX * 2;
-  static constexpr int BYTES = F32_PAIR_BYTES > NHWC_BYTES_MAX ? F32_PAIR_BYTES : NHWC_BYTES_MAX;
-};
 #if defined(ELFB200_SIMT_EMU)
-#define ELFB200_FEAT_SMEM(N) __align__(16) __shared__ unsigned char feat_smem[FeatTile<N>::BYTES]
+#define ELFB200_FEAT_SMEM(N) __align__(16) __shared__ unsigned char feat_smem[Geo<N>::P * FEAT_CPAD_MAX * 2]
 #else
 #define ELFB200_FEAT_SMEM(N) extern __shared__ __align__(16) unsigned char feat_smem[]
 #endif
 
-// One CTA of a feature kernel: float32 NCHW -> the CTA stages TWO consecutive positions (25,992 B each
-// at 19x19: only a pair is a 16-byte multiple) and flushes them with one bulk store; 16-bit NHWC ->
-// one position per CTA.  `gather(slot, rows, hn, next, d4)` is called by ALL threads of the CTA and
-// fills rows[t][y] (t < 8 history positions, newest first) for output slot `slot`.
+// bits [lo, lo+32) of the index range [a, b) as a word
+__device__ __forceinline__ uint32_t range_bits(int lo, int a, int b) {
+  const int s = max(a, lo) - lo, e = min(b, lo + 32) - lo;
+  if (e <= s) return 0u;
+  return ((e - s) >= 32 ? 0xFFFFFFFFu : ((1u << (e - s)) - 1u)) << s;
+}
+
+// One CTA of a feature kernel = one position.  `gather(slot, rows, hn, next, d4)` is called by ALL
+// threads of the CTA and fills rows[t][y] (t < 8 history positions, newest first) for output `slot`.
+//
+// BoardFeature::extractAGZ (board_feature.cc:247-290) in three bit-level steps instead of one float
+// at a time:
+//  1. the 16 stone planes as TRANSFORMED bit rows T[plane][tx] (bit ty = output cell (tx,ty)): under
+//     the D4 code an output row is a board row or a board column, read forwards or backwards
+//     (InvTransform, board_feature.h:115-130, decomposed into {transposed, reversed index, reversed
+//     bits}; the tables are checked against d4_inverse by brute force in tests/test_feature_tables.py);
+//  2. float32 NCHW: the whole position as ONE flat bit string FW (18*N*N bits, planes 16/17 constant);
+//     16-bit NHWC: per cell the 18 bits across planes;
+//  3. float32: every thread expands 4 consecutive bits into a float4 -- fully coalesced 16-byte
+//     stores, no staging (a position is 25,992 B: an odd slot starts 8 bytes off a 16-byte boundary,
+//     so its first two floats go out as one 8-byte store and the groups shift by two bits);
+//     16-bit NHWC: the cells are staged in shared memory and leave as one bulk (TMA) store.
 template <int N, class Gather>
 __device__ __forceinline__ void features_cta(Gather gather, int n_pos, void* __restrict__ out, int fmt, int cpad,
-                                             int tma, int align8) {
-  constexpr int P = Geo<N>::P, TOTAL = 18 * P;
+                                             int tma) {
+  constexpr int P = Geo<N>::P, TOTAL = 18 * P, NW = (TOTAL + 31) / 32;
   ELFB200_FEAT_SMEM(N);
-  __shared__ uint64_t rows[2][8][N];
-  if (fmt == FEAT_F32_NCHW) {
-    const int first = blockIdx.x * 2;
-    if (first >= n_pos) return;
-    const int here = min(2, n_pos - first);
-    float* buf = reinterpret_cast<float*>(feat_smem);
-    for (int p = 0; p < here; ++p) {
-      int hn, next, d4;
-      gather(first + p, rows[p], hn, next, d4);
-      __syncthreads();
-      write_agz_planes<N>(rows[p], hn, next, d4, buf + p * TOTAL);
+  __shared__ uint64_t rows[8][N];
+  __shared__ uint32_t T[16][N];
+  __shared__ uint32_t FW[NW + 1];
+  const int slot = blockIdx.x;
+  if (slot >= n_pos) return;
+  int hn, next, d4;
+  gather(slot, rows, hn, next, d4);
+  __syncthreads();
+  const bool bf = next == S_BLACK;  // even planes = side to move (board_feature.cc:268-281)
+  const bool transposed = (0xA5u >> d4) & 1u, rev_idx = (0x6Cu >> d4) & 1u, rev_bits = (0xC6u >> d4) & 1u;
+  for (int item = threadIdx.x; item < 16 * N; item += blockDim.x) {
+    const int pl = item / N, tx = item - pl * N, t = pl >> 1;
+    uint32_t o = 0;
+    if (t < hn) {
+      const bool want_black = ((pl & 1) == 0) == bf;
+      const int src = rev_idx ? N - 1 - tx : tx;
+      if (!transposed) {
+        const uint64_t r = rows[t][src];
+        o = (want_black ? (uint32_t)r : (uint32_t)(r >> 32)) & Geo<N>::ROWMASK;
+      } else {
+        const int sh = src + (want_black ? 0 : 32);
+#pragma unroll
+        for (int y = 0; y < N; ++y) o |= (uint32_t)((rows[t][y] >> sh) & 1ull) << y;
+      }
+      if (rev_bits) o = __brev(o) >> (32 - N);
     }
-    float* dst = reinterpret_cast<float*>(out) + (size_t)first * TOTAL;
-    if (here == 2 && !align8)
-      flush_tile(dst, buf, 2 * TOTAL * 4, tma);
-    else
-      flush_tile(dst, buf, here * TOTAL * 4, 0, 1);  // odd tail / 8-byte aligned destination
-  } else {
-    const int slot = blockIdx.x;
-    if (slot >= n_pos) return;
-    int hn, next, d4;
-    gather(slot, rows[0], hn, next, d4);
+    T[pl][tx] = o;
+  }
+  __syncthreads();
+  if (fmt == FEAT_F32_NCHW) {
+    for (int j = threadIdx.x; j <= NW; j += blockDim.x) {
+      const int lo = 32 * j;
+      uint32_t w = 0;
+      if (lo < 16 * P) {  // stitch the bit rows that overlap this word
+        int pl = lo / P;
+        const int c = lo - pl * P;
+        int tx = c / N, ty = c - tx * N, pos = 0;
+        while (pos < 32 && pl < 16) {
+          w |= (T[pl][tx] >> ty) << pos;  // N - ty valid bits, zeros above
+          pos += N - ty;
+          ty = 0;
+          if (++tx == N) {
+            tx = 0;
+            ++pl;
+          }
+        }
+      }
+      w |= range_bits(lo, 16 * P, 17 * P) & (bf ? 0xFFFFFFFFu : 0u);  // plane 16: black to move
+      w |= range_bits(lo, 17 * P, 18 * P) & (bf ? 0u : 0xFFFFFFFFu);  // plane 17: white to move
+      FW[j] = w;
+    }
     __syncthreads();
+    float* dst = reinterpret_cast<float*>(out) + (size_t)slot * TOTAL;
+    const int h = (reinterpret_cast<uintptr_t>(dst) & 15) ? 2 : 0;  // dst is at least 8-byte aligned
+    constexpr int NQ = (TOTAL - 2) / 4;  // float4 groups (TOTAL = 4*NQ + 2 for both board sizes)
+    static_assert(TOTAL == 4 * NQ + 2, "a position is a whole number of float4 plus one float2");
+    for (int q = threadIdx.x; q < NQ; q += blockDim.x) {
+      const int b0 = h + 4 * q;
+      const uint32_t w = __funnelshift_r(FW[b0 >> 5], FW[(b0 >> 5) + 1], b0 & 31);
+      float4 v;
+      v.x = (w & 1u) ? 1.0f : 0.0f;
+      v.y = (w & 2u) ? 1.0f : 0.0f;
+      v.z = (w & 4u) ? 1.0f : 0.0f;
+      v.w = (w & 8u) ? 1.0f : 0.0f;
+      *reinterpret_cast<float4*>(dst + b0) = v;
+    }
+    if (threadIdx.x == 0) {  // the float2 that does not fit the float4 grid: first two floats or last two
+      const int b0 = h ? 0 : TOTAL - 2;
+      const uint32_t w = FW[b0 >> 5] >> (b0 & 31);
+      *reinterpret_cast<float2*>(dst + b0) = make_float2((w & 1u) ? 1.0f : 0.0f, (w & 2u) ? 1.0f : 0.0f);
+    }
+  } else {
     uint16_t* buf = reinterpret_cast<uint16_t*>(feat_smem);
-    write_agz_nhwc16<N>(rows[0], hn, next, d4, fmt == FEAT_F16_NHWC ? 0x3C00u : 0x3F80u, cpad, buf);
+    const uint32_t one = fmt == FEAT_F16_NHWC ? 0x3C00u : 0x3F80u;
+    for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
+      const int tx = cell / N, ty = cell - tx * N;
+      uint32_t bits = bf ? (1u << 16) : (1u << 17);  // bit c = plane c of this cell
+#pragma unroll
+      for (int pl = 0; pl < 16; ++pl) bits |= ((T[pl][tx] >> ty) & 1u) << pl;
+      uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)cell * cpad);
+      for (int k = 0; k < cpad / 8; ++k) {
+        const uint32_t b8 = k < 4 ? (bits >> (8 * k)) & 0xFFu : 0u;
+        uint4 v;
+        v.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
+        v.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
+        v.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
+        v.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
+        dst[k] = v;
+      }
+    }
     flush_tile(reinterpret_cast<uint16_t*>(out) + (size_t)slot * P * cpad, buf, (uint32_t)(P * cpad * 2), tma);
   }
 }
 
 template <int N>
 inline size_t feature_smem_bytes(int fmt, int cpad) {
-  return fmt == FEAT_F32_NCHW ? (size_t)FeatTile<N>::F32_PAIR_BYTES : (size_t)Geo<N>::P * cpad * 2;
+  return fmt == FEAT_F32_NCHW ? (size_t)0 : (size_t)Geo<N>::P * cpad * 2;
 }
-inline int feature_grid(int n_pos, int fmt) { return fmt == FEAT_F32_NCHW ? (n_pos + 1) / 2 : n_pos; }
+constexpr int FEAT_THREADS = 128;
 
 }  // namespace elfb200
 

@@ -263,10 +263,9 @@ struct RingGather {
 };
 
 template <int N>
-__global__ void __launch_bounds__(384)
-    k_features(DevState st, const int32_t* __restrict__ d4codes, void* __restrict__ out, int fmt, int cpad, int tma,
-               int align8) {
-  features_cta<N>(RingGather<N>{st, d4codes}, st.G, out, fmt, cpad, tma, align8);
+__global__ void __launch_bounds__(FEAT_THREADS)
+    k_features(DevState st, const int32_t* __restrict__ d4codes, void* __restrict__ out, int fmt, int cpad, int tma) {
+  features_cta<N>(RingGather<N>{st, d4codes}, st.G, out, fmt, cpad, tma);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -543,8 +542,6 @@ int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out)
   auto build = [&]() -> int {
   const size_t N = board_size, G = num_games, P = N * N, MAXPLY = 2 * P;
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  // the float32 feature tile (two positions, 51,984 B at 19x19) is above the 48 KB default
-  CK(cudaFuncSetAttribute(k_features<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, FeatTile<19>::BYTES));
   CK(cudaMalloc(&c->st.cur, G * N * 8));
   CK(cudaMalloc(&c->st.ring, G * 8 * N * 8));
   CK(cudaMalloc(&c->st.legal, G * N * 4));
@@ -773,13 +770,11 @@ int elfb200_evaluate(elfb200_ctx* c, float komi, float* value_host) {
   return ELFB200_OK;
 }
 
-static int check_feature_args(const void* out, int format, int cpad, int* align8) {
+static int check_feature_args(const void* out, int format, int cpad) {
   if (format < FEAT_F32_NCHW || format > FEAT_BF16_NHWC) return elfb200_fail(ELFB200_ERR_ARG, "unknown feature format %d", format);
   const uintptr_t a = (uintptr_t)out;
-  *align8 = 0;
   if (format == FEAT_F32_NCHW) {
     if (a & 7) return elfb200_fail(ELFB200_ERR_ARG, "feature buffer must be 8-byte aligned");
-    *align8 = (a & 15) ? 1 : 0;
   } else {
     if (cpad < 24 || cpad > FEAT_CPAD_MAX || (cpad & 7))
       return elfb200_fail(ELFB200_ERR_ARG, "channel padding must be 24 or 32 (got %d)", cpad);
@@ -790,16 +785,14 @@ static int check_feature_args(const void* out, int format, int cpad, int* align8
 
 int elfb200_features_dev_ex(elfb200_ctx* c, const int32_t* d4_dev, void* out_dev, int format, int cpad) {
   if (!c || !out_dev) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
-  int align8 = 0;
-  int rc = check_feature_args(out_dev, format, cpad, &align8);
+  int rc = check_feature_args(out_dev, format, cpad);
   if (rc) return rc;
   CK(cudaSetDevice(c->device));
-  const int grid = feature_grid(c->G, format);
   DISPATCH_N(c,
-             (k_features<19><<<grid, 384, feature_smem_bytes<19>(format, cpad), c->stream>>>(
-                 c->st, d4_dev, out_dev, format, cpad, c->feat_tma, align8)),
-             (k_features<9><<<grid, 96, feature_smem_bytes<9>(format, cpad), c->stream>>>(
-                 c->st, d4_dev, out_dev, format, cpad, c->feat_tma, align8)));
+             (k_features<19><<<c->G, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
+                 c->st, d4_dev, out_dev, format, cpad, c->feat_tma)),
+             (k_features<9><<<c->G, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
+                 c->st, d4_dev, out_dev, format, cpad, c->feat_tma)));
   c->launches++;
   CK(cudaGetLastError());
   return ELFB200_OK;

@@ -529,10 +529,10 @@ struct LeafGather {
 };
 
 template <int N>
-__global__ void __launch_bounds__(384)
-    k_leaf_features(DevState st, TreeDev tr, void* __restrict__ out, int fmt, int cpad, int tma, int align8) {
+__global__ void __launch_bounds__(FEAT_THREADS)
+    k_leaf_features(DevState st, TreeDev tr, void* __restrict__ out, int fmt, int cpad, int tma) {
   __shared__ int s_src[8];
-  features_cta<N>(LeafGather<N>{st, tr, s_src}, *tr.eval_count, out, fmt, cpad, tma, align8);
+  features_cta<N>(LeafGather<N>{st, tr, s_src}, *tr.eval_count, out, fmt, cpad, tma);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1238,7 +1238,6 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   CK(cudaMemsetAsync(t.errors, 0, 16, c->stream));
   CK(cudaMalloc(&t.stats, 64));
   CK(cudaMemsetAsync(t.stats, 0, 64, c->stream));
-  CK(cudaFuncSetAttribute(k_leaf_features<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, FeatTile<19>::BYTES));
   CK(cudaMemsetAsync(t.hdr, 0, GC * sizeof(NodeHdr), c->stream));
   CK(cudaMemsetAsync(t.active, 1, G, c->stream));
   CK(cudaMemsetAsync(t.eval_count, 0, 4, c->stream));
@@ -1350,7 +1349,6 @@ int elfb200_mcts_begin_move(elfb200_mcts* m, const uint8_t* active_host) {
 int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad, int32_t* n_leaves) {
   if (!m || !feat_dev) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   elfb200_ctx* c = m->ctx;
-  int align8 = 0;
   if (format < FEAT_F32_NCHW || format > FEAT_BF16_NHWC) return elfb200_fail(ELFB200_ERR_ARG, "unknown feature format %d", format);
   if (format != FEAT_F32_NCHW && (cpad < 24 || cpad > FEAT_CPAD_MAX || (cpad & 7)))
     return elfb200_fail(ELFB200_ERR_ARG, "channel padding must be 24 or 32 (got %d)", cpad);
@@ -1386,13 +1384,12 @@ int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad
   m->last_eval_count = n;
   if (n != 0) {
     const int npos = n > 0 ? n : c->G * m->tr.B;
-    const int grid = feature_grid(npos, format);
     CK(cudaEventRecord(m->ev[2], c->stream));
     DISPATCH_N(c,
-               (k_leaf_features<19><<<grid, 384, feature_smem_bytes<19>(format, cpad), c->stream>>>(
-                   c->st, m->tr, feat_dev, format, cpad, c->feat_tma, align8)),
-               (k_leaf_features<9><<<grid, 96, feature_smem_bytes<9>(format, cpad), c->stream>>>(
-                   c->st, m->tr, feat_dev, format, cpad, c->feat_tma, align8)));
+               (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
+                   c->st, m->tr, feat_dev, format, cpad, c->feat_tma)),
+               (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
+                   c->st, m->tr, feat_dev, format, cpad, c->feat_tma)));
     c->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m->ev[3], c->stream));
