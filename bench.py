@@ -772,6 +772,8 @@ def run_selfplay(args):
             note("cpu_baseline: reference search on the host cores")
             cb = ref_selfplay(actor, dev, steps=args.cpu_steps, warmup=1)
             line["cpu_baseline"] = cb
+        if world == 1 and not args.no_cpu_baseline and args.fake_net:
+            line["cpu_baseline"] = ref_selfplay_fake_net(min(args.cpu_seconds, 15.0))
         emit(line)
     if dist is not None:
         dist.barrier()
@@ -947,6 +949,36 @@ def ref_selfplay(actor, dev, steps, warmup, slice_rollouts=80):
             "sample": (f"reference TreeSearchT (oracle/_ref), {steps} steps x {results[best]['game_threads']} game threads x "
                        f"{slice_rollouts} rollouts (= {slice_rollouts / ROLLOUTS:.2f} move each) on {cores} host cores, "
                        f"driving the same GPU network; better of {list(results)}")}
+
+
+def ref_selfplay_fake_net(seconds):
+    """the reference TreeSearchT with the shim's deterministic fake net (no network
+    cost at all) on every host core, one game per thread: the engine-only rate of the CPU search"""
+    from tests import oracles
+
+    if not oracles.have_ref(BOARD):
+        return {"unavailable": "oracle/_ref not built"}
+    cores = effective_cores()
+    done = [0] * cores
+    t0 = time.perf_counter()
+    deadline = t0 + seconds
+
+    def work(tid):
+        st = oracles.Ref(BOARD)
+        m = oracles.RefMcts(BOARD, num_rollouts=ROLLOUTS, num_rollouts_per_batch=PER_BATCH, virtual_loss=1,
+                            persistent_tree=1, c_puct=1.5, seed=tid)
+        while time.perf_counter() < deadline and not st.terminated():
+            r = m.act(st)
+            st.forward(r["best_action"])
+            done[tid] += 1
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    return {"value": sum(done) / dt, "unit": "moves/s", "cores": cores, "kind": "reference",
+            "sample": f"reference TreeSearchT, {ROLLOUTS} rollouts/move, 1 search thread per game, fake net (no NN cost): "
+                      f"{sum(done)} moves in {dt:.1f} s on {cores} threads"}
 
 
 def run_reference_selfplay(args):
