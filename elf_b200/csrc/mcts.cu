@@ -484,45 +484,35 @@ template <int N>
 struct LeafGather {
   DevState st;
   TreeDev tr;
-  int* s_src;  // shared, 8 ints: >=0 node local id, <0: -(ring slot)-1, INT_MIN: none
   __device__ __forceinline__ void operator()(int slot, uint64_t (*rows)[N], int& hn, int& next, int& d4) const {
     const int g = tr.eval_game[slot];
     const int leaf = tr.eval_node[slot];
     const size_t nb = (size_t)g * tr.C;
+    // three independent loads (one round trip): the leaf's meta, its ancestor ids, the root's ply
     const BoardMeta meta = load_meta(&tr.meta[nb + leaf]);
+    const uint4 a4 = tr.anc[nb + leaf];
+    const int pr = st.meta[g].ply;            // ply of the root == ply of the game
     hn = min(8, (int)meta.ply - 1);
     next = meta.next;
     d4 = tr.eval_d4[slot];
-    __syncthreads();  // s_src may still be read for the CTA's previous position
-    if (threadIdx.x < 8) {
-      // history slot t: the leaf (t = 0), its t-th ancestor while still inside the current tree,
-      // then the game's own ring (the root is ring slot (ply_root-2)&7, go_state.cc:90-92)
-      const int t = threadIdx.x;
-      const int pr = st.meta[g].ply;            // ply of the root == ply of the game
-      const int depth = (int)meta.ply - pr;     // leaf depth below the root
-      int src = INT_MIN;
-      if (t < hn) {
-        if (t == 0) {
-          src = leaf;
-        } else if (t <= depth) {
-          const uint4 a4 = tr.anc[nb + leaf];
-          const uint32_t w = (t - 1) < 2 ? a4.x : (t - 1) < 4 ? a4.y : (t - 1) < 6 ? a4.z : a4.w;
-          src = (int)((w >> (((t - 1) & 1) * 16)) & 0xFFFFu);
-        } else {
-          src = -(((pr - 2 - (t - depth)) & 7)) - 1;
-        }
-      }
-      s_src[t] = src;
-    }
-    __syncthreads();
+    const int depth = (int)meta.ply - pr;     // leaf depth below the root
+    // history slot t: the leaf (t = 0), its t-th ancestor while still inside the current tree, then
+    // the game's own ring (the root is ring slot (ply_root-2)&7, go_state.cc:90-92)
     for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
       const int t = i / N, y = i - t * N;
-      const int src = s_src[t];
       uint64_t v = 0;
-      if (src >= 0)
-        v = tr.pos[(nb + src) * N + y];
-      else if (src != INT_MIN)
-        v = st.ring[((size_t)g * 8 + (-src - 1)) * N + y];
+      if (t < hn) {
+        if (t <= depth) {
+          int src = leaf;
+          if (t > 0) {
+            const uint32_t w = (t - 1) < 2 ? a4.x : (t - 1) < 4 ? a4.y : (t - 1) < 6 ? a4.z : a4.w;
+            src = (int)((w >> (((t - 1) & 1) * 16)) & 0xFFFFu);
+          }
+          v = tr.pos[(nb + src) * N + y];
+        } else {
+          v = st.ring[((size_t)g * 8 + ((pr - 2 - (t - depth)) & 7)) * N + y];
+        }
+      }
       rows[t][y] = v;
     }
   }
@@ -531,8 +521,7 @@ struct LeafGather {
 template <int N>
 __global__ void __launch_bounds__(FEAT_THREADS)
     k_leaf_features(DevState st, TreeDev tr, void* __restrict__ out, int fmt, int cpad, int tma) {
-  __shared__ int s_src[8];
-  features_cta<N>(LeafGather<N>{st, tr, s_src}, *tr.eval_count, out, fmt, cpad, tma);
+  features_cta<N>(LeafGather<N>{st, tr}, *tr.eval_count, out, fmt, cpad, tma);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -123,4 +123,15 @@ int ref_offline_sample(const char* record_json, int move_to, int d4, int num_fut
   return 0;
 }
 
+// The resignation rule as the reference evaluates it: GoStateExt::shouldResign (go_state_ext.h:207-214)
+// on the reference's own ResignCheck (game_utils.h:15-54), then the ply test of GoGameSelfPlay::act
+// (game_selfplay.cc:387-391).  `never_resign` fixes ResignCheck's single random draw (ratio 1 -> the game
+// never resigns, ratio 0 -> it may).  `value` is the black-perspective predicted value.
+int ref_should_resign(float resign_thres, int never_resign, float value, int next_player, int ply) {
+  ResignCheck rc(resign_thres, never_resign ? 1.0f : 0.0f);
+  std::mt19937 rng(0);
+  const bool r = next_player == S_BLACK ? rc.check(value, &rng) : rc.check(-value, &rng);
+  return (r && ply >= 50) ? 1 : 0;
+}
+
 } // extern "C"

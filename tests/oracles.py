@@ -202,6 +202,15 @@ def ref_quantise_policy(actions, visits, n):
     return out
 
 
+def ref_should_resign(resign_thres, never_resign, value, next_player, ply, n=9):
+    """the reference's ResignCheck::check through GoStateExt::shouldResign's colour handling and the
+    ply >= 50 test of GoGameSelfPlay::act (oracle/ref_offline_shim.cc)"""
+    L = load_ref(n)
+    L.ref_should_resign.restype = ctypes.c_int
+    L.ref_should_resign.argtypes = [ctypes.c_float, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int]
+    return bool(L.ref_should_resign(float(resign_thres), int(never_resign), float(value), int(next_player), int(ply)))
+
+
 def ref_offline_sample(record_json, move_to, d4, num_future, n):
     """one training sample from the reference's GoStateExtOffline + GoFeature extractors"""
     L = load_ref(n)

@@ -650,6 +650,37 @@ def test_device_move_choice_sampling_argmax_and_resign():
     assert a[0] == -1 and a[2] == -1 and a[1] >= 0 and a[3] >= 0
     a, _ = mc2.choose(policy_distri_cutoff=0, resign_thres=0.0, seed=1)
     assert (a >= 0).all()                        # value can never be below -1
+    # the same decisions from the reference's own ResignCheck (game_utils.h:15-54) through
+    # GoStateExt::shouldResign and the ply test of GoGameSelfPlay::act: 64 games around ply 50 with both
+    # colours to move, a spread of predicted values, several thresholds, mixed never-resign flags
+    if oracles.have_ref(n):
+        G3 = 64
+        gb3 = elf_b200.GoBatch(G3, board_size=n)
+        os3 = [oracles.Oracle(n) for _ in range(G3)]
+        for t in range(51):
+            acts = np.full(G3, -1, np.int32)
+            for g, s_ in enumerate(os3):
+                if t >= 47 + g % 4:   # games stop at plies 48..51: both sides of the ply-50 test, both colours
+                    continue
+                idx = np.flatnonzero(s_.legal() & (1 - s_.true_eyes(int(s_.info()[1]))))
+                acts[g] = int(rng.choice(idx)) if len(idx) else n * n
+                s_.forward(acts[g])
+            gb3.forward(acts)
+        info = gb3.info()
+        assert set(info[:, 1]) == {1, 2} and info[:, 0].min() < 50 <= info[:, 0].max()
+        mc3 = elf_b200.MctsBatch(gb3, rotation_flip=0, num_rollouts=32, num_rollouts_per_batch=4)
+        mc3.act(fake_actor(mc3, n))
+        never = (np.arange(G3) % 3 == 0).astype(np.uint8)
+        decided = 0
+        for thres in (0.05, 0.4, 0.9, 1.3, 2.0):
+            a, val = mc3.choose(policy_distri_cutoff=0, resign_thres=thres, never_resign=never, seed=1)
+            for g in range(G3):
+                want = oracles.ref_should_resign(thres, never[g], val[g], info[g, 1], info[g, 0], n)
+                assert (a[g] == -1) == want, (thres, g, val[g], info[g, :2], never[g])
+                decided += want
+        assert decided > 20
+        mc3.close()
+        gb3.close()
 
 
 def test_selfplay_soak_tree_reuse_over_many_moves():
