@@ -595,6 +595,28 @@ def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512, layout=0):
         gb.synchronize()
         ms += a.elapsed_time(b)
         tot += gb.playout_results()["total_plies"]
+    # the host-driven flavour of the board step: one elfb200_step() per ply with HOST action / accept buffers
+    # (GoState::forward for the whole batch per call; zero-copy mapped window, one launch + one wait)
+    host = None
+    try:
+        import numpy as np
+
+        gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"playouts_{BOARD}.json")))
+        mv = next(e["moves"] for e in gold["games"] if "moves" in e)
+        acts = np.empty(G, np.int32)
+        gb.reset()
+        gb.forward(np.full(G, mv[0], np.int32))
+        gb.reset()
+        t0 = time.perf_counter()
+        for a_ in mv:
+            acts.fill(a_)
+            ok = gb.forward(acts)
+        dt = time.perf_counter() - t0
+        host = {"value": G * len(mv) / dt, "unit": "moves/s", "us_per_call": 1e6 * dt / len(mv), "all_accepted": bool(ok.all()),
+                "bytes_per_call_over_pcie": 5 * G,
+                "note": "elfb200_step(): every game replays one reference move list, one call per ply, host buffers"}
+    except Exception as e:
+        host = {"unmeasured": str(e)}
     gb.close()
     peak, peak_src = measured_peaks()
     kname = f"k_playout{2 if layout else ''}<{BOARD}>"
@@ -607,7 +629,8 @@ def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512, layout=0):
                         "frac": algo * rate / 1e9 / peak, "traffic": prof.get("dram_bytes_per_launch"),
                         "peak_source": peak_src, "kernel": kname, "algorithmic_bytes_per_ply": algo,
                         "note": "SURVEY 8d byte formula; the position lives in registers, DRAM is idle -- the honest roof is issue_roof"},
-           "lane_layout": "two board rows per lane, three games per warp" if layout else "one board row per lane, one game per warp"}
+           "lane_layout": "two board rows per lane, three games per warp" if layout else "one board row per lane, one game per warp",
+           "host_driven": host}
     wi = prof.get("warp_inst_per_ply")
     if wi:
         try:
@@ -723,6 +746,10 @@ def run_selfplay(args):
 
     note("kernel timings done; board-step probe")
     board = board_step_probe(local, layout=args.playout_layout) if rank == 0 and not args.no_board_step else None
+    if board is not None and BOARD == 19:
+        # the same kernel family where it is issue-bound rather than latency-bound: 16384 games, two rows per lane
+        big = board_step_probe(local, steps=4, warmup=3, G=16384, layout=1)
+        board["at_16384_games_two_rows_per_lane"] = {k: big[k] for k in ("value", "unit", "ms_per_step", "lane_layout")}
 
     # ---- reduce over ranks (MAX of times, SUM of counters) ----------------------------------------------
     if dist is not None:
