@@ -173,30 +173,49 @@ __device__ __forceinline__ void features_cta(Gather gather, int n_pos, void* __r
   __shared__ uint64_t rows[8][N];
   __shared__ uint32_t T[16][N];
   __shared__ uint32_t FW[NW + 1];
+  __shared__ float4 LUT[16];  // 4 bits -> 4 floats
   const int slot = blockIdx.x;
   if (slot >= n_pos) return;
+  if (threadIdx.x < 16)
+    LUT[threadIdx.x] = make_float4((threadIdx.x & 1) ? 1.f : 0.f, (threadIdx.x & 2) ? 1.f : 0.f,
+                                   (threadIdx.x & 4) ? 1.f : 0.f, (threadIdx.x & 8) ? 1.f : 0.f);
   int hn, next, d4;
   gather(slot, rows, hn, next, d4);
   __syncthreads();
   const bool bf = next == S_BLACK;  // even planes = side to move (board_feature.cc:268-281)
   const bool transposed = (0xA5u >> d4) & 1u, rev_idx = (0x6Cu >> d4) & 1u, rev_bits = (0xC6u >> d4) & 1u;
-  for (int item = threadIdx.x; item < 16 * N; item += blockDim.x) {
-    const int pl = item / N, tx = item - pl * N, t = pl >> 1;
-    uint32_t o = 0;
-    if (t < hn) {
-      const bool want_black = ((pl & 1) == 0) == bf;
-      const int src = rev_idx ? N - 1 - tx : tx;
-      if (!transposed) {
-        const uint64_t r = rows[t][src];
+  if (!transposed) {
+    // output row tx is board row src, read forwards or backwards: one word per (plane, row)
+    for (int item = threadIdx.x; item < 16 * N; item += blockDim.x) {
+      const int pl = item / N, tx = item - pl * N, t = pl >> 1;
+      uint32_t o = 0;
+      if (t < hn) {
+        const bool want_black = ((pl & 1) == 0) == bf;
+        const uint64_t r = rows[t][rev_idx ? N - 1 - tx : tx];
         o = (want_black ? (uint32_t)r : (uint32_t)(r >> 32)) & Geo<N>::ROWMASK;
-      } else {
-        const int sh = src + (want_black ? 0 : 32);
-#pragma unroll
-        for (int y = 0; y < N; ++y) o |= (uint32_t)((rows[t][y] >> sh) & 1ull) << y;
+        if (rev_bits) o = __brev(o) >> (32 - N);
       }
-      if (rev_bits) o = __brev(o) >> (32 - N);
+      T[pl][tx] = o;
     }
-    T[pl][tx] = o;
+  } else {
+    // output row tx is a board COLUMN: every (plane, board row y) scatters its (few) stones, stone
+    // (x, y) becomes bit ty of T[plane][tx] with tx = x or N-1-x and ty = y or N-1-y
+    for (int item = threadIdx.x; item < 16 * N; item += blockDim.x) (&T[0][0])[item] = 0u;
+    __syncthreads();
+    for (int item = threadIdx.x; item < 16 * N; item += blockDim.x) {
+      const int pl = item / N, y = item - pl * N, t = pl >> 1;
+      if (t < hn) {
+        const bool want_black = ((pl & 1) == 0) == bf;
+        const uint64_t r = rows[t][y];
+        uint32_t word = (want_black ? (uint32_t)r : (uint32_t)(r >> 32)) & Geo<N>::ROWMASK;
+        const uint32_t bit = 1u << (rev_bits ? N - 1 - y : y);
+        while (word) {
+          const int x = __ffs(word) - 1;
+          word &= word - 1;
+          atomicOr(&T[pl][rev_idx ? N - 1 - x : x], bit);
+        }
+      }
+    }
   }
   __syncthreads();
   if (fmt == FEAT_F32_NCHW) {
@@ -229,12 +248,7 @@ __device__ __forceinline__ void features_cta(Gather gather, int n_pos, void* __r
     for (int q = threadIdx.x; q < NQ; q += blockDim.x) {
       const int b0 = h + 4 * q;
       const uint32_t w = __funnelshift_r(FW[b0 >> 5], FW[(b0 >> 5) + 1], b0 & 31);
-      float4 v;
-      v.x = (w & 1u) ? 1.0f : 0.0f;
-      v.y = (w & 2u) ? 1.0f : 0.0f;
-      v.z = (w & 4u) ? 1.0f : 0.0f;
-      v.w = (w & 8u) ? 1.0f : 0.0f;
-      *reinterpret_cast<float4*>(dst + b0) = v;
+      *reinterpret_cast<float4*>(dst + b0) = LUT[w & 15u];
     }
     if (threadIdx.x == 0) {  // the float2 that does not fit the float4 grid: first two floats or last two
       const int b0 = h ? 0 : TOTAL - 2;
