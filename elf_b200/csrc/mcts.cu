@@ -1388,6 +1388,27 @@ int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad
   return ELFB200_OK;
 }
 
+int elfb200_mcts_leaf_features(elfb200_mcts* m, void* feat_dev, int format, int cpad) {
+  if (!m || !feat_dev) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  if (format < FEAT_F32_NCHW || format > FEAT_BF16_NHWC) return elfb200_fail(ELFB200_ERR_ARG, "unknown feature format %d", format);
+  if (format != FEAT_F32_NCHW && (cpad < 24 || cpad > FEAT_CPAD_MAX || (cpad & 7)))
+    return elfb200_fail(ELFB200_ERR_ARG, "channel padding must be 24 or 32 (got %d)", cpad);
+  if ((uintptr_t)feat_dev & 15) return elfb200_fail(ELFB200_ERR_ARG, "leaf feature buffer must be 16-byte aligned");
+  CK(cudaSetDevice(c->device));
+  const int n = m->last_eval_count;
+  if (n == 0) return ELFB200_OK;
+  const int npos = n > 0 ? n : c->G * m->tr.B;
+  DISPATCH_N(c,
+             (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
+                 c->st, m->tr, feat_dev, format, cpad, c->feat_tma)),
+             (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
+                 c->st, m->tr, feat_dev, format, cpad, c->feat_tma)));
+  c->launches++;
+  CK(cudaGetLastError());
+  return ELFB200_OK;
+}
+
 int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves) {
   if (!n_leaves) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
   return elfb200_mcts_select_ex(m, feat_dev, FEAT_F32_NCHW, 0, n_leaves);

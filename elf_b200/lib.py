@@ -66,6 +66,7 @@ SIGNATURES = {
     "elfb200_mcts_select": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_mcts_select_ex": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp]),
     "elfb200_mcts_leaf_count": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_leaf_features": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int]),
     "elfb200_mcts_leaf_info": (ctypes.c_int, [vp, vp, vp, vp, vp]),
     "elfb200_mcts_expand_backup": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_mcts_results": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),

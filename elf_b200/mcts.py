@@ -113,6 +113,13 @@ class MctsBatch:
         self._n = n.value if wait else -1
         return self.feat[: n.value] if wait else self.feat
 
+    def leaf_features_again(self, out=None, fmt=None, cpad=None):
+        """write the planes of the pending leaves once more (default: into the batch tensor, same
+        format); asynchronous on the context stream"""
+        t = self.feat if out is None else out
+        _l.check(self._lib, self._lib.elfb200_mcts_leaf_features(self._m, t.data_ptr(), self._fmt if fmt is None else fmt,
+                                                                 self.cpad if cpad is None else cpad))
+
     def leaf_count(self):
         n = ctypes.c_int32()
         _l.check(self._lib, self._lib.elfb200_mcts_leaf_count(self._m, ctypes.byref(n)))

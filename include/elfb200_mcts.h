@@ -86,6 +86,10 @@ int elfb200_mcts_select(elfb200_mcts* m, float* feat_dev, int32_t* n_leaves);
  * device-side count, so the caller evaluates all elfb200_mcts_max_leaves rows (rows past the count
  * are stale and ignored) or asks for the count later with elfb200_mcts_leaf_count. */
 int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad, int32_t* n_leaves);
+/* The planes of the leaves claimed by the last select once more, into feat_dev in the given format
+ * (idempotent: e.g. the float32 contract tensor next to a 16-bit batch, or for timing).
+ * Asynchronous on the context stream. */
+int elfb200_mcts_leaf_features(elfb200_mcts* m, void* feat_dev, int format, int cpad);
 /* Number of leaves the last select claimed (waits for the context stream). */
 int elfb200_mcts_leaf_count(elfb200_mcts* m, int32_t* n_leaves);
 /* Hash / game index / ply / D4 code of the pending leaves (host, each may be NULL); test & debug aid. */
