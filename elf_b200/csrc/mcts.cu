@@ -69,6 +69,8 @@ struct TreeDev {
   int32_t* eval_game;   // [G*B]
   uint16_t* eval_node;  // [G*B]
   uint8_t* eval_d4;     // [G*B]
+  uint64_t* hist;       // [G*B][8][N] history rows of every claimed leaf, newest first (k_leaf_gather)
+  uint32_t* hinfo;      // [G*B] hn | side to move << 8 | d4 << 16
   uint16_t* bfs_q;      // [G][C]
   int32_t* errors;      // [4]: root-hash mismatches, pool overflows, ...
   unsigned long long* stats;  // [4]: descent steps, edge records read, nodes created, stored edges of visited nodes
@@ -480,48 +482,71 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
 // ancestors up to the root, then the game's own ring (go_state.cc:90-92).  Staging, output formats
 // and the bulk store are features_cta's (common.cuh); the grid may be larger than the number of
 // claimed leaves (device-side count), so a wave needs no host round trip before this launch.
+// Two kernels.  k_leaf_gather (one WARP per leaf) chases the pointers -- leaf meta + ancestor ids + root
+// ply, then up to 8 x 152 B of position rows scattered over a multi-GB node pool (TLB-miss latency, not
+// bandwidth) -- and lays the history out contiguously: hist[slot][t][y], 1,216 B per leaf.  With a warp
+// per leaf 64 leaves per SM are in flight, which hides that latency far better than the feature CTAs
+// could (16 per SM, each stalled through three dependent round trips).  k_leaf_features then streams:
+// contiguous reads, coalesced 16-byte stores, exactly the board batch's k_features.
 template <int N>
-struct LeafGather {
-  DevState st;
-  TreeDev tr;
-  __device__ __forceinline__ void operator()(int slot, uint64_t (*rows)[N], int& hn, int& next, int& d4) const {
-    const int g = tr.eval_game[slot];
-    const int leaf = tr.eval_node[slot];
-    const size_t nb = (size_t)g * tr.C;
-    // three independent loads (one round trip): the leaf's meta, its ancestor ids, the root's ply
-    const BoardMeta meta = load_meta(&tr.meta[nb + leaf]);
-    const uint4 a4 = tr.anc[nb + leaf];
-    const int pr = st.meta[g].ply;            // ply of the root == ply of the game
-    hn = min(8, (int)meta.ply - 1);
-    next = meta.next;
-    d4 = tr.eval_d4[slot];
-    const int depth = (int)meta.ply - pr;     // leaf depth below the root
-    // history slot t: the leaf (t = 0), its t-th ancestor while still inside the current tree, then
-    // the game's own ring (the root is ring slot (ply_root-2)&7, go_state.cc:90-92)
-    for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) {
-      const int t = i / N, y = i - t * N;
-      uint64_t v = 0;
-      if (t < hn) {
-        if (t <= depth) {
-          int src = leaf;
-          if (t > 0) {
-            const uint32_t w = (t - 1) < 2 ? a4.x : (t - 1) < 4 ? a4.y : (t - 1) < 6 ? a4.z : a4.w;
-            src = (int)((w >> (((t - 1) & 1) * 16)) & 0xFFFFu);
-          }
-          v = tr.pos[(nb + src) * N + y];
-        } else {
-          v = st.ring[((size_t)g * 8 + ((pr - 2 - (t - depth)) & 7)) * N + y];
+__global__ void __launch_bounds__(BLOCK) k_leaf_gather(DevState st, TreeDev tr) {
+  const int lane = threadIdx.x & 31;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= *tr.eval_count) return;
+  const int g = tr.eval_game[slot];
+  const int leaf = tr.eval_node[slot];
+  const size_t nb = (size_t)g * tr.C;
+  // three independent loads (one round trip): the leaf's meta, its ancestor ids, the root's ply
+  const BoardMeta meta = load_meta(&tr.meta[nb + leaf]);
+  const uint4 a4 = tr.anc[nb + leaf];
+  const int pr = st.meta[g].ply;            // ply of the root == ply of the game
+  const int hn = min(8, (int)meta.ply - 1);
+  const int depth = (int)meta.ply - pr;     // leaf depth below the root
+  uint64_t* out = tr.hist + (size_t)slot * 8 * N;
+  // history slot t: the leaf (t = 0), its t-th ancestor while still inside the current tree, then
+  // the game's own ring (the root is ring slot (ply_root-2)&7, go_state.cc:90-92)
+  uint64_t v[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {  // 8 independent loads in flight per lane
+    v[t] = 0;
+    if (t < hn && lane < N) {
+      if (t <= depth) {
+        int src = leaf;
+        if (t > 0) {
+          const uint32_t w = (t - 1) < 2 ? a4.x : (t - 1) < 4 ? a4.y : (t - 1) < 6 ? a4.z : a4.w;
+          src = (int)((w >> (((t - 1) & 1) * 16)) & 0xFFFFu);
         }
+        v[t] = tr.pos[(nb + src) * N + lane];
+      } else {
+        v[t] = st.ring[((size_t)g * 8 + ((pr - 2 - (t - depth)) & 7)) * N + lane];
       }
-      rows[t][y] = v;
     }
+  }
+  if (lane < N) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) out[t * N + lane] = v[t];
+  }
+  if (lane == 0) tr.hinfo[slot] = (uint32_t)hn | ((uint32_t)meta.next << 8) | ((uint32_t)tr.eval_d4[slot] << 16);
+}
+
+template <int N>
+struct StagedGather {
+  const uint64_t* hist;
+  const uint32_t* hinfo;
+  __device__ __forceinline__ void operator()(int slot, uint64_t (*rows)[N], int& hn, int& next, int& d4) const {
+    const uint32_t hi = hinfo[slot];
+    hn = (int)(hi & 0xFFu);
+    next = (int)((hi >> 8) & 0xFFu);
+    d4 = (int)((hi >> 16) & 0xFFu);
+    const uint64_t* src = hist + (size_t)slot * 8 * N;
+    for (int i = threadIdx.x; i < 8 * N; i += blockDim.x) (&rows[0][0])[i] = src[i];
   }
 };
 
 template <int N>
 __global__ void __launch_bounds__(FEAT_THREADS)
-    k_leaf_features(DevState st, TreeDev tr, void* __restrict__ out, int fmt, int cpad, int tma) {
-  features_cta<N>(LeafGather<N>{st, tr}, *tr.eval_count, out, fmt, cpad, tma);
+    k_leaf_features(TreeDev tr, void* __restrict__ out, int fmt, int cpad, int tma) {
+  features_cta<N>(StagedGather<N>{tr.hist, tr.hinfo}, *tr.eval_count, out, fmt, cpad, tma);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1222,6 +1247,8 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   CK(cudaMalloc(&t.eval_game, G * B * 4));
   CK(cudaMalloc(&t.eval_node, G * B * 2));
   CK(cudaMalloc(&t.eval_d4, G * B));
+  CK(cudaMalloc(&t.hist, G * B * 8 * N * 8));
+  CK(cudaMalloc(&t.hinfo, G * B * 4));
   CK(cudaMalloc(&t.bfs_q, GC * 2));
   CK(cudaMalloc(&t.errors, 16));
   CK(cudaMemsetAsync(t.errors, 0, 16, c->stream));
@@ -1279,7 +1306,7 @@ void elfb200_mcts_destroy(elfb200_mcts* m) {
   TreeDev& t = m->tr;
   void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.anc, t.free_list,
                   t.free_n,    t.root,      t.leaves,    t.active,     t.eval_count,  t.eval_game,  t.eval_node,
-                  t.eval_d4,   t.bfs_q,     t.errors,    t.stats,     m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
+                  t.eval_d4,   t.hist,      t.hinfo,     t.bfs_q,     t.errors,    t.stats,     m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
                   m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4, m->d_priors};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -1374,12 +1401,14 @@ int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad
   if (n != 0) {
     const int npos = n > 0 ? n : c->G * m->tr.B;
     CK(cudaEventRecord(m->ev[2], c->stream));
+    DISPATCH_N(c, (k_leaf_gather<19><<<warp_grid(npos), BLOCK, 0, c->stream>>>(c->st, m->tr)),
+               (k_leaf_gather<9><<<warp_grid(npos), BLOCK, 0, c->stream>>>(c->st, m->tr)));
     DISPATCH_N(c,
                (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
-                   c->st, m->tr, feat_dev, format, cpad, c->feat_tma)),
+                   m->tr, feat_dev, format, cpad, c->feat_tma)),
                (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
-                   c->st, m->tr, feat_dev, format, cpad, c->feat_tma)));
-    c->launches++;
+                   m->tr, feat_dev, format, cpad, c->feat_tma)));
+    c->launches += 2;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m->ev[3], c->stream));
     m->pending_feat = true;
@@ -1399,12 +1428,14 @@ int elfb200_mcts_leaf_features(elfb200_mcts* m, void* feat_dev, int format, int 
   const int n = m->last_eval_count;
   if (n == 0) return ELFB200_OK;
   const int npos = n > 0 ? n : c->G * m->tr.B;
+  DISPATCH_N(c, (k_leaf_gather<19><<<warp_grid(npos), BLOCK, 0, c->stream>>>(c->st, m->tr)),
+             (k_leaf_gather<9><<<warp_grid(npos), BLOCK, 0, c->stream>>>(c->st, m->tr)));
   DISPATCH_N(c,
              (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
-                 c->st, m->tr, feat_dev, format, cpad, c->feat_tma)),
+                 m->tr, feat_dev, format, cpad, c->feat_tma)),
              (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
-                 c->st, m->tr, feat_dev, format, cpad, c->feat_tma)));
-  c->launches++;
+                 m->tr, feat_dev, format, cpad, c->feat_tma)));
+  c->launches += 2;
   CK(cudaGetLastError());
   return ELFB200_OK;
 }
