@@ -742,6 +742,7 @@ def run_selfplay(args):
                 for sp in eng.sp:
                     mc = sp.mcts
                     mc._pad = int(getattr(eng.actor, "batchsize", 0) or 0)
+                    torch.cuda.synchronize()  # nothing else on the GPU: the other part's network batch has drained
                     s_ = mc.wave_select()
                     if s_ is not None:
                         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -754,6 +755,7 @@ def run_selfplay(args):
                         feat_pos += 10 * mc._n
                         feat_launches += 10
                     mc.wave_finish(mc.wave_eval(eng.actor, s_))
+                    torch.cuda.synchronize()
                 eng.wave_in_move += 1
                 if eng.wave_in_move == eng.wpm:
                     eng.pipe.drain()
