@@ -847,13 +847,13 @@ def kernel_rooflines(kern, prof, peak, peak_src, parts):
     feat_gbs = k32["feat_pos"] * feat_bytes / (k32["feat_ms"] / 1e3) / 1e9 if k32["feat_ms"] > 0 else 0.0
     traffic = prof.get("k_leaf_features<19>", {}).get("dram_bytes_per_launch")
     out["roofline"] = {"bound": "hbm", "achieved": feat_gbs, "peak": peak, "unit": "GB/s", "frac": feat_gbs / peak,
-                       "traffic": traffic, "peak_source": peak_src, "kernel": "k_leaf_gather<19> + k_leaf_features<19> (float32 NCHW, the GoFeature contract)",
+                       "traffic": traffic, "peak_source": peak_src, "kernel": "k_leaf_features<19> (float32 NCHW, the GoFeature contract)",
                        "algorithmic_bytes_per_position": feat_bytes,
                        "positions_per_launch": k32["feat_pos"] / max(k32["feat_launches"], 1),
                        "ms_per_launch": k32["feat_ms"] / max(k32["feat_launches"], 1),
-                       "note": "CUDA events around 10 back-to-back launch PAIRS (history gather, one warp per leaf, then the "
-                               "streaming plane writer) on the pending leaves of a wave (idempotent), 3 waves x parts; a launch "
-                               "covers one part's leaves; the gather's 2 x 1,216 B/position of staging traffic is not counted"}
+                       "note": "CUDA events around 10 back-to-back launches on the pending leaves of a wave (idempotent), GPU "
+                               "otherwise idle, 3 waves x parts; a launch covers one part's leaves (their 8-position histories "
+                               "were laid out contiguously by k_select when it claimed them)"}
     sel_formula = int(st[0]) * (32 + 4) + int(st[3]) * 16  # header + E_n*16 + vl write (full scan)
     sel_prefix = int(st[0]) * (32 + 4) + int(st[1]) * 16   # what the prefix scan touches
     sel_ms = ms[0]

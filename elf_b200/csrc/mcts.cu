@@ -17,7 +17,7 @@
 //                               packed word: virtual-loss applications (low 16) | child id (high 16)}
 //   elink  uint32 [G*C][E]      per edge action (low 16) | child id (high 16, 0xFFFF = none); only read
 //                               when a child is created and by results/advance (off the hot loop)
-//   anc    8 x uint16 [G*C]     the node's 8 nearest ancestors (valid up to the current root)
+//   hist   uint64 [G*B][8][N]   the 8-position history of every leaf claimed in the current wave (for the feature writer)
 // E = N*N+1.  Edges of a node are stored in descending-prior order (the order the reference
 // inserts them, go/mcts/mcts.h:292-329), only the legal ones.
 //
@@ -59,7 +59,6 @@ struct TreeDev {
   NodeHdr* hdr;
   float4* estat;
   uint32_t* elink;
-  uint4* anc;           // [G*C] 8 x u16: ids of the 8 nearest ancestors (parent first), for the history gather
   uint16_t* free_list;  // [G][C] stack of free local ids
   int32_t* free_n;      // [G]
   uint16_t* root;       // [G]
@@ -69,7 +68,7 @@ struct TreeDev {
   int32_t* eval_game;   // [G*B]
   uint16_t* eval_node;  // [G*B]
   uint8_t* eval_d4;     // [G*B]
-  uint64_t* hist;       // [G*B][8][N] history rows of every claimed leaf, newest first (k_leaf_gather)
+  uint64_t* hist;       // [G*B][8][N] history rows of every claimed leaf, newest first (written by k_select)
   uint32_t* hinfo;      // [G*B] hn | side to move << 8 | d4 << 16
   uint16_t* bfs_q;      // [G][C]
   int32_t* errors;      // [4]: root-hash mismatches, pool overflows, ...
@@ -251,7 +250,6 @@ __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int ro
       h.pass_edge = NONE16;
       h.pad = 0;
       store_hdr(&tr.hdr[nb + id], h);
-      tr.anc[nb + id] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
       tr.root[g] = (uint16_t)id;
     }
   }
@@ -294,6 +292,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
   uint64_t* skg = st.sk + (size_t)g * Geo<N>::MAX_PLY;
   const int nsk0 = st.sk_n[g];
   uint32_t* path = s_path[threadIdx.x >> 5];
+  const int rootply = st.meta[g].ply;  // ply of the root == ply of the game
   unsigned st_steps = 0, st_edges = 0, st_new = 0, st_term = 0;
 
   for (int j = 0; j < tr.B; ++j) {
@@ -419,14 +418,6 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           tr.elink[(nb + node) * E + ei] = (uint32_t)action | ((uint32_t)child << 16);
           float* wp = &tr.estat[(nb + node) * E + ei].w;
           *wp = __uint_as_float((__float_as_uint(*wp) & 0xFFFFu) | ((uint32_t)child << 16));
-          // ancestors of the child = {node, node's ancestors[0..6]}
-          const uint4 pa = tr.anc[nb + node];
-          uint4 ca;
-          ca.x = (uint32_t)node | (pa.x << 16);
-          ca.y = (pa.x >> 16) | (pa.y << 16);
-          ca.z = (pa.y >> 16) | (pa.z << 16);
-          ca.w = (pa.z >> 16) | (pa.w << 16);
-          tr.anc[nb + child] = ca;
         }
       }
       __syncwarp();
@@ -435,6 +426,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
     }
     // ---- leaf claim: requestEvaluation (tree_search_node.h:157-167) + pre_evaluate (mcts.h:185)
     const NodeHdr lh = load_hdr(&tr.hdr[nb + node]);
+    __syncwarp();  // every lane has read the status before lane 0 changes it below (the branch holds collectives)
     if (lh.status == NS_UNVISITED) {
       const BoardMeta meta = load_meta(&tr.meta[nb + node]);
       if (is_terminated<N>(meta)) {
@@ -454,16 +446,43 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           h2.n_edges = 0;
           store_hdr(&tr.hdr[nb + node], h2);
         }
-      } else if (L.lane == 0) {
-        tr.hdr[nb + node].status = NS_REQUESTED;
-        const int slot = atomicAdd(tr.eval_count, 1);
-        tr.eval_game[slot] = g;
-        tr.eval_node[slot] = (uint16_t)node;
+      } else {
+        int slot = 0;
         uint8_t d4 = 0;
-        if (o.rotation_flip)
-          d4 = (uint8_t)(pp_splitmix64(((uint64_t)o.seed << 40) ^ ((uint64_t)g << 20) ^
-                                       ((uint64_t)wave << 8) ^ (uint64_t)node ^ tr.hash[nb + node]) & 7u);
-        tr.eval_d4[slot] = d4;
+        if (L.lane == 0) {
+          tr.hdr[nb + node].status = NS_REQUESTED;
+          slot = atomicAdd(tr.eval_count, 1);
+          tr.eval_game[slot] = g;
+          tr.eval_node[slot] = (uint16_t)node;
+          if (o.rotation_flip)
+            d4 = (uint8_t)(pp_splitmix64(((uint64_t)o.seed << 40) ^ ((uint64_t)g << 20) ^
+                                         ((uint64_t)wave << 8) ^ (uint64_t)node ^ tr.hash[nb + node]) & 7u);
+          tr.eval_d4[slot] = d4;
+        }
+        slot = __shfl_sync(FULL, slot, 0);
+        // The leaf's 8-position history for the feature writer, laid out contiguously per evaluation slot
+        // (hist[slot][t][y]): the leaf, its ancestors along THIS descent's path (still in shared memory),
+        // then the game's own ring (go_state.cc:90-92).  Done here because the descent is latency-bound
+        // with idle issue slots: these scattered 152-byte reads over a multi-GB pool (TLB misses) cost the
+        // select kernel almost nothing, and the plane writer then streams contiguous memory.
+        const int hn = min(8, (int)meta.ply - 1);
+        uint64_t* ho = tr.hist + (size_t)slot * 8 * N;
+        if (L.active) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            uint64_t v = 0;
+            if (t < hn) {
+              if (t <= depth) {
+                const int src = t == 0 ? node : (int)(path[depth - t] & 0xFFFFu);
+                v = tr.pos[(nb + src) * N + L.row];
+              } else {
+                v = st.ring[((size_t)g * 8 + ((rootply - 2 - (t - depth)) & 7)) * N + L.row];
+              }
+            }
+            ho[t * N + L.row] = v;
+          }
+        }
+        if (L.lane == 0) tr.hinfo[slot] = (uint32_t)hn | ((uint32_t)meta.next << 8) | ((uint32_t)d4 << 16);
       }
     }
     if (L.lane == 0) tr.leaves[(size_t)g * tr.B + j] = (uint16_t)node;
@@ -482,53 +501,9 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
 // ancestors up to the root, then the game's own ring (go_state.cc:90-92).  Staging, output formats
 // and the bulk store are features_cta's (common.cuh); the grid may be larger than the number of
 // claimed leaves (device-side count), so a wave needs no host round trip before this launch.
-// Two kernels.  k_leaf_gather (one WARP per leaf) chases the pointers -- leaf meta + ancestor ids + root
-// ply, then up to 8 x 152 B of position rows scattered over a multi-GB node pool (TLB-miss latency, not
-// bandwidth) -- and lays the history out contiguously: hist[slot][t][y], 1,216 B per leaf.  With a warp
-// per leaf 64 leaves per SM are in flight, which hides that latency far better than the feature CTAs
-// could (16 per SM, each stalled through three dependent round trips).  k_leaf_features then streams:
-// contiguous reads, coalesced 16-byte stores, exactly the board batch's k_features.
-template <int N>
-__global__ void __launch_bounds__(BLOCK) k_leaf_gather(DevState st, TreeDev tr) {
-  const int lane = threadIdx.x & 31;
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (slot >= *tr.eval_count) return;
-  const int g = tr.eval_game[slot];
-  const int leaf = tr.eval_node[slot];
-  const size_t nb = (size_t)g * tr.C;
-  // three independent loads (one round trip): the leaf's meta, its ancestor ids, the root's ply
-  const BoardMeta meta = load_meta(&tr.meta[nb + leaf]);
-  const uint4 a4 = tr.anc[nb + leaf];
-  const int pr = st.meta[g].ply;            // ply of the root == ply of the game
-  const int hn = min(8, (int)meta.ply - 1);
-  const int depth = (int)meta.ply - pr;     // leaf depth below the root
-  uint64_t* out = tr.hist + (size_t)slot * 8 * N;
-  // history slot t: the leaf (t = 0), its t-th ancestor while still inside the current tree, then
-  // the game's own ring (the root is ring slot (ply_root-2)&7, go_state.cc:90-92)
-  uint64_t v[8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) {  // 8 independent loads in flight per lane
-    v[t] = 0;
-    if (t < hn && lane < N) {
-      if (t <= depth) {
-        int src = leaf;
-        if (t > 0) {
-          const uint32_t w = (t - 1) < 2 ? a4.x : (t - 1) < 4 ? a4.y : (t - 1) < 6 ? a4.z : a4.w;
-          src = (int)((w >> (((t - 1) & 1) * 16)) & 0xFFFFu);
-        }
-        v[t] = tr.pos[(nb + src) * N + lane];
-      } else {
-        v[t] = st.ring[((size_t)g * 8 + ((pr - 2 - (t - depth)) & 7)) * N + lane];
-      }
-    }
-  }
-  if (lane < N) {
-#pragma unroll
-    for (int t = 0; t < 8; ++t) out[t * N + lane] = v[t];
-  }
-  if (lane == 0) tr.hinfo[slot] = (uint32_t)hn | ((uint32_t)meta.next << 8) | ((uint32_t)tr.eval_d4[slot] << 16);
-}
-
+// The history rows of every claimed leaf were laid out contiguously by k_select (hist[slot][t][y],
+// 1,216 B per leaf, plus hinfo[slot]): the plane writer streams -- contiguous reads, coalesced 16-byte
+// stores, exactly the board batch's k_features.
 template <int N>
 struct StagedGather {
   const uint64_t* hist;
@@ -1237,7 +1212,6 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   CK(cudaMalloc(&t.hdr, GC * sizeof(NodeHdr)));
   CK(cudaMalloc(&t.estat, GC * E * sizeof(float4)));
   CK(cudaMalloc(&t.elink, GC * E * 4));
-  CK(cudaMalloc(&t.anc, GC * sizeof(uint4)));
   CK(cudaMalloc(&t.free_list, GC * 2));
   CK(cudaMalloc(&t.free_n, G * 4));
   CK(cudaMalloc(&t.root, G * 2));
@@ -1304,7 +1278,7 @@ void elfb200_mcts_destroy(elfb200_mcts* m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   TreeDev& t = m->tr;
-  void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.anc, t.free_list,
+  void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.free_list,
                   t.free_n,    t.root,      t.leaves,    t.active,     t.eval_count,  t.eval_game,  t.eval_node,
                   t.eval_d4,   t.hist,      t.hinfo,     t.bfs_q,     t.errors,    t.stats,     m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
                   m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4, m->d_priors};
@@ -1401,14 +1375,12 @@ int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad
   if (n != 0) {
     const int npos = n > 0 ? n : c->G * m->tr.B;
     CK(cudaEventRecord(m->ev[2], c->stream));
-    DISPATCH_N(c, (k_leaf_gather<19><<<warp_grid(npos), BLOCK, 0, c->stream>>>(c->st, m->tr)),
-               (k_leaf_gather<9><<<warp_grid(npos), BLOCK, 0, c->stream>>>(c->st, m->tr)));
     DISPATCH_N(c,
                (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
                    m->tr, feat_dev, format, cpad, c->feat_tma)),
                (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
                    m->tr, feat_dev, format, cpad, c->feat_tma)));
-    c->launches += 2;
+    c->launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(m->ev[3], c->stream));
     m->pending_feat = true;
@@ -1428,14 +1400,12 @@ int elfb200_mcts_leaf_features(elfb200_mcts* m, void* feat_dev, int format, int 
   const int n = m->last_eval_count;
   if (n == 0) return ELFB200_OK;
   const int npos = n > 0 ? n : c->G * m->tr.B;
-  DISPATCH_N(c, (k_leaf_gather<19><<<warp_grid(npos), BLOCK, 0, c->stream>>>(c->st, m->tr)),
-             (k_leaf_gather<9><<<warp_grid(npos), BLOCK, 0, c->stream>>>(c->st, m->tr)));
   DISPATCH_N(c,
              (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
                  m->tr, feat_dev, format, cpad, c->feat_tma)),
              (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
                  m->tr, feat_dev, format, cpad, c->feat_tma)));
-  c->launches += 2;
+  c->launches++;
   CK(cudaGetLastError());
   return ELFB200_OK;
 }
