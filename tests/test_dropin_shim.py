@@ -156,3 +156,26 @@ def test_unmodified_game_py_selfplay_on_the_shim(reference_python, monkeypatch, 
     assert seen["actor_black"] > 0
     wr = GC.GC.getClient().getGameStats().getWinRateStats()
     assert wr.total_games >= 3
+
+
+def test_unmodified_selfplay_script_end_to_end(tmp_path):
+    """the reference's own scripts/elfgames/go/selfplay.py, unmodified, as __main__: rlpytorch's load_env
+    (option parsing through elf.options on the shim's _options), its df_model3 network loaded from
+    save-<ver>.bin in the game_start callback after getClient().setRequest, Evaluator.actor as the
+    model callback, GC.run() until --suicide_after_n_games, GC.stop().  Subprocess: the script owns
+    sys.argv and global logger state (tests/dropin_selfplay_driver.py)."""
+    import subprocess
+
+    if not os.path.isdir(os.path.join(REF, "src_py", "rlpytorch")):
+        pytest.skip("reference tree not present")
+    from tests import emu as E
+
+    try:
+        E.emu_lib()
+    except Exception as e:
+        pytest.skip(f"SIMT emulator build unavailable: {e}")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_selfplay_driver.py"), str(tmp_path)],
+                       capture_output=True, text=True, timeout=600, cwd=os.path.dirname(HERE))
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "DROPIN-SELFPLAY-OK" in out, out[-3000:]
+    assert "In game start" in out and "Finished loading model" in out and "#suicide_after_n_games: 2, total_games: 2" in out
