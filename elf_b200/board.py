@@ -146,6 +146,17 @@ class GoBatch:
         _l.check(self._lib, self._lib.elfb200_features(self._ctx, d.ctypes.data if d is not None else None, o.ctypes.data))
         return o
 
+    def features_df(self, d4=None):
+        """BoardFeature::extract: the 25 DarkForest planes (GameOptions::use_df_feature), float32 [G,25,N,N]"""
+        n = self.board_size
+        o = np.empty((self.num_games, 25, n, n), np.float32)
+        d = None
+        if d4 is not None:
+            d = np.ascontiguousarray(d4, dtype=np.int32)
+            assert d.shape == (self.num_games,)
+        _l.check(self._lib, self._lib.elfb200_features_df(self._ctx, d.ctypes.data if d is not None else None, o.ctypes.data))
+        return o
+
     def features_dev(self, out_ptr, d4_ptr=None, fmt=_l.FEAT_F32_NCHW, cpad=0):
         """planes of every game straight into device memory at ``out_ptr``: float32 ``[G,18,N,N]``
         or, in the 16-bit channels-last formats (``lib.FEAT_F16_NHWC`` / ``FEAT_BF16_NHWC``),

@@ -85,6 +85,20 @@ __device__ __forceinline__ Lane make_lane() {
   return L;
 }
 
+template <int N>
+__device__ __forceinline__ Lane make_lane_single() {  // one game per warp, also for 9x9
+  Lane L;
+  L.lane = threadIdx.x & 31;
+  L.active = L.lane < N;
+  L.sub = 0;
+  L.row = L.active ? L.lane : 0;
+  L.base = 0;
+  L.rm = L.active ? Geo<N>::ROWMASK : 0u;
+  L.segmask = Geo<N>::ROWMASK;
+  return L;
+}
+
+
 // ---- neighbour shifts -------------------------------------------------------
 template <int N>
 __device__ __forceinline__ uint32_t up_of(uint32_t v, const Lane& L) {  // value of row y-1

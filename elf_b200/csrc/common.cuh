@@ -68,6 +68,7 @@ struct DevState {
   BoardMeta* meta;
   uint64_t* sk;
   int32_t* sk_n;
+  uint16_t* placed;  // [G][N*N] ply at which the stone on a point was placed (Info::last_placed, board.h:68)
   int G;
 };
 
@@ -317,6 +318,7 @@ struct elfb200_ctx {
   int32_t* d_words = nullptr;   // G * 12 export buffer
   int32_t* d_d4 = nullptr;
   float* d_feat = nullptr;      // lazily allocated G*18*P floats
+  float* d_exp_table = nullptr; // exp(-k/10), k = 0 .. 2*N*N (host libm, so the DarkForest history planes match bit for bit)
   int playout_layout = 0;       // k_playout: 0 = one board row per lane, 1 = two rows per lane (19x19, three games per warp)
   int feat_tma = 1;             // feature tiles leave shared memory by one bulk (TMA) store; 0 = vector stores
   // playout outputs

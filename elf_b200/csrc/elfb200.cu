@@ -18,7 +18,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "board2.cuh"
@@ -36,6 +38,7 @@ __global__ void __launch_bounds__(BLOCK) k_reset(DevState st, const uint8_t* __r
   st.cur[(size_t)g * N + L.row] = 0;
   st.legal[(size_t)g * N + L.row] = Geo<N>::ROWMASK;  // every point of the empty board is legal
   for (int s = 0; s < 8; ++s) st.ring[((size_t)g * 8 + s) * N + L.row] = 0;
+  for (int x = 0; x < N; ++x) st.placed[(size_t)g * Geo<N>::P + L.row * N + x] = 0;
   if (L.row == 0) {
     st.hash[g] = 0;
     store_meta(&st.meta[g], initial_meta());
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(BLOCK)
       if (L.row == 0) {
         st.hash[g] = hash;
         store_meta(&st.meta[g], meta);
+        if (pm >= 0) st.placed[(size_t)g * Geo<N>::P + pm] = (uint16_t)(meta.ply - 1);  // Info::last_placed = _ply (board.cc:680,1379)
       }
     }
     if (ok && L.row == 0) ok[g] = pm != MV_NONE ? 1 : 0;
@@ -135,8 +139,11 @@ __global__ void __launch_bounds__(BLOCK)
   uint64_t hash = 0;
   uint32_t lrow = valid ? Geo<N>::ROWMASK : 0u;  // every point of the empty board is legal
   int nsk = 0;
-  if (valid)
+  if (valid) {
     for (int s = 0; s < 8; ++s) st.ring[((size_t)g * 8 + s) * N + L.row] = 0;
+    for (int x = 0; x < N; ++x) st.placed[(size_t)g * Geo<N>::P + L.row * N + x] = 0;
+  }
+  __syncwarp();
   const int n = valid ? count[gs] : 0;
   const int nmax = __reduce_max_sync(FULL, n);
   uint64_t* skg = st.sk + (size_t)gs * Geo<N>::MAX_PLY;
@@ -173,6 +180,7 @@ __global__ void __launch_bounds__(BLOCK)
     if (valid && pm != MV_NONE) {
       lrow = lnew;
       st.ring[((size_t)g * 8 + ((meta.ply - 2) & 7)) * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);  // go_state.cc:90-92
+      if (pm >= 0 && L.row == 0) st.placed[(size_t)g * Geo<N>::P + pm] = (uint16_t)(meta.ply - 1);
     }
     __syncwarp();
   }
@@ -266,6 +274,112 @@ template <int N>
 __global__ void __launch_bounds__(FEAT_THREADS)
     k_features(DevState st, const int32_t* __restrict__ d4codes, void* __restrict__ out, int fmt, int cpad, int tma) {
   features_cta<N>(RingGather<N>{st, d4codes}, st.G, out, fmt, cpad, tma);
+}
+
+// ---------------------------------------------------------------------------------------
+// BoardFeature::extract (board_feature.cc:209-237): the 25-plane DarkForest feature set
+// (GameOptions::use_df_feature), float32 [G][25][N][N] under a D4 code.  Filled planes (board_feature.h:19-36):
+// 0-2 our groups with 1 / 2 / >=3 liberties, 3-5 the opponent's, 6 the simple-ko point, 7 / 8 / 9 our /
+// opponent / empty points, 10 / 11 exp((last_placed - ply) / 10) on our / the opponent's stones, 14 / 15 the
+// L1 distance to the nearest stone of ours / theirs (10000 if there is none), 16 / 17 black / white to move;
+// the other planes stay zero.  One warp = one game (row per lane); the planes are staged in shared
+// memory in OUTPUT order (cell = Transform(x, y), board_feature.h:97-113) and leave coalesced.
+// Not on the self-play hot path (AGZ features are); built for parity of the offline/DF path.
+template <int N>
+__global__ void __launch_bounds__(32)
+    k_features_df(DevState st, const int32_t* __restrict__ d4codes, const float* __restrict__ exp_tab,
+                  float* __restrict__ out) {
+  constexpr int P = Geo<N>::P;
+  __shared__ float tile[25 * P];
+  __shared__ uint8_t hd[N][N];
+  const Lane L = make_lane_single<N>();
+  const int g = blockIdx.x;
+  if (g >= st.G) return;
+  const uint64_t rowv = L.active ? st.cur[(size_t)g * N + L.row] : 0ull;
+  const uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
+  const BoardMeta meta = load_meta(&st.meta[g]);
+  const int d4 = d4codes ? d4codes[g] : 0;
+  const bool bf = meta.next == S_BLACK;
+  const uint32_t own = bf ? b : w, opp = bf ? w : b;
+  const uint32_t e = ~(own | opp) & L.rm;
+  for (int i = L.lane; i < 25 * P; i += 32) tile[i] = 0.f;
+  __syncwarp();
+  auto cell = [&](int x, int y) -> int {  // Transform: rotate, then flip
+    int ta, tb;
+    switch (d4 & 3) {
+      case 1: ta = y; tb = N - 1 - x; break;
+      case 2: ta = N - 1 - x; tb = N - 1 - y; break;
+      case 3: ta = N - 1 - y; tb = x; break;
+      default: ta = x; tb = y; break;
+    }
+    return (d4 & 4) ? tb * N + ta : ta * N + tb;
+  };
+  const uint16_t* placed = st.placed + (size_t)g * P;
+  if (L.active) {
+    for (int x = 0; x < N; ++x) {
+      const int c = cell(x, L.row);
+      const bool ob = (own >> x) & 1u, pb = (opp >> x) & 1u;
+      tile[7 * P + c] = ob ? 1.f : 0.f;
+      tile[8 * P + c] = pb ? 1.f : 0.f;
+      tile[9 * P + c] = (ob || pb) ? 0.f : 1.f;
+      if (ob || pb) tile[(ob ? 10 : 11) * P + c] = exp_tab[(int)meta.ply - (int)placed[L.row * N + x]];
+      tile[(bf ? 16 : 17) * P + c] = 1.f;
+    }
+  }
+  if (L.lane == 0 && (meta.flags & F_KO_ACTIVE) && meta.ko_pt >= 0)  // getSimpleKoLocation, board.cc:466-474
+    tile[6 * P + cell(meta.ko_pt % N, meta.ko_pt / N)] = 1.f;
+  // liberty classes, group by group (getLibertyMap3binary, board_feature.cc:93-113)
+  {
+    const Links k = make_links<N>(own, opp, L);
+    uint32_t todo = own | opp;
+    while (__any_sync(FULL, todo != 0u)) {
+      const uint32_t bal = __ballot_sync(FULL, todo != 0u);
+      const int src = __ffs(bal) - 1;
+      uint32_t grp = (L.lane == src) ? (todo & (0u - todo)) : 0u;
+      while (true) {
+        const uint32_t g1 = grow_link(grp, k);
+        const uint32_t g2 = grow_link(g1, k);
+        const bool ch = g2 != grp;
+        grp = g2;
+        if (!__any_sync(FULL, ch)) break;
+      }
+      const int nl = __reduce_add_sync(FULL, __popc(nbr4<N>(grp, L) & e));
+      const bool ours = __any_sync(FULL, (grp & own) != 0u);
+      const int plane = (ours ? 0 : 3) + (nl == 1 ? 0 : nl == 2 ? 1 : 2);
+      for (uint32_t m = grp; m; m &= m - 1) tile[plane * P + cell(__ffs(m) - 1, L.row)] = 1.f;
+      todo &= ~grp;
+    }
+  }
+  // distance to the nearest stone of each colour (getDistanceMap + DistanceTransform, board_feature.cc:20-40,
+  // 181-196): the two 1-D min-plus sweeps there are the exact L1 distance transform, which commutes with D4
+  for (int side = 0; side < 2; ++side) {
+    const uint32_t row = side == 0 ? own : opp;
+    __syncwarp();
+    if (L.active) {
+      for (int x = 0; x < N; ++x) {
+        int d = 255;
+        const uint32_t lo = row & ((2u << x) - 1u), hi = row >> x;
+        if (lo) d = x - (31 - __clz(lo));
+        if (hi) d = min(d, __ffs(hi) - 1);
+        hd[L.row][x] = (uint8_t)d;
+      }
+    }
+    __syncwarp();
+    const bool none = !__any_sync(FULL, row != 0u);
+    if (L.active) {
+      for (int x = 0; x < N; ++x) {
+        int best = 100000;
+        for (int y2 = 0; y2 < N; ++y2) {
+          const int h = hd[y2][x];
+          if (h != 255) best = min(best, h + (y2 > L.row ? y2 - L.row : L.row - y2));
+        }
+        tile[(14 + side) * P + cell(x, L.row)] = none ? 10000.f : (float)best;
+      }
+    }
+  }
+  __syncwarp();
+  float* dst = out + (size_t)g * 25 * P;
+  for (int i = L.lane; i < 25 * P; i += 32) dst[i] = tile[i];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -549,6 +663,13 @@ int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out)
   CK(cudaMalloc(&c->st.meta, G * sizeof(BoardMeta)));
   CK(cudaMalloc(&c->st.sk, G * MAXPLY * 8));
   CK(cudaMalloc(&c->st.sk_n, G * 4));
+  CK(cudaMalloc(&c->st.placed, G * P * 2));
+  {
+    std::vector<float> tab(MAXPLY + 2);
+    for (size_t k = 0; k < tab.size(); ++k) tab[k] = (float)exp(-(double)k / 10.0);  // board_feature.cc:getHistoryExp
+    CK(cudaMalloc(&c->d_exp_table, tab.size() * 4));
+    CK(cudaMemcpy(c->d_exp_table, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  }
   c->st.G = num_games;
   CK(cudaMalloc(&c->d_actions, G * 4));
   CK(cudaMalloc(&c->d_ok, G));
@@ -585,7 +706,7 @@ void elfb200_destroy(elfb200_ctx* c) {
   void* ptrs[] = {c->st.cur,  c->st.ring, c->st.legal, c->st.hash,   c->st.meta,   c->st.sk,
                   c->st.sk_n, c->d_actions, c->d_ok,   c->d_bytes,   c->d_words,   c->d_d4,
                   c->d_feat,  c->d_po_sk, c->d_po_chk, c->d_po_hash, c->d_po_plies, c->d_po_score,
-                  c->d_replay};
+                  c->d_replay, c->st.placed, c->d_exp_table};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -800,6 +921,39 @@ int elfb200_features_dev_ex(elfb200_ctx* c, const int32_t* d4_dev, void* out_dev
 
 int elfb200_features_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) {
   return elfb200_features_dev_ex(c, d4_dev, out_dev, FEAT_F32_NCHW, 0);
+}
+
+int elfb200_features_df_dev(elfb200_ctx* c, const int32_t* d4_dev, float* out_dev) {
+  if (!c || !out_dev) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  DISPATCH_N(c, (k_features_df<19><<<c->G, 32, 0, c->stream>>>(c->st, d4_dev, c->d_exp_table, out_dev)),
+             (k_features_df<9><<<c->G, 32, 0, c->stream>>>(c->st, d4_dev, c->d_exp_table, out_dev)));
+  c->launches++;
+  CK(cudaGetLastError());
+  return ELFB200_OK;
+}
+
+int elfb200_features_df(elfb200_ctx* c, const int32_t* d4_host, float* out_host) {
+  if (!c || !out_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)c->G * 25 * c->N * c->N * 4;
+  float* d_out = nullptr;
+  CK(cudaMalloc(&d_out, bytes));
+  const int32_t* d4 = nullptr;
+  if (d4_host) {
+    memcpy(c->h_pin, d4_host, (size_t)c->G * 4);
+    if (cudaMemcpyAsync(c->d_d4, c->h_pin, (size_t)c->G * 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+      cudaFree(d_out);
+      return elfb200_fail(ELFB200_ERR_CUDA, "copy of the D4 codes failed");
+    }
+    d4 = c->d_d4;
+  }
+  int rc = elfb200_features_df_dev(c, d4, d_out);
+  if (!rc && (cudaMemcpyAsync(out_host, d_out, bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+              cudaStreamSynchronize(c->stream) != cudaSuccess))
+    rc = elfb200_fail(ELFB200_ERR_CUDA, "DarkForest feature read-back failed");
+  cudaFree(d_out);
+  return rc;
 }
 
 int elfb200_set_playout_layout(elfb200_ctx* c, int layout) {

@@ -82,19 +82,6 @@ struct SearchOpts {
   float c_puct, komi;
 };
 
-template <int N>
-__device__ __forceinline__ Lane make_lane_single() {  // one game per warp, also for 9x9
-  Lane L;
-  L.lane = threadIdx.x & 31;
-  L.active = L.lane < N;
-  L.sub = 0;
-  L.row = L.active ? L.lane : 0;
-  L.base = 0;
-  L.rm = L.active ? Geo<N>::ROWMASK : 0u;
-  L.segmask = Geo<N>::ROWMASK;
-  return L;
-}
-
 // NOTE: the board primitives take the reductions' lane set from Lane::segmask / Lane::active when
 // Geo<N>::GPW != 1, so a single-segment Lane gives a one-game-per-warp mode for 9x9 as well.
 
@@ -525,82 +512,57 @@ __global__ void __launch_bounds__(FEAT_THREADS)
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-wide STABLE least-significant-digit radix sort of 32*R (key, payload) pairs in shared memory
-// (element p of the sequence lives at index p; a lane owns p = r*32 + lane), ascending by key: 4 passes
-// of 8 bits.  Per pass every element gets its stable rank inside its digit bucket from __match_any_sync
-// (lanes of the round that share the digit, in lane order) plus the bucket's running count over the
-// earlier rounds; an exclusive scan of the 256 bucket counts gives the bucket bases; scatter.
-// ~1,000 instructions per lane for 384 elements, against ~4,700 for the 512-key bitonic network it
-// replaces.  After the (even number of) passes the result is back in keyA / valA.
+// Warp-wide bitonic sort of 32*R 64-bit keys held R per lane (key index i = lane*R + r), ascending.
+// Compare-exchange distances below R stay inside a lane's registers (fully unrolled, static
+// indices); larger distances exchange whole registers with the partner lane via SHFL.
 template <int R>
-__device__ __forceinline__ void warp_radix_sort(uint32_t* keyA, uint16_t* valA, uint32_t* keyB, uint16_t* valB,
-                                                uint32_t* hist, int lane) {
-  uint32_t *ks = keyA, *kd = keyB;
-  uint16_t *vs = valA, *vd = valB;
-  const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 8 * pass;
-    for (int i = lane; i < 256; i += 32) hist[i] = 0u;
-    __syncwarp();
-    uint32_t lr[R];
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[R], int lane) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const uint32_t d = (ks[r * 32 + lane] >> shift) & 255u;
-      const unsigned m = __match_any_sync(FULL, d);
-      const uint32_t before = hist[d];
-      __syncwarp();
-      if ((__ffs(m) - 1) == lane) hist[d] = before + (uint32_t)__popc(m);
-      __syncwarp();
-      lr[r] = before + (uint32_t)__popc(m & lt);
-    }
-    // exclusive scan of the 256 bucket counts: 8 buckets per lane + a warp scan
-    uint32_t loc[8], sum = 0;
+  for (int k = 2; k <= 32 * R; k <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      loc[j] = hist[lane * 8 + j];
-      sum += loc[j];
-    }
-    uint32_t incl = sum;
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= R) {  // partner lane, same register
+        const int lj = j / R;
+        const bool lower = (lane & lj) == 0;
+        const bool asc = k >= 32 * R ? true : ((lane & (k / R)) == 0);
+        const bool keep_min = lower == asc;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(FULL, incl, d);
-      if (lane >= d) incl += t;
-    }
-    uint32_t base = incl - sum;
-    __syncwarp();
+        for (int r = 0; r < R; ++r) {
+          const uint64_t mine = key[r];
+          const uint32_t olo = __shfl_xor_sync(FULL, (uint32_t)mine, lj);
+          const uint32_t ohi = __shfl_xor_sync(FULL, (uint32_t)(mine >> 32), lj);
+          const uint64_t other = ((uint64_t)ohi << 32) | olo;
+          const bool mine_small = mine < other;
+          key[r] = (mine_small == keep_min) ? mine : other;
+        }
+      } else {  // inside the lane
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      hist[lane * 8 + j] = base;
-      base += loc[j];
+        for (int r = 0; r < R; ++r) {
+          if ((r & j) == 0) {
+            const int q = r | j;
+            // ascending block iff bit k of the global index is clear
+            const bool asc = k < R ? ((r & k) == 0) : (k >= 32 * R ? true : ((lane & (k / R)) == 0));
+            const uint64_t a0 = key[r], a1 = key[q];
+            const bool sw = (a0 > a1) == asc;
+            key[r] = sw ? a1 : a0;
+            key[q] = sw ? a0 : a1;
+          }
+        }
+      }
     }
-    __syncwarp();
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const uint32_t k = ks[r * 32 + lane];
-      const uint32_t dst = hist[(k >> shift) & 255u] + lr[r];
-      kd[dst] = k;
-      vd[dst] = vs[r * 32 + lane];
-    }
-    __syncwarp();
-    uint32_t* tk = ks; ks = kd; kd = tk;
-    uint16_t* tv = vs; vs = vd; vd = tv;
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // Expansion: MCTSActor::post_nn_result / remove_pass_if_dangerous / pi2response / normalize
 // (go/mcts/mcts.h:209-332) + NodeT::setEvaluation (tree_search_node.h:176-203).  One warp per
-// claimed leaf; the candidate list is radix-sorted (stable) in shared memory by descending probability.
+// claimed leaf; the candidate list is bitonic-sorted in shared memory by descending probability.
 template <int N>
 __global__ void __launch_bounds__(BLOCK)
     k_expand(DevState st, TreeDev tr, SearchOpts o, const float* __restrict__ pi, const float* __restrict__ val) {
   constexpr int P = Geo<N>::P;
-  constexpr int R = (P + 1 + 31) / 32;  // rounds of 32 candidates: 12 (19x19), 3 (9x9)
-  constexpr int SORTN = 32 * R;
-  __shared__ uint32_t s_keyA[WARPS][SORTN], s_keyB[WARPS][SORTN];
-  __shared__ uint16_t s_valA[WARPS][SORTN], s_valB[WARPS][SORTN];
-  __shared__ uint32_t s_hist[WARPS][256];
+  constexpr int SORTN = P + 1 <= 128 ? 128 : 512;
+  __shared__ uint64_t s_key[WARPS][SORTN];
   __shared__ float s_tot[WARPS];
   __shared__ uint32_t s_legal[WARPS][N];
   const Lane L = make_lane_single<N>();
@@ -625,50 +587,46 @@ __global__ void __launch_bounds__(BLOCK)
     const bool black_win = ((float)sc - o.komi) > 0;
     if ((black_win && meta.next == S_WHITE) || (!black_win && meta.next == S_BLACK)) pass_enabled = false;
   }
+  // candidates: NN action a -> board action through the inverse D4 (board_feature.h:139-144)
   if (L.active) s_legal[wib][L.row] = legal;
   __syncwarp();
-  // Candidates in ascending BOARD-action order (act = x*N + y, pass last): the sort is stable, so equal
-  // probabilities keep that order -- descending probability, then action, as before.  The network's
-  // probability of board point (x, y) sits at NN index Transform(x, y) (board_feature.h:97-113, the forward
-  // of the inverse used by the feature planes).
-  uint32_t* keyA = s_keyA[wib];
-  uint16_t* valA = s_valA[wib];
+  uint64_t* key = s_key[wib];
   const float* pr = pi + (size_t)slot * (P + 1);
-  int nvalid = 0;
+  constexpr int R = SORTN / 32;  // keys per lane
+  uint64_t kr[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const int act = L.lane + 32 * r;
-    uint32_t k = 0xFFFFFFFFu;  // not a candidate: sorts behind every probability
-    if (act <= P) {
-      int a = P;
-      bool ok = pass_enabled;
-      if (act < P) {
-        const int x = act / N, y = act - x * N;
-        int ta, tb;  // rotate, then flip (Transform)
-        switch (d4 & 3) {
-          case 1: ta = y; tb = N - 1 - x; break;
-          case 2: ta = N - 1 - x; tb = N - 1 - y; break;
-          case 3: ta = N - 1 - y; tb = x; break;
-          default: ta = x; tb = y; break;
-        }
-        a = (d4 & 4) ? tb * N + ta : ta * N + tb;
+    const int a = L.lane + 32 * r;  // any assignment of candidates to slots will do before sorting
+    uint64_t k = ~0ull;
+    if (a <= P) {
+      int act;
+      bool ok;
+      if (a == P) {
+        act = P;
+        ok = pass_enabled;
+      } else {
+        int x, y;
+        d4_inverse(N, d4, a / N, a - (a / N) * N, x, y);
+        act = x * N + y;
         ok = (s_legal[wib][y] >> x) & 1u;
       }
-      // probabilities are non-negative floats: their bit patterns order like the values; 0xFFFFFFFE - bits
-      // keeps a +0.0 probability (key 0xFFFFFFFE) ahead of the non-candidates (0xFFFFFFFF)
-      if (ok) k = 0xFFFFFFFEu - __float_as_uint(pr[a]);
+      // probabilities are non-negative floats: their bit patterns order like the values
+      if (ok) k = ((uint64_t)(0xFFFFFFFFu - __float_as_uint(pr[a])) << 32) | (uint32_t)act;
     }
-    keyA[act] = k;
-    valA[act] = (uint16_t)act;
-    nvalid += k != 0xFFFFFFFFu;
+    kr[r] = k;
   }
-  nvalid = __reduce_add_sync(FULL, nvalid);
+  // ascending on the composite key == descending probability, then action
+  warp_bitonic_sort<R>(kr, L.lane);
+#pragma unroll
+  for (int r = 0; r < R; ++r) key[L.lane * R + r] = kr[r];
   __syncwarp();
-  warp_radix_sort<R>(keyA, valA, s_keyB[wib], s_valB[wib], s_hist[wib], L.lane);
-  // sequential float sum in sorted order (normalize, mcts.h:244-254)
+  // count valid, sequential float sum in sorted order (normalize, mcts.h:244-254)
+  int nvalid = 0;
+  for (int a = L.lane; a < SORTN; a += 32) nvalid += key[a] != ~0ull;
+  nvalid = __reduce_add_sync(FULL, nvalid);
   if (L.lane == 0) {
     float tot = 1e-10f;
-    for (int i = 0; i < nvalid; ++i) tot += __uint_as_float(0xFFFFFFFEu - keyA[i]);
+    for (int i = 0; i < nvalid; ++i) tot += __uint_as_float(0xFFFFFFFFu - (uint32_t)(key[i] >> 32));
     s_tot[wib] = tot;
   }
   __syncwarp();
@@ -685,9 +643,10 @@ __global__ void __launch_bounds__(BLOCK)
     }
   } else {
     for (int i = L.lane; i < nvalid; i += 32) {
-      const float p = __uint_as_float(0xFFFFFFFEu - keyA[i]);
+      const uint64_t k = key[i];
+      const float p = __uint_as_float(0xFFFFFFFFu - (uint32_t)(k >> 32));
       es[i] = make_float4(p / tot, __int_as_float(0), 0.f, __uint_as_float(0xFFFF0000u));
-      el[i] = (uint32_t)valA[i] | ((uint32_t)NONE16 << 16);
+      el[i] = (uint32_t)(k & 0xFFFFu) | ((uint32_t)NONE16 << 16);
     }
   }
   // index of the pass edge (if any) for the descent's pass test
@@ -696,7 +655,7 @@ __global__ void __launch_bounds__(BLOCK)
     pass_idx = 0;
   } else {
     for (int i = L.lane; i < nvalid; i += 32)
-      if ((int)valA[i] == P) pass_idx = i;
+      if ((int)(key[i] & 0xFFFFu) == P) pass_idx = i;
   }
   pass_idx = __reduce_min_sync(FULL, pass_idx);
   __syncwarp();

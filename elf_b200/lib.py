@@ -45,6 +45,8 @@ SIGNATURES = {
     "elfb200_evaluate": (ctypes.c_int, [vp, ctypes.c_float, vp]),
     "elfb200_features": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_features_dev": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_features_df": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_features_df_dev": (ctypes.c_int, [vp, vp, vp]),
     "elfb200_features_dev_ex": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, ctypes.c_int]),
     "elfb200_set_feature_store": (ctypes.c_int, [vp, ctypes.c_int]),
     "elfb200_set_playout_layout": (ctypes.c_int, [vp, ctypes.c_int]),

@@ -87,6 +87,12 @@ int elfb200_evaluate(elfb200_ctx* ctx, float komi, float* value_host);
  * d4[g] (board_feature.h:88-95; NULL = identity): float32 [G][18][N][N]. */
 int elfb200_features(elfb200_ctx* ctx, const int32_t* d4_host, float* out_host);
 int elfb200_features_dev(elfb200_ctx* ctx, const int32_t* d4_dev, float* out_dev);
+/* BoardFeature::extract (board_feature.cc:209-237), the 25-plane DarkForest feature set selected by
+ * GameOptions::use_df_feature (common/game_feature.h:22-33): float32 [G][25][N][N] under D4 code d4[g]
+ * (NULL = identity).  Planes as in board_feature.h:19-36. */
+int elfb200_features_df(elfb200_ctx* ctx, const int32_t* d4_host, float* out_host);
+int elfb200_features_df_dev(elfb200_ctx* ctx, const int32_t* d4_dev, float* out_dev);
+
 /* Feature formats.  ELFB200_FEAT_F32_NCHW is the GoFeature tensor contract "s"
  * (common/game_feature.h:159-206).  The 16-bit channels-last formats are a fast mode for a network
  * that runs in half precision: [n][N][N][cpad] halves (binary16 / bfloat16), planes 0..17 in

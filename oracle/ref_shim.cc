@@ -150,6 +150,13 @@ void ref_features_agz(void* p, int d4, float* out) {
   bf.extractAGZ(out);
 }
 
+// BoardFeature::extract (board_feature.cc:209-237): the 25-plane DarkForest feature set.
+void ref_features_df(void* p, int d4, float* out) {
+  BoardFeature bf(*static_cast<RefState*>(p));
+  bf.setD4Code(d4);
+  bf.extract(out);
+}
+
 // BoardFeature::action2Coord / coord2Action under a D4 code, in action space.
 int ref_d4_action2action(int d4, int nn_action) {
   RefState s;

@@ -300,6 +300,14 @@ class Ref(_Base):
     def terminated(self):
         return bool(self.info()[9])
 
+    def features_df(self, d4=0):
+        """BoardFeature::extract: the 25 DarkForest planes"""
+        o = np.zeros((25, self.n, self.n), np.float32)
+        self.L.ref_features_df.argtypes = [vp, ctypes.c_int, vp]
+        self.L.ref_features_df.restype = None
+        self.L.ref_features_df(self.p, int(d4), o.ctypes.data)
+        return o
+
 
 def oracle_playout(n, seed, gid, max_plies=None, trace=False, lib=None):
     L = lib or load_oracle()

@@ -707,3 +707,35 @@ def test_fast_feature_formats_async_waves_prune_and_mismatch(emu, n):
         m3.advance(r["best_action"])
     e = m3.errors()
     assert e[0] == 0 and e[1] == 0 and e[2] == 0 and e[3] > 0, e
+
+
+@pytest.mark.parametrize("n,G", [(9, 4), (19, 3)])
+def test_darkforest_features_vs_reference(emu, n, G):
+    """k_features_df == the compiled reference's BoardFeature::extract (25 DarkForest planes: liberty
+    classes, simple ko, stones, exp(last_placed - ply) history, L1 distance maps, side indicators) under
+    every D4 code, on positions with captures and kos; elfb200_replay keeps the placement plies too"""
+    if not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built")
+    gb = emu.emu_batch(G, n)
+    refs = [oracles.Ref(n) for _ in range(G)]
+    rng = np.random.default_rng(n)
+    lists = [[] for _ in range(G)]
+    for t in range(70 if n == 9 else 170):
+        acts = np.empty(G, np.int32)
+        for g, r in enumerate(refs):
+            idx = np.flatnonzero(r.legal() & (1 - r.true_eyes(int(r.info()[1]))))
+            acts[g] = int(rng.choice(idx)) if len(idx) else n * n
+            assert r.forward(acts[g])
+            lists[g].append(int(acts[g]))
+        assert gb.forward(acts).all()
+        if t % 13 == 5 or t > (60 if n == 9 else 160):
+            d4 = rng.integers(0, 8, G).astype(np.int32)
+            got = gb.features_df(d4)
+            for g, r in enumerate(refs):
+                want = r.features_df(int(d4[g]))
+                for pl in range(25):
+                    np.testing.assert_array_equal(got[g, pl], want[pl], err_msg=f"plane {pl} game {g} ply {t} d4 {d4[g]}")
+    assert sum(int(r.info()[2] + r.info()[3]) for r in refs) > 0  # captures happened
+    gb2 = emu.emu_batch(G, n)
+    gb2.replay(lists)
+    np.testing.assert_array_equal(gb2.features_df(), gb.features_df())

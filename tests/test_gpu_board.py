@@ -353,3 +353,38 @@ def test_feature_formats_and_store_modes(n, G):
                 assert (got[:, 18:] == 0).all() and (o16[G] == 5.0).all()
     del stream
     gb.close()
+
+
+@pytest.mark.parametrize("n,G", [(9, 40), (19, 24)])
+def test_darkforest_features_vs_compiled_reference(n, G):
+    """row f4 remainder: BoardFeature::extract (the 25 DarkForest planes, GameOptions::use_df_feature) on the
+    device == the compiled reference's, plane by plane, under random D4 codes, along games with captures and
+    kos; the placement plies behind the history planes survive elfb200_replay"""
+    if not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built")
+    gb = _gobatch(G, n)
+    refs = [oracles.Ref(n) for _ in range(G)]
+    rng = np.random.default_rng(100 + n)
+    lists = [[] for _ in range(G)]
+    plies = 75 if n == 9 else 260
+    for t in range(plies):
+        acts = np.empty(G, np.int32)
+        for g, r in enumerate(refs):
+            idx = np.flatnonzero(r.legal() & (1 - r.true_eyes(int(r.info()[1]))))
+            acts[g] = int(rng.choice(idx)) if len(idx) else n * n
+            assert r.forward(acts[g])
+            lists[g].append(int(acts[g]))
+        assert gb.forward(acts).all()
+        if t % 17 == 3 or t >= plies - 3:
+            d4 = rng.integers(0, 8, G).astype(np.int32)
+            got = gb.features_df(d4)
+            for g, r in enumerate(refs):
+                want = r.features_df(int(d4[g]))
+                for pl in range(25):
+                    np.testing.assert_array_equal(got[g, pl], want[pl], err_msg=f"plane {pl} game {g} ply {t} d4 {d4[g]}")
+    assert sum(int(r.info()[2] + r.info()[3]) for r in refs) > G  # plenty of captures
+    gb2 = _gobatch(G, n)
+    gb2.replay(lists)
+    np.testing.assert_array_equal(gb2.features_df(), gb.features_df())
+    gb.close()
+    gb2.close()
