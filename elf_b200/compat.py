@@ -186,8 +186,9 @@ class Context:
         n, a = self._engine.board_size, self._engine.num_action
         bs = self._batchsize
         k = int(getattr(self._engine, "num_future_actions", 1))
+        planes = int(getattr(self._engine, "num_planes", 18))
         table = {  # GoFeature::registerExtractor, common/game_feature.h:159-183
-            "s": ("float", [bs, 18, n, n]), "pi": ("float", [bs, a]), "V": ("float", [bs]),
+            "s": ("float", [bs, planes, n, n]), "pi": ("float", [bs, a]), "V": ("float", [bs]),
             "a": ("int64_t", [bs]), "rv": ("int64_t", [bs]),
             "black_ver": ("int64_t", [bs]), "white_ver": ("int64_t", [bs]), "selfplay_ver": ("int64_t", [bs]),
             "offline_a": ("int64_t", [bs, k]), "winner": ("float", [bs]), "predicted_value": ("float", [bs]),
@@ -327,9 +328,10 @@ class GameContext:
 
     def getParams(self):  # GoFeature::getParams, common/game_feature.h:208-221
         n = self._engine.board_size
+        df = int(getattr(self._engine, "num_planes", 18)) == 25  # GoFeature ctor, game_feature.h:22-33
         return {
-            "num_action": n * n + 1, "board_size": n, "num_future_actions": 1, "num_planes": 18,
-            "our_stone_plane": 0, "opponent_stone_plane": 1,
+            "num_action": n * n + 1, "board_size": n, "num_future_actions": int(getattr(self._engine, "num_future_actions", 1)),
+            "num_planes": 25 if df else 18, "our_stone_plane": 7 if df else 0, "opponent_stone_plane": 8 if df else 1,
             "ACTION_SKIP": -100, "ACTION_PASS": -99, "ACTION_RESIGN": -98, "ACTION_CLEAR": -97,
         }
 
@@ -608,6 +610,7 @@ class TrainEngine:
         self.board_size = replay_batch.N
         self.num_action = replay_batch.N * replay_batch.N + 1
         self.num_future_actions = replay_batch.K
+        self.num_planes = int(getattr(replay_batch, "num_planes", 18))
         self.batches = 0
 
     def start(self):
@@ -747,7 +750,8 @@ def game_context(co, opt, board_size=19, device=0, factories=None):
         from .replay import ReplayBatch
 
         kw = dict(num_states=int(co.batchsize), board_size=board_size, device=device,
-                  num_future_actions=int(opt.num_future_actions), seed=int(opt.seed))
+                  num_future_actions=int(opt.num_future_actions), seed=int(opt.seed),
+                  use_df_feature=bool(getattr(opt, "use_df_feature", False)))
         rb = f.get("replay", ReplayBatch)(**kw)
         return GameContext(TrainEngine(rb), batchsize=int(co.batchsize))
     raise ValueError("Unknown mode! " + str(opt.mode))  # "options.mode not recognized!" (distri_client.h:294)

@@ -67,7 +67,12 @@ def nn_to_board_action(a, n, code):
 
 
 class ReplayBatch:
-    def __init__(self, num_states, board_size=19, device=0, num_future_actions=1, seed=0, board=None):
+    def __init__(self, num_states, board_size=19, device=0, num_future_actions=1, seed=0, board=None,
+                 use_df_feature=False):
+        # GameOptions::use_df_feature (common/game_feature.h:22-33): "s" carries the 25 DarkForest planes
+        # (BoardFeature::extract) instead of the 18 AGZ planes
+        self.use_df_feature = bool(use_df_feature)
+        self.num_planes = 25 if self.use_df_feature else 18
         if board is None:
             from .board import GoBatch
 
@@ -146,14 +151,20 @@ class ReplayBatch:
         if s_out is not None:
             import torch
 
-            assert tuple(s_out.shape) == (B, 18, n, n) and s_out.dtype == torch.float32 and s_out.is_contiguous()
+            assert tuple(s_out.shape) == (B, self.num_planes, n, n) and s_out.dtype == torch.float32 and s_out.is_contiguous()
             d4_dev = torch.as_tensor(d4, device=s_out.device)
             if s_out.is_cuda:
                 torch.cuda.current_stream(s_out.device).synchronize()  # d4_dev is ready, s_out is free
-            self.board.features_dev(s_out.data_ptr(), d4_dev.data_ptr())
+            if self.use_df_feature:
+                _l = self.board._lib
+                from .lib import check
+
+                check(_l, _l.elfb200_features_df_dev(self.board._ctx, d4_dev.data_ptr(), s_out.data_ptr()))
+            else:
+                self.board.features_dev(s_out.data_ptr(), d4_dev.data_ptr())
             self.board.synchronize()
         out = {
-            "s": s_out if s_out is not None else self.board.features(d4),
+            "s": s_out if s_out is not None else (self.board.features_df(d4) if self.use_df_feature else self.board.features(d4)),
             "offline_a": np.zeros((B, K), np.int64),
             "winner": np.array([r["winner"] for r in recs], np.float32),
             "mcts_scores": np.zeros((B, A), np.float32),
