@@ -68,6 +68,7 @@ struct DevState {
   BoardMeta* meta;
   uint64_t* sk;
   int32_t* sk_n;
+  uint64_t* sa;      // [G][N] incremental group status rows: safe (>= 2 liberties) | atari (exactly 1) << 32, see board.cuh
   uint16_t* placed;  // [G][N*N] ply at which the stone on a point was placed (Info::last_placed, board.h:68)
   int G;
 };

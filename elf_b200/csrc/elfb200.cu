@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(BLOCK) k_reset(DevState st, const uint8_t* __r
   if (!valid) return;
   if (mask && !mask[g]) return;
   st.cur[(size_t)g * N + L.row] = 0;
+  st.sa[(size_t)g * N + L.row] = 0;
   st.legal[(size_t)g * N + L.row] = Geo<N>::ROWMASK;  // every point of the empty board is legal
   for (int s = 0; s < 8; ++s) st.ring[((size_t)g * 8 + s) * N + L.row] = 0;
   for (int x = 0; x < N; ++x) st.placed[(size_t)g * Geo<N>::P + L.row * N + x] = 0;
@@ -60,6 +61,10 @@ __global__ void __launch_bounds__(BLOCK)
 
   uint64_t rowv = valid ? st.cur[(size_t)gs * N + L.row] : 0ull;
   uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
+  // the incremental group status (safe / atari masks, board.cuh) is part of the stored position: a step
+  // recounts only the groups the move touched instead of classifying every group from scratch
+  const uint64_t sav = valid ? st.sa[(size_t)gs * N + L.row] : 0ull;
+  uint32_t safe = (uint32_t)sav, atari = (uint32_t)(sav >> 32);
   BoardMeta meta = load_meta(&st.meta[gs]);
   uint64_t hash = st.hash[gs];
   const uint32_t lrow = valid ? st.legal[(size_t)gs * N + L.row] : 0u;
@@ -83,7 +88,7 @@ __global__ void __launch_bounds__(BLOCK)
     if (pm >= 0 && !is_legal) pm = MV_NONE;
   }
   const uint64_t pre_hash = hash;
-  play_move<N>(b, w, meta, hash, pm, s_zob, L);
+  play_move_cached<N>(b, w, meta, hash, pm, s_zob, L, safe, atari);
 
   // superko (go_state.cc:96-121): compare with the recorded pre-move positions, then record.
   const uint64_t* skg = st.sk + (size_t)gs * Geo<N>::MAX_PLY;
@@ -99,12 +104,13 @@ __global__ void __launch_bounds__(BLOCK)
   // legal mask of the new position
   const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
   const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
-  const uint32_t lnew = legal_rows<N>(own, opp, L, ko_applies, meta.ko_pt);
+  const uint32_t lnew = legal_rows_cached<N>(own, opp, safe, atari, L, ko_applies, meta.ko_pt);
 
   if (valid) {
     if (pm != MV_NONE) {
       const uint64_t nv = (uint64_t)b | ((uint64_t)w << 32);
       st.cur[(size_t)g * N + L.row] = nv;
+      st.sa[(size_t)g * N + L.row] = (uint64_t)safe | ((uint64_t)atari << 32);
       st.ring[((size_t)g * 8 + ((meta.ply - 2) & 7)) * N + L.row] = nv;  // go_state.cc:90-92
       st.legal[(size_t)g * N + L.row] = lnew;
       if (L.row == 0) {
@@ -134,7 +140,7 @@ __global__ void __launch_bounds__(BLOCK)
   const int g = warp_game<N>(L, st.G, valid);
   const int gs = valid ? g : 0;  // safe index for idle lanes (loads only)
 
-  uint32_t b = 0, w = 0;
+  uint32_t b = 0, w = 0, safe = 0, atari = 0;
   BoardMeta meta = initial_meta();
   uint64_t hash = 0;
   uint32_t lrow = valid ? Geo<N>::ROWMASK : 0u;  // every point of the empty board is legal
@@ -166,7 +172,7 @@ __global__ void __launch_bounds__(BLOCK)
       if (pm >= 0 && !is_legal) pm = MV_NONE;
     }
     const uint64_t pre_hash = hash;
-    play_move<N>(b, w, meta, hash, pm, s_zob, L);
+    play_move_cached<N>(b, w, meta, hash, pm, s_zob, L, safe, atari);
     const bool sko = superko_scan<N>(skg, pm >= 0 ? nsk : 0, hash, L);
     __syncwarp();
     if (pm >= 0) {
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(BLOCK)
     }
     const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
     const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
-    const uint32_t lnew = legal_rows<N>(own, opp, L, ko_applies, meta.ko_pt);
+    const uint32_t lnew = legal_rows_cached<N>(own, opp, safe, atari, L, ko_applies, meta.ko_pt);
     if (valid && pm != MV_NONE) {
       lrow = lnew;
       st.ring[((size_t)g * 8 + ((meta.ply - 2) & 7)) * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);  // go_state.cc:90-92
@@ -186,6 +192,7 @@ __global__ void __launch_bounds__(BLOCK)
   }
   if (valid) {
     st.cur[(size_t)g * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);
+    st.sa[(size_t)g * N + L.row] = (uint64_t)safe | ((uint64_t)atari << 32);
     st.legal[(size_t)g * N + L.row] = lrow;
     if (L.row == 0) {
       st.hash[g] = hash;
@@ -664,6 +671,7 @@ int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out)
   CK(cudaMalloc(&c->st.sk, G * MAXPLY * 8));
   CK(cudaMalloc(&c->st.sk_n, G * 4));
   CK(cudaMalloc(&c->st.placed, G * P * 2));
+  CK(cudaMalloc(&c->st.sa, G * N * 8));
   {
     std::vector<float> tab(MAXPLY + 2);
     for (size_t k = 0; k < tab.size(); ++k) tab[k] = (float)exp(-(double)k / 10.0);  // board_feature.cc:getHistoryExp
@@ -706,7 +714,7 @@ void elfb200_destroy(elfb200_ctx* c) {
   void* ptrs[] = {c->st.cur,  c->st.ring, c->st.legal, c->st.hash,   c->st.meta,   c->st.sk,
                   c->st.sk_n, c->d_actions, c->d_ok,   c->d_bytes,   c->d_words,   c->d_d4,
                   c->d_feat,  c->d_po_sk, c->d_po_chk, c->d_po_hash, c->d_po_plies, c->d_po_score,
-                  c->d_replay, c->st.placed, c->d_exp_table};
+                  c->d_replay, c->st.placed, c->st.sa, c->d_exp_table};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pin) cudaFreeHost(c->h_pin);
