@@ -337,6 +337,8 @@ struct elfb200_ctx {
   void* h_map = nullptr;
   int32_t* d_map_actions = nullptr;
   uint8_t* d_map_ok = nullptr;
+  unsigned* d_done = nullptr;   // CTAs of the running host-driven k_step that have finished
+  uint32_t step_seq = 0;        // sequence number the last CTA writes into the mapped completion flag
   int64_t launches = 0;
   // move lists of elfb200_replay (grown on demand)
   int16_t* d_replay = nullptr;

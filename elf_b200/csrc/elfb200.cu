@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(BLOCK) k_reset(DevState st, const uint8_t* __r
 // GoState::forward (go_state.cc:74-94) for all games.
 template <int N>
 __global__ void __launch_bounds__(BLOCK)
-    k_step(DevState st, const int32_t* __restrict__ actions, uint8_t* __restrict__ ok) {
+    k_step(DevState st, const int32_t* __restrict__ actions, uint8_t* __restrict__ ok, unsigned* done_count,
+           volatile uint32_t* done_flag, uint32_t seq) {
   __shared__ uint64_t s_zob[Geo<N>::ZOB];
   load_zobrist<N>(s_zob);
   const Lane L = make_lane<N>();
@@ -120,6 +121,20 @@ __global__ void __launch_bounds__(BLOCK)
       }
     }
     if (ok && L.row == 0) ok[g] = pm != MV_NONE ? 1 : 0;
+  }
+  // host-driven step (elfb200_step): the last CTA to finish raises a flag in mapped host memory, so the host
+  // can spin on it instead of paying a stream synchronisation.  Every CTA publishes its accept flags
+  // (system-wide fence) before it counts itself done.
+  if (done_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      if (atomicAdd(done_count, 1u) == gridDim.x - 1) {
+        *done_count = 0u;
+        __threadfence_system();
+        *done_flag = seq;
+      }
+    }
   }
 }
 
@@ -691,7 +706,10 @@ int elfb200_create(int board_size, int num_games, int device, elfb200_ctx** out)
   CK(cudaMalloc(&c->d_po_score, G * 4));
   c->h_pin_bytes = G * (P + 1) > G * 64 ? G * (P + 1) : G * 64;
   CK(cudaMallocHost(&c->h_pin, c->h_pin_bytes));
-  CK(cudaHostAlloc(&c->h_map, G * 5, cudaHostAllocMapped));
+  CK(cudaHostAlloc(&c->h_map, G * 5 + 64, cudaHostAllocMapped));  // actions, accept flags, completion flag
+  memset(c->h_map, 0, G * 5 + 64);
+  CK(cudaMalloc(&c->d_done, 4));
+  CK(cudaMemset(c->d_done, 0, 4));
   CK(cudaHostGetDevicePointer(&c->d_map_actions, c->h_map, 0));
   c->d_map_ok = reinterpret_cast<uint8_t*>(c->d_map_actions) + G * 4;
   return elfb200_reset(c, nullptr);
@@ -714,7 +732,7 @@ void elfb200_destroy(elfb200_ctx* c) {
   void* ptrs[] = {c->st.cur,  c->st.ring, c->st.legal, c->st.hash,   c->st.meta,   c->st.sk,
                   c->st.sk_n, c->d_actions, c->d_ok,   c->d_bytes,   c->d_words,   c->d_d4,
                   c->d_feat,  c->d_po_sk, c->d_po_chk, c->d_po_hash, c->d_po_plies, c->d_po_score,
-                  c->d_replay, c->st.placed, c->st.sa, c->d_exp_table};
+                  c->d_replay, c->st.placed, c->st.sa, c->d_exp_table, c->d_done};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (c->h_pin) cudaFreeHost(c->h_pin);
@@ -754,8 +772,8 @@ int elfb200_reset(elfb200_ctx* c, const uint8_t* mask_host) {
 int elfb200_step_dev(elfb200_ctx* c, const int32_t* actions_dev, uint8_t* ok_dev) {
   if (!c || !actions_dev) return elfb200_fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
   CK(cudaSetDevice(c->device));
-  DISPATCH_N(c, (k_step<19><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, actions_dev, ok_dev)),
-             (k_step<9><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, actions_dev, ok_dev)));
+  DISPATCH_N(c, (k_step<19><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, actions_dev, ok_dev, nullptr, nullptr, 0u)),
+             (k_step<9><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, actions_dev, ok_dev, nullptr, nullptr, 0u)));
   c->launches++;
   CK(cudaGetLastError());
   return ELFB200_OK;
@@ -764,13 +782,36 @@ int elfb200_step_dev(elfb200_ctx* c, const int32_t* actions_dev, uint8_t* ok_dev
 int elfb200_step(elfb200_ctx* c, const int32_t* actions_host, uint8_t* ok_host) {
   if (!c || !actions_host) return elfb200_fail(ELFB200_ERR_ARG, "ctx/actions is NULL");
   CK(cudaSetDevice(c->device));
-  // host buffers, no copy engine: the actions go into the mapped pinned window, k_step reads them and
-  // writes the accept flags there over PCIe (16 KB + 4 KB at 4096 games), one launch, one wait
-  memcpy(c->h_map, actions_host, (size_t)c->G * 4);
-  int rc = elfb200_step_dev(c, c->d_map_actions, c->d_map_ok);
-  if (rc) return rc;
+  // host buffers, no copy engine and no stream synchronisation: the actions go into the mapped pinned
+  // window, k_step reads them and writes the accept flags there over PCIe (16 KB + 4 KB at 4096 games),
+  // the last CTA raises the completion flag in the same window and the host spins on it
+  uint8_t* win = reinterpret_cast<uint8_t*>(c->h_map);
+  volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(win + (size_t)c->G * 5 + 16 - ((size_t)c->G * 5) % 16);
+  volatile uint32_t* dflag = reinterpret_cast<volatile uint32_t*>(
+      reinterpret_cast<uint8_t*>(c->d_map_actions) + (reinterpret_cast<const uint8_t*>(const_cast<const uint32_t*>(flag)) - win));
+  memcpy(win, actions_host, (size_t)c->G * 4);
+  const uint32_t seq = ++c->step_seq;
+  DISPATCH_N(c, (k_step<19><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, c->d_map_actions, c->d_map_ok, c->d_done, dflag, seq)),
+             (k_step<9><<<grid_for(c), BLOCK, 0, c->stream>>>(c->st, c->d_map_actions, c->d_map_ok, c->d_done, dflag, seq)));
+  c->launches++;
+  CK(cudaGetLastError());
+#if defined(ELFB200_SIMT_EMU)
   CK(cudaStreamSynchronize(c->stream));
-  if (ok_host) memcpy(ok_host, reinterpret_cast<const uint8_t*>(c->h_map) + (size_t)c->G * 4, c->G);
+#else
+  {
+    // ~20 ms of spinning covers any healthy launch; afterwards (or on a failed launch) fall back to the runtime
+    bool done = false;
+    for (long spin = 0; spin < 20000000L; ++spin) {
+      if (*flag == seq) {
+        done = true;
+        break;
+      }
+      if ((spin & 1023) == 1023 && cudaStreamQuery(c->stream) != cudaErrorNotReady) break;
+    }
+    if (!done) CK(cudaStreamSynchronize(c->stream));
+  }
+#endif
+  if (ok_host) memcpy(ok_host, win + (size_t)c->G * 4, c->G);
   return ELFB200_OK;
 }
 

@@ -518,6 +518,7 @@ inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new simt_event(); retu
 inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline void __threadfence_system() {}
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
   return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31));
 }
