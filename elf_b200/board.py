@@ -52,9 +52,14 @@ class GoBatch:
         Returns bool array [G]: move accepted (GoState::forward's return value)."""
         a = np.ascontiguousarray(actions, dtype=np.int32)
         assert a.shape == (self.num_games,)
-        ok = np.empty(self.num_games, np.uint8)
-        _l.check(self._lib, self._lib.elfb200_step(self._ctx, a.ctypes.data, ok.ctypes.data))
-        return ok.astype(bool)
+        ok = getattr(self, "_ok_buf", None)
+        if ok is None:  # one result buffer per batch (its address is looked up once: this call is latency-critical)
+            ok = self._ok_buf = np.empty(self.num_games, np.uint8)
+            self._ok_ptr = ok.ctypes.data
+        rc = self._lib.elfb200_step(self._ctx, a.__array_interface__["data"][0], self._ok_ptr)
+        if rc:
+            _l.check(self._lib, rc)
+        return ok.view(np.bool_).copy()
 
     def forward_dev(self, actions_ptr, ok_ptr=None):
         _l.check(self._lib, self._lib.elfb200_step_dev(self._ctx, actions_ptr, ok_ptr))
