@@ -338,6 +338,7 @@ struct elfb200_ctx {
   int32_t* d_map_actions = nullptr;
   uint8_t* d_map_ok = nullptr;
   unsigned* d_done = nullptr;   // CTAs of the running host-driven k_step that have finished
+  size_t map_ok_off = 0, map_flag_off = 0;  // byte offsets of the accept flags / completion flag in the mapped window
   uint32_t step_seq = 0;        // sequence number the last CTA writes into the mapped completion flag
   int64_t launches = 0;
   // move lists of elfb200_replay (grown on demand)

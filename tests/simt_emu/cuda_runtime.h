@@ -519,6 +519,7 @@ inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSucces
 inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
 inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline void __threadfence_system() {}
+template <class T> inline T __ldcg(const T* p) { return *p; }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift) {
   return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (shift & 31));
 }
