@@ -69,6 +69,7 @@ out32 = torch.empty((G, 18, N, N), dtype=torch.float32, device=dev)
 out16 = torch.empty((G, N, N, 24), dtype=torch.float16, device=dev)
 gb.features_dev(out32.data_ptr())                         # k_features float32
 gb.features_dev(out16.data_ptr(), None, L.FEAT_F16_NHWC, 24)  # k_features fp16 NHWC
+df = gb.features_df()                  # k_features_df (DarkForest 25 planes)
 gb.legal_mask()                       # k_export
 gb.tt_score()
 moves = [list(rng.integers(0, N * N, 120)) for _ in range(256)]
@@ -79,6 +80,9 @@ m[::2] = 1
 mc.reset(m)                           # k_tree_reset
 gb.reset(m)                           # k_reset
 gb.playout_stream_launch(20260922, 0, 512)  # k_playout, the bench's configs[1] step
+gb.set_playout_layout(1)
+gb.playout_stream_launch(20260922, 0, 512)  # k_playout2 (two rows per lane)
+gb.set_playout_layout(0)
 gb.synchronize()
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
