@@ -643,6 +643,22 @@ def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512, layout=0):
     return out
 
 
+def selfplay_config(args, world, net_desc):
+    """the `config` object of the bench line: identical for both arms at the same N"""
+    G_total = args.games
+    moves_per_step = G_total * PER_BATCH / ROLLOUTS
+    return {
+        "workload": (f"configs[{2 if world == 1 else 3}]: {G_total} concurrent {BOARD}x{BOARD} self-play games in total "
+                     f"({G_total // world} per GPU), {ROLLOUTS} MCTS rollouts/move in waves of {PER_BATCH}, puct 1.5, "
+                     f"virtual loss 1, persistent tree, NN batch {args.nn_batch}; step = one wave of every game "
+                     f"(= {moves_per_step:.2f} moves), steady state after 16 random opening plies"),
+        "net": net_desc, "games_total": G_total, "games_per_gpu": G_total // world, "rollouts_per_move": ROLLOUTS,
+        "rollouts_per_wave": PER_BATCH, "nn_batch": args.nn_batch, "board": BOARD, "parts_per_gpu": args.parts,
+        "l2": "inputs larger than L2: the node pool is %.1f GB per GPU and a wave's leaf batch %.0f MB" % (
+            (G_total // world) * (2 * ROLLOUTS + 256) * 7.4e3 / 1e9, (G_total // world) * PER_BATCH * 17328 / 1e6),
+        "parallelism": f"games sharded x{world}, NCCL weight broadcast only"}
+
+
 def run_selfplay(args):
     import numpy as np
     import torch
@@ -798,16 +814,7 @@ def run_selfplay(args):
             "metric": "self-play moves/sec (MCTS, 19x19)", "value": value, "unit": "moves/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 search statistics / fp16 network", "data": "synthetic",
-            "config": {
-                "workload": (f"configs[{2 if world == 1 else 3}]: {G_total} concurrent {BOARD}x{BOARD} self-play games in total "
-                             f"({G_total // world} per GPU), {ROLLOUTS} MCTS rollouts/move in waves of {PER_BATCH}, puct 1.5, "
-                             f"virtual loss 1, persistent tree, NN batch {args.nn_batch}; step = one wave of every game "
-                             f"(= {moves_per_step:.2f} moves), steady state after 16 random opening plies"),
-                "net": net_desc, "games_total": G_total, "games_per_gpu": G_total // world, "rollouts_per_move": ROLLOUTS,
-                "rollouts_per_wave": PER_BATCH, "nn_batch": args.nn_batch, "board": BOARD, "parts_per_gpu": args.parts,
-                "l2": "inputs larger than L2: the node pool is %.1f GB per GPU and a wave's leaf batch %.0f MB" % (
-                    (G_total // world) * (2 * ROLLOUTS + 256) * 7.4e3 / 1e9, (G_total // world) * PER_BATCH * 17328 / 1e6),
-                "parallelism": f"games sharded x{world}, NCCL weight broadcast only"},
+            "config": selfplay_config(args, world, net_desc),
             "e2e": {"value": Ke * moves_per_step / e2e_s, "unit": "moves/s", "steps": Ke,
                     "h2d_bytes_per_step": int(hb_h2d), "d2h_bytes_per_step": int(hb_d2h),
                     "note": "same waves through the reference's tensor boundary with HOST buffers: float32 s -> pinned host -> GPU -> "
@@ -1066,13 +1073,10 @@ def run_reference_selfplay(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 search statistics / fp16 network", "data": "synthetic",
-        "config": {"workload": (f"configs[{2 if world == 1 else 3}]: {BOARD}x{BOARD} self-play, {ROLLOUTS} MCTS rollouts/move in waves of "
-                                f"{PER_BATCH}, puct 1.5, virtual loss 1, persistent tree, NN batch <= {args.nn_batch}; the reference keeps as "
-                                f"many games in flight as its host threads can drive (not {args.games}); step = every game thread "
-                                f"advances its search by 80 rollouts (0.1 move)"),
-                   "net": net_desc, "games_total": args.games, "rollouts_per_move": ROLLOUTS, "rollouts_per_wave": PER_BATCH,
-                   "nn_batch": args.nn_batch, "board": BOARD,
-                   "parallelism": "host threads of rank 0's process; the network runs on its GPU"},
+        "config": selfplay_config(args, world, net_desc),
+        "reference_arm": ("the reference cannot hold 4096 games: it keeps as many games in flight as its host threads can drive "
+                          "(cpu_baseline.modes.*.game_threads) on the same per-move search; a step = every game thread advances its "
+                          "search by 80 rollouts (0.1 move); moves/s counts completed rollouts / 800"),
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
