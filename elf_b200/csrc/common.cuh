@@ -185,6 +185,56 @@ __device__ __forceinline__ void features_cta(Gather gather, int n_pos, void* __r
   gather(slot, rows, hn, next, d4);
   __syncthreads();
   const bool bf = next == S_BLACK;  // even planes = side to move (board_feature.cc:268-281)
+  if (fmt != FEAT_F32_NCHW) {
+    // 16-bit channels-last: per output cell the 18 plane bits, then 8 channels at a time through a table.
+    // Stones are sparse: every (plane, board row) scatters its stones into C[cell] (bit = plane) instead of
+    // every cell gathering 16 planes.
+    __shared__ uint32_t C[P];
+    __shared__ uint4 LUT8[256];  // 8 plane bits -> 8 halves
+    const uint32_t one = fmt == FEAT_F16_NHWC ? 0x3C00u : 0x3F80u;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+      uint4 v;
+      v.x = ((i & 1) ? one : 0u) | ((i & 2) ? one << 16 : 0u);
+      v.y = ((i & 4) ? one : 0u) | ((i & 8) ? one << 16 : 0u);
+      v.z = ((i & 16) ? one : 0u) | ((i & 32) ? one << 16 : 0u);
+      v.w = ((i & 64) ? one : 0u) | ((i & 128) ? one << 16 : 0u);
+      LUT8[i] = v;
+    }
+    for (int i = threadIdx.x; i < P; i += blockDim.x) C[i] = bf ? (1u << 16) : (1u << 17);
+    __syncthreads();
+    for (int item = threadIdx.x; item < 16 * N; item += blockDim.x) {
+      const int pl = item / N, y = item - pl * N, t = pl >> 1;
+      if (t < hn) {
+        const bool want_black = ((pl & 1) == 0) == bf;
+        const uint64_t r = rows[t][y];
+        uint32_t word = (want_black ? (uint32_t)r : (uint32_t)(r >> 32)) & Geo<N>::ROWMASK;
+        while (word) {
+          const int x = __ffs(word) - 1;
+          word &= word - 1;
+          int ta, tb;  // Transform (board -> output cell): rotate, then flip (board_feature.h:97-113)
+          switch (d4 & 3) {
+            case 1: ta = y; tb = N - 1 - x; break;
+            case 2: ta = N - 1 - x; tb = N - 1 - y; break;
+            case 3: ta = N - 1 - y; tb = x; break;
+            default: ta = x; tb = y; break;
+          }
+          atomicOr(&C[(d4 & 4) ? tb * N + ta : ta * N + tb], 1u << pl);
+        }
+      }
+    }
+    __syncthreads();
+    uint16_t* buf = reinterpret_cast<uint16_t*>(feat_smem);
+    for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
+      const uint32_t bits = C[cell];
+      uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)cell * cpad);
+      dst[0] = LUT8[bits & 255u];
+      dst[1] = LUT8[(bits >> 8) & 255u];
+      dst[2] = LUT8[(bits >> 16) & 255u];
+      for (int k = 3; k < cpad / 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    flush_tile(reinterpret_cast<uint16_t*>(out) + (size_t)slot * P * cpad, buf, (uint32_t)(P * cpad * 2), tma);
+    return;
+  }
   const bool transposed = (0xA5u >> d4) & 1u, rev_idx = (0x6Cu >> d4) & 1u, rev_bits = (0xC6u >> d4) & 1u;
   if (!transposed) {
     // output row tx is board row src, read forwards or backwards: one word per (plane, row)
@@ -257,26 +307,6 @@ __device__ __forceinline__ void features_cta(Gather gather, int n_pos, void* __r
       const uint32_t w = FW[b0 >> 5] >> (b0 & 31);
       *reinterpret_cast<float2*>(dst + b0) = make_float2((w & 1u) ? 1.0f : 0.0f, (w & 2u) ? 1.0f : 0.0f);
     }
-  } else {
-    uint16_t* buf = reinterpret_cast<uint16_t*>(feat_smem);
-    const uint32_t one = fmt == FEAT_F16_NHWC ? 0x3C00u : 0x3F80u;
-    for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
-      const int tx = cell / N, ty = cell - tx * N;
-      uint32_t bits = bf ? (1u << 16) : (1u << 17);  // bit c = plane c of this cell
-#pragma unroll
-      for (int pl = 0; pl < 16; ++pl) bits |= ((T[pl][tx] >> ty) & 1u) << pl;
-      uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)cell * cpad);
-      for (int k = 0; k < cpad / 8; ++k) {
-        const uint32_t b8 = k < 4 ? (bits >> (8 * k)) & 0xFFu : 0u;
-        uint4 v;
-        v.x = ((b8 & 1u) ? one : 0u) | ((b8 & 2u) ? one << 16 : 0u);
-        v.y = ((b8 & 4u) ? one : 0u) | ((b8 & 8u) ? one << 16 : 0u);
-        v.z = ((b8 & 16u) ? one : 0u) | ((b8 & 32u) ? one << 16 : 0u);
-        v.w = ((b8 & 64u) ? one : 0u) | ((b8 & 128u) ? one << 16 : 0u);
-        dst[k] = v;
-      }
-    }
-    flush_tile(reinterpret_cast<uint16_t*>(out) + (size_t)slot * P * cpad, buf, (uint32_t)(P * cpad * 2), tma);
   }
 }
 
