@@ -223,16 +223,29 @@ __device__ __forceinline__ void features_cta(Gather gather, int n_pos, void* __r
       }
     }
     __syncthreads();
-    uint16_t* buf = reinterpret_cast<uint16_t*>(feat_smem);
-    for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
-      const uint32_t bits = C[cell];
-      uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)cell * cpad);
-      dst[0] = LUT8[bits & 255u];
-      dst[1] = LUT8[(bits >> 8) & 255u];
-      dst[2] = LUT8[(bits >> 16) & 255u];
-      for (int k = 3; k < cpad / 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+    uint16_t* gdst = reinterpret_cast<uint16_t*>(out) + (size_t)slot * P * cpad;
+    if (!tma) {
+      // direct: the position as a flat array of 16-byte pieces (cpad/8 per cell), one piece per thread and
+      // iteration -- fully coalesced STG.E.128, no staging
+      const int per = cpad / 8;
+      uint4* g4 = reinterpret_cast<uint4*>(gdst);
+      for (int j = threadIdx.x; j < P * per; j += blockDim.x) {
+        const int cell = j / per, k = j - cell * per;
+        g4[j] = k < 3 ? LUT8[(C[cell] >> (8 * k)) & 255u] : make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else {
+      // staged: the cells go to shared memory and leave as ONE bulk (TMA) store
+      uint16_t* buf = reinterpret_cast<uint16_t*>(feat_smem);
+      for (int cell = threadIdx.x; cell < P; cell += blockDim.x) {
+        const uint32_t bits = C[cell];
+        uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)cell * cpad);
+        dst[0] = LUT8[bits & 255u];
+        dst[1] = LUT8[(bits >> 8) & 255u];
+        dst[2] = LUT8[(bits >> 16) & 255u];
+        for (int k = 3; k < cpad / 8; ++k) dst[k] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      flush_tile(gdst, buf, (uint32_t)(P * cpad * 2), 1);
     }
-    flush_tile(reinterpret_cast<uint16_t*>(out) + (size_t)slot * P * cpad, buf, (uint32_t)(P * cpad * 2), tma);
     return;
   }
   const bool transposed = (0xA5u >> d4) & 1u, rev_idx = (0x6Cu >> d4) & 1u, rev_bits = (0xC6u >> d4) & 1u;
@@ -311,8 +324,8 @@ __device__ __forceinline__ void features_cta(Gather gather, int n_pos, void* __r
 }
 
 template <int N>
-inline size_t feature_smem_bytes(int fmt, int cpad) {
-  return fmt == FEAT_F32_NCHW ? (size_t)0 : (size_t)Geo<N>::P * cpad * 2;
+inline size_t feature_smem_bytes(int fmt, int cpad, int tma) {
+  return (fmt == FEAT_F32_NCHW || !tma) ? (size_t)0 : (size_t)Geo<N>::P * cpad * 2;
 }
 constexpr int FEAT_THREADS = 128;
 

@@ -975,9 +975,9 @@ int elfb200_features_dev_ex(elfb200_ctx* c, const int32_t* d4_dev, void* out_dev
   if (rc) return rc;
   CK(cudaSetDevice(c->device));
   DISPATCH_N(c,
-             (k_features<19><<<c->G, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
+             (k_features<19><<<c->G, FEAT_THREADS, feature_smem_bytes<19>(format, cpad, c->feat_tma), c->stream>>>(
                  c->st, d4_dev, out_dev, format, cpad, c->feat_tma)),
-             (k_features<9><<<c->G, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
+             (k_features<9><<<c->G, FEAT_THREADS, feature_smem_bytes<9>(format, cpad, c->feat_tma), c->stream>>>(
                  c->st, d4_dev, out_dev, format, cpad, c->feat_tma)));
   c->launches++;
   CK(cudaGetLastError());

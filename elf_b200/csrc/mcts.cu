@@ -1363,9 +1363,9 @@ int elfb200_mcts_select_ex(elfb200_mcts* m, void* feat_dev, int format, int cpad
     const int npos = n > 0 ? n : c->G * m->tr.B;
     CK(cudaEventRecord(m->ev[2], c->stream));
     DISPATCH_N(c,
-               (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
+               (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad, c->feat_tma), c->stream>>>(
                    m->tr, feat_dev, format, cpad, c->feat_tma)),
-               (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
+               (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad, c->feat_tma), c->stream>>>(
                    m->tr, feat_dev, format, cpad, c->feat_tma)));
     c->launches++;
     CK(cudaGetLastError());
@@ -1388,9 +1388,9 @@ int elfb200_mcts_leaf_features(elfb200_mcts* m, void* feat_dev, int format, int 
   if (n == 0) return ELFB200_OK;
   const int npos = n > 0 ? n : c->G * m->tr.B;
   DISPATCH_N(c,
-             (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad), c->stream>>>(
+             (k_leaf_features<19><<<npos, FEAT_THREADS, feature_smem_bytes<19>(format, cpad, c->feat_tma), c->stream>>>(
                  m->tr, feat_dev, format, cpad, c->feat_tma)),
-             (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad), c->stream>>>(
+             (k_leaf_features<9><<<npos, FEAT_THREADS, feature_smem_bytes<9>(format, cpad, c->feat_tma), c->stream>>>(
                  m->tr, feat_dev, format, cpad, c->feat_tma)));
   c->launches++;
   CK(cudaGetLastError());

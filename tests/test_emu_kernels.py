@@ -653,6 +653,7 @@ def test_fast_feature_formats_async_waves_prune_and_mismatch(emu, n):
     r0 = m0.act(actor_for(m0, log0))
     for fmt, cpad in (("f16", 24), ("bf16", 32)):
         gb1, m1 = make(feature_format=fmt, cpad=cpad)
+        gb1.set_feature_store(1 if fmt == "f16" else 0)  # staged + bulk store / direct 16-byte stores
         log1 = []
         r1 = m1.act(actor_for(m1, log1))
         assert len(log0) == len(log1)
