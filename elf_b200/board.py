@@ -173,7 +173,7 @@ class GoBatch:
         _l.check(self._lib, self._lib.elfb200_set_playout_layout(self._ctx, int(layout)))
 
     def set_feature_store(self, mode):
-        """1 = feature tiles leave shared memory by one bulk (TMA) store (default), 0 = vector stores"""
+        """16-bit NHWC planes: 0 = direct coalesced 16-byte stores (default), 1 = staged tile + one bulk (TMA) store"""
         _l.check(self._lib, self._lib.elfb200_set_feature_store(self._ctx, int(mode)))
 
     # -- random-policy playouts (BASELINE configs 1/2/5) ------------------------------------

@@ -103,8 +103,10 @@ int elfb200_features_df_dev(elfb200_ctx* ctx, const int32_t* d4_dev, float* out_
 /* elfb200_features_dev with an explicit format.  out_dev: 16-byte aligned (float32: 8-byte aligned
  * is accepted, e.g. an odd row of a larger tensor, at the price of narrower stores). */
 int elfb200_features_dev_ex(elfb200_ctx* ctx, const int32_t* d4_dev, void* out_dev, int format, int cpad);
-/* How staged feature tiles leave shared memory: 1 = one bulk (TMA) store per tile (default),
- * 0 = 16-byte vector stores by all threads.  Same bytes either way; a tuning/diagnostic knob. */
+/* How the 16-bit NHWC planes are written: 0 = direct coalesced 16-byte vector stores (default; measured
+ * 0.74 of the HBM copy peak), 1 = the position staged in shared memory and stored by one bulk (TMA,
+ * cp.async.bulk) instruction (0.60).  Same bytes either way; the float32 format always uses 16-byte
+ * vector stores.  A tuning/diagnostic knob. */
 int elfb200_set_feature_store(elfb200_ctx* ctx, int mode);
 
 /* The deterministic random-playout workload (include/elfb200_playout_policy.h; BASELINE

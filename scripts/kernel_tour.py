@@ -55,10 +55,10 @@ torch.cuda.profiler.start()
 mc.wave(actor)                        # k_select, k_leaf_features (float32 NCHW, bulk store), k_expand, k_backup
 mc.set_feature_format("f16")
 mc.wave(actor)                        # k_leaf_features fp16 NHWC
-mc.set_feature_format("f32")
-gb.set_feature_store(0)
-mc.wave(actor)                        # k_leaf_features float32 with vector stores (for comparison)
 gb.set_feature_store(1)
+mc.wave(actor)                        # k_leaf_features fp16 NHWC, staged tile + bulk (TMA) store (for comparison)
+gb.set_feature_store(0)
+mc.set_feature_format("f32")
 mc.results()                          # k_results
 a, _ = mc.choose(0, 0.0)              # k_choose
 mc.root_priors()                      # k_root_priors
