@@ -10,6 +10,7 @@
 //
 // Node pool (structure of arrays; game g owns slots [g*C, (g+1)*C), 16-bit local ids):
 //   pos    uint64 [G*C][N]      position rows (black | white << 32), set when the node is created
+//   sa     uint64 [G*C][N]      the position's incremental group status rows (safe | atari << 32)
 //   hash   uint64 [G*C]         Zobrist hash
 //   meta   BoardMeta [G*C]      ply, side, ko, last moves, terminal flags
 //   hdr    NodeHdr [G*C]        visits, V, running unsigned mean Q, parent link, status
@@ -54,6 +55,7 @@ static_assert(sizeof(NodeHdr) == 32, "NodeHdr must be 32 bytes");
 
 struct TreeDev {
   uint64_t* pos;
+  uint64_t* sa;          // [G*C][N] incremental group status of the node's position: safe | atari << 32 (board.cuh)
   uint64_t* hash;
   BoardMeta* meta;
   NodeHdr* hdr;
@@ -219,7 +221,10 @@ __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int ro
     int id = 0;
     if (L.lane == 0) id = pop_free(tr, g);
     id = __shfl_sync(FULL, id, 0);
-    if (L.active) tr.pos[(nb + id) * N + L.row] = st.cur[(size_t)g * N + L.row];
+    if (L.active) {
+      tr.pos[(nb + id) * N + L.row] = st.cur[(size_t)g * N + L.row];
+      tr.sa[(nb + id) * N + L.row] = st.sa[(size_t)g * N + L.row];
+    }
     if (L.lane == 0) {
       tr.hash[nb + id] = st.hash[g];
       tr.meta[nb + id] = st.meta[g];
@@ -377,14 +382,19 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           cnt += __popc(bal);
         }
         const uint64_t rowv = L.active ? tr.pos[(nb + node) * N + L.row] : 0ull;
+        const uint64_t sav = L.active ? tr.sa[(nb + node) * N + L.row] : 0ull;
         uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
+        uint32_t safe = (uint32_t)sav, atari = (uint32_t)(sav >> 32);
         BoardMeta meta = load_meta(&tr.meta[nb + node]);
         uint64_t hash = tr.hash[nb + node];
         const int pm = action == Geo<N>::P ? MV_PASS : (action % N) * N + action / N;
         __syncwarp();
-        play_move<N>(b, w, meta, hash, pm, s_zob, L);
+        play_move_cached<N>(b, w, meta, hash, pm, s_zob, L, safe, atari);  // recounts only the groups the move touched
         if (pm >= 0 && superko_scan<N>(skg, cnt, hash, L)) meta.flags |= F_SUPERKO;
-        if (L.active) tr.pos[(nb + child) * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);
+        if (L.active) {
+          tr.pos[(nb + child) * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);
+          tr.sa[(nb + child) * N + L.row] = (uint64_t)safe | ((uint64_t)atari << 32);
+        }
         if (L.lane == 0) {
           tr.hash[nb + child] = hash;
           store_meta(&tr.meta[nb + child], meta);
@@ -574,11 +584,13 @@ __global__ void __launch_bounds__(BLOCK)
   const int d4 = tr.eval_d4[slot];
   const size_t nb = (size_t)g * tr.C;
   const uint64_t rowv = L.active ? tr.pos[(nb + node) * N + L.row] : 0ull;
+  const uint64_t sav = L.active ? tr.sa[(nb + node) * N + L.row] : 0ull;
   const uint32_t b = (uint32_t)rowv, w = (uint32_t)(rowv >> 32);
   const BoardMeta meta = load_meta(&tr.meta[nb + node]);
   const uint32_t own = meta.next == S_BLACK ? b : w, opp = meta.next == S_BLACK ? w : b;
   const bool ko_applies = (meta.flags & F_KO_ACTIVE) && meta.ko_color == meta.next;
-  const uint32_t legal = legal_rows<N>(own, opp, L, ko_applies, meta.ko_pt);
+  // legality straight from the node's incremental safe/atari masks (no group classification fills)
+  const uint32_t legal = legal_rows_cached<N>(own, opp, (uint32_t)sav, (uint32_t)(sav >> 32), L, ko_applies, meta.ko_pt);
   // pass handling (mcts.h:225-242)
   bool pass_enabled = (int)meta.ply >= o.ply_pass_enabled;
   if (o.remove_pass_if_dangerous && pass_enabled && meta.last1 != MV_PASS) {
@@ -1194,6 +1206,7 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   t.B = B;
   t.E = (int)E;
   CK(cudaMalloc(&t.pos, GC * N * 8));
+  CK(cudaMalloc(&t.sa, GC * N * 8));
   CK(cudaMalloc(&t.hash, GC * 8));
   CK(cudaMalloc(&t.meta, GC * sizeof(BoardMeta)));
   CK(cudaMalloc(&t.hdr, GC * sizeof(NodeHdr)));
@@ -1265,7 +1278,7 @@ void elfb200_mcts_destroy(elfb200_mcts* m) {
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
   TreeDev& t = m->tr;
-  void* ptrs[] = {t.pos,       t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.free_list,
+  void* ptrs[] = {t.pos,       t.sa,        t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.free_list,
                   t.free_n,    t.root,      t.leaves,    t.active,     t.eval_count,  t.eval_game,  t.eval_node,
                   t.eval_d4,   t.hist,      t.hinfo,     t.bfs_q,     t.errors,    t.stats,     m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
                   m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4, m->d_priors};
