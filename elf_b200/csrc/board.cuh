@@ -230,88 +230,6 @@ __device__ __forceinline__ uint32_t grow_link(uint32_t g, const Links& k) {
          (__shfl_down_sync(FULL, g, 1) & k.d);
 }
 
-// Classify the groups of BOTH colours that touch `focus`: `safe` = stones of groups with >= 2
-// liberties, `atari` = stones of groups with exactly one (other groups may stay unclassified).
-// `c` = all stones, `e` = empty points.
-//
-// Cheap sufficient tests for ">= 2 liberties", run as two lock-step fills over both colours:
-//   (a) a stone touching two empties;  (b) liberties of both checkerboard parities (a point's
-//   neighbours all have the opposite parity, so liberty-touching stones of different parity can
-//   never share a liberty):  X = fill(even-touching | t2), Y = fill(odd-touching | t2),
-//   safe = X & Y.  Whatever stays unresolved is counted group by group.
-template <int N>
-__device__ __forceinline__ void classify_groups(uint32_t own, uint32_t opp, uint32_t e, uint32_t focus,
-                                                const Lane& L, uint32_t& safe, uint32_t& atari) {
-  const uint32_t c = own | opp;
-  const uint32_t e_l = e << 1, e_r = e >> 1, e_u = up_of<N>(e, L), e_d = dn_of<N>(e, L);
-  const uint32_t aL = c & e_l, aR = c & e_r, aU = c & e_u, aD = c & e_d;
-  const uint32_t touch = aL | aR | aU | aD;
-  const uint32_t t2 = (aL & (aR | aU | aD)) | (aR & (aU | aD)) | (aU & aD);
-  atari = 0;
-  // every focus stone touches two empties itself: nothing to propagate
-  if (!__any_sync(FULL, (c & focus & ~t2) != 0u)) {
-    safe = t2;
-    return;
-  }
-  const Links k = make_links<N>(own, opp, L);
-  // checkerboard: bit x of row y is "even" iff (x + y) even
-  const uint32_t even = (L.row & 1) ? 0xAAAAAAAAu : 0x55555555u;
-  uint32_t gx = (touch & even) | t2, gy = (touch & ~even) | t2;
-  while (true) {  // two lock-step fills, two dilations per vote
-    const uint32_t x1 = grow_link(gx, k), y1 = grow_link(gy, k);
-    const uint32_t x2 = grow_link(x1, k), y2 = grow_link(y1, k);
-    const bool ch = (x2 != gx) | (y2 != gy);
-    gx = x2;
-    gy = y2;
-    if (!__any_sync(FULL, ch)) break;
-  }
-  safe = gx & gy;
-  uint32_t cand = c & ~safe & focus;  // seeds of unresolved groups we care about
-  while (__any_sync(FULL, cand != 0u)) {
-    // every game picks the lowest stone of its lowest non-empty row
-    const uint32_t bal = __ballot_sync(FULL, cand != 0u) & L.segmask;
-    const int src = __ffs(bal) - 1;
-    uint32_t grp = (L.lane == src) ? (cand & (0u - cand)) : 0u;
-    while (true) {
-      const uint32_t g1 = grow_link(grp, k);
-      const uint32_t g2 = grow_link(g1, k);
-      const bool ch = g2 != grp;
-      grp = g2;
-      if (!__any_sync(FULL, ch)) break;
-    }
-    const int nl = game_sum<N>(__popc(nbr4<N>(grp, L) & e), L);
-    if (nl == 1)
-      atari |= grp;
-    else
-      safe |= grp;
-    cand &= ~grp;
-  }
-}
-
-// Legal-move rows for the side to move (`own`), TryPlay semantics (board.cc:788-827):
-// empty, not the active simple-ko point for this player (board.cc:234-240), not suicide
-// (board.cc:201-232: an empty neighbour, or a friendly neighbour group with >1 liberty, or
-// an enemy neighbour group with exactly 1 liberty).
-template <int N>
-__device__ __forceinline__ uint32_t legal_rows(uint32_t own, uint32_t opp, const Lane& L,
-                                               bool ko_applies, int ko_pt) {
-  const uint32_t e = ~(own | opp) & L.rm;
-  const uint32_t en = nbr4<N>(e, L);
-  uint32_t legal = e & en;
-  const uint32_t hard = e & ~en;  // empties with no empty neighbour
-  if (__any_sync(FULL, hard != 0u)) {
-    const uint32_t focus = nbr4<N>(hard, L);
-    uint32_t safe, atari;
-    classify_groups<N>(own, opp, e, focus, L, safe, atari);
-    legal |= hard & (nbr4<N>(safe & own, L) | nbr4<N>(atari & opp, L));
-  }
-  if (ko_applies) {
-    int ky = ko_pt / N, kx = ko_pt - ky * N;
-    if (L.row == ky) legal &= ~(1u << kx);
-  }
-  return legal & L.rm;
-}
-
 // Own true eyes: isEye && !isFakeEye (board.cc:1850-1910).
 template <int N>
 __device__ __forceinline__ uint32_t true_eye_rows(uint32_t own, uint32_t opp, const Lane& L) {
@@ -340,77 +258,11 @@ __device__ __forceinline__ int tt_score(uint32_t b, uint32_t w, const Lane& L) {
 }
 
 // ---- applying a move ----------------------------------------------------------
-// Play (board.cc:1297-1401) for a move already known to be legal.  `b`,`w` are this lane's
-// rows; `meta`,`hash` are game-uniform.  `p` = y*N+x, MV_PASS, or MV_NONE (leave the game
-// untouched).  Fully predicated: the games sharing a warp may take different cases.
-// Returns the number of stones captured.
+// `p` = y*N+x, MV_PASS, or MV_NONE (leave the game untouched).
 enum : int { MV_NONE = -3 };
 
-template <int N>
-__device__ __forceinline__ int play_move(uint32_t& b, uint32_t& w, BoardMeta& meta, uint64_t& hash,
-                                         int p, const uint64_t* __restrict__ zob, const Lane& L) {
-  const int player = meta.next;
-  const int oppc = S_BLACK + S_WHITE - player;
-  const bool is_stone = p >= 0;
-  uint32_t own = player == S_BLACK ? b : w;
-  uint32_t opp = player == S_BLACK ? w : b;
-  const int y = is_stone ? p / N : 0, x = is_stone ? p - y * N : 0;
-  const uint32_t mybit = (is_stone && L.row == y && L.active) ? (1u << x) : 0u;
-  const uint32_t nb = nbr4<N>(mybit, L) & L.rm;  // the (<=4) neighbour points
-  const bool single = !game_any<N>((nb & own) != 0u, L);
-  own |= mybit;
-  uint64_t dh = 0;
-  int ncap = 0;
-  uint32_t dead = 0;
-  if (__any_sync(FULL, (nb & opp) != 0u)) {
-    // enemy stones still connected to a liberty once our stone is down; the rest is captured
-    // (EmptyGroup, board.cc:548-572).  Only groups next to the new stone can have died.
-    const uint32_t e = ~(own | opp) & L.rm;
-    const uint32_t alive = flood<N>(opp & nbr4<N>(e, L), opp, L);
-    dead = opp & ~alive;
-    if (__any_sync(FULL, dead != 0u)) {
-      ncap = game_sum<N>(__popc(dead), L);
-      opp &= ~dead;
-      dh = zob_color(game_xor64<N>(zob_row<N>(zob, L.row, dead), L), oppc);
-    }
-  }
-  if (is_stone) {
-    hash ^= dh ^ zob_color(zob[(y + 1) * Geo<N>::E + (x + 1)], player);  // set_color, board.cc:38-51
-    if (player == S_BLACK) {
-      b = own; w = opp; meta.b_cap += ncap;  // board.cc:1348-1351
-    } else {
-      w = own; b = opp; meta.w_cap += ncap;
-    }
-  }
-  // simple ko (board.cc:1384-1393): the new group is one stone with one liberty and exactly one
-  // stone was captured; the ko point is where that stone stood.
-  const int libs = game_sum<N>(__popc(nb & ~(own | opp)), L);
-  {
-    uint32_t bal = __ballot_sync(FULL, dead != 0u) & L.segmask;
-    int src = __ffs(bal) - 1;
-    int dx = __shfl_sync(FULL, __ffs(dead) - 1, src & 31);
-    if (is_stone) {
-      if (ncap == 1 && single && libs == 1) {
-        meta.ko_pt = (int16_t)((src - L.base) * N + dx);
-        meta.ko_color = (uint8_t)oppc;
-        meta.flags |= F_KO_ACTIVE;
-      } else {
-        meta.flags &= ~F_KO_ACTIVE;  // _ko_age++ : cannot be 0 again until a new ko
-      }
-    }
-  }
-  if (p != MV_NONE) {
-    // update_next_move (board.cc:1225-1238); a pass leaves the ko state untouched (board.cc:1306)
-    meta.next = (uint8_t)oppc;
-    meta.last2 = meta.last1;
-    meta.last1 = (int16_t)p;
-    meta.ply++;
-  }
-  return ncap;
-}
-
-// ---- incremental group status (playout kernel) ------------------------------------------------
-// The playout kernel keeps, across plies, two masks over ALL stones: `safe` (stone belongs to a
+// ---- legality and moves on the incremental group status --------------------------------------------
+// Every stored position (board batch, search node, the playout kernel's registers) carries two masks over ALL stones: `safe` (stone belongs to a
 // group with >= 2 liberties) and `atari` (exactly 1).  A group's liberty count only changes when a
 // stone lands on one of its liberties, when it merges, or when stones next to it are captured, so
 // after a move only the groups touching the new stone or the captured stones are recounted
@@ -419,8 +271,10 @@ __device__ __forceinline__ int play_move(uint32_t& b, uint32_t& w, BoardMeta& me
 //   * captures: the enemy neighbour groups of the new stone that are in `atari` (their single
 //     liberty is necessarily the point just played) -- no global "still alive" fill;
 //   * legality of dead-end points straight from the masks.
-// Same observable behaviour as legal_rows()/play_move(); the playout checksum (hash, captures,
-// legal mask of every position) pins it against the oracle.
+// TryPlay semantics for legality (board.cc:788-827: empty, not the active simple-ko point for this
+// player, board.cc:234-240, not suicide, board.cc:201-232) and Play (board.cc:1297-1401) for the move;
+// the per-ply parity tests (hash, captures, full legal mask against the oracle and the compiled
+// reference) pin both.
 template <int N>
 __device__ __forceinline__ uint32_t legal_rows_cached(uint32_t own, uint32_t opp, uint32_t safe,
                                                       uint32_t atari, const Lane& L, bool ko_applies,
