@@ -722,25 +722,32 @@ def run_selfplay(args):
     note(f"timed region: {K} steps in {dev_ms:.1f} ms device / {wall * 1e3:.1f} ms wall, {evals} evaluations")
 
     # ---- e2e: the same waves through the host-buffer tensor boundary (float32 "s"), wall clock --------
-    eng.set_feature_format("f32")
     Ke = min(K, args.e2e_steps)
-    hb = HostBoundary(actor, max(sp.mcts.max_leaves for sp in eng.sp), BOARD, dev)
-    eng.step(pipelined=False, actor=hb)  # warm (pinned buffers, eager shapes)
-    hb.h2d = hb.d2h = 0
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        eng.step(pipelined=False, actor=hb)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    hb_h2d, hb_d2h = hb.h2d / Ke, hb.d2h / Ke
-    note(f"e2e (host-buffer boundary): {Ke} steps in {e2e_s * 1e3:.1f} ms wall")
+    e2e_s, hb_h2d, hb_d2h, e2e_err = None, 0, 0, None
+    try:
+        eng.set_feature_format("f32")
+        hb = HostBoundary(actor, max(sp.mcts.max_leaves for sp in eng.sp), BOARD, dev)
+        eng.step(pipelined=False, actor=hb)  # warm (pinned buffers, eager shapes)
+        hb.h2d = hb.d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            eng.step(pipelined=False, actor=hb)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        hb_h2d, hb_d2h = hb.h2d / Ke, hb.d2h / Ke
+        note(f"e2e (host-buffer boundary): {Ke} steps in {e2e_s * 1e3:.1f} ms wall")
+        del hb
+    except Exception as e:  # never lose the device-timed line over the secondary reading
+        e2e_err = repr(e)
+        note("e2e phase failed: " + e2e_err)
+        if dist is not None:
+            raise
 
     # ---- kernel timings, alone (no overlap with the network): CUDA events inside the library ---------
     # The feature writer is timed as 10 back-to-back launches on the same pending leaves (idempotent), so
     # the event pair brackets a busy stream and excludes launch latency.
-    kern = None
-    if rank == 0:
+    def time_kernels():
         kern = {}
         for fmt in ("f32", "f16"):
             if args.fake_net and fmt != "f32":
@@ -784,21 +791,34 @@ def run_selfplay(args):
             st = np.sum([sp.mcts.stats().astype(np.int64) for sp in eng.sp], axis=0) - st0
             kern[fmt] = {"ms": ms, "waves": waves, "stats": st, "evals": eng.evals() - e0,
                          "feat_ms": feat_ms, "feat_pos": feat_pos, "feat_launches": feat_launches}
+        return kern
+
+    kern = None
+    if rank == 0:
+        try:
+            kern = time_kernels()
+        except Exception as e:
+            note("kernel timing phase failed: " + repr(e))
     errs = eng.errors()
     eng.close()
-    del eng, hb
+    del eng
     torch.cuda.empty_cache()
 
     note("kernel timings done; board-step probe")
-    board = board_step_probe(local, layout=args.playout_layout) if rank == 0 and not args.no_board_step else None
-    if board is not None and BOARD == 19:
-        # the same kernel family where it is issue-bound rather than latency-bound: 16384 games, two rows per lane
-        big = board_step_probe(local, steps=4, warmup=3, G=16384, layout=1)
-        board["at_16384_games_two_rows_per_lane"] = {k: big[k] for k in ("value", "unit", "ms_per_step", "lane_layout")}
+    board = None
+    if rank == 0 and not args.no_board_step:
+        try:  # a secondary reading must never cost the headline line
+            board = board_step_probe(local, layout=args.playout_layout)
+            if BOARD == 19:
+                # the same kernel family where it is issue-bound rather than latency-bound: 16384 games, two rows per lane
+                big = board_step_probe(local, steps=4, warmup=3, G=16384, layout=1)
+                board["at_16384_games_two_rows_per_lane"] = {k: big[k] for k in ("value", "unit", "ms_per_step", "lane_layout")}
+        except Exception as e:
+            board = {"unmeasured": repr(e)} if board is None else dict(board, at_16384_games_two_rows_per_lane={"unmeasured": repr(e)})
 
     # ---- reduce over ranks (MAX of times, SUM of counters) ----------------------------------------------
     if dist is not None:
-        t = torch.tensor([dev_ms, wall, e2e_s, t_bcast], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, wall, e2e_s or 0.0, t_bcast], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall, e2e_s, t_bcast = t.tolist()
         c = torch.tensor([launches, evals, real_moves, int(errs[1]), int(errs[3])], dtype=torch.int64, device=dev)
@@ -815,7 +835,7 @@ def run_selfplay(args):
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 search statistics / fp16 network", "data": "synthetic",
             "config": selfplay_config(args, world, net_desc),
-            "e2e": {"value": Ke * moves_per_step / e2e_s, "unit": "moves/s", "steps": Ke,
+            "e2e": {"value": (Ke * moves_per_step / e2e_s) if e2e_s else None, "unit": "moves/s", "steps": Ke, "error": e2e_err,
                     "h2d_bytes_per_step": int(hb_h2d), "d2h_bytes_per_step": int(hb_d2h),
                     "note": "same waves through the reference's tensor boundary with HOST buffers: float32 s -> pinned host -> GPU -> "
                             "network -> pi/V -> pinned host -> GPU (rank 0's bytes per step), wall clock, no overlap between parts"},
@@ -829,14 +849,22 @@ def run_selfplay(args):
         }
         if kern:
             line.update(kernel_rooflines(kern, prof, peak, peak_src, args.parts))
+        else:
+            line["roofline"] = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                                "kernel": "k_leaf_features<19>", "note": "kernel timing phase did not run (see stderr)"}
         if board is not None:
             line["board_step"] = board
         if world == 1 and not args.no_cpu_baseline and not args.fake_net:
             note("cpu_baseline: reference search on the host cores")
-            cb = ref_selfplay(actor, dev, steps=args.cpu_steps, warmup=1)
-            line["cpu_baseline"] = cb
+            try:
+                line["cpu_baseline"] = ref_selfplay(actor, dev, steps=args.cpu_steps, warmup=1)
+            except Exception as e:
+                line["cpu_baseline"] = {"unavailable": repr(e)}
         if world == 1 and not args.no_cpu_baseline and args.fake_net:
-            line["cpu_baseline"] = ref_selfplay_fake_net(min(args.cpu_seconds, 15.0))
+            try:
+                line["cpu_baseline"] = ref_selfplay_fake_net(min(args.cpu_seconds, 15.0))
+            except Exception as e:
+                line["cpu_baseline"] = {"unavailable": repr(e)}
         emit(line)
     if dist is not None:
         dist.barrier()
