@@ -659,6 +659,44 @@ def selfplay_config(args, world, net_desc):
         "parallelism": f"games sharded x{world}, NCCL weight broadcast only"}
 
 
+def feature_writer_probe(local, G=32768, reps=10):
+    """the board batch's k_features (same CTA code as k_leaf_features, history from the ring) at 32768
+    positions: float32 NCHW and fp16 NHWC, CUDA events around back-to-back launches"""
+    import numpy as np
+    import torch
+
+    import elf_b200
+    from elf_b200 import lib as L
+
+    gb = elf_b200.GoBatch(G, board_size=BOARD, device=local)
+    dev = torch.device("cuda", local)
+    st = torch.cuda.ExternalStream(gb.stream, device=dev)
+    rng = np.random.default_rng(5)
+    random_opening(gb, 12, rng)
+    d4 = torch.from_numpy(rng.integers(0, 8, G).astype(np.int32)).to(dev)
+    P = BOARD * BOARD
+    o32 = torch.empty((G, 18, BOARD, BOARD), dtype=torch.float32, device=dev)
+    o16 = torch.empty((G, BOARD, BOARD, 24), dtype=torch.float16, device=dev)
+    peak, _ = measured_peaks()
+    out = {}
+    for name, fn, byts in (("float32_nchw", lambda: gb.features_dev(o32.data_ptr(), d4.data_ptr()), 800 + 18 * P * 4),
+                           ("fp16_nhwc", lambda: gb.features_dev(o16.data_ptr(), d4.data_ptr(), L.FEAT_F16_NHWC, 24), 800 + P * 48)):
+        fn()
+        gb.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(reps):
+            fn()
+        b.record(st)
+        gb.synchronize()
+        ms = a.elapsed_time(b) / reps
+        out[name] = {"ms_per_launch": ms, "achieved": G * byts / ms / 1e6, "unit": "GB/s", "peak": peak,
+                     "frac": G * byts / ms / 1e6 / peak, "algorithmic_bytes_per_position": byts}
+    gb.close()
+    out["note"] = f"k_features<{BOARD}>, {G} positions per launch, {reps} launches back to back (outputs 852 MB / 568 MB: larger than L2)"
+    return out
+
+
 def run_selfplay(args):
     import numpy as np
     import torch
@@ -815,6 +853,12 @@ def run_selfplay(args):
                 board["at_16384_games_two_rows_per_lane"] = {k: big[k] for k in ("value", "unit", "ms_per_step", "lane_layout")}
         except Exception as e:
             board = {"unmeasured": repr(e)} if board is None else dict(board, at_16384_games_two_rows_per_lane={"unmeasured": repr(e)})
+    featw = None
+    if rank == 0 and not args.no_board_step:
+        try:
+            featw = feature_writer_probe(local)
+        except Exception as e:
+            featw = {"unmeasured": repr(e)}
 
     # ---- reduce over ranks (MAX of times, SUM of counters) ----------------------------------------------
     if dist is not None:
@@ -854,6 +898,8 @@ def run_selfplay(args):
                                 "kernel": "k_leaf_features<19>", "note": "kernel timing phase did not run (see stderr)"}
         if board is not None:
             line["board_step"] = board
+        if featw is not None:
+            line.setdefault("rooflines", {})["k_features_board_batch"] = featw
         if world == 1 and not args.no_cpu_baseline and not args.fake_net:
             note("cpu_baseline: reference search on the host cores")
             try:
