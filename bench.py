@@ -995,12 +995,19 @@ def ref_selfplay(actor, dev, steps, warmup, slice_rollouts=80):
     P1 = BOARD * BOARD + 1
     lock = threading.Lock()
 
+    tls = threading.local()
+
     def net(feats):  # feats: float32 numpy [m,18,N,N] -> pi [m,P1], v [m]; pads to a power of two (static shapes)
         m = feats.shape[0]
         mp = 8
         while mp < m:
             mp *= 2
-        x = torch.zeros((mp, 18, BOARD, BOARD), dtype=torch.float32, pin_memory=dev.type == "cuda")
+        bufs = getattr(tls, "bufs", None)
+        if bufs is None:
+            bufs = tls.bufs = {}
+        x = bufs.get(mp)
+        if x is None:  # one pinned staging buffer per thread and padded size (a pinned allocation per call would
+            x = bufs[mp] = torch.zeros((mp, 18, BOARD, BOARD), dtype=torch.float32, pin_memory=dev.type == "cuda")  # handicap this arm)
         x[:m] = torch.from_numpy(feats)
         with lock, torch.no_grad():
             out = actor({"s": x.to(dev, non_blocking=True)})
