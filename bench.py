@@ -648,14 +648,15 @@ def selfplay_config(args, world, net_desc):
     G_total = args.games
     moves_per_step = G_total * PER_BATCH / ROLLOUTS
     return {
-        "workload": (f"configs[{2 if world == 1 else 3}]: {G_total} concurrent {BOARD}x{BOARD} self-play games in total "
+        "workload": (f"configs[{(2 if world == 1 else 3) if BOARD == 19 else 4}]: {G_total} concurrent {BOARD}x{BOARD} self-play games in total "
                      f"({G_total // world} per GPU), {ROLLOUTS} MCTS rollouts/move in waves of {PER_BATCH}, puct 1.5, "
                      f"virtual loss 1, persistent tree, NN batch {args.nn_batch}; step = one wave of every game "
                      f"(= {moves_per_step:.2f} moves), steady state after 16 random opening plies"),
         "net": net_desc, "games_total": G_total, "games_per_gpu": G_total // world, "rollouts_per_move": ROLLOUTS,
         "rollouts_per_wave": PER_BATCH, "nn_batch": args.nn_batch, "board": BOARD, "parts_per_gpu": args.parts,
         "l2": "inputs larger than L2: the node pool is %.1f GB per GPU and a wave's leaf batch %.0f MB" % (
-            (G_total // world) * (2 * ROLLOUTS + 256) * 7.4e3 / 1e9, (G_total // world) * PER_BATCH * 17328 / 1e6),
+            (G_total // world) * (2 * ROLLOUTS + 256) * (BOARD * BOARD + 1) * 20.5 / 1e9,
+            (G_total // world) * PER_BATCH * BOARD * BOARD * 48 / 1e6),
         "parallelism": f"games sharded x{world}, NCCL weight broadcast only"}
 
 
@@ -895,7 +896,7 @@ def run_selfplay(args):
             line.update(kernel_rooflines(kern, prof, peak, peak_src, args.parts))
         else:
             line["roofline"] = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                                "kernel": "k_leaf_features<19>", "note": "kernel timing phase did not run (see stderr)"}
+                                "kernel": f"k_leaf_features<{BOARD}>", "note": "kernel timing phase did not run (see stderr)"}
         if board is not None:
             line["board_step"] = board
         if featw is not None:
@@ -924,11 +925,14 @@ def kernel_rooflines(kern, prof, peak, peak_src, parts):
     k32 = kern["f32"]
     w = max(int(k32["waves"]), 1)
     ms, st, ev = k32["ms"], k32["stats"], k32["evals"]
-    feat_bytes = 26792  # 8 history pairs 768 B + meta 32 B + 18 planes float32 25,992 B
+    P = BOARD * BOARD
+    hist_bytes = 8 * 2 * 8 * ((P + 63) // 64) + 32  # 8 history pairs of packed colour bitboards + meta
+    feat_bytes = hist_bytes + 18 * P * 4  # + 18 float32 planes: 26,792 B at 19x19
+    kq = f"<{BOARD}>"
     feat_gbs = k32["feat_pos"] * feat_bytes / (k32["feat_ms"] / 1e3) / 1e9 if k32["feat_ms"] > 0 else 0.0
-    traffic = prof.get("k_leaf_features<19>", {}).get("dram_bytes_per_launch")
+    traffic = prof.get("k_leaf_features" + kq, {}).get("dram_bytes_per_launch")
     out["roofline"] = {"bound": "hbm", "achieved": feat_gbs, "peak": peak, "unit": "GB/s", "frac": feat_gbs / peak,
-                       "traffic": traffic, "peak_source": peak_src, "kernel": "k_leaf_features<19> (float32 NCHW, the GoFeature contract)",
+                       "traffic": traffic, "peak_source": peak_src, "kernel": f"k_leaf_features{kq} (float32 NCHW, the GoFeature contract)",
                        "algorithmic_bytes_per_position": feat_bytes,
                        "positions_per_launch": k32["feat_pos"] / max(k32["feat_launches"], 1),
                        "ms_per_launch": k32["feat_ms"] / max(k32["feat_launches"], 1),
@@ -938,12 +942,12 @@ def kernel_rooflines(kern, prof, peak, peak_src, parts):
     sel_formula = int(st[0]) * (32 + 4) + int(st[3]) * 16  # header + E_n*16 + vl write (full scan)
     sel_prefix = int(st[0]) * (32 + 4) + int(st[1]) * 16   # what the prefix scan touches
     sel_ms = ms[0]
-    sel = {"bound": "hbm", "kernel": "k_select<19>", "unit": "GB/s", "peak": peak,
+    sel = {"bound": "hbm", "kernel": "k_select" + kq, "unit": "GB/s", "peak": peak,
            "formula_GBps": sel_formula / (sel_ms / 1e3) / 1e9, "prefix_scan_GBps": sel_prefix / (sel_ms / 1e3) / 1e9,
            "ms_per_wave": sel_ms / w, "nodes_visited": int(st[0]), "edges_scanned": int(st[1]), "edges_stored": int(st[3])}
-    dsel = prof.get("k_select<19>", {}).get("dram_bytes_per_launch")
-    if dsel and prof.get("k_select<19>", {}).get("launch_ms"):
-        p = prof["k_select<19>"]
+    dsel = prof.get("k_select" + kq, {}).get("dram_bytes_per_launch")
+    if dsel and prof.get("k_select" + kq, {}).get("launch_ms"):
+        p = prof["k_select" + kq]
         sel["measured_dram_GBps"] = p["dram_bytes_per_launch"] / (p["launch_ms"] / 1e3) / 1e9
         sel["achieved"] = sel["measured_dram_GBps"]
         sel["frac"] = sel["measured_dram_GBps"] / peak
@@ -960,7 +964,7 @@ def kernel_rooflines(kern, prof, peak, peak_src, parts):
     out["rooflines"]["k_backup"] = {"ms_per_wave": ms[3] / w, "bound": "latency (pointer chase)"}
     if "f16" in kern:
         k16 = kern["f16"]
-        b16 = 768 + 32 + 361 * 24 * 2
+        b16 = hist_bytes + P * 24 * 2
         g16 = k16["feat_pos"] * b16 / (k16["feat_ms"] / 1e3) / 1e9 if k16["feat_ms"] > 0 else 0.0
         out["rooflines"]["k_leaf_features_f16_nhwc"] = {
             "bound": "hbm", "achieved": g16, "peak": peak, "unit": "GB/s", "frac": g16 / peak,
@@ -1066,7 +1070,7 @@ def ref_selfplay(actor, dev, steps, warmup, slice_rollouts=80):
                 start.wait()
                 r = m.act(st)
                 slices += 1
-                if slices * slice_rollouts >= ROLLOUTS:
+                if slices * slice_rollouts >= ROLLOUTS:  # (80 divides both 800 and 400)
                     if not st.terminated():
                         st.forward(r["best_action"])
                     slices = 0
@@ -1210,8 +1214,11 @@ def main():
         if args.steps == 20:
             args.steps = 30
         return run_reference_playout(args) if args.impl == "reference" else run_playout(args)
-    if BOARD != 19:
-        raise SystemExit("the self-play workload is 19x19 (configs[2]/[3]); use --workload playout --board 9 for configs[4]")
+    global ROLLOUTS
+    if BOARD == 9:  # BASELINE configs[4]: 9x9, 16384 concurrent games, 400 rollouts per move
+        ROLLOUTS = 400
+        if args.games == GAMES_PER_GPU:
+            args.games = 16384
     return run_reference_selfplay(args) if args.impl == "reference" else run_selfplay(args)
 
 
