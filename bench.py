@@ -233,8 +233,8 @@ def run_playout(args):
 
     G = args.games
     gb = elf_b200.GoBatch(G, board_size=BOARD, device=local)
-    if args.playout_layout:
-        gb.set_playout_layout(args.playout_layout)
+    eff_layout = args.playout_layout if args.playout_layout >= 0 else (1 if (BOARD == 19 and G >= 12288) else 0)
+    gb.set_playout_layout(eff_layout)
     stream = torch.cuda.ExternalStream(gb.stream, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")  # > 126 MB L2
 
@@ -366,7 +366,7 @@ def run_playout(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic("k_playout<19>") if BOARD == 19 else None, "peak_source": peak_src,
-                         "kernel": f"k_playout{2 if args.playout_layout else ''}<{BOARD}>", "algorithmic_bytes_per_ply": algo,
+                         "kernel": f"k_playout{2 if eff_layout else ''}<{BOARD}>", "algorithmic_bytes_per_ply": algo,
                          "note": "position and group masks live in registers, the superko record in L2: DRAM is idle and the kernel is bound by the integer ALU pipe (profiles/r1_playout_F.md)"},
             "clocks": clocks, "wall_s_timed_region": t_wall, "parity_spot_check": parity, "step_api": step_api,
             "batch_to_terminal": {"value": tt_plies / (tt_ms / 1e3) * 1.0, "unit": "moves/s (this rank)",
@@ -576,8 +576,7 @@ def board_step_probe(local, steps=10, warmup=3, G=4096, plies=512, layout=0):
     import elf_b200
 
     gb = elf_b200.GoBatch(G, board_size=BOARD, device=local)
-    if layout:
-        gb.set_playout_layout(layout)
+    gb.set_playout_layout(layout)
     stream = torch.cuda.ExternalStream(gb.stream, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
     for w in range(warmup):
@@ -847,7 +846,7 @@ def run_selfplay(args):
     board = None
     if rank == 0 and not args.no_board_step:
         try:  # a secondary reading must never cost the headline line
-            board = board_step_probe(local, layout=args.playout_layout)
+            board = board_step_probe(local, layout=max(args.playout_layout, 0))
             if BOARD == 19:
                 # the same kernel family where it is issue-bound rather than latency-bound: 16384 games, two rows per lane
                 big = board_step_probe(local, steps=4, warmup=3, G=16384, layout=1)
@@ -1199,8 +1198,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-board-step", action="store_true")
     ap.add_argument("--plies-per-slot", type=int, default=512)
-    ap.add_argument("--playout-layout", type=int, default=0, choices=[0, 1],
-                    help="playout kernel: 0 = one board row per lane, 1 = two rows per lane (19x19, three games per warp)")
+    ap.add_argument("--playout-layout", type=int, default=-1, choices=[-1, 0, 1],
+                    help="playout kernel: 0 = one board row per lane, 1 = two rows per lane (19x19, three games per warp), "
+                         "-1 = the library's choice (two rows per lane from 12,288 19x19 games up)")
     ap.add_argument("--parts", type=int, default=2, help="selfplay: half batches interleaved per GPU")
     ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--blocks", type=int, default=20)

@@ -363,7 +363,8 @@ struct elfb200_ctx {
   int32_t* d_d4 = nullptr;
   float* d_feat = nullptr;      // lazily allocated G*18*P floats
   float* d_exp_table = nullptr; // exp(-k/10), k = 0 .. 2*N*N (host libm, so the DarkForest history planes match bit for bit)
-  int playout_layout = 0;       // k_playout: 0 = one board row per lane, 1 = two rows per lane (19x19, three games per warp)
+  int playout_layout = -1;      // k_playout: 0 = one board row per lane, 1 = two rows per lane (19x19, three games per warp),
+                                // -1 = automatic: two rows per lane from 12,288 19x19 games up (where it measures faster)
   int feat_tma = 0;             // 16-bit NHWC planes: 0 = direct coalesced 16-byte stores (measured faster), 1 = staged tile + one bulk (TMA) store
   // playout outputs
   uint64_t* d_po_sk = nullptr;

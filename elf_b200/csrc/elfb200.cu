@@ -1022,7 +1022,7 @@ int elfb200_features_df(elfb200_ctx* c, const int32_t* d4_host, float* out_host)
 }
 
 int elfb200_set_playout_layout(elfb200_ctx* c, int layout) {
-  if (!c || layout < 0 || layout > 1) return elfb200_fail(ELFB200_ERR_ARG, "layout must be 0 (row per lane) or 1 (two rows per lane)");
+  if (!c || layout < -1 || layout > 1) return elfb200_fail(ELFB200_ERR_ARG, "layout must be -1 (automatic), 0 (row per lane) or 1 (two rows per lane)");
   if (layout == 1 && c->N != 19) return elfb200_fail(ELFB200_ERR_ARG, "the two-rows-per-lane layout is 19x19 only");
   c->playout_layout = layout;
   return ELFB200_OK;
@@ -1057,7 +1057,8 @@ static int playout_launch(elfb200_ctx* c, uint64_t seed, uint64_t first_game_id,
   if (max_plies <= 0) return elfb200_fail(ELFB200_ERR_ARG, "max_plies must be positive");
   if (stream_plies < 0) return elfb200_fail(ELFB200_ERR_ARG, "plies_per_slot must be positive");
   CK(cudaSetDevice(c->device));
-  if (c->N == 19 && c->playout_layout == 1) {
+  const int layout = c->playout_layout >= 0 ? c->playout_layout : ((c->N == 19 && c->G >= 12288) ? 1 : 0);
+  if (c->N == 19 && layout == 1) {
     const int pgrid2 = ((c->G + Geo2<19>::GPW - 1) / Geo2<19>::GPW + PLAYOUT_WARPS - 1) / PLAYOUT_WARPS;
     k_playout2<19><<<pgrid2, PLAYOUT_WARPS * 32, 0, c->stream>>>(c->G, seed, first_game_id, max_plies, stream_plies, c->d_po_sk,
                                                                c->d_po_chk, c->d_po_plies, c->d_po_score, c->d_po_hash);
