@@ -44,7 +44,7 @@ def main():
     import torch
 
     import elf_b200
-    from elf_b200.model import Actor, PolicyValueNet, broadcast_weights, load_reference_state_dict
+    from elf_b200.model import FusedActor, PolicyValueNet, broadcast_weights, load_reference_state_dict
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -62,14 +62,17 @@ def main():
         missing, unexpected = load_reference_state_dict(net, sd)
         print(f"[selfplay] loaded {args.load}: {len(missing)} missing / {len(unexpected)} unexpected keys", file=sys.stderr)
     broadcast_weights(net)
-    actor = Actor(net, batchsize=args.nn_batch)
+    # frozen-network inference engine: BatchNorm folded, fused cuDNN epilogues, a full NN batch as a CUDA graph;
+    # the search hands it the leaf batch as fp16 channels-last (no cast/permute pass)
+    actor = FusedActor(net.eval(), batchsize=args.nn_batch, dtype=torch.float16, cuda_graph=True)
     sp = elf_b200.selfplay.SelfPlay(
         actor, num_games=args.games, board_size=args.board, device=local,
         policy_distri_cutoff=args.policy_distri_cutoff, resign_thres=args.resign_thres,
         never_resign_ratio=args.never_resign_ratio, komi=args.komi, seed=args.seed + rank,
         record_games=args.records_out is not None, num_rollouts=args.rollouts,
         num_rollouts_per_batch=args.per_batch, c_puct=args.puct, virtual_loss=args.virtual_loss,
-        persistent_tree=1, root_epsilon=args.root_epsilon, root_alpha=args.root_alpha, rotation_flip=1)
+        persistent_tree=1, root_epsilon=args.root_epsilon, root_alpha=args.root_alpha, rotation_flip=1,
+        feature_format="f16")
     t0 = time.perf_counter()
     steps = 0
     while (sp.games_finished < args.finish) if args.finish > 0 else (steps < args.moves):
@@ -86,7 +89,7 @@ def main():
             json.dump(sp.records, f)
     print(json.dumps({"rank": rank, "moves": sp.moves_played, "games_finished": sp.games_finished,
                       "seconds": dt, "moves_per_s": sp.moves_played / dt, "nn_positions": actor.num_positions,
-                      "tree_drops": int(sp.mcts.errors()[1])}), flush=True)
+                      "tree_prunes": int(sp.mcts.errors()[3]), "pool_overflows": int(sp.mcts.errors()[1])}), flush=True)
     sp.close()
     if world > 1:
         dist.barrier()

@@ -57,7 +57,7 @@ def main():
             gb2.forward(a)
             mc.advance(a)
         mc.root_priors()
-        print(f"{n}x{n}: no ASan report; tree drops {int(mc.errors()[1])}", flush=True)
+        print(f"{n}x{n}: no ASan report; tree prunes {int(mc.errors()[3])}, pool overflows {int(mc.errors()[1])}", flush=True)
         mc.close(), gb2.close(), gb.close()
     print("ASAN RUN CLEAN")
 
