@@ -179,3 +179,28 @@ def test_unmodified_selfplay_script_end_to_end(tmp_path):
     out = r.stdout + r.stderr
     assert r.returncode == 0 and "DROPIN-SELFPLAY-OK" in out, out[-3000:]
     assert "In game start" in out and "Finished loading model" in out and "#suicide_after_n_games: 2, total_games: 2" in out
+
+
+def test_unmodified_gtp_console_script_end_to_end(tmp_path):
+    """the reference's own scripts/elfgames/go/df_console.py, unmodified, as __main__ (online mode): GTP
+    commands on stdin -- genmove (MCTS on the engine with the reference's network through Evaluator.actor),
+    play, showboard (GameContext.getGame(0).showBoard()), final_score, quit (tests/dropin_console_driver.py)"""
+    import re
+    import subprocess
+
+    if not os.path.isdir(os.path.join(REF, "src_py", "rlpytorch")):
+        pytest.skip("reference tree not present")
+    from tests import emu as E
+
+    try:
+        E.emu_lib()
+    except Exception as e:
+        pytest.skip(f"SIMT emulator build unavailable: {e}")
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_console_driver.py"), str(tmp_path)],
+                       capture_output=True, text=True, timeout=600, cwd=os.path.dirname(HERE))
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "DROPIN-CONSOLE-OK" in out, out[-3000:]
+    moves = re.findall(r"^= ([A-HJ][1-9])\s*$", out, re.M)
+    assert len(moves) == 2, out[-2000:]          # two genmove answers
+    assert "Last move: " + moves[1] in out and "nextPlayer: White" in out  # showboard after B, W(E5), B
+    assert re.search(r"^ 5 .*O", out, re.M)      # the human's stone at E5
