@@ -14,6 +14,7 @@ import torch
 REF = "/root/reference"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 work = sys.argv[1]
+match = len(sys.argv) > 2 and sys.argv[2] == "match"  # evaluation match: two model versions, actor_white
 sys.path[:0] = [os.path.join(ROOT, "elf_b200", "shim"), os.path.join(REF, "src_py"),
                 os.path.join(REF, "scripts", "elfgames", "go"), ROOT]
 os.environ.update(game="elfgames.go.game", model="df_pred", model_file="elfgames.go.df_model3", ELFB200_BOARD="9", root=work)
@@ -28,6 +29,11 @@ torch.manual_seed(0)
 sd = {("resnet.resnet." + k[len("resnet."):] if k.startswith("resnet.") else k): v
       for k, v in PolicyValueNet(n, num_block=1, dim=8).state_dict().items()}
 torch.save({"state_dict": sd, "step": 0, "options": {}}, os.path.join(work, "save-3.bin"))
+if match:
+    torch.manual_seed(1)
+    sd4 = {("resnet.resnet." + k[len("resnet."):] if k.startswith("resnet.") else k): v
+           for k, v in PolicyValueNet(n, num_block=1, dim=8).state_dict().items()}
+    torch.save({"state_dict": sd4, "step": 0, "options": {}}, os.path.join(work, "save-4.bin"))
 
 E.emu_lib()
 import _elfgames_go as go  # noqa: E402
@@ -39,7 +45,8 @@ def make_selfplay(**kw):
             "unexplored_q_zero", "root_unexplored_q_zero", "root_epsilon", "root_alpha", "komi", "ply_pass_enabled")
     mo = {k: v for k, v in kw.items() if k in keys}
     rest = {k: v for k, v in kw.items() if k not in mo and k not in ("board_size", "device")}
-    return SelfPlay(board=gb, search=E.EmuSearch(gb, **mo), board_size=n, **rest, **mo)
+    white = E.EmuSearch(gb, **mo) if match else None  # the second AI's tree (GoGameSelfPlay::_ai2)
+    return SelfPlay(board=gb, search=E.EmuSearch(gb, **mo), search_white=white, board_size=n, **rest, **mo)
 
 
 go.FACTORIES = {"selfplay": make_selfplay}
@@ -50,6 +57,6 @@ sys.argv = ["selfplay.py", "--mode", "selfplay", "--num_games", "2", "--batchsiz
             "--policy_distri_cutoff", "4", "--resign_thres", "0.0", "--move_cutoff", "8", "--selfplay_timeout_usec", "10",
             "--num_block0", "1", "--dim0", "8", "--num_block1", "1", "--dim1", "8", "--keys_in_reply", "V", "rv",
             "--gpu", "-1", "--suicide_after_n_games", "2", "--no_check_loaded_options0", "--no_check_loaded_options1",
-            "--eval_model_pair", "3,-1"]
+            "--eval_model_pair", "3,4" if match else "3,-1"]
 runpy.run_path(os.path.join(REF, "scripts", "elfgames", "go", "selfplay.py"), run_name="__main__")
 print("DROPIN-SELFPLAY-OK")

@@ -158,8 +158,11 @@ def test_unmodified_game_py_selfplay_on_the_shim(reference_python, monkeypatch, 
     assert wr.total_games >= 3
 
 
-def test_unmodified_selfplay_script_end_to_end(tmp_path):
-    """the reference's own scripts/elfgames/go/selfplay.py, unmodified, as __main__: rlpytorch's load_env
+@pytest.mark.parametrize("kind", ["selfplay", "match"])
+def test_unmodified_selfplay_script_end_to_end(tmp_path, kind):
+    """(kind "match": --eval_model_pair 3,4 -- an evaluation match, two model versions loaded in game_start,
+    the second AI served through the actor_white label)
+    the reference's own scripts/elfgames/go/selfplay.py, unmodified, as __main__: rlpytorch's load_env
     (option parsing through elf.options on the shim's _options), its df_model3 network loaded from
     save-<ver>.bin in the game_start callback after getClient().setRequest, Evaluator.actor as the
     model callback, GC.run() until --suicide_after_n_games, GC.stop().  Subprocess: the script owns
@@ -174,11 +177,12 @@ def test_unmodified_selfplay_script_end_to_end(tmp_path):
         E.emu_lib()
     except Exception as e:
         pytest.skip(f"SIMT emulator build unavailable: {e}")
-    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_selfplay_driver.py"), str(tmp_path)],
+    r = subprocess.run([sys.executable, os.path.join(HERE, "dropin_selfplay_driver.py"), str(tmp_path), kind],
                        capture_output=True, text=True, timeout=600, cwd=os.path.dirname(HERE))
     out = r.stdout + r.stderr
     assert r.returncode == 0 and "DROPIN-SELFPLAY-OK" in out, out[-3000:]
     assert "In game start" in out and "Finished loading model" in out and "#suicide_after_n_games: 2, total_games: 2" in out
+    assert out.count("Finished loading model") == (2 if kind == "match" else 1)
 
 
 def test_unmodified_gtp_console_script_end_to_end(tmp_path):
