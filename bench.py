@@ -478,7 +478,7 @@ class HostBoundary:
 class SelfPlayEngine:
     """G games on one GPU as `parts` SelfPlay batches driven wave by wave through a WavePipeline"""
 
-    def __init__(self, actor, G, parts, local, rank, feature_format):
+    def __init__(self, actor, G, parts, local, rank, feature_format, opening_plies=16):
         import numpy as np
 
         import elf_b200
@@ -492,7 +492,7 @@ class SelfPlayEngine:
             for i, g in enumerate(sizes) if g > 0]
         rng = np.random.default_rng(99 + rank)
         for sp in self.sp:
-            random_opening(sp.gb, 16, rng)
+            random_opening(sp.gb, opening_plies, rng)
         self.actor = actor
         self.pipe = WavePipeline([sp.mcts for sp in self.sp], actor)
         self.wpm = self.pipe.waves_per_move
@@ -650,7 +650,7 @@ def selfplay_config(args, world, net_desc):
         "workload": (f"configs[{(2 if world == 1 else 3) if BOARD == 19 else 4}]: {G_total} concurrent {BOARD}x{BOARD} self-play games in total "
                      f"({G_total // world} per GPU), {ROLLOUTS} MCTS rollouts/move in waves of {PER_BATCH}, puct 1.5, "
                      f"virtual loss 1, persistent tree, NN batch {args.nn_batch}; step = one wave of every game "
-                     f"(= {moves_per_step:.2f} moves), steady state after 16 random opening plies"),
+                     f"(= {moves_per_step:.2f} moves), steady state after {args.opening_plies} random opening plies"),
         "net": net_desc, "games_total": G_total, "games_per_gpu": G_total // world, "rollouts_per_move": ROLLOUTS,
         "rollouts_per_wave": PER_BATCH, "nn_batch": args.nn_batch, "board": BOARD, "parts_per_gpu": args.parts,
         "l2": "inputs larger than L2: the node pool is %.1f GB per GPU and a wave's leaf batch %.0f MB" % (
@@ -738,7 +738,7 @@ def run_selfplay(args):
             print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
     note(f"network ready ({net_desc}); building {G} games in {args.parts} part(s)")
-    eng = SelfPlayEngine(actor, G, args.parts, local, rank, "f32" if args.fake_net else "f16")
+    eng = SelfPlayEngine(actor, G, args.parts, local, rank, "f32" if args.fake_net else "f16", args.opening_plies)
     streams = eng.streams()
     K, W = args.steps, args.warmup
     note("engine ready, warm-up")
@@ -1203,6 +1203,7 @@ def main():
                          "-1 = the library's choice (two rows per lane from 12,288 19x19 games up)")
     ap.add_argument("--parts", type=int, default=2, help="selfplay: half batches interleaved per GPU")
     ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--opening-plies", type=int, default=16, help="random plies every game has played when the search starts")
     ap.add_argument("--blocks", type=int, default=20)
     ap.add_argument("--dim", type=int, default=256)
     ap.add_argument("--nn-batch", type=int, default=NN_BATCH)

@@ -628,14 +628,39 @@ __global__ void __launch_bounds__(BLOCK)
     kr[r] = k;
   }
   // ascending on the composite key == descending probability, then action
-  warp_bitonic_sort<R>(kr, L.lane);
-#pragma unroll
-  for (int r = 0; r < R; ++r) key[L.lane * R + r] = kr[r];
-  __syncwarp();
-  // count valid, sequential float sum in sorted order (normalize, mcts.h:244-254)
   int nvalid = 0;
-  for (int a = L.lane; a < SORTN; a += 32) nvalid += key[a] != ~0ull;
+#pragma unroll
+  for (int r = 0; r < R; ++r) nvalid += kr[r] != ~0ull;
   nvalid = __reduce_add_sync(FULL, nvalid);
+  constexpr int RH = R / 2;  // half-size network: the sort costs O(n log^2 n)
+  if (R >= 8 && nvalid <= 32 * RH) {
+    // at most half the slots hold a candidate (every 19x19 position past the opening: <= 256 legal moves):
+    // compact them (ballot prefix, any order -- the sort follows) and run the half-size network, 2.5x cheaper
+    int base = 0;
+    const uint32_t lt = (1u << L.lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool v = kr[r] != ~0ull;
+      const uint32_t bal = __ballot_sync(FULL, v);
+      if (v) key[base + __popc(bal & lt)] = kr[r];
+      base += __popc(bal);
+    }
+    for (int i = nvalid + L.lane; i < 32 * RH; i += 32) key[i] = ~0ull;
+    __syncwarp();
+    uint64_t kh[RH > 0 ? RH : 1];
+#pragma unroll
+    for (int r = 0; r < RH; ++r) kh[r] = key[L.lane * RH + r];
+    __syncwarp();
+    warp_bitonic_sort<(RH > 0 ? RH : 1)>(kh, L.lane);
+#pragma unroll
+    for (int r = 0; r < RH; ++r) key[L.lane * RH + r] = kh[r];
+  } else {
+    warp_bitonic_sort<R>(kr, L.lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) key[L.lane * R + r] = kr[r];
+  }
+  __syncwarp();
+  // sequential float sum in sorted order (normalize, mcts.h:244-254)
   if (L.lane == 0) {
     float tot = 1e-10f;
     for (int i = 0; i < nvalid; ++i) tot += __uint_as_float(0xFFFFFFFFu - (uint32_t)(key[i] >> 32));

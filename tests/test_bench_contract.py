@@ -11,7 +11,7 @@ from tests import oracles
 
 
 def test_both_arms_print_the_same_config_object():
-    a = argparse.Namespace(games=4096, nn_batch=256, parts=2)
+    a = argparse.Namespace(games=4096, nn_batch=256, parts=2, opening_plies=16)
     for world in (1, 2, 8):
         ours = bench.selfplay_config(a, world, "net")
         ref = bench.selfplay_config(a, world, "net")

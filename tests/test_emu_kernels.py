@@ -740,3 +740,42 @@ def test_darkforest_features_vs_reference(emu, n, G):
     gb2 = emu.emu_batch(G, n)
     gb2.replay(lists)
     np.testing.assert_array_equal(gb2.features_df(), gb.features_df())
+
+
+def test_expand_half_size_sort_network_on_late_positions(emu, oracle_lib):
+    """19x19 positions past the opening have at most 256 candidates: k_expand compacts them and sorts with
+    the half-size network.  Same priors, same visits as the search restatement; the boundary (a position
+    with more than 256 legal moves next to ones with fewer) is crossed inside one batch."""
+    n, G = 19, 3
+    opts = dict(num_rollouts=24, num_rollouts_per_batch=4, c_puct=1.5, virtual_loss=1, persistent_tree=1)
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, rotation_flip=0, **opts)
+    os_ = [oracles.Oracle(n, oracle_lib) for _ in range(G)]
+    oms = [oracles.OracleMcts(n, lib=oracle_lib, **opts) for _ in range(G)]
+    rng = np.random.default_rng(8)
+    plies = [150, 104, 20]  # ~215 legal moves, around the 256 boundary, > 256 (full network)
+    for t in range(max(plies)):
+        acts = np.full(G, -1, np.int32)
+        for g, o in enumerate(os_):
+            if t < plies[g]:
+                idx = np.flatnonzero(o.legal() & (1 - o.true_eyes(int(o.info()[1]))))
+                acts[g] = int(rng.choice(idx)) if len(idx) else n * n
+                o.forward(int(acts[g]))
+        gb.forward(acts)
+    counts = [int(o.legal().sum()) for o in os_]
+    assert counts[0] < 256 and counts[2] > 256, counts
+    actor = fake_actor(mc, n)
+    for _ in range(2):
+        res = mc.act(actor)
+        pri = mc.root_priors()
+        want = [om.act(o) for om, o in zip(oms, os_)]
+        for g in range(G):
+            np.testing.assert_array_equal(res["visits"][g], want[g]["visits"])
+            w = np.where(want[g]["visits"] >= 0, want[g]["prior"], -1.0).astype(np.float32)
+            np.testing.assert_array_equal(pri[g], w)  # priors bit-identical (sorted order drives the float sum)
+        acts = np.array([w["best_action"] for w in want], np.int32)
+        gb.forward(acts)
+        mc.advance(acts)
+        for o, a in zip(os_, acts):
+            o.forward(int(a))
+    assert (mc.errors() == 0).all()
