@@ -410,6 +410,19 @@ __device__ __forceinline__ bool superko_scan(const uint64_t* __restrict__ hist, 
     for (int i = L.row; i < n; i += N) found |= (hist[i] == hash);
   return game_any<N>(found, L);
 }
+// Same test for the one-game-per-warp kernels (k_select): all 32 lanes scan, four independent
+// loads in flight per lane, so a 250-entry record costs two round trips instead of fourteen.
+__device__ __forceinline__ bool superko_scan_warp(const uint64_t* __restrict__ hist, int n, uint64_t hash) {
+  const int lane = threadIdx.x & 31;
+  bool found = false;
+  int i = lane;
+  for (; i + 96 < n; i += 128) {
+    const uint64_t h0 = hist[i], h1 = hist[i + 32], h2 = hist[i + 64], h3 = hist[i + 96];
+    found |= (h0 == hash) | (h1 == hash) | (h2 == hash) | (h3 == hash);
+  }
+  for (; i < n; i += 32) found |= (hist[i] == hash);
+  return __any_sync(FULL, found);
+}
 
 // k-th (0-based) set point of `cand` in ascending ACTION order a = x*N + y (x outer, y inner);
 // returns the point p = y*N + x.  Requires k < number of candidates of this game.

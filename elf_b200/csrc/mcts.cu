@@ -75,6 +75,11 @@ struct TreeDev {
   uint16_t* bfs_q;      // [G][C]
   int32_t* errors;      // [4]: root-hash mismatches, pool overflows, ...
   unsigned long long* stats;  // [4]: descent steps, edge records read, nodes created, stored edges of visited nodes
+  // optional host-supplied D4 codes (elfb200_mcts_set_d4_stream): the next code of game g is
+  // d4_stream[g * d4_cap + d4_used[g]]; NULL = the counter-based generator
+  const uint8_t* d4_stream;
+  int32_t* d4_used;  // [G]
+  int d4_cap;
   int C, B, E;
 };
 
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
         const int pm = action == Geo<N>::P ? MV_PASS : (action % N) * N + action / N;
         __syncwarp();
         play_move_cached<N>(b, w, meta, hash, pm, s_zob, L, safe, atari);  // recounts only the groups the move touched
-        if (pm >= 0 && superko_scan<N>(skg, cnt, hash, L)) meta.flags |= F_SUPERKO;
+        if (pm >= 0 && superko_scan_warp(skg, cnt, hash)) meta.flags |= F_SUPERKO;
         if (L.active) {
           tr.pos[(nb + child) * N + L.row] = (uint64_t)b | ((uint64_t)w << 32);
           tr.sa[(nb + child) * N + L.row] = (uint64_t)safe | ((uint64_t)atari << 32);
@@ -451,9 +456,18 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
           slot = atomicAdd(tr.eval_count, 1);
           tr.eval_game[slot] = g;
           tr.eval_node[slot] = (uint16_t)node;
-          if (o.rotation_flip)
-            d4 = (uint8_t)(pp_splitmix64(((uint64_t)o.seed << 40) ^ ((uint64_t)g << 20) ^
-                                         ((uint64_t)wave << 8) ^ (uint64_t)node ^ tr.hash[nb + node]) & 7u);
+          if (o.rotation_flip) {
+            if (tr.d4_stream) {
+              // one code per evaluated leaf, in descent order (MCTSActor::evaluate walks the claimed
+              // leaves of a wave in trajectory order, go/mcts/mcts.h:86-93)
+              const int u = tr.d4_used[g];
+              d4 = tr.d4_stream[(size_t)g * tr.d4_cap + min(u, tr.d4_cap - 1)] & 7u;
+              tr.d4_used[g] = u + 1;
+            } else {
+              d4 = (uint8_t)(pp_splitmix64(((uint64_t)o.seed << 40) ^ ((uint64_t)g << 20) ^
+                                           ((uint64_t)wave << 8) ^ (uint64_t)node ^ tr.hash[nb + node]) & 7u);
+            }
+          }
           tr.eval_d4[slot] = d4;
         }
         slot = __shfl_sync(FULL, slot, 0);
@@ -1097,6 +1111,48 @@ __global__ void __launch_bounds__(BLOCK) k_root_priors(int G, TreeDev tr, float*
     out[(size_t)g * P1 + (tr.elink[(nb + root) * tr.E + i] & 0xFFFFu)] = tr.estat[(nb + root) * tr.E + i].x;
 }
 
+// Root edges in STORAGE order (= the order pi2response produced them, go/mcts/mcts.h:255-332):
+// action, N, W, P per edge and the edge count (0 for a root that is missing or not expanded yet).
+__global__ void __launch_bounds__(BLOCK)
+    k_root_edges(int G, TreeDev tr, int32_t* __restrict__ n_out, int16_t* __restrict__ act, int32_t* __restrict__ vis,
+                 float* __restrict__ wsum, float* __restrict__ pri, int P1) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= G) return;
+  const int root = tr.root[g];
+  const size_t nb = (size_t)g * tr.C;
+  int ne = 0;
+  if (root != NONE16 && tr.hdr[nb + root].status == NS_VISITED) ne = tr.hdr[nb + root].n_edges;
+  if (lane == 0) n_out[g] = ne;
+  for (int i = lane; i < P1; i += 32) {
+    const bool in = i < ne;
+    const float4 e = in ? tr.estat[(nb + root) * tr.E + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t o = (size_t)g * P1 + i;
+    act[o] = in ? (int16_t)(tr.elink[(nb + root) * tr.E + i] & 0xFFFFu) : (int16_t)-1;
+    vis[o] = in ? __float_as_int(e.y) : 0;
+    wsum[o] = e.z;
+    pri[o] = e.x;
+  }
+}
+
+// New priors for the root edges (storage order) of the selected games: the device end of a root
+// noise computed by the caller (elfb200_refstream_root_noise).  The priors are no longer sorted, so
+// the node is flagged for a full PUCT scan like after k_root_noise.
+__global__ void __launch_bounds__(BLOCK)
+    k_set_root_priors(int G, TreeDev tr, const uint8_t* __restrict__ mask, const float* __restrict__ pri, int P1) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= G || (mask && !mask[g])) return;
+  const int root = tr.root[g];
+  if (root == NONE16) return;
+  const size_t nb = (size_t)g * tr.C;
+  if (tr.hdr[nb + root].status != NS_VISITED) return;
+  const int ne = tr.hdr[nb + root].n_edges;
+  if (ne == 0) return;
+  for (int i = lane; i < ne; i += 32) tr.estat[(nb + root) * tr.E + i].x = pri[(size_t)g * P1 + i];
+  if (lane == 0) tr.hdr[nb + root].flags |= NF_FULLSCAN;
+}
+
 __global__ void k_tree_reset(int G, TreeDev tr, const uint8_t* __restrict__ mask) {
   const int lane = threadIdx.x & 31;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1154,6 +1210,14 @@ struct elfb200_mcts {
   int last_eval_count = 0;
   uint32_t move_counter = 0;
   float* d_priors = nullptr;
+  // elfb200_mcts_root_edges / _set_root_priors / _set_d4_stream (allocated on first use)
+  int32_t* d_edge_n = nullptr;
+  int16_t* d_edge_act = nullptr;
+  int32_t* d_edge_vis = nullptr;
+  float* d_edge_w = nullptr;
+  float* d_edge_p = nullptr;
+  uint8_t* d_d4_stream = nullptr;
+  int d4_cap_alloc = 0;
   // per-kernel device timing (CUDA events on the context stream), accumulated on the host
   cudaEvent_t ev[7] = {};  // sel0 sel1 feat0 feat1 exp0 exp1 bak1
   bool pending_sel = false, pending_feat = false, pending_eb = false;
@@ -1306,7 +1370,8 @@ void elfb200_mcts_destroy(elfb200_mcts* m) {
   void* ptrs[] = {t.pos,       t.sa,        t.hash,      t.meta,      t.hdr,        t.estat,       t.elink,      t.free_list,
                   t.free_n,    t.root,      t.leaves,    t.active,     t.eval_count,  t.eval_game,  t.eval_node,
                   t.eval_d4,   t.hist,      t.hinfo,     t.bfs_q,     t.errors,    t.stats,     m->d_mask,    m->d_actions,  m->d_best,    m->d_visits,
-                  m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4, m->d_priors};
+                  m->d_rootv,  m->d_bestq,  m->d_total,  m->d_leaf_hash, m->d_leaf_game, m->d_leaf_ply, m->d_leaf_d4, m->d_priors,
+                  m->d_edge_n, m->d_edge_act, m->d_edge_vis, m->d_edge_w, m->d_edge_p, m->d_d4_stream, t.d4_used};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& e : m->ev)
@@ -1565,6 +1630,88 @@ int elfb200_mcts_root_priors(elfb200_mcts* m, float* priors_host) {
   c->launches++;
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(priors_host, m->d_priors, G * P1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_root_edges(elfb200_mcts* m, int32_t* n_edges_host, int16_t* actions_host, int32_t* visits_host,
+                            float* wsum_host, float* priors_host) {
+  if (!m || !n_edges_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t G = c->G, P1 = (size_t)c->N * c->N + 1;
+  if (!m->d_edge_n) CK(cudaMalloc(&m->d_edge_n, G * 4));
+  if (!m->d_edge_act) CK(cudaMalloc(&m->d_edge_act, G * P1 * 2));
+  if (!m->d_edge_vis) CK(cudaMalloc(&m->d_edge_vis, G * P1 * 4));
+  if (!m->d_edge_w) CK(cudaMalloc(&m->d_edge_w, G * P1 * 4));
+  if (!m->d_edge_p) CK(cudaMalloc(&m->d_edge_p, G * P1 * 4));
+  k_root_edges<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, m->d_edge_n, m->d_edge_act, m->d_edge_vis,
+                                                          m->d_edge_w, m->d_edge_p, (int)P1);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(n_edges_host, m->d_edge_n, G * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (actions_host) CK(cudaMemcpyAsync(actions_host, m->d_edge_act, G * P1 * 2, cudaMemcpyDeviceToHost, c->stream));
+  if (visits_host) CK(cudaMemcpyAsync(visits_host, m->d_edge_vis, G * P1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (wsum_host) CK(cudaMemcpyAsync(wsum_host, m->d_edge_w, G * P1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (priors_host) CK(cudaMemcpyAsync(priors_host, m->d_edge_p, G * P1 * 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_set_root_priors(elfb200_mcts* m, const uint8_t* mask_host, const float* priors_host) {
+  if (!m || !priors_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t G = c->G, P1 = (size_t)c->N * c->N + 1;
+  if (!m->d_edge_p) CK(cudaMalloc(&m->d_edge_p, G * P1 * 4));
+  const uint8_t* dm = nullptr;
+  if (mask_host) {
+    CK(cudaMemcpyAsync(m->d_mask, mask_host, G, cudaMemcpyHostToDevice, c->stream));
+    dm = m->d_mask;
+  }
+  CK(cudaMemcpyAsync(m->d_edge_p, priors_host, G * P1 * 4, cudaMemcpyHostToDevice, c->stream));
+  k_set_root_priors<<<warp_grid(c->G), BLOCK, 0, c->stream>>>(c->G, m->tr, dm, m->d_edge_p, (int)P1);
+  c->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));  // the host tables may be reused by the caller
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_set_d4_stream(elfb200_mcts* m, const uint8_t* codes_host, int count) {
+  if (!m) return elfb200_fail(ELFB200_ERR_ARG, "mcts is NULL");
+  elfb200_ctx* c = m->ctx;
+  CK(cudaSetDevice(c->device));
+  const size_t G = c->G;
+  if (!codes_host) {  // back to the counter-based generator
+    m->tr.d4_stream = nullptr;
+    return ELFB200_OK;
+  }
+  if (count < m->waves_per_move * m->tr.B)
+    return elfb200_fail(ELFB200_ERR_ARG, "a move may evaluate %d leaves per game: %d codes are not enough",
+                        m->waves_per_move * m->tr.B, count);
+  if (count > m->d4_cap_alloc) {
+    CK(cudaStreamSynchronize(c->stream));
+    if (m->d_d4_stream) CK(cudaFree(m->d_d4_stream));
+    m->d_d4_stream = nullptr;
+    m->d4_cap_alloc = 0;
+    CK(cudaMalloc(&m->d_d4_stream, G * (size_t)count));
+    m->d4_cap_alloc = count;
+  }
+  if (!m->tr.d4_used) CK(cudaMalloc(&m->tr.d4_used, G * 4));
+  CK(cudaMemcpyAsync(m->d_d4_stream, codes_host, G * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(m->tr.d4_used, 0, G * 4, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  m->tr.d4_stream = m->d_d4_stream;
+  m->tr.d4_cap = count;
+  return ELFB200_OK;
+}
+
+int elfb200_mcts_d4_used(elfb200_mcts* m, int32_t* used_host) {
+  if (!m || !used_host) return elfb200_fail(ELFB200_ERR_ARG, "NULL argument");
+  elfb200_ctx* c = m->ctx;
+  if (!m->tr.d4_stream || !m->tr.d4_used) return elfb200_fail(ELFB200_ERR_STATE, "no D4 stream is set");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(used_host, m->tr.d4_used, (size_t)c->G * 4, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return ELFB200_OK;
 }

@@ -76,6 +76,20 @@ SIGNATURES = {
     "elfb200_mcts_choose": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_float, vp, ctypes.c_uint64, vp, vp]),
     "elfb200_mcts_errors": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_root_priors": (ctypes.c_int, [vp, vp]),
+    "elfb200_mcts_root_edges": (ctypes.c_int, [vp, vp, vp, vp, vp, vp]),
+    "elfb200_mcts_set_root_priors": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_mcts_set_d4_stream": (ctypes.c_int, [vp, vp, ctypes.c_int]),
+    "elfb200_mcts_d4_used": (ctypes.c_int, [vp, vp]),
+    "elfb200_refstream_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(vp)]),
+    "elfb200_refstream_destroy": (None, [vp]),
+    "elfb200_refstream_init_actor": (ctypes.c_int, [vp, ctypes.c_int, vp]),
+    "elfb200_refstream_game_u32": (ctypes.c_int, [vp, vp, vp]),
+    "elfb200_refstream_game_uniform": (ctypes.c_int, [vp, vp, ctypes.c_double, ctypes.c_double, vp]),
+    "elfb200_refstream_actor_d4": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, vp]),
+    "elfb200_refstream_actor_discard": (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
+    "elfb200_refstream_root_noise": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float]),
+    "elfb200_refstream_choose": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    "elfb200_refstream_edge_order": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, vp, vp]),
     "elfb200_mcts_eval_count": (ctypes.c_int64, [vp]),
     "elfb200_mcts_stats": (ctypes.c_int, [vp, vp]),
     "elfb200_mcts_timings": (ctypes.c_int, [vp, vp, vp, ctypes.c_int]),

@@ -11,9 +11,10 @@ import ctypes
 import numpy as np
 
 from . import lib as _l
+from .refstream import RefStreamSearch
 
 
-class MctsBatch:
+class MctsBatch(RefStreamSearch):
     """``feature_format``: "f32" = the GoFeature contract, ``batch["s"]`` float32 ``[n,18,N,N]``
     (default); "f16" / "bf16" = the fast mode for a half-precision channels-last network: the leaf
     batch is written as ``batch["s_nhwc"]`` ``[n,N,N,cpad]`` (planes in channels 0..17, zeros above),
@@ -87,12 +88,15 @@ class MctsBatch:
             pass
 
     def reset(self, mask=None):
+        self._ref_settle()
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         _l.check(self._lib, self._lib.elfb200_mcts_reset(self._m, m.ctypes.data if m is not None else None))
 
     def begin_move(self, active=None):
+        self._ref_settle()
         a = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
         _l.check(self._lib, self._lib.elfb200_mcts_begin_move(self._m, a.ctypes.data if a is not None else None))
+        self._ref_begin(a)
         if self.strict_root:
             bad = int(self.errors()[0])
             if bad != self._mismatches:
@@ -173,6 +177,7 @@ class MctsBatch:
         return a, v
 
     def advance(self, actions):
+        self._ref_settle()
         a = np.ascontiguousarray(actions, dtype=np.int32)
         _l.check(self._lib, self._lib.elfb200_mcts_advance(self._m, a.ctypes.data))
 

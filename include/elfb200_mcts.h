@@ -117,6 +117,26 @@ int elfb200_mcts_advance(elfb200_mcts* m, const int32_t* actions_host);
 /* float[G][N*N+1]: current prior of every root edge by action (-1 where the root has no such
  * edge), after any exploration noise (NodeT::enhanceExploration, tree_search_node.h:132-155). */
 int elfb200_mcts_root_priors(elfb200_mcts* m, float* priors_host);
+/* The root edges of every game in STORAGE order -- the order MCTSActor::pi2response produced them
+ * and NodeT::setEvaluation inserted them into the reference's edge container (go/mcts/mcts.h:255-332,
+ * tree_search_node.h:176-203): n_edges int32[G] (0 = no expanded root), and per edge, row stride
+ * N*N+1: action int16 (-1 past the end), visit count N int32, reward sum W float, prior P float.
+ * Any table but n_edges may be NULL.  With elfb200_refstream.h this is what the reference's
+ * container-order consumers need (first-maximum tie-break, sample_multinomial, root noise). */
+int elfb200_mcts_root_edges(elfb200_mcts* m, int32_t* n_edges_host, int16_t* actions_host, int32_t* visits_host,
+                            float* wsum_host, float* priors_host);
+/* Overwrite the priors of the root edges (storage order, float[G][N*N+1]) of the selected games
+ * (mask uint8[G], NULL = all): the device end of NodeT::enhanceExploration when the noise is drawn
+ * by the caller (elfb200_refstream_root_noise) instead of the built-in counter-based generator
+ * (create the search with root_epsilon = 0 then).  Call between begin_move and the first wave. */
+int elfb200_mcts_set_root_priors(elfb200_mcts* m, const uint8_t* mask_host, const float* priors_host);
+/* rotation_flip from a caller-supplied stream: codes uint8[G][count], the D4 codes game g's next
+ * evaluated leaves receive, in the order the leaves are claimed (BoardFeature::RandomShuffle draws
+ * them from the actor's generator in that order, board_feature.h:74-78, go/mcts/mcts.h:86-93).
+ * count >= num_rollouts rounded up to whole waves; resets the per-game consumption counters, which
+ * elfb200_mcts_d4_used reads back (int32[G]).  codes = NULL returns to the built-in generator. */
+int elfb200_mcts_set_d4_stream(elfb200_mcts* m, const uint8_t* codes_host, int count);
+int elfb200_mcts_d4_used(elfb200_mcts* m, int32_t* used_host);
 /* int32[4]: [0] root-hash mismatches (the reference throws "Root state is not the same as the input
  * state", tree_search.h:488-492; here the stale tree is discarded and rebuilt from the board),
  * [1] node-pool exhaustion during a descent (rollout cut short), [2] descents cut at 128 plies

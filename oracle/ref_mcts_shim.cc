@@ -36,6 +36,7 @@
 #include "elfgames/go/mcts/mcts.h"
 #undef private
 #undef protected
+#include "elfgames/go/common/game_utils.h"
 
 #include "fakenet.h"
 
@@ -191,7 +192,22 @@ extern "C" {
 //        [3] persistent_tree, [4] use_prior, [5] unexplored_q_zero, [6] root_unexplored_q_zero,
 //        [7] ply_pass_enabled, [8] remove_pass_if_dangerous, [9] seed, [10] num_threads
 // fopts: [0] c_puct, [1] komi, [2] root_epsilon, [3] root_alpha
+static void* ref_mcts_build(const int32_t* iopts, const float* fopts, eval_cb_t cb, int rotation_flip,
+                            uint64_t seed);
+
 void* ref_mcts_new(const int32_t* iopts, const float* fopts, eval_cb_t cb) {
+  return ref_mcts_build(iopts, fopts, cb, 0, (uint64_t)iopts[9]);
+}
+
+// Same, with the two things GoGameSelfPlay::init_ai leaves to the game thread's generator and the
+// defaults: rotation_flip as MCTSActorParams has it (true, go/mcts/mcts.h:26) and
+// params.seed = _rng() (game_selfplay.cc:47), a full 32-bit value.
+void* ref_mcts_new_ex(const int32_t* iopts, const float* fopts, eval_cb_t cb, int rotation_flip, uint32_t seed) {
+  return ref_mcts_build(iopts, fopts, cb, rotation_flip, (uint64_t)seed);
+}
+
+static void* ref_mcts_build(const int32_t* iopts, const float* fopts, eval_cb_t cb, int rotation_flip,
+                            uint64_t seed) {
   TSOptions opt;
   opt.num_threads = iopts[10] > 0 ? iopts[10] : 1;
   opt.num_rollouts_per_thread = iopts[0];
@@ -211,9 +227,9 @@ void* ref_mcts_new(const int32_t* iopts, const float* fopts, eval_cb_t cb) {
   params.actor_name = "shim";
   params.ply_pass_enabled = iopts[7];
   params.remove_pass_if_dangerous = iopts[8] != 0;
-  params.seed = (uint64_t)iopts[9];
+  params.seed = seed;
   params.komi = fopts[1];
-  params.rotation_flip = false;  // D4 is drawn from a per-actor mt19937 in the reference
+  params.rotation_flip = rotation_flip != 0;  // D4 is drawn from the per-actor mt19937
   params.required_version = -1;
 
   RefMcts* m = new RefMcts();
@@ -253,6 +269,46 @@ int ref_mcts_act(void* p, void* state, int32_t* visits, float* wsum, float* prio
   if (best_q) *best_q = res.total_visits == 0 ? res.root_value : res.best_edge_info.getQSA();
   if (total_visits) *total_visits = res.total_visits;
   return c2a(c);
+}
+
+// The root edges of the last search in the order MCTSResultT::addActions walked the root's
+// stateActions_ (tree_search_base.h:237-294): actions[i] = action index of the i-th edge.
+int ref_mcts_last_order(void* p, int32_t* actions) {
+  RefMcts* m = static_cast<RefMcts*>(p);
+  const auto& res = m->ai->getLastResult();
+  int i = 0;
+  for (const auto& ae : res.action_edge_pairs) actions[i++] = c2a(ae.first);
+  return i;
+}
+
+// A game thread's generator (GoGameBase::_rng, game_base.h:38,62).
+void* ref_rng_new(uint64_t seed) {
+  std::mt19937* r = new std::mt19937();
+  r->seed(seed);
+  return r;
+}
+void ref_rng_free(void* r) { delete static_cast<std::mt19937*>(r); }
+uint32_t ref_rng_next(void* r) { return (uint32_t)(*static_cast<std::mt19937*>(r))(); }
+
+// The sampling lines of GoGameSelfPlay::mcts_make_diverse_move (game_selfplay.cc:80-88):
+// MCTSGoAI::getMCTSPolicy (go/mcts/mcts.h:367-372) then MCTSPolicy::sampleAction on the game
+// thread's generator.
+int ref_mcts_sample(void* p, void* rng) {
+  RefMcts* m = static_cast<RefMcts*>(p);
+  auto policy = m->ai->getLastResult().mcts_policy;
+  policy.normalize();
+  return c2a(policy.sampleAction(static_cast<std::mt19937*>(rng)));
+}
+
+// GoStateExt::shouldResign on a persistent ResignCheck (go_state_ext.h:207-214, game_utils.h:15-54):
+// the never-resign draw happens at the first call after a reset, from the game thread's generator.
+void* ref_resign_new(float thres, float never_resign_ratio) { return new ResignCheck(thres, never_resign_ratio); }
+void ref_resign_free(void* rc) { delete static_cast<ResignCheck*>(rc); }
+void ref_resign_reset(void* rc) { static_cast<ResignCheck*>(rc)->reset(); }
+int ref_resign_check(void* rc, float value, int next_player, void* rng) {
+  ResignCheck* c = static_cast<ResignCheck*>(rc);
+  std::mt19937* r = static_cast<std::mt19937*>(rng);
+  return (next_player == S_BLACK ? c->check(value, r) : c->check(-value, r)) ? 1 : 0;
 }
 
 long ref_mcts_num_evals(void* p) {

@@ -9,6 +9,7 @@ import numpy as np
 
 from elf_b200 import lib as _l
 from elf_b200.board import GoBatch
+from elf_b200.refstream import RefStreamSearch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
@@ -35,7 +36,7 @@ def emu_batch(G, n):
     return gb
 
 
-class EmuSearch:
+class EmuSearch(RefStreamSearch):
     """MctsBatch's interface (begin_move / select / leaf_info / expand_backup / results / choose /
     advance / reset / search / act) over the emulated C ABI with CPU torch tensors"""
 
@@ -75,12 +76,15 @@ class EmuSearch:
             self._m = None
 
     def reset(self, mask=None):
+        self._ref_settle()
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         _l.check(self._lib, self._lib.elfb200_mcts_reset(self._m, m.ctypes.data if m is not None else None))
 
     def begin_move(self, active=None):
+        self._ref_settle()
         a = None if active is None else np.ascontiguousarray(active, dtype=np.uint8)
         _l.check(self._lib, self._lib.elfb200_mcts_begin_move(self._m, a.ctypes.data if a is not None else None))
+        self._ref_begin(a)
         if self.strict_root:
             bad = int(self.errors()[0])
             if bad != self._mismatches:
@@ -134,6 +138,7 @@ class EmuSearch:
         return a, v
 
     def advance(self, actions):
+        self._ref_settle()
         a = np.ascontiguousarray(actions, dtype=np.int32)
         _l.check(self._lib, self._lib.elfb200_mcts_advance(self._m, a.ctypes.data))
 

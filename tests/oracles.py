@@ -405,7 +405,8 @@ class RefMcts:
 
     def __init__(self, n, num_rollouts=200, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1,
                  use_prior=1, unexplored_q_zero=0, root_unexplored_q_zero=0, ply_pass_enabled=0,
-                 remove_pass_if_dangerous=1, seed=7, c_puct=1.5, komi=7.5, callback=None):
+                 remove_pass_if_dangerous=1, seed=7, c_puct=1.5, komi=7.5, callback=None, root_epsilon=0.0,
+                 root_alpha=0.0, rotation_flip=0):
         self.L = load_ref(n)
         self.n = n
         L = self.L
@@ -417,8 +418,8 @@ class RefMcts:
         L.ref_mcts_num_evals.argtypes = [vp]
         iopts = np.array([num_rollouts, num_rollouts_per_batch, virtual_loss, persistent_tree, use_prior,
                           unexplored_q_zero, root_unexplored_q_zero, ply_pass_enabled, remove_pass_if_dangerous,
-                          seed, 1], np.int32)
-        fopts = np.array([c_puct, komi, 0, 0], np.float32)
+                          int(seed) & 0x7FFFFFFF, 1], np.int32)  # [9] only feeds TSOptions::seed (unused by the search)
+        fopts = np.array([c_puct, komi, root_epsilon, root_alpha], np.float32)
         self._cb = None
         if callback is not None:
             CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64),
@@ -433,7 +434,23 @@ class RefMcts:
                 np.ctypeslib.as_array(v, shape=(cnt,))[:] = val
 
             self._cb = CB(tramp)
-        self.m = L.ref_mcts_new(iopts.ctypes.data, fopts.ctypes.data, ctypes.cast(self._cb, vp) if self._cb else None)
+        L.ref_mcts_new_ex.restype = vp
+        L.ref_mcts_new_ex.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_uint32]
+        L.ref_mcts_last_order.argtypes = [vp, vp]
+        L.ref_mcts_sample.argtypes = [vp, vp]
+        cbp = ctypes.cast(self._cb, vp) if self._cb else None
+        # seed: MCTSActorParams::seed, a full 32-bit value when it comes from the game thread's generator
+        self.m = L.ref_mcts_new_ex(iopts.ctypes.data, fopts.ctypes.data, cbp, int(rotation_flip), int(seed) & 0xFFFFFFFF)
+
+    def last_order(self):
+        """actions of the root edges in the order MCTSResultT::addActions walked the container"""
+        a = np.zeros(self.n * self.n + 1, np.int32)
+        k = self.L.ref_mcts_last_order(self.m, a.ctypes.data)
+        return a[:k].copy()
+
+    def sample(self, rng):
+        """mcts_make_diverse_move's sampling on the game thread's generator (a RefRng)"""
+        return int(self.L.ref_mcts_sample(self.m, rng.p))
 
     def act(self, ref_state):
         P1 = self.n * self.n + 1
@@ -455,6 +472,51 @@ class RefMcts:
         if getattr(self, "m", None):
             self.L.ref_mcts_free(self.m)
             self.m = None
+
+
+class RefRng:
+    """a reference game thread's std::mt19937 (GoGameBase::_rng) through oracle/_ref"""
+
+    def __init__(self, n, seed):
+        self.L = L = load_ref(n)
+        L.ref_rng_new.restype = vp
+        L.ref_rng_new.argtypes = [ctypes.c_uint64]
+        L.ref_rng_free.argtypes = [vp]
+        L.ref_rng_next.restype = ctypes.c_uint32
+        L.ref_rng_next.argtypes = [vp]
+        self.p = L.ref_rng_new(int(seed))
+
+    def next(self):
+        return int(self.L.ref_rng_next(self.p))
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            self.L.ref_rng_free(self.p)
+            self.p = None
+
+
+class RefResign:
+    """the reference's ResignCheck as GoStateExt::shouldResign drives it, with its random draw"""
+
+    def __init__(self, n, thres, never_resign_ratio):
+        self.L = L = load_ref(n)
+        L.ref_resign_new.restype = vp
+        L.ref_resign_new.argtypes = [ctypes.c_float, ctypes.c_float]
+        L.ref_resign_free.argtypes = [vp]
+        L.ref_resign_reset.argtypes = [vp]
+        L.ref_resign_check.argtypes = [vp, ctypes.c_float, ctypes.c_int, vp]
+        self.p = L.ref_resign_new(float(thres), float(never_resign_ratio))
+
+    def check(self, value, next_player, rng):
+        return bool(self.L.ref_resign_check(self.p, float(value), int(next_player), rng.p))
+
+    def reset(self):
+        self.L.ref_resign_reset(self.p)
+
+    def __del__(self):
+        if getattr(self, "p", None):
+            self.L.ref_resign_free(self.p)
+            self.p = None
 
 
 class OracleMcts:

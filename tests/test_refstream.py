@@ -1,0 +1,125 @@
+"""The reference's random streams (include/elfb200_refstream.h, elf_b200/refstream.py) against the
+COMPILED reference (oracle/_ref): container order of the root edges, root Dirichlet noise, the D4
+code of every evaluated leaf, sampled moves and the never-resign draw -- whole self-play games, move
+for move.  The search kernels run on the SIMT emulator here (tests/test_gpu_mcts.py has the device
+twin)."""
+import numpy as np
+import pytest
+import torch
+
+from elf_b200.refstream import RefStream
+from tests import emu, oracles
+
+pytestmark = pytest.mark.skipif(not oracles.have_ref(9), reason="compiled reference (oracle/_ref) not available")
+
+
+def plane_actor(n):
+    def actor(batch):
+        pi, v = oracles.feature_net(batch["s"].float().numpy(), n * n + 1)
+        return {"pi": torch.from_numpy(pi), "V": torch.from_numpy(v)}
+
+    return actor
+
+
+def ref_net(n):
+    return lambda feats, hashes: oracles.feature_net(feats, n * n + 1)
+
+
+def test_edge_order_is_the_reference_containers():
+    n = 9
+    st = oracles.Ref(n)
+    rng = np.random.default_rng(5)
+    for ply in range(30):
+        ref = oracles.RefMcts(n, num_rollouts=24, num_rollouts_per_batch=4, callback=ref_net(n))
+        r = ref.act(st)
+        order = ref.last_order()
+        has = np.flatnonzero(r["visits"] >= 0)
+        assert sorted(order.tolist()) == has.tolist()
+        pri = r["prior"][has]
+        assert len(np.unique(pri)) == len(pri)  # distinct priors: the insertion order is well defined
+        inserted = has[np.argsort(-pri, kind="stable")]  # pi2response: descending prior
+        ours = inserted[RefStream.edge_order(n, inserted)]
+        np.testing.assert_array_equal(ours, order)
+        legal = np.flatnonzero(st.legal())
+        st.forward(int(rng.choice(legal)) if len(legal) else n * n)
+
+
+def play_reference_game(n, seed, opts, eps, alpha, flip, cutoff, thres, ratio, max_moves):
+    """one game thread of GoGameSelfPlay::act (game_selfplay.cc:272-430) composed from the reference's
+    own pieces: init_ai's seed draw, MCTSAI_T::act, mcts_make_diverse_move, shouldResign, forward"""
+    g = oracles.RefRng(n, seed)
+    ref = oracles.RefMcts(n, callback=ref_net(n), root_epsilon=eps, root_alpha=alpha, rotation_flip=flip,
+                          seed=g.next(), **opts)
+    rc = oracles.RefResign(n, thres, ratio)
+    st = oracles.Ref(n)
+    log = []
+    for _ in range(max_moves):
+        info = st.info()
+        ply, nxt = int(info[0]), int(info[1])
+        r = ref.act(st)
+        a = r["best_action"]
+        if ply <= cutoff:
+            a = ref.sample(g)
+        resign = rc.check(r["best_q"], nxt, g) and ply >= 50
+        log.append({"visits": r["visits"].copy(), "prior": r["prior"].copy(), "action": int(a), "value": r["best_q"],
+                    "resign": bool(resign), "best": int(r["best_action"])})
+        if resign:
+            break
+        assert st.forward(int(a))
+        if st.info()[9]:
+            break
+    return log
+
+
+@pytest.mark.parametrize("eps,flip", [(0.25, 1), (0.0, 1), (0.25, 0)])
+def test_whole_games_move_for_move(eps, flip):
+    n, G, seed, moves = 9, 3, 20240917, 40
+    opts = dict(num_rollouts=32, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5, komi=7.5)
+    cutoff, thres, ratio, alpha = 12, 0.05, 0.1, 0.3
+    seeds = [seed, seed, seed + 1]  # GameOptions::seed seeds every game thread alike; one more for variety
+    logs = [play_reference_game(n, s, opts, eps, alpha, flip, cutoff, thres, ratio, moves) for s in seeds]
+
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, rotation_flip=flip, **opts)
+    rs = RefStream(G, n, np.array(seeds, np.uint64))
+    rs.init_actor(0)
+    mc.attach_ref_stream(rs, 0, eps, alpha)
+    actor = plane_actor(n)
+    alive = np.ones(G, bool)
+    drawn = np.zeros(G, bool)
+    never = np.zeros(G, bool)
+    for t in range(moves):
+        info = gb.info()
+        mc.search(actor, active=alive.astype(np.uint8))
+        res = mc.results()
+        pri = mc.root_priors()
+        cho = mc.ref_choose(sample=(info[:, 0] <= cutoff), mask=alive.astype(np.uint8))
+        need = alive & ~drawn
+        u = rs.game_uniform(need.astype(np.uint8))
+        never[need] = u[need] < ratio
+        drawn |= need
+        side = np.where(info[:, 1] == 1, cho["value"], -cho["value"]).astype(np.float64)
+        resign = alive & ~never & ~(side >= -1.0 + float(np.float32(thres))) & (info[:, 0] >= 50)
+        acts = np.full(G, -2, np.int32)
+        for g in np.flatnonzero(alive):
+            L = logs[g][t]
+            np.testing.assert_array_equal(res["visits"][g], L["visits"], err_msg=f"game {g} move {t}: visits")
+            has = L["visits"] >= 0
+            np.testing.assert_array_equal(pri[g][has], L["prior"][has], err_msg=f"game {g} move {t}: priors")
+            assert cho["best_action"][g] == L["best"], (g, t)
+            assert cho["action"][g] == L["action"], (g, t)
+            # W is a float sum whose order the reference leaves to the addresses of its leaf nodes
+            # (batch_rollouts walks an unordered_map keyed by Node*): equal up to the last bits
+            assert np.isclose(cho["value"][g], L["value"], rtol=2e-6, atol=1e-7, equal_nan=True), (g, t)
+            assert bool(resign[g]) == L["resign"]
+            acts[g] = cho["action"][g]
+            if t + 1 == len(logs[g]):
+                alive[g] = False
+        gb.forward(acts)
+        mc.advance(acts)
+        if not alive.any():
+            break
+    assert t >= 20
+    # the two game threads with the same GameOptions::seed played the same game; the third did not
+    assert [m["action"] for m in logs[0]] == [m["action"] for m in logs[1]]
+    assert [m["action"] for m in logs[0]] != [m["action"] for m in logs[2]]
