@@ -735,6 +735,10 @@ def game_context(co, opt, board_size=19, device=0, factories=None):
                                                              opt.white_mcts_rollout_per_batch, opt.white_puct).items()
                              if v != common.get(k)},
             **common)
+        if int(opt.seed) != 0 and not (kw["black_use_policy_network_only"] or kw["white_use_policy_network_only"]):
+            # GameOptions::seed != 0: every game thread's generator starts from it (game_base.h:32-38) and
+            # the reference's games are reproducible -- ours are then the same games (elf_b200.refstream)
+            kw["rng"] = "reference"
         sp = f.get("selfplay", SelfPlay)(**kw)
         return GameContext(SelfPlayEngine(sp), batchsize=int(co.batchsize))
     if opt.mode == "online":

@@ -8,8 +8,14 @@ one MCTS per move, ``mcts_make_diverse_move`` (sample from the visit distributio
 ``GoState::forward``, game end on two passes / ply cap / superko / ``move_cutoff`` with the final
 value from ``GoState::evaluate(komi)`` (``go_state_ext.h:79-105``), then restart.
 
-Randomness (move sampling, never-resign draw) comes from a numpy Generator, not from the
-reference's per-game ``std::mt19937`` streams: distributions are the same, streams are not.
+Randomness: by default move sampling runs on the device (counter-based generator) and the
+never-resign draw comes from a numpy Generator -- the reference's distributions, not its streams.
+``rng="reference"`` switches to the reference's own streams (``elf_b200.refstream``): every game
+owns the two ``std::mt19937`` generators of a reference game thread seeded from ``seed``
+(``GameOptions::seed``; an array gives every game its own), root noise / D4 codes / sampled moves /
+the never-resign draw consume them exactly where ``GoGameSelfPlay::act`` does, and ties between
+equally visited moves resolve in the reference's container order: the batch then plays, move for
+move, the games the reference's game threads play with that seed (single search thread).
 """
 import numpy as np
 
@@ -22,7 +28,7 @@ class SelfPlay:
                  resign_thres=0.05, never_resign_ratio=0.1, move_cutoff=-1, komi=7.5, seed=0,
                  record_games=False, actor_white=None, board=None, search=None, search_white=None,
                  white_mcts_opts=None, black_use_policy_network_only=False, white_use_policy_network_only=False,
-                 policy_distri_training_for_all=False, num_games_per_thread=-1, **mcts_opts):
+                 policy_distri_training_for_all=False, num_games_per_thread=-1, rng="numpy", **mcts_opts):
         # board / search / search_white: pre-built GoBatch / MctsBatch objects (or duck-typed stand-ins:
         # the CPU tests of the host logic inject oracle-backed ones); by default they are created here
         self.gb = board if board is not None else GoBatch(num_games, board_size=board_size, device=device)
@@ -31,15 +37,32 @@ class SelfPlay:
         # the second AI may search differently (GameOptions::white_puct / white_mcts_rollout_per_batch /
         # white_mcts_rollout_per_thread, game_selfplay.cc:175-182): overrides on top of the common options
         self._white_opts = {**mcts_opts, **(white_mcts_opts or {})}
-        self.mcts = search if search is not None else MctsBatch(self.gb, **mcts_opts)
+        if rng not in ("numpy", "reference"):
+            raise ValueError("rng must be 'numpy' or 'reference'")
+        self.ref = None
+        if rng == "reference":
+            if black_use_policy_network_only or white_use_policy_network_only:
+                raise NotImplementedError("rng='reference' covers the searched colours only")
+            from .refstream import RefStream
+
+            self.ref = RefStream(num_games, board_size, seed)
+            self._ref_started = False  # the actors are seeded at the first restart() (game_selfplay.cc:151-200)
+            self._nr_drawn = np.zeros(num_games, bool)  # ResignCheck::has_calculated_never_resign
+            seed = int(np.asarray(seed).reshape(-1)[0])
+        self.mcts = search if search is not None else self._make_search(mcts_opts, 0)
+        if search is not None and self.ref is not None:
+            search.attach_ref_stream(self.ref, 0, float(mcts_opts.get("root_epsilon", 0)), float(mcts_opts.get("root_alpha", 0)))
         self.actor = actor
         # evaluation matches (GoGameSelfPlay::_ai2, game_selfplay.cc:366-367): a second AI with its own
         # tree plays white; both trees follow every move (MCTSAI_T::advanceMoves)
         self.actor_white = actor_white
         if search_white is not None:
             self.mcts2 = search_white
+            if self.ref is not None:
+                search_white.attach_ref_stream(self.ref, 1, float(self._white_opts.get("root_epsilon", 0)),
+                                               float(self._white_opts.get("root_alpha", 0)))
         else:
-            self.mcts2 = MctsBatch(self.gb, **self._white_opts) if (actor_white is not None and search is None) else None
+            self.mcts2 = self._make_search(self._white_opts, 1) if (actor_white is not None and search is None) else None
         # server requests (MsgRequest: model versions + client control), see set_request()
         self.request = {"black_ver": -1, "white_ver": -1, "player_swap": False, "async": False,
                         "num_game_thread_used": -1}
@@ -59,7 +82,7 @@ class SelfPlay:
         self.rng = np.random.default_rng(seed)
         self._seed = int(seed)
         self._move_counter = 0
-        self.never_resign = self.rng.random(num_games) < never_resign_ratio
+        self.never_resign = (self.rng.random(num_games) < never_resign_ratio) if self.ref is None else np.zeros(num_games, bool)
         self.moves_played = 0
         self.games_finished = 0
         self.results = []  # (final_value, plies, reason) of finished games
@@ -75,6 +98,54 @@ class SelfPlay:
         self.num_games_per_thread = int(num_games_per_thread)
         self.games_per_slot = np.zeros(num_games, np.int64)
         self.stopped = np.zeros(num_games, bool)
+
+    def _make_search(self, opts, which):
+        """the search of AI ``which`` (0 = _ai, 1 = _ai2); under rng='reference' its root noise is drawn
+        on the host from that AI's generator, so the device's own noise stays off"""
+        if self.ref is None:
+            return MctsBatch(self.gb, **opts)
+        o = dict(opts)
+        eps, alpha = float(o.pop("root_epsilon", 0.0)), float(o.pop("root_alpha", 0.0))
+        mc = MctsBatch(self.gb, **o)
+        mc.attach_ref_stream(self.ref, which, eps, alpha)
+        return mc
+
+    def _ref_start(self):
+        """GoGameSelfPlay::restart for a batch that never saw a request: init_ai seeds _ai (and _ai2)
+        from the game generator (game_selfplay.cc:47,165-182)"""
+        if self.ref is not None and not self._ref_started:
+            self.ref.init_actor(0)
+            if self.mcts2 is not None:
+                self.ref.init_actor(1)
+            self._ref_started = True
+
+    def _choose_reference(self, info):
+        """mcts_make_diverse_move + mcts_update_info + shouldResign (game_selfplay.cc:80-101,387-391) on
+        the reference's streams: returns (actions, values) like ``MctsBatch.choose``"""
+        G = self.G
+        searched = np.ones(G, bool) if self.idle is None else ~self.idle
+        sample = info[:, 0] <= self.policy_distri_cutoff
+        if self.mcts2 is None:
+            c = self.mcts.ref_choose(sample, mask=searched.astype(np.uint8))
+            acts, vals = c["action"].copy(), c["value"].copy()
+        else:
+            first = (info[:, 1] == 1) != self.swap  # games whose mover was searched by self.mcts (see phases)
+            c1 = self.mcts.ref_choose(sample, mask=(searched & first).astype(np.uint8))
+            c2 = self.mcts2.ref_choose(sample, mask=(searched & ~first).astype(np.uint8))
+            acts = np.where(first, c1["action"], c2["action"]).astype(np.int32)
+            vals = np.where(first, c1["value"], c2["value"]).astype(np.float32)
+        # ResignCheck::check: the first call of a game draws never_resign (game_utils.h:25-30); it is
+        # called every move, whatever the ply (game_selfplay.cc:387)
+        need = searched & ~self._nr_drawn
+        if need.any():
+            u = self.ref.game_uniform(need.astype(np.uint8))
+            self.never_resign[need] = u[need] < float(np.float32(self.never_resign_ratio))
+            self._nr_drawn |= need
+        side = np.where(info[:, 1] == 1, vals, -vals).astype(np.float64)
+        resign = searched & ~self.never_resign & ~(side >= -1.0 + float(np.float32(self.resign_thres))) & (info[:, 0] >= 50)
+        acts[resign] = -1
+        acts[~searched] = -2
+        return acts, vals
 
     def close(self):
         self.mcts.close()
@@ -96,6 +167,7 @@ class SelfPlay:
         One AI for self-play; for a match ``_ai`` (label actor_black) takes the black-to-move games
         and ``_ai2`` (actor_white) the others -- the other way round under player_swap
         (GoGameSelfPlay::restart swaps the two pointers, game_selfplay.cc:185-188)."""
+        self._ref_start()
         act = None if self.idle is None else ~self.idle
         if self.mcts2 is None:
             return [(self.mcts, self.actor, "actor_black", None if act is None else act.astype(np.uint8))]
@@ -109,6 +181,7 @@ class SelfPlay:
     def step(self):
         """one move of every game; returns the number of moves played"""
         info = self.gb.info()
+        self._ref_start()
         if self.policy_only[1] or self.policy_only[2]:
             return self.finish_move(info, chosen=self._search_with_policy_only(info))
         if self.mcts2 is None and self.idle is None:
@@ -214,7 +287,7 @@ class SelfPlay:
         idle = idle | self.stopped  # slots that have played their num_games_per_thread stay out
         self.idle = idle if idle.any() else None
         if new["white_ver"] >= 0 and self.mcts2 is None:  # a match needs the second AI
-            self.mcts2 = MctsBatch(self.gb, **self._white_opts)
+            self.mcts2 = self._make_search(self._white_opts, 1)
         two = new["white_ver"] >= 0
         if not two and self.mcts2 is not None and self.actor_white is None and was_protocol:
             # back to self-play (ModelPair::is_selfplay): _ai2 is dropped
@@ -258,7 +331,17 @@ class SelfPlay:
         if self.mcts2 is not None:
             self.mcts2.reset(m)
         sel = m.astype(bool)
-        self.never_resign[sel] = self.rng.random(int(sel.sum())) < self.never_resign_ratio
+        if self.ref is None:
+            self.never_resign[sel] = self.rng.random(int(sel.sum())) < self.never_resign_ratio
+        else:
+            # restart(): _ai, then _ai2, are re-created -- init_ai draws their seeds from the game
+            # generator in that order (game_selfplay.cc:165-182); _state_ext.restart() resets ResignCheck
+            self.ref.init_actor(0, m)
+            if self.mcts2 is not None:
+                self.ref.init_actor(1, m)
+            self._ref_started = True
+            self.never_resign[sel] = False
+            self._nr_drawn[sel] = False
         if self.recorders is not None:
             for g in np.flatnonzero(sel):
                 self.recorders[g].restart()
@@ -273,9 +356,11 @@ class SelfPlay:
         nr = self.never_resign.astype(np.uint8)
         if chosen is not None:
             acts, vals = chosen
+        elif self.ref is not None:
+            acts, vals = self._choose_reference(info)
         else:
             acts, vals = self.mcts.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
-        if chosen is None and self.mcts2 is not None:
+        if chosen is None and self.ref is None and self.mcts2 is not None:
             black = (info[:, 1] == 1) != self.swap  # games whose mover was searched by self.mcts (see phases)
             a2, v2 = self.mcts2.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
             acts = np.where(black, acts, a2)
@@ -330,7 +415,11 @@ class SelfPlay:
             self.mcts.reset(m)
             if self.mcts2 is not None:
                 self.mcts2.reset(m)
-            self.never_resign[done] = self.rng.random(int(done.sum())) < self.never_resign_ratio
+            if self.ref is None:
+                self.never_resign[done] = self.rng.random(int(done.sum())) < self.never_resign_ratio
+            else:  # GoStateExt::restart -> ResignCheck::reset: the next game draws again at its first move
+                self.never_resign[done] = False
+                self._nr_drawn[done] = False
             self.games_finished += int(done.sum())
             if self.num_games_per_thread > 0:
                 self.games_per_slot[done] += 1

@@ -442,6 +442,11 @@ class RefMcts:
         # seed: MCTSActorParams::seed, a full 32-bit value when it comes from the game thread's generator
         self.m = L.ref_mcts_new_ex(iopts.ctypes.data, fopts.ctypes.data, cbp, int(rotation_flip), int(seed) & 0xFFFFFFFF)
 
+    def end_game(self, ref_state):
+        """MCTSAI_T::endGame: the tree is reset (finish_game, game_selfplay.cc:139-143)"""
+        self.L.ref_mcts_end_game.argtypes = [vp, vp]
+        self.L.ref_mcts_end_game(self.m, ref_state.p)
+
     def last_order(self):
         """actions of the root edges in the order MCTSResultT::addActions walked the container"""
         a = np.zeros(self.n * self.n + 1, np.int32)

@@ -187,6 +187,7 @@ def test_game_context_from_reference_options():
     assert got["policy_distri_cutoff"] == 30 and got["resign_thres"] == 0.01 and got["move_cutoff"] == 200 and got["seed"] == 5
     assert got["never_resign_ratio"] == 0.1 and got["komi"] == 7.5 and got["actor"] is None
     assert got["white_mcts_opts"] == {"c_puct": 0.85, "num_rollouts": 400}  # only what differs for the second AI
+    assert got["rng"] == "reference"  # GameOptions::seed != 0: the reference's games are reproducible, ours are the same games
     # online and train modes
     opt.mode, opt.preload_sgf, opt.preload_sgf_move_to, opt.following_pass = "online", "g.sgf", 12, True
 
@@ -219,3 +220,8 @@ def test_game_context_from_reference_options():
     opt.mode, opt.white_use_policy_network_only = "selfplay", True
     GC = compat.game_context(co, opt, factories={"selfplay": FakeSelfPlay})
     assert isinstance(GC._engine, compat.SelfPlayEngine) and got["white_use_policy_network_only"] is True
+    assert "rng" not in got  # a policy-only colour keeps the default generators
+    opt.white_use_policy_network_only, opt.seed = False, 0
+    got.clear()
+    compat.game_context(co, opt, factories={"selfplay": FakeSelfPlay})
+    assert "rng" not in got  # seed 0: the reference seeds from the clock

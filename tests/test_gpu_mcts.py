@@ -855,3 +855,63 @@ def test_shim_modules_drive_the_real_engine(monkeypatch):
     ctx.stop()
     wr = GC.getClient().getGameStats().getWinRateStats()
     assert ends >= 8 and batches > 20 and wr.total_games >= 8
+
+
+@pytest.mark.skipif(not oracles.have_ref(9), reason="compiled reference (oracle/_ref) not available")
+def test_selfplay_on_the_reference_random_streams():
+    """SelfPlay(rng="reference") on the device: root noise, D4 code per evaluated leaf, sampled moves and
+    the never-resign draw from the reference's own mt19937 streams -- the games of two reference game
+    threads (composed from the compiled reference's pieces as GoGameSelfPlay::act orders them), move for
+    move, across a game end.  CPU twin on the emulator: tests/test_refstream.py."""
+    import torch
+
+    import elf_b200
+    from elf_b200.selfplay import SelfPlay
+
+    n, G, moves = 9, 3, 26
+    opts = dict(num_rollouts=24, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5, komi=7.5)
+    eps, alpha, cutoff, thres, ratio, move_cutoff = 0.25, 0.3, 8, 0.05, 0.1, 11
+    seeds = np.array([777, 778, 777], np.uint64)
+    net = lambda feats, hashes: oracles.feature_net(feats, n * n + 1)  # noqa: E731
+    expect = []
+    for s in seeds:
+        g = oracles.RefRng(n, int(s))
+        ref = oracles.RefMcts(n, callback=net, root_epsilon=eps, root_alpha=alpha, rotation_flip=1, seed=g.next(), **opts)
+        rc = oracles.RefResign(n, thres, ratio)
+        st = oracles.Ref(n)
+        played = []
+        for _ in range(moves):
+            ply = int(st.info()[0])
+            r = ref.act(st)
+            a = ref.sample(g) if ply <= cutoff else r["best_action"]
+            rc.check(r["best_q"], int(st.info()[1]), g)
+            assert st.forward(int(a))
+            played.append(int(a))
+            if st.info()[9] or int(st.info()[0]) >= move_cutoff:
+                ref.end_game(st)
+                st = oracles.Ref(n)
+                rc.reset()
+        expect.append(played)
+
+    def actor(batch):
+        pi, v = oracles.feature_net(batch["s"].float().cpu().numpy(), n * n + 1)
+        return {"pi": torch.from_numpy(pi).to(batch["s"].device), "V": torch.from_numpy(v).to(batch["s"].device)}
+
+    sp = SelfPlay(actor, num_games=G, board_size=n, rng="reference", seed=seeds, policy_distri_cutoff=cutoff,
+                  resign_thres=thres, never_resign_ratio=ratio, move_cutoff=move_cutoff, root_epsilon=eps,
+                  root_alpha=alpha, rotation_flip=1, **opts)
+    got = [[] for _ in range(G)]
+    fwd = sp.gb.forward
+
+    def logged(acts):
+        for g in range(G):
+            got[g].append(int(acts[g]))
+        return fwd(acts)
+
+    sp.gb.forward = logged
+    for _ in range(moves):
+        sp.step()
+    assert got == expect
+    assert got[0] == got[2] and got[0] != got[1]  # GameOptions::seed: same seed, same game
+    assert sp.games_finished >= 2 * G and (sp.mcts.errors() == 0).all()
+    sp.close()

@@ -25,11 +25,13 @@ def ref_net(n):
     return lambda feats, hashes: oracles.feature_net(feats, n * n + 1)
 
 
-def test_edge_order_is_the_reference_containers():
-    n = 9
+@pytest.mark.parametrize("n", [9, 19])
+def test_edge_order_is_the_reference_containers(n):
+    if not oracles.have_ref(n):
+        pytest.skip("compiled reference not available")
     st = oracles.Ref(n)
     rng = np.random.default_rng(5)
-    for ply in range(30):
+    for ply in range(30 if n == 9 else 8):
         ref = oracles.RefMcts(n, num_rollouts=24, num_rollouts_per_batch=4, callback=ref_net(n))
         r = ref.act(st)
         order = ref.last_order()
@@ -71,9 +73,11 @@ def play_reference_game(n, seed, opts, eps, alpha, flip, cutoff, thres, ratio, m
     return log
 
 
-@pytest.mark.parametrize("eps,flip", [(0.25, 1), (0.0, 1), (0.25, 0)])
-def test_whole_games_move_for_move(eps, flip):
-    n, G, seed, moves = 9, 3, 20240917, 40
+@pytest.mark.parametrize("n,eps,flip,moves", [(9, 0.25, 1, 40), (9, 0.0, 1, 40), (9, 0.25, 0, 40), (19, 0.25, 1, 10)])
+def test_whole_games_move_for_move(n, eps, flip, moves):
+    if not oracles.have_ref(n):
+        pytest.skip("compiled reference not available")
+    G, seed = 3, 20240917
     opts = dict(num_rollouts=32, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5, komi=7.5)
     cutoff, thres, ratio, alpha = 12, 0.05, 0.1, 0.3
     seeds = [seed, seed, seed + 1]  # GameOptions::seed seeds every game thread alike; one more for variety
@@ -119,7 +123,60 @@ def test_whole_games_move_for_move(eps, flip):
         mc.advance(acts)
         if not alive.any():
             break
-    assert t >= 20
+    assert t >= min(20, moves - 1)
     # the two game threads with the same GameOptions::seed played the same game; the third did not
     assert [m["action"] for m in logs[0]] == [m["action"] for m in logs[1]]
     assert [m["action"] for m in logs[0]] != [m["action"] for m in logs[2]]
+
+
+def test_selfplay_driver_on_the_reference_streams():
+    """SelfPlay(rng="reference"): the whole per-move driver (search, choice, resign check, forward, tree
+    advance, restart) replays the reference game threads' games, including the game after a restart"""
+    from elf_b200.selfplay import SelfPlay
+
+    n, G, moves = 9, 2, 26
+    opts = dict(num_rollouts=24, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5, komi=7.5)
+    eps, alpha, cutoff, thres, ratio, move_cutoff = 0.25, 0.3, 8, 0.05, 0.1, 11
+    seeds = np.array([777, 778], np.uint64)
+
+    # reference side: one generator per game thread lives across games; move_cutoff ends a game
+    # (finish_game -> endGame resets the tree, _state_ext.restart() resets ResignCheck)
+    expect = []
+    for s in seeds:
+        g = oracles.RefRng(n, int(s))
+        ref = oracles.RefMcts(n, callback=ref_net(n), root_epsilon=eps, root_alpha=alpha, rotation_flip=1,
+                              seed=g.next(), **opts)
+        rc = oracles.RefResign(n, thres, ratio)
+        st = oracles.Ref(n)
+        played = []
+        for _ in range(moves):
+            ply = int(st.info()[0])
+            r = ref.act(st)
+            a = ref.sample(g) if ply <= cutoff else r["best_action"]
+            rc.check(r["best_q"], int(st.info()[1]), g)
+            assert st.forward(int(a))
+            played.append(int(a))
+            if st.info()[9] or int(st.info()[0]) >= move_cutoff:
+                ref.end_game(st)
+                st = oracles.Ref(n)
+                rc.reset()
+        expect.append(played)
+
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, rotation_flip=1, **opts)
+    sp = SelfPlay(plane_actor(n), num_games=G, board_size=n, board=gb, search=mc, rng="reference", seed=seeds,
+                  policy_distri_cutoff=cutoff, resign_thres=thres, never_resign_ratio=ratio, move_cutoff=move_cutoff,
+                  root_epsilon=eps, root_alpha=alpha, **opts)
+    got = [[] for _ in range(G)]
+    fwd = gb.forward
+
+    def logged(acts):
+        for g in range(G):
+            got[g].append(int(acts[g]))
+        return fwd(acts)
+
+    gb.forward = logged
+    for _ in range(moves):
+        sp.step()
+    assert got == expect
+    assert sp.games_finished >= 2 * G
