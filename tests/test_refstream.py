@@ -180,3 +180,67 @@ def test_selfplay_driver_on_the_reference_streams():
         sp.step()
     assert got == expect
     assert sp.games_finished >= 2 * G
+
+
+def test_game_context_with_a_seed_runs_the_reference_streams():
+    """compat.game_context with GameOptions::seed != 0: the wait()/step() pump (begin_move by the engine,
+    finish_move at the end of a move) consumes the streams exactly as SelfPlay.step() does -- same games"""
+    from elf_b200 import compat, lib as _l
+    from elf_b200.selfplay import SelfPlay
+
+    n, G = 9, 2
+    co, opt = compat.ContextOptions(), compat.GameOptions()
+    co.num_games, co.batchsize = G, 8
+    m = co.mcts_options
+    m.num_threads, m.num_rollouts_per_thread, m.num_rollouts_per_batch, m.virtual_loss, m.persistent_tree = 1, 16, 4, 1, True
+    m.alg_opt.c_puct, m.root_epsilon, m.root_alpha = 1.5, 0.25, 0.3
+    opt.mode, opt.policy_distri_cutoff, opt.move_cutoff, opt.seed = "selfplay", 6, 9, 4242
+    logs = []
+
+    def factory(**kw):
+        assert kw["rng"] == "reference"
+        fields = {f[0] for f in _l.MctsOptions._fields_}
+        gb = emu.emu_batch(kw["num_games"], kw["board_size"])
+        mk = {k: v for k, v in kw.items() if k in fields and k not in ("seed", "root_epsilon", "root_alpha")}
+        sp = SelfPlay(board=gb, search=emu.EmuSearch(gb, **mk), **kw)
+        log, fwd = [], gb.forward
+
+        def logged(acts):
+            log.append([int(a) for a in acts])
+            return fwd(acts)
+
+        gb.forward = logged
+        logs.append(log)
+        return sp
+
+    # (1) through the pump
+    GC = compat.game_context(co, opt, board_size=n, factories={"selfplay": factory})
+    ctx = GC.ctx()
+    sm = ctx.allocateSharedMem(ctx.createSharedMemOptions("actor_black", 8), ["s", "pi", "V", "a", "rv"])
+    bufs = {}
+    for k in ("s", "pi", "V", "a", "rv"):
+        f = sm[k].field()
+        dt = {"float": torch.float32, "int64_t": torch.int64, "int32_t": torch.int32}[f.type_name()]
+        bufs[k] = torch.zeros(*f.sz().vec(), dtype=dt)
+        sm[k].set(bufs[k].data_ptr(), [i * bufs[k].element_size() for i in bufs[k].stride()])
+    ctx.start()
+    sp = GC._engine.sp
+    it = 0
+    while len(logs[0]) < 14 and it < 2000:
+        s = ctx.wait()
+        k = s.effective_batchsize()
+        pi, v = oracles.feature_net(bufs["s"][:k].numpy(), n * n + 1)
+        bufs["pi"][:k] = torch.from_numpy(pi)
+        bufs["V"][:k] = torch.from_numpy(v)
+        ctx.step()
+        it += 1
+    ctx.stop()
+    assert len(logs[0]) >= 14 and sp.games_finished >= G
+    # (2) the same options through SelfPlay.step()
+    GC2 = compat.game_context(co, opt, board_size=n, factories={"selfplay": factory})
+    sp2 = GC2._engine.sp
+    sp2.actor = plane_actor(n)
+    for _ in range(14):
+        sp2.step()
+    assert logs[0][:14] == logs[1][:14]
+    assert all(a[0] == a[1] for a in logs[1])  # GameOptions::seed seeds every game thread alike: identical games
