@@ -801,6 +801,116 @@ __global__ void __launch_bounds__(BLOCK) k_backup(int G, TreeDev tr, int virtual
 }
 
 // ---------------------------------------------------------------------------------------
+// "First maximum in container order".  MCTSResultT::addActions (tree_search_base.h:237-294) walks the
+// root's std::unordered_map<Coord, EdgeInfo> and keeps the first edge with the strictly largest visit
+// count, so an exact most-visited TIE is resolved by the hash table's iteration order.  That order is a
+// function of the insertion sequence alone (NodeT::setEvaluation inserts the edges in storage order):
+// libstdc++'s table is one forward list; a key whose bucket is empty goes to the FRONT of the list, a
+// key whose bucket is in use goes right behind that bucket's "before" node (i.e. to the front of its
+// bucket's run); hash(Coord) = Coord, bucket = key % bucket_count; bucket counts 13, 29, 59, 127, 257,
+// 541, growing when the 14th, 30th, 60th, 128th, 258th key arrives, and a rehash re-inserts the list,
+// front to back, by the same two rules (hashtable.h _M_insert_bucket_begin / _M_rehash_aux,
+// hashtable_policy.h _Prime_rehash_policy).  Pinned against std::unordered_map itself and against
+// the compiled reference (tests/test_refstream.py, tests/test_emu_kernels.py).
+// Lane 0 replays the insertions in shared memory; only called when the maximum is actually tied.
+struct OrderScratch {
+  uint16_t nxt[448];  // forward list: key -> next key
+  uint16_t idx[448];  // key -> storage index of the edge
+  uint16_t bkt[544];  // bucket -> key of the node BEFORE the bucket's first node
+};
+constexpr uint16_t OS_NIL = 0xFFFFu, OS_HEAD = 0xFFFEu, OS_EMPTY = 0xFFFDu;
+
+template <int N>
+__device__ __forceinline__ int action_to_coord(int a) {  // board.h:183-184; pass = M_PASS = 0
+  return a >= N * N ? 0 : ((a % N) + 1) * (N + 2) + (a / N) + 1;
+}
+
+__device__ __forceinline__ void os_link(OrderScratch& s, uint16_t& head, int nb, int key) {
+  const int b = key % nb;
+  const uint16_t before = s.bkt[b];
+  if (before == OS_EMPTY) {  // new bucket: the node becomes the list's first
+    s.nxt[key] = head;
+    if (head != OS_NIL) s.bkt[head % nb] = (uint16_t)key;
+    head = (uint16_t)key;
+    s.bkt[b] = OS_HEAD;
+  } else if (before == OS_HEAD) {
+    s.nxt[key] = head;
+    head = (uint16_t)key;
+  } else {
+    s.nxt[key] = s.nxt[before];
+    s.nxt[before] = (uint16_t)key;
+  }
+}
+
+template <int N>
+__device__ int first_max_in_container_order(const uint32_t* __restrict__ el, const float4* __restrict__ es, int ne,
+                                            int bestn, OrderScratch& s, int lane) {
+  int res = 0;
+  if (lane == 0) {
+    int nb = 13;
+    uint16_t head = OS_NIL;
+    for (int b = 0; b < nb; ++b) s.bkt[b] = OS_EMPTY;
+    for (int i = 0; i < ne; ++i) {
+      if (i == 13 || i == 29 || i == 59 || i == 127 || i == 257) {  // the table grows before key i+1 goes in
+        nb = i == 13 ? 29 : i == 29 ? 59 : i == 59 ? 127 : i == 127 ? 257 : 541;
+        for (int b = 0; b < nb; ++b) s.bkt[b] = OS_EMPTY;
+        uint16_t p = head;
+        head = OS_NIL;
+        while (p != OS_NIL) {
+          const uint16_t q = s.nxt[p];
+          os_link(s, head, nb, p);
+          p = q;
+        }
+      }
+      const int key = action_to_coord<N>((int)(el[i] & 0xFFFFu));
+      s.idx[key] = (uint16_t)i;
+      os_link(s, head, nb, key);
+    }
+    res = 0x7FFFFFFF;
+    for (uint16_t p = head; p != OS_NIL; p = s.nxt[p]) {
+      const int i = s.idx[p];
+      if (__float_as_int(es[i].y) == bestn) {
+        res = i;
+        break;
+      }
+    }
+  }
+  return __shfl_sync(FULL, res, 0);
+}
+
+// most visited root edge (first maximum in the reference's container order) and the visit total
+template <int N>
+__device__ __forceinline__ void root_best(const uint32_t* __restrict__ el, const float4* __restrict__ es, int ne,
+                                          OrderScratch& scratch, int lane, int& besti, int& tot) {
+  int bestn = -1;
+  besti = 0x7FFFFFFF;
+  tot = 0;
+  for (int i = lane; i < ne; i += 32) {
+    const int n = __float_as_int(es[i].y);
+    tot += n;
+    if (n > bestn) {
+      bestn = n;
+      besti = i;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const int on = __shfl_xor_sync(FULL, bestn, d), oi = __shfl_xor_sync(FULL, besti, d);
+    if (on > bestn || (on == bestn && oi < besti)) {
+      bestn = on;
+      besti = oi;
+    }
+    tot += __shfl_xor_sync(FULL, tot, d);
+  }
+  int ties = 0;
+  for (int i = lane; i < ne; i += 32) ties += __float_as_int(es[i].y) == bestn;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ties += __shfl_xor_sync(FULL, ties, d);
+  if (ties > 1) besti = first_max_in_container_order<N>(el, es, ne, bestn, scratch, lane);
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------
 // Results at the root: TreeSearchT::chooseAction / MCTSResultT::addActions (most_visited,
 // tree_search.h:495-528, tree_search_base.h:237-294) and MCTSGoAI::getValue (go/mcts/mcts.h:358).
 template <int N>
@@ -808,6 +918,7 @@ __global__ void __launch_bounds__(BLOCK)
     k_results(int G, TreeDev tr, int32_t* __restrict__ best_action, int32_t* __restrict__ visits,
               float* __restrict__ root_value, float* __restrict__ best_q, int32_t* __restrict__ total_visits) {
   constexpr int P1 = Geo<N>::P + 1;
+  __shared__ OrderScratch scratch[BLOCK / 32];
   const int lane = threadIdx.x & 31;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= G) return;
@@ -828,25 +939,10 @@ __global__ void __launch_bounds__(BLOCK)
   const NodeHdr h = load_hdr(&tr.hdr[nb + root]);
   const float4* es = tr.estat + (nb + root) * tr.E;
   const uint32_t* el = tr.elink + (nb + root) * tr.E;
-  int bestn = -1, besti = 0x7FFFFFFF, tot = 0;
-  for (int i = lane; i < h.n_edges; i += 32) {
-    const int n = __float_as_int(es[i].y);
-    if (visits) visits[(size_t)g * P1 + (el[i] & 0xFFFFu)] = n;
-    tot += n;
-    if (n > bestn) {
-      bestn = n;
-      besti = i;
-    }
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const int on = __shfl_xor_sync(FULL, bestn, d), oi = __shfl_xor_sync(FULL, besti, d);
-    if (on > bestn || (on == bestn && oi < besti)) {
-      bestn = on;
-      besti = oi;
-    }
-    tot += __shfl_xor_sync(FULL, tot, d);
-  }
+  if (visits)
+    for (int i = lane; i < h.n_edges; i += 32) visits[(size_t)g * P1 + (el[i] & 0xFFFFu)] = __float_as_int(es[i].y);
+  int besti, tot;
+  root_best<N>(el, es, h.n_edges, scratch[threadIdx.x >> 5], lane, besti, tot);
   if (lane == 0) {
     const bool any = h.n_edges > 0 && besti != 0x7FFFFFFF;
     if (best_action) best_action[g] = any ? (int)(el[besti] & 0xFFFFu) : -1;
@@ -871,7 +967,7 @@ __device__ __forceinline__ float rng_u01(uint64_t key, uint32_t& ctr);  // defin
 //   ply <= policy_distri_cutoff : sample the move from the visit distribution
 //       (MCTSPolicy::sampleAction -> elf_utils::sample_multinomial, elf/utils/utils.h:158-181:
 //        rd uniform in [0, sum N), first edge whose running sum exceeds rd);
-//   otherwise                   : the most visited edge (first maximum in edge order);
+//   otherwise                   : the most visited edge (first maximum in the reference's container order);
 //   resign (action -1)          : the side to move's value (best edge W/N, root V if unvisited) is
 //       below -1 + resign_thres, ply >= 50, and the game is not one of the never-resign games.
 // The uniform comes from a counter-based generator (seed, game, ply): same distribution as the
@@ -880,6 +976,7 @@ template <int N>
 __global__ void __launch_bounds__(BLOCK)
     k_choose(DevState st, TreeDev tr, int cutoff, float resign_thres, const uint8_t* __restrict__ never_resign,
              uint64_t seed, int32_t* __restrict__ action_out, float* __restrict__ value_out) {
+  __shared__ OrderScratch scratch[BLOCK / 32];
   const int lane = threadIdx.x & 31;
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (g >= st.G) return;
@@ -896,25 +993,9 @@ __global__ void __launch_bounds__(BLOCK)
   const BoardMeta meta = load_meta(&st.meta[g]);
   const float4* es = tr.estat + (nb + root) * tr.E;
   const uint32_t* el = tr.elink + (nb + root) * tr.E;
-  // most visited + total
-  int bestn = -1, besti = 0x7FFFFFFF, tot = 0;
-  for (int i = lane; i < h.n_edges; i += 32) {
-    const int n = __float_as_int(es[i].y);
-    tot += n;
-    if (n > bestn) {
-      bestn = n;
-      besti = i;
-    }
-  }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
-    const int on = __shfl_xor_sync(FULL, bestn, d), oi = __shfl_xor_sync(FULL, besti, d);
-    if (on > bestn || (on == bestn && oi < besti)) {
-      bestn = on;
-      besti = oi;
-    }
-    tot += __shfl_xor_sync(FULL, tot, d);
-  }
+  // most visited (first maximum in the reference's container order) + total
+  int besti, tot;
+  root_best<N>(el, es, h.n_edges, scratch[threadIdx.x >> 5], lane, besti, tot);
   int pick = besti;
   if ((int)meta.ply <= cutoff && tot > 0) {
     uint32_t ctr = 0;

@@ -15,7 +15,8 @@
  *
  * Two things the reference leaves to its containers are fixed here (and in the CUDA path):
  *  - edges are kept in the order pi2response produces them (descending prior); the reference
- *    iterates an unordered_map, so equal-score ties may resolve differently;
+ *    iterates an unordered_map, so equal PUCT-score ties inside the tree may resolve differently
+ *    (the most-visited choice at the root does follow the container order: container_order below);
  *  - unique leaves of a batch are backed up in first-occurrence order (the reference iterates an
  *    unordered_map keyed by node address).
  * Both only matter for exact float ties / last-bit rounding of reward sums, hence the +-1 visit
@@ -326,6 +327,66 @@ static void batch_rollouts(MctsOracle* m) {
   free(leaves);
 }
 
+/* Iteration order of the reference's edge container, std::unordered_map<Coord, EdgeInfo>
+ * (tree_search_node.h:310), after NodeT::setEvaluation (:176-203) inserted the edges in storage order.
+ * libstdc++ keeps one forward list: a key whose bucket is empty goes to the front of the list, a key
+ * whose bucket is in use goes right behind the node before that bucket's first node; hash = identity,
+ * bucket = key % count, counts 13, 29, 59, 127, 257, 541 growing when key 14, 30, 60, 128, 258
+ * arrives; a rehash re-inserts the list front to back by the same rules.  order[i] = storage index of
+ * the i-th edge visited.  Pinned against the compiled reference (ref_mcts_last_order) in
+ * tests/test_mcts_oracle_vs_ref.py. */
+#define CO_NIL (-1)
+#define CO_HEAD (-2)
+#define CO_EMPTY (-3)
+static void co_link(int* nxt, int* bkt, int* head, int nb, int key) {
+  const int b = key % nb, before = bkt[b];
+  if (before == CO_EMPTY) {
+    nxt[key] = *head;
+    if (*head != CO_NIL) bkt[*head % nb] = key;
+    *head = key;
+    bkt[b] = CO_HEAD;
+  } else if (before == CO_HEAD) {
+    nxt[key] = *head;
+    *head = key;
+  } else {
+    nxt[key] = nxt[before];
+    nxt[before] = key;
+  }
+}
+static void container_order(int N, const Edge* edges, int n, int* order) {
+  int nxt[448], idx[448], bkt[544];
+  int nb = 13, head = CO_NIL;
+  for (int b = 0; b < nb; ++b) bkt[b] = CO_EMPTY;
+  for (int i = 0; i < n; ++i) {
+    if (i == 13 || i == 29 || i == 59 || i == 127 || i == 257) {
+      nb = i == 13 ? 29 : i == 29 ? 59 : i == 59 ? 127 : i == 127 ? 257 : 541;
+      for (int b = 0; b < nb; ++b) bkt[b] = CO_EMPTY;
+      int p = head;
+      head = CO_NIL;
+      while (p != CO_NIL) {
+        const int q = nxt[p];
+        co_link(nxt, bkt, &head, nb, p);
+        p = q;
+      }
+    }
+    const int a = edges[i].action;
+    const int key = a >= N * N ? 0 : ((a % N) + 1) * (N + 2) + (a / N) + 1; /* board.h:183-184, M_PASS = 0 */
+    idx[key] = i;
+    co_link(nxt, bkt, &head, nb, key);
+  }
+  int k = 0;
+  for (int p = head; p != CO_NIL; p = nxt[p]) order[k++] = idx[p];
+}
+
+/* the root edges' actions in container order (as ref_mcts_last_order); returns their number */
+int mo_last_order(MctsOracle* m, int32_t* actions) {
+  const Node* root = &m->nodes[m->root];
+  int order[512];
+  container_order(m->N, root->edges, root->n_edges, order);
+  for (int i = 0; i < root->n_edges; ++i) actions[i] = root->edges[order[i]].action;
+  return root->n_edges;
+}
+
 /* MCTSAI_T::act, mcts.h:59-81.  Outputs by action index as ref_mcts_act. */
 int mo_act(MctsOracle* m, const GoOracle* s, int32_t* visits, float* wsum, float* prior,
            float* root_value, float* best_q, int32_t* total_visits) {
@@ -352,7 +413,10 @@ int mo_act(MctsOracle* m, const GoOracle* s, int32_t* visits, float* wsum, float
     if (prior) prior[a] = 0;
   }
   int best = -1, bestn = -1, tot = 0;
-  for (int i = 0; i < root->n_edges; ++i) { /* addActions, tree_search_base.h:237-294 */
+  int order[512];
+  container_order(m->N, root->edges, root->n_edges, order);
+  for (int k = 0; k < root->n_edges; ++k) { /* addActions, tree_search_base.h:237-294: container order */
+    const int i = order[k];
     const Edge* e = &root->edges[i];
     if (visits) visits[e->action] = e->visits;
     if (wsum) wsum[e->action] = e->reward;

@@ -562,6 +562,13 @@ class OracleMcts:
     def num_evals(self):
         return int(self.L.mo_num_evals(self.m))
 
+    def last_order(self):
+        """actions of the root edges in the reference's container order (as RefMcts.last_order)"""
+        a = np.zeros(self.n * self.n + 1, np.int32)
+        self.L.mo_last_order.argtypes = [vp, vp]
+        k = self.L.mo_last_order(self.m, a.ctypes.data)
+        return a[:k].copy()
+
     def prefix_stats(self):
         """(violations, checks) of the selected-prefix property the CUDA select kernel relies on"""
         self.L.mo_prefix_violations.restype = ctypes.c_long

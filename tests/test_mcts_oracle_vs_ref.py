@@ -40,7 +40,7 @@ def opening(n, G, open_plies, make):
     return states
 
 
-def run_search(sc, make_state, make_mcts, forced=None):
+def run_search(sc, make_state, make_mcts, forced=None, orders=None):
     """search `moves` moves in each of G games; the move played is the searcher's own choice or,
     when `forced` (a list in the same order as the returned results) is given, that action -- used to
     keep two implementations on the same trajectory when they break a most-visited TIE differently
@@ -52,6 +52,8 @@ def run_search(sc, make_state, make_mcts, forced=None):
         for s, m in zip(states, ms):
             r = m.act(s)
             a = r["best_action"] if forced is None else forced[len(out)]
+            if orders is not None:
+                orders.append(m.last_order())
             out.append(r)
             s.forward(a)
     return out, sum(m.num_evals() for m in ms)
@@ -63,13 +65,15 @@ def test_restatement_equals_reference(name, oracle_lib):
     n = sc["n"]
     if not oracles.have_ref(n):
         pytest.skip("oracle/_ref not built (needs /root/reference)")
-    a, ea = run_search(sc, lambda: oracles.Ref(n), lambda: oracles.RefMcts(n, **sc["opts"]))
+    oa, ob = [], []
+    a, ea = run_search(sc, lambda: oracles.Ref(n), lambda: oracles.RefMcts(n, **sc["opts"]), orders=oa)
     b, eb = run_search(sc, lambda: oracles.Oracle(n, oracle_lib), lambda: oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]),
-                       forced=[r["best_action"] for r in a])
+                       forced=[r["best_action"] for r in a], orders=ob)
     assert ea == eb
     for i, (ra, rb) in enumerate(zip(a, b)):
-        # same most-visited count (the chosen action itself may differ on an exact tie)
-        assert ra["visits"][ra["best_action"]] == rb["visits"][rb["best_action"]], i
+        # the most-visited move is the first maximum in the reference's container order: same move, ties included
+        assert ra["best_action"] == rb["best_action"], i
+        np.testing.assert_array_equal(oa[i], ob[i], err_msg=f"container order, step {i}")
         np.testing.assert_array_equal(ra["visits"], rb["visits"], err_msg=f"step {i}")
         np.testing.assert_array_equal(ra["prior"], rb["prior"], err_msg=f"step {i}")
         np.testing.assert_allclose(ra["wsum"], rb["wsum"], rtol=0, atol=1e-4)
@@ -88,7 +92,7 @@ def test_restatement_equals_golden(name, oracle_lib):
     assert eb == gold["num_evals"]
     assert len(b) == len(gold["steps"])
     for r, gsv in zip(b, gold["steps"]):
-        assert r["visits"][r["best_action"]] == gsv["visits"][str(gsv["best_action"])]
+        assert r["best_action"] == gsv["best_action"]  # ties included (container order)
         assert r["total_visits"] == gsv["total_visits"]
         vis = {int(a): int(v) for a, v in zip(np.flatnonzero(r["visits"] >= 0), r["visits"][r["visits"] >= 0])}
         assert vis == {int(k): v for k, v in gsv["visits"].items()}
@@ -114,6 +118,7 @@ def test_restatement_equals_reference_on_random_option_sets(oracle_lib):
                            forced=[r["best_action"] for r in a])
         assert ea == eb, (case, opts)
         for i, (ra, rb) in enumerate(zip(a, b)):
+            assert ra["best_action"] == rb["best_action"], (case, i, opts)
             np.testing.assert_array_equal(ra["visits"], rb["visits"], err_msg=f"case {case} step {i} {opts}")
             np.testing.assert_array_equal(ra["prior"], rb["prior"], err_msg=f"case {case} step {i}")
             assert ra["root_value"] == rb["root_value"]

@@ -73,7 +73,7 @@ def play_reference_game(n, seed, opts, eps, alpha, flip, cutoff, thres, ratio, m
     return log
 
 
-@pytest.mark.parametrize("n,eps,flip,moves", [(9, 0.25, 1, 40), (9, 0.0, 1, 40), (9, 0.25, 0, 40), (19, 0.25, 1, 10)])
+@pytest.mark.parametrize("n,eps,flip,moves", [(9, 0.25, 1, 30), (9, 0.0, 1, 16), (9, 0.25, 0, 16), (19, 0.25, 1, 8)])
 def test_whole_games_move_for_move(n, eps, flip, moves):
     if not oracles.have_ref(n):
         pytest.skip("compiled reference not available")
@@ -244,3 +244,41 @@ def test_game_context_with_a_seed_runs_the_reference_streams():
         sp2.step()
     assert logs[0][:14] == logs[1][:14]
     assert all(a[0] == a[1] for a in logs[1])  # GameOptions::seed seeds every game thread alike: identical games
+
+
+@pytest.mark.parametrize("n,R", [(9, 12), (9, 40), (19, 16)])
+def test_device_tie_break_is_the_reference_container_order(n, R):
+    """DEFAULT path (no reference stream attached): the most visited root edge reported by k_results and
+    played by k_choose is the FIRST maximum in the reference's container order -- the kernels replay
+    libstdc++'s hash-table insertions (a 19x19 root has ~355 edges: every bucket count 13..541 is crossed) -- checked against
+    std::unordered_map itself (RefStream.edge_order) and, through it, the compiled reference"""
+    G = 6
+    gb = emu.emu_batch(G, n)
+    rng = np.random.default_rng(n + R)
+    os_ = [oracles.Oracle(n) for _ in range(G)]
+    for _ in range(6):
+        acts = np.array([int(rng.choice(np.flatnonzero(o.legal()))) for o in os_], np.int32)
+        for o, a in zip(os_, acts):
+            o.forward(int(a))
+        assert gb.forward(acts).all()
+    mc = emu.EmuSearch(gb, num_rollouts=R, num_rollouts_per_batch=4, rotation_flip=0)
+    actor = plane_actor(n)
+    tied = differs = 0
+    for mv in range(3):
+        res = mc.act(actor)
+        e = mc.root_edges()
+        a_dev, _ = mc.choose(0, 0.0, None, 0)  # cutoff 0: most visited
+        for g in range(G):
+            k = int(e["n_edges"][g])
+            act, vis = e["actions"][g, :k], e["visits"][g, :k]
+            order = RefStream.edge_order(n, act)
+            top = vis.max()
+            first = next(int(i) for i in order if vis[i] == top)
+            assert res["best_action"][g] == act[first], (mv, g)
+            assert a_dev[g] == act[first], (mv, g)
+            if (vis == top).sum() > 1:
+                tied += 1
+                differs += first != int(np.flatnonzero(vis == top)[0])
+        gb.forward(a_dev)
+        mc.advance(a_dev)
+    assert tied >= 3 and differs >= 1, (tied, differs)  # ties happen, and storage order would have chosen differently
