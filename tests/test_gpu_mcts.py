@@ -917,3 +917,17 @@ def test_selfplay_on_the_reference_random_streams():
     assert got[0] == got[2] and got[0] != got[1]  # GameOptions::seed: same seed, same game
     assert sp.games_finished >= 2 * G and (sp.mcts.errors() == 0).all()
     sp.close()
+
+
+@pytest.mark.parametrize("case", range(2))
+def test_reference_stream_games_equal_the_golden_reference_games_on_device(case):
+    """tests/golden/refstream_games.json (games of the compiled reference's game threads with a seed:
+    noise, D4 per leaf, sampled moves, never-resign draw; 9x9 across game ends and 19x19) replayed by
+    SelfPlay(rng="reference") on the device -- needs no oracle/_ref on the box"""
+    import elf_b200
+    from tests.test_refstream_golden import GOLD, run_case
+
+    c = json.load(open(GOLD))[case]
+    got = run_case(c, lambda G, n: elf_b200.GoBatch(G, board_size=n), lambda gb, **o: elf_b200.MctsBatch(gb, **o))
+    for g, game in enumerate(c["games"]):
+        assert got[g] == game["actions"], f"game {g} (seed {game['seed']})"
