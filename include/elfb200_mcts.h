@@ -134,7 +134,8 @@ int elfb200_mcts_set_root_priors(elfb200_mcts* m, const uint8_t* mask_host, cons
  * evaluated leaves receive, in the order the leaves are claimed (BoardFeature::RandomShuffle draws
  * them from the actor's generator in that order, board_feature.h:74-78, go/mcts/mcts.h:86-93).
  * count >= num_rollouts rounded up to whole waves; resets the per-game consumption counters, which
- * elfb200_mcts_d4_used reads back (int32[G]).  codes = NULL returns to the built-in generator. */
+ * elfb200_mcts_d4_used reads back (int32[G]) -- set a fresh stream before every move (a game that ran
+ * past its codes would keep receiving the last one).  codes = NULL returns to the built-in generator. */
 int elfb200_mcts_set_d4_stream(elfb200_mcts* m, const uint8_t* codes_host, int count);
 int elfb200_mcts_d4_used(elfb200_mcts* m, int32_t* used_host);
 /* int32[4]: [0] root-hash mismatches (the reference throws "Root state is not the same as the input
