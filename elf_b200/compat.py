@@ -408,6 +408,19 @@ class SelfPlayEngine:
                     for mc, _, label, active, waves, post in sp.policy_only_plan(info, *self._chosen)]
         return [(mc, label, active, None, None) for mc, _, label, active in sp.phases(info)]
 
+    def _begin_phase(self, i):
+        mc, _, active, waves, _ = self._plan[i]
+        # a policy-only phase (waves given) takes no root noise (TreeSearchT::runPolicyOnly)
+        noise = getattr(mc, "set_root_noise_enabled", None)
+        if noise is not None:
+            noise(waves is None)
+        try:
+            mc.begin_move(active)
+        finally:
+            if noise is not None:
+                noise(True)
+        self._wave_idx = 0
+
     def _advance_until_leaves(self):
         import torch
 
@@ -424,8 +437,7 @@ class SelfPlayEngine:
                 self._plan = self._phases(self._info)
                 self._phase = 0
                 self._res = []
-                self._plan[0][0].begin_move(self._plan[0][2])
-                self._wave_idx = 0
+                self._begin_phase(0)
                 self._in_move = True
             mc, label, _, waves, post = self._plan[self._phase]
             if self._wave_idx >= (mc.waves_per_move if waves is None else waves):
@@ -435,8 +447,7 @@ class SelfPlayEngine:
                 if self._phase == len(self._plan):
                     self._finish_move()
                 else:
-                    self._plan[self._phase][0].begin_move(self._plan[self._phase][2])
-                    self._wave_idx = 0
+                    self._begin_phase(self._phase)
                 continue
             s = mc.select()
             self._wave_idx += 1
@@ -735,7 +746,7 @@ def game_context(co, opt, board_size=19, device=0, factories=None):
                                                              opt.white_mcts_rollout_per_batch, opt.white_puct).items()
                              if v != common.get(k)},
             **common)
-        if int(opt.seed) != 0 and not (kw["black_use_policy_network_only"] or kw["white_use_policy_network_only"]):
+        if int(opt.seed) != 0:
             # GameOptions::seed != 0: every game thread's generator starts from it (game_base.h:32-38) and
             # the reference's games are reproducible -- ours are then the same games (elf_b200.refstream)
             kw["rng"] = "reference"

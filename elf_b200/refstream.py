@@ -115,6 +115,13 @@ class RefStreamSearch:
     counter-based noise off)."""
 
     _ref = None
+    _ref_noise = True
+
+    def set_root_noise_enabled(self, enabled):
+        """TreeSearchT::runPolicyOnly (tree_search.h:387-408) does not call enhanceExploration: the
+        per-move driver switches the reference-stream root noise off around the ``begin_move`` of a
+        policy-only phase.  No effect without an attached stream."""
+        self._ref_noise = bool(enabled)
 
     def root_edges(self):
         """root edges in storage order: n_edges int32 [G]; actions int16, visits int32, wsum float32,
@@ -167,7 +174,7 @@ class RefStreamSearch:
             return
         rs, which, eps, alpha = self._ref
         act = np.ones(self.gb.num_games, np.uint8) if active is None else np.ascontiguousarray(active, dtype=np.uint8)
-        if eps > 0:
+        if eps > 0 and self._ref_noise:
             e = self.root_edges()
             if (e["n_edges"][act.astype(bool)] > 0).any():
                 rs.root_noise(which, e["n_edges"], e["actions"], e["priors"], eps, alpha, mask=act)

@@ -41,8 +41,6 @@ class SelfPlay:
             raise ValueError("rng must be 'numpy' or 'reference'")
         self.ref = None
         if rng == "reference":
-            if black_use_policy_network_only or white_use_policy_network_only:
-                raise NotImplementedError("rng='reference' covers the searched colours only")
             from .refstream import RefStream
 
             self.ref = RefStream(num_games, board_size, seed)
@@ -134,18 +132,29 @@ class SelfPlay:
             c2 = self.mcts2.ref_choose(sample, mask=(searched & ~first).astype(np.uint8))
             acts = np.where(first, c1["action"], c2["action"]).astype(np.int32)
             vals = np.where(first, c1["value"], c2["value"]).astype(np.float32)
-        # ResignCheck::check: the first call of a game draws never_resign (game_utils.h:25-30); it is
-        # called every move, whatever the ply (game_selfplay.cc:387)
+        self._resign_reference(info, acts, vals, searched)
+        acts[~searched] = -2
+        return acts, vals
+
+    def _resign_reference(self, info, acts, vals, searched):
+        """GoStateExt::shouldResign on the reference's streams, in place on ``acts`` (-1 = resign).
+        ResignCheck::check: the first call of a game draws never_resign from the game generator
+        (game_utils.h:25-30); it is called every move, whatever the ply (game_selfplay.cc:387)"""
         need = searched & ~self._nr_drawn
         if need.any():
             u = self.ref.game_uniform(need.astype(np.uint8))
             self.never_resign[need] = u[need] < float(np.float32(self.never_resign_ratio))
             self._nr_drawn |= need
+        self._resign(info, acts, vals, searched)
+
+    def _resign(self, info, acts, vals, sel):
+        """ResignCheck::check after the never-resign draw, for the games in ``sel``: resign unless
+        ``value >= -1 + resign_thres`` (game_utils.h:36-39, a float compared in double; written the
+        reference's way round, so a NaN value -- the 0/0 of an unvisited edge, see policy_only_plan --
+        resigns as it does there) and only from ply 50 on (game_selfplay.cc:388)"""
         side = np.where(info[:, 1] == 1, vals, -vals).astype(np.float64)
-        resign = searched & ~self.never_resign & ~(side >= -1.0 + float(np.float32(self.resign_thres))) & (info[:, 0] >= 50)
+        resign = sel & ~self.never_resign & ~(side >= -1.0 + float(np.float32(self.resign_thres))) & (info[:, 0] >= 50)
         acts[resign] = -1
-        acts[~searched] = -2
-        return acts, vals
 
     def close(self):
         self.mcts.close()
@@ -196,21 +205,31 @@ class SelfPlay:
         ``(search, actor, label, active mask, waves, post)``: run ``waves`` waves (None = a whole
         move's, 0 = none) for the games in ``active``, then call ``post()``, which fills ``acts`` /
         ``vals`` for those games.  Policy-only games get their root evaluated if it is not yet
-        (TreeSearchT::runPolicyOnly, tree_search.h:387-408) and play the arg-max prior (rank criterion
-        PRIOR, first maximum in edge order); the other games search as usual.  The predicted value of a
-        policy-only move is the root's network value (MCTSGoAI::getValue falls back to it for an
-        unvisited best edge).  Shared by ``step()`` and the wait/step pump of ``compat``."""
+        (TreeSearchT::runPolicyOnly, tree_search.h:387-408: no root noise, one D4 draw if the network is
+        asked) and play the edge with the largest prior (rank criterion PRIOR, first maximum in the
+        reference's container order); the other games search as usual.  The predicted value of a
+        policy-only move is MCTSGoAI::getValue of that result (go/mcts/mcts.h:358-365): the root's
+        network value while the root edges have no visits, else W/N of the CHOSEN edge -- in a tree
+        shared with a searching colour the root usually has visits, and an unvisited largest-prior edge
+        then yields 0/0 = NaN, which ResignCheck::check treats as "resign" (see ``_resign``).  Callers
+        switch the reference-stream root noise off for the phases whose ``waves`` is not None
+        (``set_root_noise_enabled``).  Shared by ``step()`` and the wait/step pump of ``compat``."""
         G = self.G
         po_colour = np.array([self.policy_only[int(c)] for c in info[:, 1]], bool)
         nr = self.never_resign.astype(np.uint8)
         seed = (self._seed << 20) ^ (self._move_counter + 1)
+        sample = info[:, 0] <= self.policy_distri_cutoff
         plan = []
         for mc, actor, label, active in self.phases(info):
             act = np.ones(G, bool) if active is None else np.asarray(active).astype(bool)
             a_po, a_ts = act & po_colour, act & ~po_colour
             if a_ts.any():
                 def post_ts(mc=mc, sel=a_ts):
-                    a, v = mc.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
+                    if self.ref is not None:  # the resign check follows in finish_move (_resign_reference)
+                        c = mc.ref_choose(sample, mask=sel.astype(np.uint8))
+                        a, v = c["action"], c["value"]
+                    else:
+                        a, v = mc.choose(self.policy_distri_cutoff, self.resign_thres, nr, seed)
                     acts[sel], vals[sel] = a[sel], v[sel]
                 plan.append((mc, actor, label, a_ts.astype(np.uint8), None, post_ts))
             if a_po.any():
@@ -219,13 +238,19 @@ class SelfPlay:
                 fresh = a_po & (mc.root_priors().max(1) < 0)
 
                 def post_po(mc=mc, sel=None):
-                    pr = mc.root_priors()
+                    e = mc.root_edges()
                     rv = mc.results()["root_value"]
-                    vals[sel] = rv[sel]
-                    acts[sel] = pr[sel].argmax(1)
-                    side = np.where(info[:, 1] == 1, vals, -vals)  # GoStateExt::shouldResign
-                    resign = sel & (side < -1.0 + self.resign_thres) & (info[:, 0] >= 50) & ~self.never_resign
-                    acts[resign] = -1
+                    for g in np.flatnonzero(sel):
+                        n = int(e["n_edges"][g])
+                        b = self.first_largest(e["priors"][g, :n], e["actions"][g, :n])
+                        acts[g] = int(e["actions"][g, b])
+                        if int(e["visits"][g, :n].sum()) == 0:
+                            vals[g] = rv[g]
+                        else:
+                            with np.errstate(divide="ignore", invalid="ignore"):
+                                vals[g] = e["wsum"][g, b] / np.float32(e["visits"][g, b])  # EdgeInfo::getQSA
+                    if self.ref is None:
+                        self._resign(info, acts, vals, sel)
                 old = a_po & ~fresh
                 if old.any():
                     plan.append((mc, actor, label, old.astype(np.uint8), 0, lambda f=post_po, m=old: f(sel=m)))
@@ -234,16 +259,34 @@ class SelfPlay:
         self._po_colour = po_colour
         return plan
 
+    def first_largest(self, scores, actions):
+        """storage index of the edge MCTSResultT::addActions picks (tree_search_base.h:237-294): the first
+        strict maximum of ``scores`` walking the edges in the reference's container order"""
+        top = np.flatnonzero(scores == scores.max())
+        if len(top) == 1:
+            return int(top[0])
+        from .refstream import RefStream
+
+        is_top = np.zeros(len(scores), bool)
+        is_top[top] = True
+        for i in RefStream.edge_order(self.N, actions):
+            if is_top[i]:
+                return int(i)
+
     def _search_with_policy_only(self, info):
         """the search phase when one colour moves by policy only (see policy_only_plan); returns the
         chosen (actions, values) for finish_move"""
         acts = np.full(self.G, -2, np.int32)
         vals = np.zeros(self.G, np.float32)
         for mc, actor, _, active, waves, post in self.policy_only_plan(info, acts, vals):
-            if waves == 0:
-                mc.begin_move(active)  # marks the games whose root statistics post() reads
-            else:
-                mc.search(actor, active=active, waves=waves)
+            mc.set_root_noise_enabled(waves is None)
+            try:
+                if waves == 0:
+                    mc.begin_move(active)  # marks the games whose root statistics post() reads
+                else:
+                    mc.search(actor, active=active, waves=waves)
+            finally:
+                mc.set_root_noise_enabled(True)
             post()
         self._policy_only_moves = self._po_colour & (acts >= 0)
         return acts, vals
@@ -356,6 +399,8 @@ class SelfPlay:
         nr = self.never_resign.astype(np.uint8)
         if chosen is not None:
             acts, vals = chosen
+            if self.ref is not None:  # shouldResign after every colour's choice, on the game generator
+                self._resign_reference(info, acts, vals, acts != -2)
         elif self.ref is not None:
             acts, vals = self._choose_reference(info)
         else:

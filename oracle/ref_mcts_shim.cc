@@ -243,15 +243,10 @@ void ref_mcts_free(void* p) {
   delete static_cast<RefMcts*>(p);
 }
 
-// MCTSAI_T::act (elf/ai/tree_search/mcts.h:59-81) on reference state `state` (a RefState from
-// ref_shim.cc, which IS-A GoState).  Outputs by ACTION index (size N*N+1): visits (-1 where the
-// root has no such edge), edge reward sums W, priors.  Returns the chosen action.
-int ref_mcts_act(void* p, void* state, int32_t* visits, float* wsum, float* prior,
-                 float* root_value, float* best_q, int32_t* total_visits) {
-  RefMcts* m = static_cast<RefMcts*>(p);
-  const GoState& s = *static_cast<GoState*>(state);
-  Coord c = M_INVALID;
-  m->ai->act(s, &c);
+// Outputs of the last search by ACTION index (size N*N+1): visits (-1 where the root has no such
+// edge), edge reward sums W, priors; best_q = MCTSGoAI::getValue (go/mcts/mcts.h:358-365).
+static int report_last_result(RefMcts* m, Coord c, int32_t* visits, float* wsum, float* prior,
+                              float* root_value, float* best_q, int32_t* total_visits) {
   const auto& res = m->ai->getLastResult();
   const int P1 = BOARD_NUM_ACTION;
   for (int a = 0; a < P1; ++a) {
@@ -269,6 +264,29 @@ int ref_mcts_act(void* p, void* state, int32_t* visits, float* wsum, float* prio
   if (best_q) *best_q = res.total_visits == 0 ? res.root_value : res.best_edge_info.getQSA();
   if (total_visits) *total_visits = res.total_visits;
   return c2a(c);
+}
+
+// MCTSAI_T::act (elf/ai/tree_search/mcts.h:59-81) on reference state `state` (a RefState from
+// ref_shim.cc, which IS-A GoState).  Returns the chosen action.
+int ref_mcts_act(void* p, void* state, int32_t* visits, float* wsum, float* prior,
+                 float* root_value, float* best_q, int32_t* total_visits) {
+  RefMcts* m = static_cast<RefMcts*>(p);
+  const GoState& s = *static_cast<GoState*>(state);
+  Coord c = M_INVALID;
+  m->ai->act(s, &c);
+  return report_last_result(m, c, visits, wsum, prior, root_value, best_q, total_visits);
+}
+
+// MCTSAI_T::actPolicyOnly (elf/ai/tree_search/mcts.h:83-89 -> TreeSearchT::runPolicyOnly,
+// tree_search.h:387-408): the move of a colour with black/white_use_policy_network_only
+// (game_selfplay.cc:359-371).  Same outputs as ref_mcts_act.
+int ref_mcts_act_policy_only(void* p, void* state, int32_t* visits, float* wsum, float* prior,
+                             float* root_value, float* best_q, int32_t* total_visits) {
+  RefMcts* m = static_cast<RefMcts*>(p);
+  const GoState& s = *static_cast<GoState*>(state);
+  Coord c = M_INVALID;
+  m->ai->actPolicyOnly(s, &c);
+  return report_last_result(m, c, visits, wsum, prior, root_value, best_q, total_visits);
 }
 
 // The root edges of the last search in the order MCTSResultT::addActions walked the root's

@@ -457,7 +457,8 @@ class RefMcts:
         """mcts_make_diverse_move's sampling on the game thread's generator (a RefRng)"""
         return int(self.L.ref_mcts_sample(self.m, rng.p))
 
-    def act(self, ref_state):
+    def act(self, ref_state, policy_only=False):
+        """MCTSAI_T::act, or actPolicyOnly (the move of a *_use_policy_network_only colour)"""
         P1 = self.n * self.n + 1
         vis = np.zeros(P1, np.int32)
         w = np.zeros(P1, np.float32)
@@ -465,8 +466,10 @@ class RefMcts:
         rv = ctypes.c_float()
         bq = ctypes.c_float()
         tv = ctypes.c_int32()
-        a = self.L.ref_mcts_act(self.m, ref_state.p, vis.ctypes.data, w.ctypes.data, pr.ctypes.data,
-                                ctypes.byref(rv), ctypes.byref(bq), ctypes.byref(tv))
+        fn = self.L.ref_mcts_act_policy_only if policy_only else self.L.ref_mcts_act
+        fn.argtypes = [vp, vp] + [vp] * 6
+        a = fn(self.m, ref_state.p, vis.ctypes.data, w.ctypes.data, pr.ctypes.data,
+               ctypes.byref(rv), ctypes.byref(bq), ctypes.byref(tv))
         return {"best_action": int(a), "visits": vis, "wsum": w, "prior": pr, "root_value": rv.value,
                 "best_q": bq.value, "total_visits": tv.value}
 

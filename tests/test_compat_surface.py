@@ -220,7 +220,7 @@ def test_game_context_from_reference_options():
     opt.mode, opt.white_use_policy_network_only = "selfplay", True
     GC = compat.game_context(co, opt, factories={"selfplay": FakeSelfPlay})
     assert isinstance(GC._engine, compat.SelfPlayEngine) and got["white_use_policy_network_only"] is True
-    assert "rng" not in got  # a policy-only colour keeps the default generators
+    assert got["rng"] == "reference"  # GameOptions::seed is set: policy-only colours run on the reference streams too
     opt.white_use_policy_network_only, opt.seed = False, 0
     got.clear()
     compat.game_context(co, opt, factories={"selfplay": FakeSelfPlay})

@@ -282,3 +282,135 @@ def test_device_tie_break_is_the_reference_container_order(n, R):
         gb.forward(a_dev)
         mc.advance(a_dev)
     assert tied >= 3 and differs >= 1, (tied, differs)  # ties happen, and storage order would have chosen differently
+
+
+@pytest.mark.parametrize("two_models", [False, True])
+def test_policy_only_colour_on_the_reference_streams(two_models):
+    """white_use_policy_network_only under rng="reference" (game_selfplay.cc:359-371): white moves by
+    MCTSAI_T::actPolicyOnly -- no root noise, no sampled move, one D4 draw when its root still has to be
+    evaluated, the largest prior in container order, and MCTSGoAI::getValue of THAT result as predicted
+    value (W/N of the chosen edge once the shared tree's root has visits, NaN for an unvisited edge) --
+    while black searches; moves and predicted values equal the compiled reference's game threads"""
+    from elf_b200.selfplay import SelfPlay
+
+    n, G, moves = 9, 2, 24
+    opts = dict(num_rollouts=24, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5, komi=7.5)
+    eps, alpha, cutoff, thres, ratio, move_cutoff = 0.25, 0.3, 6, 0.05, 0.1, 15
+    seeds = np.array([991, 992], np.uint64)
+
+    expect, expect_v = [], []
+    for s in seeds:
+        g = oracles.RefRng(n, int(s))
+        mk = lambda: oracles.RefMcts(n, callback=ref_net(n), root_epsilon=eps, root_alpha=alpha, rotation_flip=1,
+                                     seed=g.next(), **opts)
+        ai = mk()  # init_ai(_ai) then init_ai(_ai2): the seeds come off the game generator in that order
+        ai2 = mk() if two_models else None
+        rc = oracles.RefResign(n, thres, ratio)
+        st = oracles.Ref(n)
+        played, values = [], []
+        for _ in range(moves):
+            ply, nxt = int(st.info()[0]), int(st.info()[1])
+            cur = ai2 if (ai2 is not None and nxt == 2) else ai
+            if nxt == 2:
+                r = cur.act(st, policy_only=True)
+                a = r["best_action"]
+            else:
+                r = cur.act(st)
+                a = cur.sample(g) if ply <= cutoff else r["best_action"]
+            rc.check(r["best_q"], nxt, g)
+            assert st.forward(int(a))
+            played.append(int(a))
+            values.append(float(r["best_q"]))
+            if st.info()[9] or int(st.info()[0]) >= move_cutoff:
+                ai.end_game(st)
+                if ai2 is not None:
+                    ai2.end_game(st)
+                st = oracles.Ref(n)
+                rc.reset()
+        expect.append(played)
+        expect_v.append(values)
+
+    gb = emu.emu_batch(G, n)
+    mc = emu.EmuSearch(gb, rotation_flip=1, **opts)
+    mc2 = emu.EmuSearch(gb, rotation_flip=1, **opts) if two_models else None
+    sp = SelfPlay(plane_actor(n), actor_white=plane_actor(n) if two_models else None, num_games=G, board_size=n, board=gb,
+                  search=mc, search_white=mc2, rng="reference", seed=seeds, policy_distri_cutoff=cutoff, resign_thres=thres,
+                  never_resign_ratio=ratio, move_cutoff=move_cutoff, root_epsilon=eps, root_alpha=alpha,
+                  white_use_policy_network_only=True, **opts)
+    got, got_v = [[] for _ in range(G)], [[] for _ in range(G)]
+    fin = sp.finish_move
+
+    def logged(info, res=None, chosen=None):
+        for g in range(G):
+            got[g].append(int(chosen[0][g]))
+            got_v[g].append(float(chosen[1][g]))
+        return fin(info, res=res, chosen=chosen)
+
+    sp.finish_move = logged
+    for _ in range(moves):
+        sp.step()
+    assert got == expect
+    # edge reward sums agree to the last bits only (see test_whole_games_move_for_move)
+    np.testing.assert_allclose(np.array(got_v), np.array(expect_v), rtol=2e-6, atol=1e-7, equal_nan=True)
+    assert sp.games_finished >= G
+
+
+def test_nan_value_resigns_like_the_reference():
+    """ResignCheck::check is written `if (value >= -1 + thres) return false; return true;`
+    (game_utils.h:36-39): the NaN predicted value of an unvisited policy-only edge resigns"""
+    from elf_b200.selfplay import SelfPlay
+
+    rc = oracles.RefResign(9, 0.05, 0.0)
+    g = oracles.RefRng(9, 1)
+    want = [bool(rc.check(v, nxt, g)) for v, nxt in ((float("nan"), 1), (float("nan"), 2), (-0.99, 1), (0.99, 2), (0.0, 1))]
+    sp = SelfPlay.__new__(SelfPlay)
+    sp.never_resign, sp.resign_thres = np.zeros(5, bool), 0.05
+    info = np.zeros((5, 12), np.int32)
+    info[:, 0], info[:, 1] = 60, [1, 2, 1, 2, 1]
+    acts = np.zeros(5, np.int32)
+    sp._resign(info, acts, np.array([np.nan, np.nan, -0.99, 0.99, 0.0], np.float32), np.ones(5, bool))
+    assert [a == -1 for a in acts] == want == [True, True, True, True, False]
+
+
+def test_policy_only_colour_default_rng_matches_the_reference():
+    """the same without random draws (no noise, no D4, nothing sampled): the device-side choice for the
+    searched colour and the host-side policy-only choice, move for move and value for value"""
+    from elf_b200.selfplay import SelfPlay
+
+    n, G, moves = 9, 3, 20
+    opts = dict(num_rollouts=24, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5, komi=7.5)
+    openings = [[], [40], [20, 60]]
+    expect, expect_v = [], []
+    for op in openings:
+        ai = oracles.RefMcts(n, callback=ref_net(n), rotation_flip=0, **opts)
+        st = oracles.Ref(n)
+        for a in op:
+            assert st.forward(a)
+        played, values = [], []
+        for _ in range(moves):
+            r = ai.act(st, policy_only=int(st.info()[1]) == 1)  # black moves by policy only here
+            assert st.forward(int(r["best_action"]))
+            played.append(int(r["best_action"]))
+            values.append(float(r["best_q"]))
+        expect.append(played)
+        expect_v.append(values)
+    gb = emu.emu_batch(G, n)
+    for t in range(2):
+        gb.forward(np.array([op[t] if t < len(op) else -2 for op in openings], np.int32))
+    mc = emu.EmuSearch(gb, rotation_flip=0, **opts)
+    sp = SelfPlay(plane_actor(n), num_games=G, board_size=n, board=gb, search=mc, policy_distri_cutoff=-1,
+                  never_resign_ratio=1.0, black_use_policy_network_only=True, **opts)
+    got, got_v = [[] for _ in range(G)], [[] for _ in range(G)]
+    fin = sp.finish_move
+
+    def logged(info, res=None, chosen=None):
+        for g in range(G):
+            got[g].append(int(chosen[0][g]))
+            got_v[g].append(float(chosen[1][g]))
+        return fin(info, res=res, chosen=chosen)
+
+    sp.finish_move = logged
+    for _ in range(moves):
+        sp.step()
+    assert got == expect
+    np.testing.assert_allclose(np.array(got_v), np.array(expect_v), rtol=2e-6, atol=1e-7, equal_nan=True)
