@@ -728,11 +728,23 @@ def game_context(co, opt, board_size=19, device=0, factories=None):
     substitute the constructors (tests)."""
     f = dict(factories or {})
     ts = co.mcts_options
+    pick = str(getattr(ts, "pick_method", "most_visited"))
+    if pick not in ("most_visited", "strongest_prior", "uniform_random"):
+        # TreeSearchT::chooseAction throws std::range_error (tree_search.h:521-524), a ValueError in Python
+        raise ValueError("MCTS Pick method unknown! " + pick)
+    if pick != "most_visited":
+        raise NotImplementedError(f"mcts_pick_method '{pick}': the device-side move choice ranks root edges by visits "
+                                  "(the default, and what every shipped script uses)")
     common = search_kwargs(ts)
     common.update(komi=float(opt.komi), ply_pass_enabled=int(opt.ply_pass_enabled))
     if opt.mode == "selfplay":
         from .selfplay import SelfPlay
 
+        for cheat in ("cheat_eval_new_model_wins_half", "cheat_selfplay_random_result"):
+            if bool(getattr(opt, cheat, False)):
+                # server-plumbing debug switches that replace a game's result by a coin flip
+                # (GoStateExt::setFinalValue, go_state_ext.h:86-99): not part of the engine, refused loudly
+                raise NotImplementedError(f"GameOptions::{cheat} is not supported by the elf_b200 engine")
         kw = dict(
             actor=None, num_games=int(co.num_games), board_size=board_size, device=device,
             policy_distri_cutoff=int(opt.policy_distri_cutoff), resign_thres=float(opt.resign_thres),

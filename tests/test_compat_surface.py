@@ -216,6 +216,14 @@ def test_game_context_from_reference_options():
     opt.mode = "bogus"
     with pytest.raises(ValueError, match="Unknown mode"):
         compat.game_context(co, opt)
+    # TSOptions::pick_method: unknown names fail like TreeSearchT::chooseAction, the two unused ones loudly
+    co.mcts_options.pick_method = "best_guess"
+    with pytest.raises(ValueError, match="MCTS Pick method unknown! best_guess"):
+        compat.game_context(co, opt)
+    co.mcts_options.pick_method = "strongest_prior"
+    with pytest.raises(NotImplementedError):
+        compat.game_context(co, opt)
+    co.mcts_options.pick_method = "most_visited"
     # policy-only colours go through the same pump (tests/test_dropin_shim.py plays such games)
     opt.mode, opt.white_use_policy_network_only = "selfplay", True
     GC = compat.game_context(co, opt, factories={"selfplay": FakeSelfPlay})
