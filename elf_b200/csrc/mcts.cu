@@ -35,7 +35,7 @@ namespace elfb200 {
 
 constexpr uint16_t NONE16 = 0xFFFFu;
 enum : uint8_t { NS_FREE = 0, NS_UNVISITED = 1, NS_REQUESTED = 2, NS_VISITED = 3 };
-enum : uint8_t { NF_FLIP = 1, NF_KEEP = 2, NF_FULLSCAN = 4 };  // FULLSCAN: priors no longer sorted (root noise)
+enum : uint8_t { NF_FLIP = 1, NF_KEEP = 2, NF_FULLSCAN = 4 };  // FULLSCAN: priors no longer sorted (root noise) or a tie broke the prefix
 
 struct __align__(16) NodeHdr {  // 32 bytes
   int32_t num_visits;    // NodeT::numVisits_
@@ -259,26 +259,180 @@ __global__ void __launch_bounds__(BLOCK) k_begin(DevState st, TreeDev tr, int ro
 // (tree_search.h:175-190) and the leaf claim of batch_rollouts (tree_search.h:222-233).
 //
 // PUCT scan: edges are stored by descending prior and an edge that was never selected has
-// N = 0, vl = 0, hence score = c_puct * P * sqrt(n) + FPU, monotone in P.  The best never-selected
-// edge is therefore the FIRST one in storage order, the selected edges always form a prefix
-// [0, n_touched), and the arg-max over all edges equals the arg-max over [0, n_touched] -- the
-// same result as the reference's full scan with O(touched) instead of O(legal moves) reads.
-// (Exact prior ties between never-selected edges resolve to the lower index; the reference
-// resolves them by unordered_map order.)  The running-mean update only involves selected edges.
+// N = 0, vl = 0, hence score = c_puct * P * sqrt(n) + FPU, monotone (not strictly: the product
+// vanishes under the rounding of q for tiny priors) in P.  The best never-selected edge is therefore
+// the FIRST one in storage order or ties with it, the selected edges form a prefix [0, n_touched),
+// and the maximum over all edges equals the maximum over [0, n_touched] -- the same result as the
+// reference's full scan with O(touched) instead of O(legal moves) reads.  The scan takes one edge
+// more, [0, n_touched + 1]: if the maximum over that range is attained once it is the reference's
+// choice; if it is tied -- within the prefix, or between the first never-selected edge and the
+// next -- the reference's answer is the first tied edge in ITS container's order, which
+// uct_tie_break reproduces from a full rescan; a node where that picked an edge beyond the prefix is
+// scanned in full from then on (NF_FULLSCAN).  The running-mean update only involves selected edges.
 //
 // The per-level dependent memory chain is one round trip: the node header and the first 32 edge
 // records are requested together; the child id rides in the edge record; the pre-move hashes the
 // superko test needs are gathered once, when a child is actually created.
 constexpr int MAX_DEPTH = 128;
 
+// ---------------------------------------------------------------------------------------
+// "First maximum in container order".  MCTSResultT::addActions (tree_search_base.h:237-294) walks the
+// root's std::unordered_map<Coord, EdgeInfo> and keeps the first edge with the strictly largest visit
+// count, so an exact most-visited TIE is resolved by the hash table's iteration order.  That order is a
+// function of the insertion sequence alone (NodeT::setEvaluation inserts the edges in storage order):
+// libstdc++'s table is one forward list; a key whose bucket is empty goes to the FRONT of the list, a
+// key whose bucket is in use goes right behind that bucket's "before" node (i.e. to the front of its
+// bucket's run); hash(Coord) = Coord, bucket = key % bucket_count; bucket counts 13, 29, 59, 127, 257,
+// 541, growing when the 14th, 30th, 60th, 128th, 258th key arrives, and a rehash re-inserts the list,
+// front to back, by the same two rules (hashtable.h _M_insert_bucket_begin / _M_rehash_aux,
+// hashtable_policy.h _Prime_rehash_policy).  Pinned against std::unordered_map itself and against
+// the compiled reference (tests/test_refstream.py, tests/test_emu_kernels.py).
+// The PUCT arg-max of every descent step (NodeT::UCT, tree_search_node.h:361-397) walks the same kind of
+// container with the same strict '>': k_select resolves exact score ties the same way (uct_tie_break).
+// Lane 0 replays the insertions in shared memory; only called when the maximum is actually tied.
+struct OrderScratch {
+  uint16_t nxt[448];  // forward list: key -> next key
+  uint16_t idx[448];  // key -> storage index of the edge
+  uint16_t bkt[544];  // bucket -> key of the node BEFORE the bucket's first node
+};
+constexpr uint16_t OS_NIL = 0xFFFFu, OS_HEAD = 0xFFFEu, OS_EMPTY = 0xFFFDu;
+
+template <int N>
+__device__ __forceinline__ int action_to_coord(int a) {  // board.h:183-184; pass = M_PASS = 0
+  return a >= N * N ? 0 : ((a % N) + 1) * (N + 2) + (a / N) + 1;
+}
+
+__device__ __forceinline__ void os_link(OrderScratch& s, uint16_t& head, int nb, int key) {
+  const int b = key % nb;
+  const uint16_t before = s.bkt[b];
+  if (before == OS_EMPTY) {  // new bucket: the node becomes the list's first
+    s.nxt[key] = head;
+    if (head != OS_NIL) s.bkt[head % nb] = (uint16_t)key;
+    head = (uint16_t)key;
+    s.bkt[b] = OS_HEAD;
+  } else if (before == OS_HEAD) {
+    s.nxt[key] = head;
+    head = (uint16_t)key;
+  } else {
+    s.nxt[key] = s.nxt[before];
+    s.nxt[before] = (uint16_t)key;
+  }
+}
+
+// lane 0 only: replay the insertions of edges [0, ne) (storage order); returns the list head
+template <int N>
+__device__ uint16_t os_build(const uint32_t* __restrict__ el, int ne, OrderScratch& s) {
+  int nb = 13;
+  uint16_t head = OS_NIL;
+  for (int b = 0; b < nb; ++b) s.bkt[b] = OS_EMPTY;
+  for (int i = 0; i < ne; ++i) {
+    if (i == 13 || i == 29 || i == 59 || i == 127 || i == 257) {  // the table grows before key i+1 goes in
+      nb = i == 13 ? 29 : i == 29 ? 59 : i == 59 ? 127 : i == 127 ? 257 : 541;
+      for (int b = 0; b < nb; ++b) s.bkt[b] = OS_EMPTY;
+      uint16_t p = head;
+      head = OS_NIL;
+      while (p != OS_NIL) {
+        const uint16_t q = s.nxt[p];
+        os_link(s, head, nb, p);
+        p = q;
+      }
+    }
+    const int key = action_to_coord<N>((int)(el[i] & 0xFFFFu));
+    s.idx[key] = (uint16_t)i;
+    os_link(s, head, nb, key);
+  }
+  return head;
+}
+
+template <int N>
+__device__ int first_max_in_container_order(const uint32_t* __restrict__ el, const float4* __restrict__ es, int ne,
+                                            int bestn, OrderScratch& s, int lane) {
+  int res = 0;
+  if (lane == 0) {
+    res = 0x7FFFFFFF;
+    for (uint16_t p = os_build<N>(el, ne, s); p != OS_NIL; p = s.nxt[p]) {
+      const int i = s.idx[p];
+      if (__float_as_int(es[i].y) == bestn) {
+        res = i;
+        break;
+      }
+    }
+  }
+  return __shfl_sync(FULL, res, 0);
+}
+
+// the same walk for an arbitrary tie set: tied[i >> 5] bit (i & 31) = edge i attains the maximum
+template <int N>
+__device__ int first_tied_in_container_order(const uint32_t* __restrict__ el, int ne, const uint32_t* tied,
+                                             OrderScratch& s, int lane) {
+  int res = 0;
+  if (lane == 0) {
+    res = 0x7FFFFFFF;
+    for (uint16_t p = os_build<N>(el, ne, s); p != OS_NIL; p = s.nxt[p]) {
+      const int i = s.idx[p];
+      if ((tied[i >> 5] >> (i & 31)) & 1u) {
+        res = i;
+        break;
+      }
+    }
+  }
+  return __shfl_sync(FULL, res, 0);
+}
+
 __device__ __forceinline__ float vl_value(uint32_t wbits, int virtual_loss) {
   return (float)((int)(wbits & 0xFFFFu) * virtual_loss);  // exact: small integers
+}
+
+// EdgeInfo::getScore + NodeT::UCT's combination for one edge record (tree_search_base.h:132-157,
+// tree_search_node.h:361-397): n = visits, nwl = visits with virtual loss; one definition for the
+// descent's scan and for the tie-break's rescans, so that "equal score" means the same bits in both
+__device__ __forceinline__ float puct_score(const float4& e, bool flip, float fpu, double sq, const SearchOpts& o,
+                                            int& n, int& nwl) {
+  n = __float_as_int(e.y);
+  const float evl = vl_value(__float_as_uint(e.w), o.virtual_loss);
+  float r = flip ? -e.z : e.z;
+  r -= evl;
+  nwl = (int)((float)n + evl);
+  const float q = nwl > 0 ? r / (float)nwl : (flip ? -fpu : fpu);
+  const float u = (float)((double)(e.x / (float)(1 + n)) * sq);
+  return o.use_prior ? __fmaf_rn(u, o.c_puct, q) : q;
+}
+
+// The maximum of a descent step is tied (exactly equal scores: priors below the rounding of q, equal
+// terminal values, or no prior term at all): the reference's loop over its unordered_map keeps the
+// FIRST maximum in the container's order.  Rescan ALL edges of the node (never-selected edges beyond
+// the scanned prefix can only tie with, never beat, the prefix's first never-selected edge -- same q,
+// smaller prior), mark the tied ones and let lane 0 walk the container.  Rare; whole warp.
+template <int N>
+__device__ int uct_tie_break(const uint32_t* __restrict__ el, const float4* __restrict__ es, int ne, bool flip,
+                             float fpu, double sq, const SearchOpts& o, OrderScratch& scratch, uint32_t* tied,
+                             int lane) {
+  float best = -FLT_MAX;
+  for (int i = lane; i < ne; i += 32) {
+    int n, nwl;
+    best = fmaxf(best, puct_score(es[i], flip, fpu, sq, o, n, nwl));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, d));
+  for (int i0 = 0; i0 < ne; i0 += 32) {
+    const int i = i0 + lane;
+    int n, nwl;
+    const bool t = i < ne && puct_score(es[i], flip, fpu, sq, o, n, nwl) == best;
+    const uint32_t bits = __ballot_sync(FULL, t);
+    if (lane == 0) tied[i0 >> 5] = bits;
+  }
+  __syncwarp();
+  const int res = first_tied_in_container_order<N>(el, ne, tied, scratch, lane);
+  __syncwarp();
+  return res;
 }
 
 template <int N>
 __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, SearchOpts o, int wave) {
   __shared__ uint64_t s_zob[Geo<N>::ZOB];
   __shared__ uint32_t s_path[WARPS][MAX_DEPTH];  // node id | is_pass << 16, root first
+  __shared__ OrderScratch s_order[WARPS];        // tie-break scratch (uct_tie_break)
+  __shared__ uint32_t s_tied[WARPS][(Geo<N>::P + 32) / 32];
   load_zobrist<N>(s_zob);
   const Lane L = make_lane_single<N>();
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -303,8 +457,9 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
         if (L.lane == 0) atomicAdd(&tr.errors[2], 1);
         break;
       }
-      // ---- UCT over the selected prefix plus the first never-selected edge ------------------------
-      const int lim = (h.flags & NF_FULLSCAN) ? (int)h.n_edges : min((int)h.n_edges, (int)h.n_touched + 1);
+      // ---- UCT over the selected prefix plus the first TWO never-selected edges ------------------
+      // (the second one only reveals a tie with the first: all later ones score no higher than it)
+      const int lim = (h.flags & NF_FULLSCAN) ? (int)h.n_edges : min((int)h.n_edges, (int)h.n_touched + 2);
       st_steps++;
       st_edges += lim;
       st_term += h.n_edges;  // stored edges: what a full scan (SURVEY 8d formula) would read
@@ -312,27 +467,25 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
       const float fpu = (o.uqz || (o.ruqz && depth == 0)) ? 0.f : h.mean_q;
       const double sq = sqrt((double)(h.num_visits + 1));  // std::sqrt(int) -> double
       float best = -FLT_MAX, tuq = 0.f;
-      int besti = 0x7FFFFFFF, tv = 0;
+      int besti = 0x7FFFFFFF, tv = 0, neq = 0;
       for (int i = L.lane; i < lim; i += 32) {
         if (i >= 32) e = es[i];
-        const int n = __float_as_int(e.y);
-        const float evl = vl_value(__float_as_uint(e.w), o.virtual_loss);
-        float r = flip ? -e.z : e.z;
-        r -= evl;
-        const int nwl = (int)((float)n + evl);
-        const float q = nwl > 0 ? r / (float)nwl : (flip ? -fpu : fpu);
+        int n, nwl;
+        const float score = puct_score(e, flip, fpu, sq, o, n, nwl);
         const float uq = n > 0 ? e.z / (float)n : fpu;
-        const float u = (float)((double)(e.x / (float)(1 + n)) * sq);
-        const float score = o.use_prior ? __fmaf_rn(u, o.c_puct, q) : q;
-        if (score > best) {  // strict >, ascending i: first maximum wins
+        if (score > best) {  // strict >
           best = score;
           besti = i;
+          neq = 1;
+        } else if (score == best) {
+          neq++;
         }
         if (nwl != 0) {
           tuq += uq;
           tv++;
         }
       }
+      const float lane_best = best;
 #pragma unroll
       for (int d = 16; d > 0; d >>= 1) {
         const float ob = __shfl_xor_sync(FULL, best, d);
@@ -344,6 +497,12 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
         tuq += __shfl_xor_sync(FULL, tuq, d);
         tv += __shfl_xor_sync(FULL, tv, d);
       }
+      // an untied maximum is the answer; a tied one goes through the reference's container order
+      const uint32_t at_max = __ballot_sync(FULL, lane_best == best);
+      const bool tie = __popc(at_max) > 1 || __any_sync(FULL, lane_best == best && neq > 1);
+      if (tie)
+        besti = uct_tie_break<N>(tr.elink + (nb + node) * E, es, (int)h.n_edges, flip, fpu, sq, o,
+                                 s_order[threadIdx.x >> 5], s_tied[threadIdx.x >> 5], L.lane);
       const int ei = besti;
       const float new_mean = (h.parent_q + tuq) / (float)(tv + 1);
       const bool is_pass = ei == (int)h.pass_edge;
@@ -356,6 +515,9 @@ __global__ void __launch_bounds__(BLOCK) k_select(DevState st, TreeDev tr, Searc
         NodeHdr* hp = &tr.hdr[nb + node];
         hp->mean_q = new_mean;
         if (ei == (int)h.n_touched) hp->n_touched = (uint16_t)(h.n_touched + 1);
+        // a tie resolved in favour of an edge beyond the first never-selected one: the selected edges
+        // of this node are no longer a prefix, it is scanned in full from now on
+        if (ei > (int)h.n_touched && !(h.flags & NF_FULLSCAN)) hp->flags = h.flags | NF_FULLSCAN;
         path[depth] = (uint32_t)node | (is_pass ? 0x10000u : 0u);
       }
       wb = __shfl_sync(FULL, wb, 0);
@@ -798,84 +960,6 @@ __global__ void __launch_bounds__(BLOCK) k_backup(int G, TreeDev tr, int virtual
     }
     __syncwarp();
   }
-}
-
-// ---------------------------------------------------------------------------------------
-// "First maximum in container order".  MCTSResultT::addActions (tree_search_base.h:237-294) walks the
-// root's std::unordered_map<Coord, EdgeInfo> and keeps the first edge with the strictly largest visit
-// count, so an exact most-visited TIE is resolved by the hash table's iteration order.  That order is a
-// function of the insertion sequence alone (NodeT::setEvaluation inserts the edges in storage order):
-// libstdc++'s table is one forward list; a key whose bucket is empty goes to the FRONT of the list, a
-// key whose bucket is in use goes right behind that bucket's "before" node (i.e. to the front of its
-// bucket's run); hash(Coord) = Coord, bucket = key % bucket_count; bucket counts 13, 29, 59, 127, 257,
-// 541, growing when the 14th, 30th, 60th, 128th, 258th key arrives, and a rehash re-inserts the list,
-// front to back, by the same two rules (hashtable.h _M_insert_bucket_begin / _M_rehash_aux,
-// hashtable_policy.h _Prime_rehash_policy).  Pinned against std::unordered_map itself and against
-// the compiled reference (tests/test_refstream.py, tests/test_emu_kernels.py).
-// Lane 0 replays the insertions in shared memory; only called when the maximum is actually tied.
-struct OrderScratch {
-  uint16_t nxt[448];  // forward list: key -> next key
-  uint16_t idx[448];  // key -> storage index of the edge
-  uint16_t bkt[544];  // bucket -> key of the node BEFORE the bucket's first node
-};
-constexpr uint16_t OS_NIL = 0xFFFFu, OS_HEAD = 0xFFFEu, OS_EMPTY = 0xFFFDu;
-
-template <int N>
-__device__ __forceinline__ int action_to_coord(int a) {  // board.h:183-184; pass = M_PASS = 0
-  return a >= N * N ? 0 : ((a % N) + 1) * (N + 2) + (a / N) + 1;
-}
-
-__device__ __forceinline__ void os_link(OrderScratch& s, uint16_t& head, int nb, int key) {
-  const int b = key % nb;
-  const uint16_t before = s.bkt[b];
-  if (before == OS_EMPTY) {  // new bucket: the node becomes the list's first
-    s.nxt[key] = head;
-    if (head != OS_NIL) s.bkt[head % nb] = (uint16_t)key;
-    head = (uint16_t)key;
-    s.bkt[b] = OS_HEAD;
-  } else if (before == OS_HEAD) {
-    s.nxt[key] = head;
-    head = (uint16_t)key;
-  } else {
-    s.nxt[key] = s.nxt[before];
-    s.nxt[before] = (uint16_t)key;
-  }
-}
-
-template <int N>
-__device__ int first_max_in_container_order(const uint32_t* __restrict__ el, const float4* __restrict__ es, int ne,
-                                            int bestn, OrderScratch& s, int lane) {
-  int res = 0;
-  if (lane == 0) {
-    int nb = 13;
-    uint16_t head = OS_NIL;
-    for (int b = 0; b < nb; ++b) s.bkt[b] = OS_EMPTY;
-    for (int i = 0; i < ne; ++i) {
-      if (i == 13 || i == 29 || i == 59 || i == 127 || i == 257) {  // the table grows before key i+1 goes in
-        nb = i == 13 ? 29 : i == 29 ? 59 : i == 59 ? 127 : i == 127 ? 257 : 541;
-        for (int b = 0; b < nb; ++b) s.bkt[b] = OS_EMPTY;
-        uint16_t p = head;
-        head = OS_NIL;
-        while (p != OS_NIL) {
-          const uint16_t q = s.nxt[p];
-          os_link(s, head, nb, p);
-          p = q;
-        }
-      }
-      const int key = action_to_coord<N>((int)(el[i] & 0xFFFFu));
-      s.idx[key] = (uint16_t)i;
-      os_link(s, head, nb, key);
-    }
-    res = 0x7FFFFFFF;
-    for (uint16_t p = head; p != OS_NIL; p = s.nxt[p]) {
-      const int i = s.idx[p];
-      if (__float_as_int(es[i].y) == bestn) {
-        res = i;
-        break;
-      }
-    }
-  }
-  return __shfl_sync(FULL, res, 0);
 }
 
 // most visited root edge (first maximum in the reference's container order) and the visit total

@@ -13,14 +13,14 @@
  * on top of the board restatement (go_oracle.c).  Pinned against the compiled reference search
  * (oracle/_ref, ref_mcts_shim.cc) in tests/test_mcts_oracle_vs_ref.py.
  *
- * Two things the reference leaves to its containers are fixed here (and in the CUDA path):
- *  - edges are kept in the order pi2response produces them (descending prior); the reference
- *    iterates an unordered_map, so equal PUCT-score ties inside the tree may resolve differently
- *    (the most-visited choice at the root does follow the container order: container_order below);
+ * What the reference leaves to its containers:
+ *  - edges are STORED in the order pi2response produces them (descending prior), but every arg-max
+ *    the reference takes by iterating its unordered_map with a strict '>' -- the PUCT choice of each
+ *    descent step (NodeT::UCT) and the most-visited choice at the root -- is the FIRST maximum in
+ *    that container's iteration order: exact score ties (frequent once priors fall below the
+ *    rounding of q, or without the prior term) are resolved through container_order below;
  *  - unique leaves of a batch are backed up in first-occurrence order (the reference iterates an
- *    unordered_map keyed by node address).
- * Both only matter for exact float ties / last-bit rounding of reward sums, hence the +-1 visit
- * tolerance of the parity tests.
+ *    unordered_map keyed by node address): only the last bits of reward sums can differ.
  */
 #include <float.h>
 #include <math.h>
@@ -46,6 +46,7 @@ typedef struct {
   Edge* edges;
   int n_edges;
   int n_touched; /* edges [0, n_touched) have been selected at least once (prefix property check) */
+  int fullscan;  /* a tie was resolved in favour of an edge beyond the prefix: the CUDA path scans all edges from then on */
   int parent, parent_edge;
   int alive;
 } Node;
@@ -62,6 +63,8 @@ typedef struct MctsOracle {
   long n_evals;
   long prefix_violations; /* times the arg-max over [0, n_touched] differed from the full arg-max */
   long prefix_checks;
+  long tie_breaks;     /* descent steps whose maximum was tied and went through the container order */
+  long tie_breaks_out; /* ... of which the chosen edge lay beyond the first never-selected one */
 } MctsOracle;
 
 static int add_node(MctsOracle* m, float parent_q, int parent, int parent_edge) {
@@ -147,11 +150,14 @@ void mo_free(MctsOracle* m) {
 
 long mo_num_evals(const MctsOracle* m) { return m->n_evals; }
 
-/* The CUDA search only scans the selected prefix of the prior-sorted edges plus the first
- * never-selected one (k_select); this restatement scans everything, like the reference, and counts
- * how often the two would disagree (must be 0 unless two priors tie exactly). */
+/* The CUDA search only scans the selected prefix of the prior-sorted edges plus the first TWO
+ * never-selected ones (k_select) and falls back to a full scan with the container-order tie-break
+ * when the maximum over that range is tied; this restatement scans everything, like the reference,
+ * and counts how often the short scan's untied maximum would not be the full answer (must be 0). */
 long mo_prefix_violations(const MctsOracle* m) { return m->prefix_violations; }
 long mo_prefix_checks(const MctsOracle* m) { return m->prefix_checks; }
+long mo_tie_breaks(const MctsOracle* m) { return m->tie_breaks; }
+long mo_tie_breaks_beyond_prefix(const MctsOracle* m) { return m->tie_breaks_out; }
 
 /* ---- evaluation: MCTSActor::evaluate for one state (go/mcts/mcts.h:73-121,185-332) ---- */
 typedef struct {
@@ -231,6 +237,8 @@ static void evaluate_node(MctsOracle* m, Node* nd) {
   free(pi);
 }
 
+static void container_order(int N, const Edge* edges, int n, int* order);
+
 /* ---- one wave: batch_rollouts, tree_search.h:201-262 ---- */
 static void batch_rollouts(MctsOracle* m) {
   const int B = m->B;
@@ -244,8 +252,9 @@ static void batch_rollouts(MctsOracle* m) {
       /* UCT, tree_search_node.h:361-397 + getScore, tree_search_base.h:132-157 */
       const double sq = sqrt((double)(nd->num_visits + 1));
       float best = -FLT_MAX, tuq = 0.0f, best_prefix = -FLT_MAX;
-      int besti = -1, tv = 0, besti_prefix = -1;
-      const int lim = nd->n_touched + 1 < nd->n_edges ? nd->n_touched + 1 : nd->n_edges;
+      int besti = -1, tv = 0, besti_prefix = -1, ties = 0, ties_prefix = 0;
+      const int lim = (nd->fullscan || nd->n_touched + 2 >= nd->n_edges) ? nd->n_edges : nd->n_touched + 2;
+      float scores[512];
       for (int i = 0; i < nd->n_edges; ++i) {
         const Edge* e = &nd->edges[i];
         float r = nd->flip ? -e->reward : e->reward;
@@ -255,22 +264,46 @@ static void batch_rollouts(MctsOracle* m) {
         const float uq = e->visits > 0 ? e->reward / (float)e->visits : nd->mean_q;
         const float u = (float)((double)(e->prior / (float)(1 + e->visits)) * sq);
         const float score = m->use_prior ? fmaf(u, m->c_puct, q) : q;
+        scores[i] = score;
         if (score > best) {
           best = score;
           besti = i;
+          ties = 1;
+        } else if (score == best) {
+          ties++;
         }
-        if (i < lim && score > best_prefix) {
-          best_prefix = score;
-          besti_prefix = i;
+        if (i < lim) {
+          if (score > best_prefix) {
+            best_prefix = score;
+            besti_prefix = i;
+            ties_prefix = 1;
+          } else if (score == best_prefix) {
+            ties_prefix++;
+          }
         }
-        if (nwl != 0 && i >= nd->n_touched) m->prefix_violations++; /* a touched edge outside the prefix */
+        if (nwl != 0 && i >= nd->n_touched && !nd->fullscan) m->prefix_violations++; /* a touched edge outside the prefix */
         if (nwl != 0) {
           tuq += uq;
           tv++;
         }
       }
+      if (ties > 1) { /* NodeT::UCT walks the unordered_map with a strict '>': first maximum in ITS order */
+        int order[512];
+        m->tie_breaks++;
+        container_order(m->N, nd->edges, nd->n_edges, order);
+        for (int k = 0; k < nd->n_edges; ++k)
+          if (scores[order[k]] == best) {
+            besti = order[k];
+            break;
+          }
+      }
       m->prefix_checks++;
-      if (besti_prefix != besti) m->prefix_violations++;
+      /* the short scan is trusted only when its maximum is untied: then it must be the answer */
+      if (ties_prefix == 1 && (besti_prefix != besti || ties != 1)) m->prefix_violations++;
+      if (besti > nd->n_touched && !nd->fullscan) {
+        nd->fullscan = 1;
+        m->tie_breaks_out++;
+      }
       if (besti == nd->n_touched) nd->n_touched++;
       nd->mean_q = (nd->parent_q + tuq) / (float)(tv + 1); /* findMove, tree_search_node.h:227 */
       Edge* e = &nd->edges[besti];

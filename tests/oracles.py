@@ -580,6 +580,12 @@ class OracleMcts:
         self.L.mo_prefix_checks.argtypes = [vp]
         return int(self.L.mo_prefix_violations(self.m)), int(self.L.mo_prefix_checks(self.m))
 
+    def tie_stats(self):
+        """(descent steps decided by the container-order tie-break, of which beyond the scanned prefix)"""
+        for f in (self.L.mo_tie_breaks, self.L.mo_tie_breaks_beyond_prefix):
+            f.restype, f.argtypes = ctypes.c_long, [vp]
+        return int(self.L.mo_tie_breaks(self.m)), int(self.L.mo_tie_breaks_beyond_prefix(self.m))
+
     def __del__(self):
         if getattr(self, "m", None):
             self.L.mo_free(self.m)

@@ -779,3 +779,45 @@ def test_expand_half_size_sort_network_on_late_positions(emu, oracle_lib):
         for o, a in zip(os_, acts):
             o.forward(int(a))
     assert (mc.errors() == 0).all()
+
+
+@pytest.mark.parametrize("name", ["9_noprior_ties", "9_rounding_ties"])
+def test_puct_ties_resolve_in_the_reference_container_order(emu, name, lane_order):
+    """k_select's uct_tie_break: exactly equal PUCT scores (no prior term; priors lost in the rounding of
+    q) go to the first tied edge in the order of the reference's unordered_map, also when that edge lies
+    beyond the scanned prefix (the node is scanned in full from then on) -- root visit tables equal the
+    COMPILED reference search's, move after move (twin of test_gpu_mcts.py::test_gpu_search_vs_reference)"""
+    from tests.test_mcts_oracle_vs_ref import SCENARIOS, scenario_openings
+
+    sc = SCENARIOS[name]
+    n, G = sc["n"], sc["G"]
+    if not oracles.have_ref(n):
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    rng = np.random.default_rng(5 + n)
+    gb = emu.emu_batch(G, n)
+    states = [oracles.Ref(n) for _ in range(G)]
+    fixed = scenario_openings(sc)
+    for t in range(sc["open_plies"]):
+        acts = np.empty(G, np.int32)
+        for g, s in enumerate(states):
+            idx = np.flatnonzero(s.legal())
+            acts[g] = int(fixed[g][t]) if fixed is not None else int(rng.choice(idx))
+            assert s.forward(acts[g])
+        assert gb.forward(acts).all()
+    mc = emu.EmuSearch(gb, rotation_flip=0, **sc["opts"])
+    refs = [oracles.RefMcts(n, **sc["opts"]) for _ in range(G)]
+    actor = fake_actor(mc, n)
+    for mv in range(sc["moves"]):
+        res = mc.act(actor)
+        acts = np.empty(G, np.int32)
+        for g in range(G):
+            rr = refs[g].act(states[g])
+            np.testing.assert_array_equal(res["visits"][g], rr["visits"], err_msg=f"move {mv} game {g}")
+            assert res["total_visits"][g] == rr["total_visits"] and res["best_action"][g] == rr["best_action"]
+            assert res["root_value"][g] == np.float32(rr["root_value"]) and abs(res["best_q"][g] - rr["best_q"]) < 1e-5
+            acts[g] = rr["best_action"]
+            assert states[g].forward(acts[g])
+        assert gb.forward(acts).all()
+        mc.advance(acts)
+    assert (mc.errors() == 0).all(), mc.errors()
+    assert mc.eval_count() == sum(c.num_evals() for c in refs)

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from tests import oracles
-from tests.test_mcts_oracle_vs_ref import SCENARIOS, GOLD
+from tests.test_mcts_oracle_vs_ref import SCENARIOS, GOLD, scenario_openings
 
 pytestmark = pytest.mark.gpu
 
@@ -35,11 +35,12 @@ def run_gpu_vs_cpu(sc, use_ref, tol=1):
     gb = elf_b200.GoBatch(G, board_size=n)
     make = (lambda: oracles.Ref(n)) if use_ref else (lambda: oracles.Oracle(n))
     states = [make() for _ in range(G)]
-    for _ in range(sc["open_plies"]):
+    fixed = scenario_openings(sc)  # explicit opening move lists (the tie scenarios) or None
+    for t in range(sc["open_plies"]):
         acts = np.empty(G, np.int32)
         for g, s in enumerate(states):
             idx = np.flatnonzero(s.legal())
-            acts[g] = int(rng.choice(idx))
+            acts[g] = int(fixed[g][t]) if fixed is not None else int(rng.choice(idx))
             assert s.forward(acts[g])
         assert gb.forward(acts).all()
     mc = elf_b200.MctsBatch(gb, rotation_flip=0, **sc["opts"])

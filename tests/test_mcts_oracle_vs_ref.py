@@ -27,14 +27,34 @@ SCENARIOS = {
     "9_uqz_pass": dict(n=9, G=4, moves=10, open_plies=50,
                        opts=dict(num_rollouts=120, num_rollouts_per_batch=6, virtual_loss=1, persistent_tree=1, c_puct=2.0,
                                  unexplored_q_zero=1, ply_pass_enabled=40, remove_pass_if_dangerous=0)),
+    # exact PUCT-score ties, which the reference resolves in the iteration order of its unordered_map
+    # (NodeT::UCT, tree_search_node.h:361-397): without the prior term every unvisited edge ties ...
+    "9_noprior_ties": dict(n=9, G=3, moves=5, open_plies=40,
+                           opts=dict(num_rollouts=60, num_rollouts_per_batch=6, virtual_loss=1, persistent_tree=1, c_puct=1.5,
+                                     use_prior=0)),
+    # ... and with it, priors small enough that c_puct * P * sqrt(n) vanishes under the rounding of q tie as
+    # well (late positions; the fixed openings were found by scripts/emu_fuzz.py)
+    "9_rounding_ties": dict(n=9, G=2, moves=4, open_plies=151, openings="mcts_tie_openings_9.json",
+                            opts=dict(num_rollouts=119, num_rollouts_per_batch=14, virtual_loss=3, persistent_tree=1, c_puct=0.3,
+                                      root_unexplored_q_zero=1, ply_pass_enabled=60, remove_pass_if_dangerous=1, komi=5.5)),
 }
 
 
-def opening(n, G, open_plies, make):
+def scenario_openings(sc):
+    """explicit opening move lists of a scenario ([G][open_plies] actions) or None (random openings)"""
+    if "openings" not in sc:
+        return None
+    return json.load(open(os.path.join(GOLD, sc["openings"])))["openings"]
+
+
+def opening(n, G, open_plies, make, fixed=None):
     rng = np.random.default_rng(5 + n)
     states = [make() for _ in range(G)]
-    for _ in range(open_plies):
-        for s in states:
+    for t in range(open_plies):
+        for g, s in enumerate(states):
+            if fixed is not None:
+                assert s.forward(int(fixed[g][t]))
+                continue
             idx = np.flatnonzero(s.legal())
             assert s.forward(int(rng.choice(idx)))
     return states
@@ -45,7 +65,7 @@ def run_search(sc, make_state, make_mcts, forced=None, orders=None):
     when `forced` (a list in the same order as the returned results) is given, that action -- used to
     keep two implementations on the same trajectory when they break a most-visited TIE differently
     (the reference resolves ties by unordered_map order, tree_search_base.h:237-294)"""
-    states = opening(sc["n"], sc["G"], sc["open_plies"], make_state)
+    states = opening(sc["n"], sc["G"], sc["open_plies"], make_state, scenario_openings(sc))
     ms = [make_mcts() for _ in range(sc["G"])]
     out = []
     for _ in range(sc["moves"]):
@@ -131,7 +151,7 @@ def test_selected_prefix_property(name, oracle_lib):
     that prefix, or that finds a selected edge outside it: must never happen."""
     sc = SCENARIOS[name]
     n = sc["n"]
-    states = opening(n, sc["G"], sc["open_plies"], lambda: oracles.Oracle(n, oracle_lib))
+    states = opening(n, sc["G"], sc["open_plies"], lambda: oracles.Oracle(n, oracle_lib), scenario_openings(sc))
     ms = [oracles.OracleMcts(n, lib=oracle_lib, **sc["opts"]) for _ in range(sc["G"])]
     for _ in range(sc["moves"]):
         for s, m in zip(states, ms):
@@ -139,3 +159,6 @@ def test_selected_prefix_property(name, oracle_lib):
     viol = sum(m.prefix_stats()[0] for m in ms)
     checks = sum(m.prefix_stats()[1] for m in ms)
     assert checks > 500 and viol == 0, (viol, checks)
+    if name.endswith("_ties"):  # these scenarios are there for the container-order tie-break
+        ties, beyond = sum(m.tie_stats()[0] for m in ms), sum(m.tie_stats()[1] for m in ms)
+        assert ties > 0 and (beyond > 0 or name == "9_rounding_ties"), (ties, beyond)
