@@ -6,7 +6,8 @@ Every "device" buffer of the C ABI is a heap allocation in the emulator build, s
 or use-after-free access by any kernel (or by the host side of the library) is reported by ASan
 with the kernel source line.  Exercised: playouts (both modes), elfb200_replay with random --
 including refused -- moves, the export and feature kernels, and the search with a node pool small
-enough to overflow (tree drops), random D4, the device-side move choice and tree advance.
+enough to overflow (tree drops), random D4, the device-side move choice and tree advance, and a
+search without the prior term (every descent step goes through the container-order tie-break).
 TEST INFRASTRUCTURE ONLY."""
 import os
 import subprocess
@@ -57,6 +58,22 @@ def main():
             gb2.forward(a)
             mc.advance(a)
         mc.root_priors()
+        # exact PUCT ties at every step (no prior term): uct_tie_break's full rescans, tie bit words and
+        # hash-table scratch, full-scan nodes
+        gb3 = E.emu_batch(G, n)
+        mt = E.EmuSearch(gb3, rotation_flip=0, num_rollouts=48, num_rollouts_per_batch=6, persistent_tree=1, use_prior=0)
+
+        def actor_t(batch):
+            h, _, _ = mt.leaf_info()
+            pi, v = oracles.fakenet(h, n * n + 1)
+            return {"pi": torch.from_numpy(pi), "V": torch.from_numpy(v)}
+
+        for mv in range(3):
+            mt.act(actor_t)
+            a, _ = mt.choose(-1, 0.05, None, mv)
+            gb3.forward(a)
+            mt.advance(a)
+        mt.close(), gb3.close()
         print(f"{n}x{n}: no ASan report; tree prunes {int(mc.errors()[3])}, pool overflows {int(mc.errors()[1])}", flush=True)
         mc.close(), gb2.close(), gb.close()
     print("ASAN RUN CLEAN")
