@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "elfb200_mcts.h"
+#include "stdsort.cuh"
 
 namespace elfb200 {
 
@@ -85,7 +86,7 @@ struct TreeDev {
 
 struct SearchOpts {
   int num_rollouts, virtual_loss, persistent, use_prior, uqz, ruqz, ply_pass_enabled,
-      remove_pass_if_dangerous, rotation_flip, seed;
+      remove_pass_if_dangerous, rotation_flip, seed, std_sort_ties;
   float c_puct, komi;
 };
 
@@ -743,7 +744,11 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t (&key)[R], int lane) 
 // Expansion: MCTSActor::post_nn_result / remove_pass_if_dangerous / pi2response / normalize
 // (go/mcts/mcts.h:209-332) + NodeT::setEvaluation (tree_search_node.h:176-203).  One warp per
 // claimed leaf; the candidate list is bitonic-sorted in shared memory by descending probability.
-template <int N>
+// EXACT (option std_sort_ties): leaves whose reply holds two legal moves with bit-equal probabilities get
+// their candidates in the order libstdc++'s std::sort leaves the reply's 362 pairs in (stdsort.cuh) instead
+// of "equal probabilities by ascending move"; a separate instantiation, so that the default kernel's code
+// and resources are exactly what they were.
+template <int N, bool EXACT>
 __global__ void __launch_bounds__(BLOCK)
     k_expand(DevState st, TreeDev tr, SearchOpts o, const float* __restrict__ pi, const float* __restrict__ val) {
   constexpr int P = Geo<N>::P;
@@ -836,6 +841,43 @@ __global__ void __launch_bounds__(BLOCK)
     for (int r = 0; r < R; ++r) key[L.lane * R + r] = kr[r];
   }
   __syncwarp();
+  if constexpr (EXACT) {
+    // probability bits, sort order and (validity << 15 | move), all by NETWORK action index
+    __shared__ uint32_t s_pb[WARPS][P + 1];
+    __shared__ uint16_t s_ord[WARPS][P + 2];
+    __shared__ uint16_t s_act[WARPS][P + 2];
+    // two candidates with the same probability bits are neighbours in the sorted list
+    bool tie = false;
+    for (int i = L.lane + 1; i < nvalid; i += 32) tie |= (uint32_t)(key[i] >> 32) == (uint32_t)(key[i - 1] >> 32);
+    if (__any_sync(FULL, tie)) {
+      // pi2response: all P+1 pairs in network-action order, std::sort by probability, THEN the legality filter
+      for (int a = L.lane; a <= P; a += 32) {
+        int act = P;
+        bool ok = pass_enabled;
+        if (a < P) {
+          int x, y;
+          d4_inverse(N, d4, a / N, a - (a / N) * N, x, y);
+          act = x * N + y;
+          ok = (s_legal[wib][y] >> x) & 1u;
+        }
+        s_pb[wib][a] = __float_as_uint(pr[a]);
+        s_ord[wib][a] = (uint16_t)a;
+        s_act[wib][a] = (uint16_t)(act | (ok ? 0x8000 : 0));
+      }
+      __syncwarp();
+      if (L.lane == 0) {
+        StdSortCtx sc{s_pb[wib]};
+        ss_sort(&sc, s_ord[wib], P + 1);
+        int k = 0;
+        for (int i = 0; i <= P; ++i) {
+          const int a = s_ord[wib][i];
+          const uint16_t av = s_act[wib][a];
+          if (av & 0x8000) key[k++] = ((uint64_t)(0xFFFFFFFFu - s_pb[wib][a]) << 32) | (uint32_t)(av & 0x7FFF);
+        }
+      }
+      __syncwarp();
+    }
+  }
   // sequential float sum in sorted order (normalize, mcts.h:244-254)
   if (L.lane == 0) {
     float tot = 1e-10f;
@@ -1507,6 +1549,7 @@ int elfb200_mcts_create(elfb200_ctx* c, const elfb200_mcts_options* opt, elfb200
   s.remove_pass_if_dangerous = opt->remove_pass_if_dangerous;
   s.rotation_flip = opt->rotation_flip;
   s.seed = opt->seed;
+  s.std_sort_ties = opt->std_sort_ties != 0;
   s.c_puct = opt->c_puct;
   s.komi = opt->komi;
   for (auto& e : m->ev) CK(cudaEventCreate(&e));
@@ -1710,8 +1753,12 @@ int elfb200_mcts_expand_backup(elfb200_mcts* m, const float* pi_dev, const float
   if (n != 0) {
     if (!pi_dev || !value_dev) return elfb200_fail(ELFB200_ERR_ARG, "pi/value is NULL with %d leaves pending", n);
     const int nw = n > 0 ? n : c->G * m->tr.B;  // n < 0: count known to the device only
-    DISPATCH_N(c, (k_expand<19><<<warp_grid(nw), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)),
-               (k_expand<9><<<warp_grid(nw), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)));
+    if (m->so.std_sort_ties)
+      DISPATCH_N(c, (k_expand<19, true><<<warp_grid(nw), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)),
+                 (k_expand<9, true><<<warp_grid(nw), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)));
+    else
+      DISPATCH_N(c, (k_expand<19, false><<<warp_grid(nw), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)),
+                 (k_expand<9, false><<<warp_grid(nw), BLOCK, 0, c->stream>>>(c->st, m->tr, m->so, pi_dev, value_dev)));
     c->launches++;
     CK(cudaGetLastError());
   }

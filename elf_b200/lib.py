@@ -105,6 +105,7 @@ class MctsOptions(ctypes.Structure):
         ("ply_pass_enabled", ctypes.c_int32), ("remove_pass_if_dangerous", ctypes.c_int32),
         ("rotation_flip", ctypes.c_int32), ("seed", ctypes.c_int32), ("nodes_per_game", ctypes.c_int32),
         ("c_puct", ctypes.c_float), ("komi", ctypes.c_float), ("root_epsilon", ctypes.c_float), ("root_alpha", ctypes.c_float),
+        ("std_sort_ties", ctypes.c_int32),
     ]
 
 

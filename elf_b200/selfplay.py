@@ -15,7 +15,9 @@ owns the two ``std::mt19937`` generators of a reference game thread seeded from 
 (``GameOptions::seed``; an array gives every game its own), root noise / D4 codes / sampled moves /
 the never-resign draw consume them exactly where ``GoGameSelfPlay::act`` does, and ties between
 equally visited moves resolve in the reference's container order: the batch then plays, move for
-move, the games the reference's game threads play with that seed (single search thread).
+move, the games the reference's game threads play with that seed (single search thread).  With a
+network whose replies hold bit-equal probabilities (half precision: equal logits) add the search
+option ``std_sort_ties=1``, which stores such moves in the order ``std::sort`` leaves them in.
 """
 import numpy as np
 

@@ -60,6 +60,12 @@ typedef struct {
   float komi;                      /* MCTSActorParams::komi */
   float root_epsilon;              /* TSOptions::root_epsilon: Dirichlet noise weight at the root (0 = off) */
   float root_alpha;                /* TSOptions::root_alpha */
+  int32_t std_sort_ties;           /* moves with bit-EQUAL network probabilities: 0 (default) = stored by ascending
+                                    * move index; 1 = in the order libstdc++'s std::sort leaves them in
+                                    * MCTSActor::pi2response (go/mcts/mcts.h:289-295), which is what the reference's
+                                    * edge containers -- and every tie-break that walks them -- then see.  Needed to
+                                    * replay the reference's games bit for bit with half-precision networks (equal
+                                    * fp16 logits are the norm); costs a sequential sort per leaf that has such a tie. */
 } elfb200_mcts_options;
 
 int elfb200_mcts_default_options(elfb200_mcts_options* opt);

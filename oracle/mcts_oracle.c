@@ -29,6 +29,7 @@
 
 #include "fakenet.h"
 #include "go_oracle.h"
+#include "stdsort_emul.h"
 
 typedef void (*mo_eval_cb)(int n, const float* feats, const uint64_t* hashes, float* pi, float* v);
 
@@ -54,6 +55,7 @@ typedef struct {
 typedef struct MctsOracle {
   int N;
   int R, B, vl, persistent, use_prior, uqz, ruqz, ply_pass_enabled, remove_pass;
+  int std_sort_ties; /* equal probabilities in std::sort's order (pi2response) instead of by ascending move */
   float c_puct, komi;
   mo_eval_cb cb;
   Node* nodes;
@@ -134,6 +136,7 @@ MctsOracle* mo_new(int N, const int32_t* iopts, const float* fopts, mo_eval_cb c
   m->ruqz = iopts[6];
   m->ply_pass_enabled = iopts[7];
   m->remove_pass = iopts[8];
+  m->std_sort_ties = iopts[11]; /* [9] seed, [10] threads: unused here */
   m->c_puct = fopts[0];
   m->komi = fopts[1];
   m->cb = cb;
@@ -217,6 +220,29 @@ static void evaluate_node(MctsOracle* m, Node* nd) {
     }
   }
   qsort(c, (size_t)nc, sizeof(Cand), cand_cmp);
+  int tie = 0;
+  for (int i = 1; i < nc; ++i) tie |= c[i].p == c[i - 1].p;
+  if (m->std_sort_ties && tie) {
+    /* pi2response as written: ALL P+1 pairs in network-action order through std::sort (comparator on the
+     * probability only), then the validity filter -- equal probabilities end up in libstdc++'s order */
+    uint32_t keys[512];
+    uint16_t ord[512];
+    for (int a = 0; a <= P; ++a) {
+      memcpy(&keys[a], &pi[a], 4);
+      ord[a] = (uint16_t)a;
+    }
+    SseCtx sc = {keys, 0};
+    sse_sort(&sc, ord, P + 1);
+    nc = 0;
+    for (int i = 0; i <= P; ++i) {
+      const int a = ord[i];
+      if ((a == P) ? pass_enabled : go_check_move(s, a)) {
+        c[nc].p = pi[a];
+        c[nc].a = a;
+        nc++;
+      }
+    }
+  }
   if (nc == 0 && !pass_enabled) {
     c[0].p = 1.0f;
     c[0].a = P;

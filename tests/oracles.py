@@ -533,7 +533,7 @@ class OracleMcts:
 
     def __init__(self, n, num_rollouts=200, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1,
                  use_prior=1, unexplored_q_zero=0, root_unexplored_q_zero=0, ply_pass_enabled=0,
-                 remove_pass_if_dangerous=1, seed=7, c_puct=1.5, komi=7.5, lib=None):
+                 remove_pass_if_dangerous=1, seed=7, c_puct=1.5, komi=7.5, lib=None, std_sort_ties=0, callback=None):
         self.L = lib or load_oracle()
         self.n = n
         L = self.L
@@ -545,9 +545,23 @@ class OracleMcts:
         L.mo_num_evals.argtypes = [vp]
         iopts = np.array([num_rollouts, num_rollouts_per_batch, virtual_loss, persistent_tree, use_prior,
                           unexplored_q_zero, root_unexplored_q_zero, ply_pass_enabled, remove_pass_if_dangerous,
-                          seed, 1], np.int32)
+                          seed, 1, std_sort_ties], np.int32)
         fopts = np.array([c_puct, komi, 0, 0], np.float32)
-        self.m = L.mo_new(n, iopts.ctypes.data, fopts.ctypes.data, None)
+        self._cb = None
+        if callback is not None:  # callback(feats [1,18,n,n], hashes [1]) -> (pi [1,P1], v [1]), as RefMcts
+            CB = ctypes.CFUNCTYPE(None, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint64),
+                                  ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float))
+            P1 = n * n + 1
+
+            def tramp(cnt, feats, hashes, pi, v):
+                f = np.ctypeslib.as_array(feats, shape=(cnt, 18, n, n))
+                h = np.ctypeslib.as_array(hashes, shape=(cnt,))
+                p, val = callback(f, h)
+                np.ctypeslib.as_array(pi, shape=(cnt, P1))[:] = p
+                np.ctypeslib.as_array(v, shape=(cnt,))[:] = val
+
+            self._cb = CB(tramp)
+        self.m = L.mo_new(n, iopts.ctypes.data, fopts.ctypes.data, ctypes.cast(self._cb, vp) if self._cb else None)
 
     def act(self, oracle_state):
         P1 = self.n * self.n + 1

@@ -7,7 +7,8 @@ or use-after-free access by any kernel (or by the host side of the library) is r
 with the kernel source line.  Exercised: playouts (both modes), elfb200_replay with random --
 including refused -- moves, the export and feature kernels, and the search with a node pool small
 enough to overflow (tree drops), random D4, the device-side move choice and tree advance, and a
-search without the prior term (every descent step goes through the container-order tie-break).
+search without the prior term (every descent step goes through the container-order tie-break) and one
+with std_sort_ties on replies full of equal probabilities (the sequential std::sort restatement).
 TEST INFRASTRUCTURE ONLY."""
 import os
 import subprocess
@@ -74,6 +75,22 @@ def main():
             gb3.forward(a)
             mt.advance(a)
         mt.close(), gb3.close()
+        # replies full of bit-equal probabilities with std_sort_ties: k_expand<N, true>'s sequential
+        # std::sort restatement (shared-memory key / order / move arrays, explicit partition stack)
+        gb4 = E.emu_batch(G, n)
+        ms = E.EmuSearch(gb4, rotation_flip=1, num_rollouts=32, num_rollouts_per_batch=8, persistent_tree=1, std_sort_ties=1)
+
+        def actor_q(batch):
+            h, _, _ = ms.leaf_info()
+            pi, v = oracles.fakenet(h, n * n + 1)
+            return {"pi": torch.from_numpy((np.floor(pi * 16) / 16).astype(np.float32)), "V": torch.from_numpy(v)}
+
+        for mv in range(3):
+            ms.act(actor_q)
+            a, _ = ms.choose(-1, 0.05, None, mv)
+            gb4.forward(a)
+            ms.advance(a)
+        ms.close(), gb4.close()
         print(f"{n}x{n}: no ASan report; tree prunes {int(mc.errors()[3])}, pool overflows {int(mc.errors()[1])}", flush=True)
         mc.close(), gb2.close(), gb.close()
     print("ASAN RUN CLEAN")

@@ -821,3 +821,49 @@ def test_puct_ties_resolve_in_the_reference_container_order(emu, name, lane_orde
         mc.advance(acts)
     assert (mc.errors() == 0).all(), mc.errors()
     assert mc.eval_count() == sum(c.num_evals() for c in refs)
+
+
+@pytest.mark.parametrize("n,quant", [(9, 16), (9, 256), (19, 256)])
+def test_equal_priors_follow_std_sort(emu, n, quant, lane_order):
+    """k_expand<N, true> (search option std_sort_ties): a reply with bit-equal probabilities is put in the
+    order libstdc++'s std::sort leaves it in (stdsort.cuh) before the legality filter, as
+    MCTSActor::pi2response does; root visit tables, priors and container order then equal the COMPILED
+    reference's on networks full of equal values (what half precision produces)"""
+    from tests.test_mcts_oracle_vs_ref import quantised_fakenet
+
+    if not oracles.have_ref(n):
+        pytest.skip("compiled reference (oracle/_ref) not available")
+    rng = np.random.default_rng(100 * n + quant)
+    net = quantised_fakenet(n, quant)
+    for case in range(3 if n == 9 else 1):
+        opts = dict(num_rollouts=int(rng.integers(20, 64 if n == 9 else 40)), num_rollouts_per_batch=int(rng.integers(1, 9)),
+                    virtual_loss=int(rng.integers(0, 3)), persistent_tree=1, c_puct=float(rng.choice([0.5, 1.5])),
+                    ply_pass_enabled=int(rng.choice([0, 40])))
+        G = 2
+        gb = emu.emu_batch(G, n)
+        refs = [oracles.Ref(n) for _ in range(G)]
+        rms = [oracles.RefMcts(n, callback=net, **opts) for _ in range(G)]
+        mc = emu.EmuSearch(gb, rotation_flip=0, std_sort_ties=1, **opts)
+
+        def actor(batch):
+            h, _, _ = mc.leaf_info()
+            pi, v = net(None, h)
+            return {"pi": torch.from_numpy(pi), "V": torch.from_numpy(v)}
+
+        for _ in range(int(rng.integers(0, 60 if n == 9 else 150))):
+            acts = np.array([int(rng.choice(np.flatnonzero(r.legal()))) for r in refs], np.int32)
+            assert gb.forward(acts).all() and all(r.forward(int(a)) for r, a in zip(refs, acts))
+        for mv in range(3):
+            res, pri = mc.act(actor), mc.root_priors()
+            acts = np.empty(G, np.int32)
+            for g in range(G):
+                w = rms[g].act(refs[g])
+                np.testing.assert_array_equal(res["visits"][g], w["visits"], err_msg=f"case {case} move {mv} game {g}")
+                has = w["visits"] >= 0
+                np.testing.assert_array_equal(pri[g][has], w["prior"][has])
+                assert res["best_action"][g] == w["best_action"]
+                acts[g] = w["best_action"]
+                assert refs[g].forward(int(acts[g]))
+            assert gb.forward(acts).all()
+            mc.advance(acts)
+        assert (mc.errors() == 0).all(), mc.errors()

@@ -162,3 +162,41 @@ def test_selected_prefix_property(name, oracle_lib):
     if name.endswith("_ties"):  # these scenarios are there for the container-order tie-break
         ties, beyond = sum(m.tie_stats()[0] for m in ms), sum(m.tie_stats()[1] for m in ms)
         assert ties > 0 and (beyond > 0 or name == "9_rounding_ties"), (ties, beyond)
+
+
+def quantised_fakenet(n, quant):
+    """the fake net with its probabilities on a grid of 1/quant: bit-equal values everywhere, as a
+    half-precision network produces them"""
+    def net(feats, hashes):
+        pi, v = oracles.fakenet(hashes, n * n + 1)
+        return (np.floor(pi * np.float32(quant)) / np.float32(quant)).astype(np.float32), v
+
+    return net
+
+
+@pytest.mark.parametrize("quant", [16, 256, 4096])
+def test_equal_priors_in_std_sort_order(quant, oracle_lib):
+    """std_sort_ties: moves with bit-equal probabilities are stored in the order libstdc++'s std::sort
+    leaves them in pi2response (go/mcts/mcts.h:289-295) -- with it the restatement reproduces the compiled
+    reference's visit tables on networks whose replies are full of equal values"""
+    n = 9
+    if not oracles.have_ref(n):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(quant)
+    for case in range(4):
+        opts = dict(num_rollouts=int(rng.integers(20, 100)), num_rollouts_per_batch=int(rng.integers(1, 9)),
+                    virtual_loss=int(rng.integers(0, 3)), persistent_tree=1, c_puct=float(rng.choice([0.5, 1.5])),
+                    ply_pass_enabled=int(rng.choice([0, 40])))
+        ref, o = oracles.Ref(n), oracles.Oracle(n, oracle_lib)
+        rm = oracles.RefMcts(n, callback=quantised_fakenet(n, quant), **opts)
+        om = oracles.OracleMcts(n, lib=oracle_lib, callback=quantised_fakenet(n, quant), std_sort_ties=1, **opts)
+        for _ in range(int(rng.integers(0, 60))):
+            a = int(rng.choice(np.flatnonzero(ref.legal())))
+            assert ref.forward(a) and o.forward(a)
+        for mv in range(4):
+            w, p = rm.act(ref), om.act(o)
+            np.testing.assert_array_equal(w["visits"], p["visits"], err_msg=f"quant {quant} case {case} move {mv}")
+            np.testing.assert_array_equal(w["prior"], p["prior"])
+            np.testing.assert_array_equal(rm.last_order(), om.last_order())
+            assert w["best_action"] == p["best_action"]
+            assert ref.forward(w["best_action"]) and o.forward(w["best_action"])

@@ -13,16 +13,26 @@ from tests import emu, oracles
 pytestmark = pytest.mark.skipif(not oracles.have_ref(9), reason="compiled reference (oracle/_ref) not available")
 
 
-def plane_actor(n):
+def _quantised(pi, quant):
+    """quant > 0: probabilities on a grid of 1/quant -- bit-equal values everywhere, like the replies of a
+    half-precision network (equal fp16 logits)"""
+    return pi if not quant else (np.floor(pi * np.float32(quant)) / np.float32(quant)).astype(np.float32)
+
+
+def plane_actor(n, quant=0):
     def actor(batch):
         pi, v = oracles.feature_net(batch["s"].float().numpy(), n * n + 1)
-        return {"pi": torch.from_numpy(pi), "V": torch.from_numpy(v)}
+        return {"pi": torch.from_numpy(_quantised(pi, quant)), "V": torch.from_numpy(v)}
 
     return actor
 
 
-def ref_net(n):
-    return lambda feats, hashes: oracles.feature_net(feats, n * n + 1)
+def ref_net(n, quant=0):
+    def net(feats, hashes):
+        pi, v = oracles.feature_net(feats, n * n + 1)
+        return _quantised(pi, quant), v
+
+    return net
 
 
 @pytest.mark.parametrize("n", [9, 19])
@@ -46,11 +56,11 @@ def test_edge_order_is_the_reference_containers(n):
         st.forward(int(rng.choice(legal)) if len(legal) else n * n)
 
 
-def play_reference_game(n, seed, opts, eps, alpha, flip, cutoff, thres, ratio, max_moves):
+def play_reference_game(n, seed, opts, eps, alpha, flip, cutoff, thres, ratio, max_moves, quant=0):
     """one game thread of GoGameSelfPlay::act (game_selfplay.cc:272-430) composed from the reference's
     own pieces: init_ai's seed draw, MCTSAI_T::act, mcts_make_diverse_move, shouldResign, forward"""
     g = oracles.RefRng(n, seed)
-    ref = oracles.RefMcts(n, callback=ref_net(n), root_epsilon=eps, root_alpha=alpha, rotation_flip=flip,
+    ref = oracles.RefMcts(n, callback=ref_net(n, quant), root_epsilon=eps, root_alpha=alpha, rotation_flip=flip,
                           seed=g.next(), **opts)
     rc = oracles.RefResign(n, thres, ratio)
     st = oracles.Ref(n)
@@ -73,22 +83,26 @@ def play_reference_game(n, seed, opts, eps, alpha, flip, cutoff, thres, ratio, m
     return log
 
 
-@pytest.mark.parametrize("n,eps,flip,moves", [(9, 0.25, 1, 30), (9, 0.0, 1, 16), (9, 0.25, 0, 16), (19, 0.25, 1, 8)])
-def test_whole_games_move_for_move(n, eps, flip, moves):
+@pytest.mark.parametrize("n,eps,flip,moves,quant", [(9, 0.25, 1, 30, 0), (9, 0.0, 1, 16, 0), (9, 0.25, 0, 16, 0),
+                                                    (19, 0.25, 1, 8, 0), (9, 0.25, 1, 24, 512), (9, 0.0, 1, 24, 64)])
+def test_whole_games_move_for_move(n, eps, flip, moves, quant):
+    """quant > 0: the network's probabilities collide bit for bit (what half precision does); the edges are
+    then stored in the order std::sort leaves equal elements in (search option std_sort_ties), which decides
+    the container order of every later tie-break"""
     if not oracles.have_ref(n):
         pytest.skip("compiled reference not available")
     G, seed = 3, 20240917
     opts = dict(num_rollouts=32, num_rollouts_per_batch=4, virtual_loss=1, persistent_tree=1, c_puct=1.5, komi=7.5)
     cutoff, thres, ratio, alpha = 12, 0.05, 0.1, 0.3
     seeds = [seed, seed, seed + 1]  # GameOptions::seed seeds every game thread alike; one more for variety
-    logs = [play_reference_game(n, s, opts, eps, alpha, flip, cutoff, thres, ratio, moves) for s in seeds]
+    logs = [play_reference_game(n, s, opts, eps, alpha, flip, cutoff, thres, ratio, moves, quant) for s in seeds]
 
     gb = emu.emu_batch(G, n)
-    mc = emu.EmuSearch(gb, rotation_flip=flip, **opts)
+    mc = emu.EmuSearch(gb, rotation_flip=flip, std_sort_ties=1, **opts)
     rs = RefStream(G, n, np.array(seeds, np.uint64))
     rs.init_actor(0)
     mc.attach_ref_stream(rs, 0, eps, alpha)
-    actor = plane_actor(n)
+    actor = plane_actor(n, quant)
     alive = np.ones(G, bool)
     drawn = np.zeros(G, bool)
     never = np.zeros(G, bool)
@@ -163,7 +177,7 @@ def test_selfplay_driver_on_the_reference_streams():
         expect.append(played)
 
     gb = emu.emu_batch(G, n)
-    mc = emu.EmuSearch(gb, rotation_flip=1, **opts)
+    mc = emu.EmuSearch(gb, rotation_flip=1, std_sort_ties=1, **opts)
     sp = SelfPlay(plane_actor(n), num_games=G, board_size=n, board=gb, search=mc, rng="reference", seed=seeds,
                   policy_distri_cutoff=cutoff, resign_thres=thres, never_resign_ratio=ratio, move_cutoff=move_cutoff,
                   root_epsilon=eps, root_alpha=alpha, **opts)
@@ -331,8 +345,8 @@ def test_policy_only_colour_on_the_reference_streams(two_models):
         expect_v.append(values)
 
     gb = emu.emu_batch(G, n)
-    mc = emu.EmuSearch(gb, rotation_flip=1, **opts)
-    mc2 = emu.EmuSearch(gb, rotation_flip=1, **opts) if two_models else None
+    mc = emu.EmuSearch(gb, rotation_flip=1, std_sort_ties=1, **opts)
+    mc2 = emu.EmuSearch(gb, rotation_flip=1, std_sort_ties=1, **opts) if two_models else None
     sp = SelfPlay(plane_actor(n), actor_white=plane_actor(n) if two_models else None, num_games=G, board_size=n, board=gb,
                   search=mc, search_white=mc2, rng="reference", seed=seeds, policy_distri_cutoff=cutoff, resign_thres=thres,
                   never_resign_ratio=ratio, move_cutoff=move_cutoff, root_epsilon=eps, root_alpha=alpha,
