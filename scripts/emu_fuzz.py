@@ -15,10 +15,25 @@ sys.path.insert(0, ROOT)
 from tests import emu, oracles  # noqa: E402
 
 
+QUANT = 0  # --quant Q: network probabilities on a grid of 1/Q (bit-equal values, as half precision gives) + std_sort_ties
+
+
+def net(n):
+    def f(feats, hashes):
+        pi, v = oracles.fakenet(hashes, n * n + 1)
+        if QUANT:
+            pi = (np.floor(pi * np.float32(QUANT)) / np.float32(QUANT)).astype(np.float32)
+        return pi, v
+
+    return f
+
+
 def fake_actor(search, n):
+    f = net(n)
+
     def actor(batch):
         h, _, _ = search.leaf_info()
-        pi, v = oracles.fakenet(h, n * n + 1)
+        pi, v = f(None, h)
         return {"pi": torch.from_numpy(pi), "V": torch.from_numpy(v)}
 
     return actor
@@ -59,7 +74,7 @@ class PortSearch:
 
     def __init__(self, n, G, opts):
         self.os = [oracles.Oracle(n) for _ in range(G)]
-        self.ms = [oracles.OracleMcts(n, **opts) for _ in range(G)]
+        self.ms = [oracles.OracleMcts(n, callback=net(n) if QUANT else None, std_sort_ties=int(QUANT > 0), **opts) for _ in range(G)]
         self.n, self.G = n, G
 
     def forward(self, acts):
@@ -97,9 +112,9 @@ def run_case(n, case, opts, G, opening, moves, dump, verbose):
     else:
         emu.emu_lib().simt_emu_set_order(case % 3)
         gb = emu.emu_batch(G, n)
-        mc = emu.EmuSearch(gb, rotation_flip=0, **opts)
+        mc = emu.EmuSearch(gb, rotation_flip=0, std_sort_ties=int(QUANT > 0), **opts)
     refs = [oracles.Ref(n) for _ in range(G)]
-    rms = [oracles.RefMcts(n, **opts) for _ in range(G)]
+    rms = [oracles.RefMcts(n, callback=net(n) if QUANT else None, **opts) for _ in range(G)]
     for row in opening:
         acts = np.array(row, np.int32)
         for g, o in enumerate(refs):
@@ -166,9 +181,10 @@ def main():
     ap.add_argument("--replay", help="run one dumped case again")
     ap.add_argument("--keep-going", action="store_true")
     ap.add_argument("--impl", choices=["emu", "port"], default="emu")
+    ap.add_argument("--quant", type=int, default=0, help="quantise the fake net's probabilities to 1/Q and search with std_sort_ties")
     a = ap.parse_args()
-    global IMPL
-    IMPL = a.impl
+    global IMPL, QUANT
+    IMPL, QUANT = a.impl, a.quant
     if a.replay:
         import json
 
