@@ -13,9 +13,9 @@
 // sort of a range when it reaches 0) + __final_insertion_sort (threshold 16).  Elements are 16-bit indices
 // into a key array, comp(a, b) = key[a] > key[b] (descending probability: the bit patterns of
 // non-negative floats order like the values).  Sequential by nature: one lane runs it on shared memory,
-// only for leaves that actually hold equal probabilities.  The same restatement in C (oracle/stdsort_emul.h,
-// test infrastructure) is pinned against the real std::sort; this copy is pinned through the search
-// (tests/test_emu_kernels.py::test_equal_priors_follow_std_sort).
+// only for leaves that actually hold equal probabilities.  Pinned against the real std::sort (this file
+// compiled for the host by tests/cxx/stdsort_check.cc: random arrays full of duplicates, adversarial inputs
+// that reach the heap sort) and through the search (tests/test_emu_kernels.py::test_equal_priors_follow_std_sort).
 #pragma once
 #include <cstdint>
 

@@ -13,6 +13,11 @@
 #include <vector>
 
 #include "../../oracle/stdsort_emul.h"
+// the product's copy of the restatement (device code: one lane of k_expand<N, true> runs it), compiled
+// for the host here and held to the same checks
+#define __device__
+#include "../../elf_b200/csrc/stdsort.cuh"
+#undef __device__
 
 typedef std::pair<unsigned short, float> data_type;
 
@@ -35,6 +40,17 @@ static bool check(const std::vector<float>& p) {
       printf("DIFF n=%d at %d: emul %d (p=%g) std::sort %d (p=%g)\n", n, i, v[i], p[v[i]], ref[i].first, ref[i].second);
       return false;
     }
+  if (n <= 511) {  // the device copy's explicit stack is sized for n <= 511 (it sorts 82 or 362 elements)
+    std::vector<uint16_t> d(n);
+    for (int i = 0; i < n; ++i) d[i] = (uint16_t)i;
+    elfb200::StdSortCtx dc{key.data()};
+    elfb200::ss_sort(&dc, d.data(), n);
+    for (int i = 0; i < n; ++i)
+      if (d[i] != ref[i].first) {
+        printf("DIFF (stdsort.cuh) n=%d at %d: %d vs std::sort %d\n", n, i, d[i], ref[i].first);
+        return false;
+      }
+  }
   return true;
 }
 

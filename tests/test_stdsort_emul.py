@@ -1,5 +1,6 @@
-"""oracle/stdsort_emul.h (the restated libstdc++ std::sort, which decides the order of moves with
-bit-equal probabilities in MCTSActor::pi2response) against the real std::sort of this toolchain:
+"""oracle/stdsort_emul.h and elf_b200/csrc/stdsort.cuh (the restated libstdc++ std::sort, which decides
+the order of moves with bit-equal probabilities in MCTSActor::pi2response; the second is the product's
+device code, compiled for the host here) against the real std::sort of this toolchain:
 tests/cxx/stdsort_check.cc sorts the same (move, probability) pairs with both -- random arrays full of
 duplicates, sizes 0..400, and adversarial inputs that drive the introsort into its heap-sort fallback."""
 import os
