@@ -412,8 +412,12 @@ __device__ __forceinline__ bool superko_scan(const uint64_t* __restrict__ hist, 
 }
 // Same test for the one-game-per-warp kernels (k_select): all 32 lanes scan, four independent
 // loads in flight per lane, so a 250-entry record costs two round trips instead of fourteen.
+// Every lane scans, but only the game's own lanes are guaranteed to hold the position hash (with three
+// 9x9 games per warp in the board kernels the per-game reductions run on a game's lanes only, and a move that
+// captures leaves the other lanes with a hash that lacks the capture's delta): the scan takes lane 0's copy.
 __device__ __forceinline__ bool superko_scan_warp(const uint64_t* __restrict__ hist, int n, uint64_t hash) {
   const int lane = threadIdx.x & 31;
+  hash = ((uint64_t)__shfl_sync(FULL, (uint32_t)(hash >> 32), 0) << 32) | __shfl_sync(FULL, (uint32_t)hash, 0);
   bool found = false;
   int i = lane;
   for (; i + 96 < n; i += 128) {

@@ -84,11 +84,12 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cases", type=int, default=10)
     ap.add_argument("--board", type=int, default=9)
+    ap.add_argument("--only", type=int, default=-1, help="run just this case index")
     a = ap.parse_args()
     if not oracles.have_ref(a.board):
         sys.exit("oracle/_ref is not built")
     bad = 0
-    for c in range(a.cases):
+    for c in (range(a.cases) if a.only < 0 else [a.only]):
         bad += not one_case(np.random.default_rng([a.seed, c]), a.board, c)
     print("cases", a.cases, "mismatches", bad)
     sys.exit(1 if bad else 0)

@@ -781,12 +781,15 @@ def test_expand_half_size_sort_network_on_late_positions(emu, oracle_lib):
     assert (mc.errors() == 0).all()
 
 
-@pytest.mark.parametrize("name", ["9_noprior_ties", "9_rounding_ties"])
+@pytest.mark.parametrize("name", ["9_noprior_ties", "9_rounding_ties", "9_superko_in_tree"])
 def test_puct_ties_resolve_in_the_reference_container_order(emu, name, lane_order):
     """k_select's uct_tie_break: exactly equal PUCT scores (no prior term; priors lost in the rounding of
     q) go to the first tied edge in the order of the reference's unordered_map, also when that edge lies
     beyond the scanned prefix (the node is scanned in full from then on) -- root visit tables equal the
-    COMPILED reference search's, move after move (twin of test_gpu_mcts.py::test_gpu_search_vs_reference)"""
+    COMPILED reference search's, move after move (twin of test_gpu_mcts.py::test_gpu_search_vs_reference).
+    9_superko_in_tree: a recapture two plies below the root repeats a position of the game -- a terminal
+    node inside the tree; the 9x9 search used to miss such a repetition when the move captured and the
+    matching record was scanned by a lane beyond the board's rows (found by scripts/emu_fuzz_streams.py)"""
     from tests.test_mcts_oracle_vs_ref import SCENARIOS, scenario_openings
 
     sc = SCENARIOS[name]

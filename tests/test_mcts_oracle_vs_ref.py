@@ -37,6 +37,12 @@ SCENARIOS = {
     "9_rounding_ties": dict(n=9, G=2, moves=4, open_plies=151, openings="mcts_tie_openings_9.json",
                             opts=dict(num_rollouts=119, num_rollouts_per_batch=14, virtual_loss=3, persistent_tree=1, c_puct=0.3,
                                       root_unexplored_q_zero=1, ply_pass_enabled=60, remove_pass_if_dangerous=1, komi=5.5)),
+    # a positional-superko repetition two plies below the root: the recapture that closes the cycle makes a
+    # terminal node inside the tree (GoState::terminated -> _check_superko, go_state.cc:96-111); the matching
+    # record sits at an index that lanes beyond the board's 9 rows scan (superko_scan_warp)
+    "9_superko_in_tree": dict(n=9, G=1, moves=3, open_plies=64, openings="mcts_superko_opening_9.json",
+                              opts=dict(num_rollouts=96, num_rollouts_per_batch=8, virtual_loss=1, persistent_tree=1, c_puct=5.0,
+                                        komi=5.5, ply_pass_enabled=30)),
 }
 
 
