@@ -19,6 +19,10 @@ class MctsBatch(RefStreamSearch):
     (default); "f16" / "bf16" = the fast mode for a half-precision channels-last network: the leaf
     batch is written as ``batch["s_nhwc"]`` ``[n,N,N,cpad]`` (planes in channels 0..17, zeros above),
     which ``elf_b200.model.FusedActor`` consumes without a cast/permute pass.
+    ``std_sort_ties=1`` (a search option like the others, ``include/elfb200_mcts.h``): moves whose network
+    probabilities are bit-equal are stored in the order ``std::sort`` leaves them in inside the reference's
+    ``pi2response`` instead of by ascending move -- needed to replay the reference's games exactly with a
+    half-precision network.
     ``strict_root``: raise when a persistent root does not match the board it is asked to search
     (the reference throws, tree_search.h:488-492); off = count it in ``errors()[0]`` and carry on
     with the tree rebuilt from the board."""
