@@ -17,22 +17,27 @@ from tests import emu, oracles  # noqa: E402
 from tests.test_refstream import plane_actor, ref_net  # noqa: E402
 
 
-def reference_thread(n, seed, opts, eps, alpha, flip, cutoff, thres, ratio, move_cutoff, po_colour, quant, moves):
+def reference_thread(n, seed, opts, eps, alpha, flip, cutoff, thres, ratio, move_cutoff, po_colour, quant, moves, two):
     g = oracles.RefRng(n, int(seed))
-    ref = oracles.RefMcts(n, callback=ref_net(n, quant), root_epsilon=eps, root_alpha=alpha, rotation_flip=flip,
-                          seed=g.next(), **opts)
+    mk = lambda: oracles.RefMcts(n, callback=ref_net(n, quant), root_epsilon=eps, root_alpha=alpha, rotation_flip=flip,
+                                 seed=g.next(), **opts)
+    ai = mk()  # init_ai(_ai), then init_ai(_ai2): the seeds come off the game generator in that order
+    ai2 = mk() if two else None
     rc = oracles.RefResign(n, thres, ratio)
     st = oracles.Ref(n)
     played = []
 
     def finish():
         nonlocal st
-        ref.end_game(st)
+        ai.end_game(st)
+        if ai2 is not None:
+            ai2.end_game(st)
         st = oracles.Ref(n)
         rc.reset()
 
     for _ in range(moves):
         ply, nxt = int(st.info()[0]), int(st.info()[1])
+        ref = ai2 if (ai2 is not None and nxt == 2) else ai  # game_selfplay.cc:366-367
         if nxt == po_colour:
             r = ref.act(st, policy_only=True)
             a = r["best_action"]
@@ -67,14 +72,17 @@ def one_case(rng, n, case):
     moves = int(rng.integers(10, 140 if n == 9 else 14))
     G = int(rng.integers(1, 4))
     seeds = np.array([int(x) for x in rng.integers(1, 2**31, G)], np.uint64)
+    two = bool(rng.random() < 0.3)  # an evaluation match: a second AI with its own tree plays white
     tag = (f"case {case}: n={n} G={G} moves={moves} eps={eps} alpha={alpha} flip={flip} cutoff={cutoff} thres={thres} "
-           f"ratio={ratio} move_cutoff={move_cutoff} policy_only={po_colour} quant={quant} {opts}")
-    expect = [reference_thread(n, s, opts, eps, alpha, flip, cutoff, thres, ratio, move_cutoff, po_colour, quant, moves)
+           f"ratio={ratio} move_cutoff={move_cutoff} policy_only={po_colour} quant={quant} two_models={two} {opts}")
+    expect = [reference_thread(n, s, opts, eps, alpha, flip, cutoff, thres, ratio, move_cutoff, po_colour, quant, moves, two)
               for s in seeds]
     emu.emu_lib().simt_emu_set_order(case % 3)
     gb = emu.emu_batch(G, n)
     mc = emu.EmuSearch(gb, rotation_flip=flip, std_sort_ties=int(quant > 0), **opts)
-    sp = SelfPlay(plane_actor(n, quant), num_games=G, board_size=n, board=gb, search=mc, rng="reference", seed=seeds,
+    mc2 = emu.EmuSearch(gb, rotation_flip=flip, std_sort_ties=int(quant > 0), **opts) if two else None
+    sp = SelfPlay(plane_actor(n, quant), actor_white=plane_actor(n, quant) if two else None, search_white=mc2,
+                  num_games=G, board_size=n, board=gb, search=mc, rng="reference", seed=seeds,
                   policy_distri_cutoff=cutoff, resign_thres=thres, never_resign_ratio=ratio, move_cutoff=move_cutoff,
                   root_epsilon=eps, root_alpha=alpha, black_use_policy_network_only=po_colour == 1,
                   white_use_policy_network_only=po_colour == 2, **opts)
@@ -89,7 +97,7 @@ def one_case(rng, n, case):
     gb.forward = logged
     for t in range(moves):
         sp.step()
-        if mc.errors()[3]:
+        if mc.errors()[3] or (mc2 is not None and mc2.errors()[3]):
             print("ok (pruned)", tag, flush=True)
             return True
     if got != expect:
